@@ -1,0 +1,84 @@
+"""ctypes binding of libfs2b200.so (the C ABI declared in include/fs2b200.h).
+
+There is deliberately NO fallback here: if the CUDA library is missing or a call fails, the product
+path raises.  The only pure-Python pieces of this package are host logic (shapes, descriptors).
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "csrc", "libfs2b200.so")
+
+c_i32, c_i64, c_f32, c_vp = ctypes.c_int32, ctypes.c_int64, ctypes.c_float, ctypes.c_void_p
+
+
+class Operand(ctypes.Structure):
+    _fields_ = [
+        ("ptr", c_vp), ("ld", c_i64), ("batch_stride", c_i64), ("inner", c_i32), ("rows", c_i32),
+        ("batches", c_i32), ("mn_major", c_i32), ("inner_base", c_i32), ("zdiv", c_i32),
+        ("zmod_stride", c_i32),
+    ]
+
+
+class Gemm(ctypes.Structure):
+    _fields_ = [
+        ("a", Operand), ("b", Operand), ("mode", c_i32), ("M", c_i32), ("N", c_i32), ("K", c_i32),
+        ("Z", c_i32), ("taps", c_i32), ("tap_shift0", c_i32), ("b_tap_kstride", c_i32),
+        ("splits", c_i32), ("epilogue", c_i32), ("d_f32", c_i32), ("d_atomic", c_i32),
+        ("d_zdiv", c_i32), ("alpha", c_f32), ("d", c_vp), ("ldd", c_i64), ("d_col_stride", c_i64),
+        ("d_tap_stride", c_i64), ("d_zdiv_stride", c_i64), ("d_zmod_stride", c_i64),
+        ("bias", c_vp), ("aux", c_vp), ("ld_aux", c_i64), ("aux_batch_stride", c_i64),
+    ]
+
+
+GEMM_NORMAL, GEMM_WGRAD = 0, 1
+EPI_NONE, EPI_RELU, EPI_RELU_BWD, EPI_ADD_AUX = 0, 1, 2, 3
+
+_lib = None
+
+
+class Fs2Error(RuntimeError):
+    pass
+
+
+def so_path():
+    return _SO
+
+
+def lib():
+    """Load the library once.  Raises (never falls back) when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_SO):
+            raise Fs2Error(
+                "libfs2b200.so is not built (%s). Run `python __graft_entry__.py build` -- this "
+                "package has no CPU / eager fallback." % _SO)
+        _lib = ctypes.CDLL(_SO)
+        _declare(_lib)
+    return _lib
+
+
+def check(rc, what):
+    if rc != 0:
+        raise Fs2Error("%s failed (rc=%d): %s" % (what, rc, lib().fs2_last_error().decode()))
+
+
+def _declare(L):
+    L.fs2_version.restype = ctypes.c_int
+    L.fs2_last_error.restype = ctypes.c_char_p
+    L.fs2_launch_count.restype = c_i64
+    L.fs2_gemm_bf16.argtypes = [ctypes.POINTER(Gemm), ctypes.c_int, c_vp]
+    L.fs2_gemm_bf16.restype = ctypes.c_int
+    for name, argtypes in _PROTOS.items():
+        fn = getattr(L, name)
+        fn.argtypes = argtypes
+        fn.restype = ctypes.c_int
+
+
+# name -> argtypes for every int-returning kernel entry point (filled by the op sections below;
+# tests/test_abi.py checks this table against include/fs2b200.h).
+_PROTOS = {}
+
+
+def launch_count():
+    return int(lib().fs2_launch_count())

@@ -1,0 +1,42 @@
+#include "common.h"
+
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+
+namespace fs2 {
+static thread_local char g_err[512] = "";
+static std::atomic<int64_t> g_launches{0};
+
+int set_error(const char* msg) {
+  std::snprintf(g_err, sizeof g_err, "%s", msg);
+  return 1;
+}
+int set_cuda_error(const char* what, cudaError_t e) {
+  std::snprintf(g_err, sizeof g_err, "%s: %s", what, cudaGetErrorString(e));
+  return 2;
+}
+int check_launch(const char* kernel_name) {
+  cudaError_t e = cudaPeekAtLastError();
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return set_cuda_error(kernel_name, e);
+  }
+  return 0;
+}
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+}  // namespace fs2
+
+extern "C" {
+int fs2_version(void) { return FS2_ABI_VERSION; }
+const char* fs2_last_error(void) { return fs2::g_err; }
+int64_t fs2_launch_count(void) { return fs2::g_launches.load(); }
+
+int fs2_gemm_bf16(const fs2_gemm* g, int impl, void* stream) {
+  if (!g) return fs2::set_error("fs2_gemm_bf16: null descriptor");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (impl == 0) return fs2::gemm_tc_launch(*g, s);
+  if (impl == 1) return fs2::gemm_simt_launch(*g, s);
+  return fs2::set_error("fs2_gemm_bf16: unknown impl");
+}
+}

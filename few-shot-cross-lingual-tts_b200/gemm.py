@@ -1,0 +1,93 @@
+"""Host-side descriptors for the tcgen05 GEMM engine (fs2_gemm_bf16, include/fs2b200.h).
+
+Only shape bookkeeping lives here; all arithmetic happens in csrc/gemm_tc.cu.
+"""
+import os
+
+import torch
+
+from . import _cabi
+from ._cabi import (EPI_ADD_AUX, EPI_NONE, EPI_RELU, EPI_RELU_BWD, GEMM_NORMAL, GEMM_WGRAD, Gemm,
+                    Operand)
+
+__all__ = ["operand", "run", "gemm", "wgrad", "EPI_NONE", "EPI_RELU", "EPI_RELU_BWD", "EPI_ADD_AUX"]
+
+
+def _impl():
+    # FS2_GEMM_IMPL=simt selects the CUDA-core cross-check kernel (debug only).
+    return 1 if os.environ.get("FS2_GEMM_IMPL", "tc") == "simt" else 0
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def operand(t, inner, rows, batches=1, ld=None, batch_stride=None, mn_major=False, inner_base=0,
+            zdiv=1, zmod_stride=0):
+    """Describe bf16 tensor `t` as [batches][rows][inner] with explicit element strides."""
+    assert t.dtype == torch.bfloat16 and t.is_cuda, "GEMM operands are bf16 CUDA tensors"
+    ld = int(ld if ld is not None else inner)
+    batch_stride = int(batch_stride if batch_stride is not None else ld * rows)
+    o = Operand()
+    o.ptr = t.data_ptr()
+    o.ld, o.batch_stride = ld, batch_stride
+    o.inner, o.rows, o.batches = int(inner), int(rows), int(batches)
+    o.mn_major = 1 if mn_major else 0
+    o.inner_base, o.zdiv, o.zmod_stride = int(inner_base), int(zdiv), int(zmod_stride)
+    return o
+
+
+def run(g, impl=None):
+    rc = _cabi.lib().fs2_gemm_bf16(g, _impl() if impl is None else impl, _stream())
+    _cabi.check(rc, "fs2_gemm_bf16")
+
+
+def gemm(a, b, d, M, N, K, Z=1, taps=1, tap_shift0=0, b_tap_kstride=0, ldd=None, bias=None,
+         epilogue=EPI_NONE, aux=None, ld_aux=0, aux_batch_stride=0, alpha=1.0, d_zdiv=1,
+         d_zdiv_stride=0, d_zmod_stride=0, impl=None):
+    """D[z] = epi(alpha * sum_tap A[z][m+shift+tap] . B[z][n][tap*kstride+k] + bias)."""
+    g = Gemm()
+    g.a, g.b = a, b
+    g.mode = GEMM_NORMAL
+    g.M, g.N, g.K, g.Z = int(M), int(N), int(K), int(Z)
+    g.taps, g.tap_shift0, g.b_tap_kstride = int(taps), int(tap_shift0), int(b_tap_kstride)
+    g.splits = 1
+    g.epilogue = epilogue
+    assert d.dtype in (torch.bfloat16, torch.float32)
+    g.d_f32 = 1 if d.dtype == torch.float32 else 0
+    g.d_atomic = 0
+    g.d_zdiv, g.d_zdiv_stride, g.d_zmod_stride = int(d_zdiv), int(d_zdiv_stride), int(d_zmod_stride)
+    g.alpha = float(alpha)
+    g.d = d.data_ptr()
+    g.ldd = int(ldd if ldd is not None else N)
+    g.d_col_stride, g.d_tap_stride = 1, 0
+    g.bias = bias.data_ptr() if bias is not None else None
+    if bias is not None:
+        assert bias.dtype == torch.float32
+    g.aux = aux.data_ptr() if aux is not None else None
+    g.ld_aux, g.aux_batch_stride = int(ld_aux), int(aux_batch_stride)
+    run(g, impl)
+
+
+def wgrad(a, b, d, M, N, taps=1, tap_shift0=0, ldd=None, d_col_stride=1, d_tap_stride=0, splits=1,
+          accumulate=True, impl=None):
+    """D[m][tap][n] (+)= sum_{z,r} A[z][r][m] * B[z][r+shift+tap][n]; D is fp32."""
+    assert d.dtype == torch.float32
+    g = Gemm()
+    g.a, g.b = a, b
+    g.mode = GEMM_WGRAD
+    g.M, g.N, g.K, g.Z = int(M), int(N), 0, 1
+    g.taps, g.tap_shift0, g.b_tap_kstride = int(taps), int(tap_shift0), 0
+    g.splits = int(splits)
+    g.epilogue = EPI_NONE
+    g.d_f32 = 1
+    g.d_atomic = 1 if (accumulate or splits > 1) else 0
+    g.d_zdiv, g.d_zdiv_stride, g.d_zmod_stride = 1, 0, 0
+    g.alpha = 1.0
+    g.d = d.data_ptr()
+    g.ldd = int(ldd if ldd is not None else N * taps)
+    g.d_col_stride, g.d_tap_stride = int(d_col_stride), int(d_tap_stride)
+    g.bias = None
+    g.aux = None
+    g.ld_aux = g.aux_batch_stride = 0
+    run(g, impl)

@@ -1,0 +1,167 @@
+"""tcgen05 GEMM engine vs a plain PyTorch fp32 reference (and vs the CUDA-core cross-check kernel).
+
+Every case feeds bf16 operands; the reference multiplies the same bf16 values in fp32.
+Tolerances: fp32 outputs rel-err <= 2e-3 (accumulation order), bf16 outputs <= 1e-2 (rounding).
+"""
+import pytest
+import torch
+
+from fs2b200 import sub
+
+pytestmark = pytest.mark.gpu
+
+G = None
+
+
+def setup_module(module):
+    global G
+    G = sub("gemm")
+
+
+def rel_err(a, b):
+    a, b = a.float(), b.float()
+    return ((a - b).norm() / (b.norm() + 1e-12)).item()
+
+
+def rnd(*shape, scale=1.0):
+    return (torch.randn(*shape, device="cuda") * scale).to(torch.bfloat16)
+
+
+IMPLS = [0, 1]  # 0 = tcgen05, 1 = CUDA-core cross-check
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+@pytest.mark.parametrize("M,N,K", [(300, 768, 256), (128, 256, 64), (1000, 256, 1024), (77, 80, 256),
+                                   (4096, 1024, 256), (513, 200, 192)])
+@pytest.mark.parametrize("relu", [False, True])
+def test_linear(impl, M, N, K, relu):
+    torch.manual_seed(M + N + K)
+    x, w = rnd(M, K), rnd(N, K, scale=K ** -0.5)
+    bias = torch.randn(N, device="cuda")
+    for out_dtype, tol in ((torch.bfloat16, 1e-2), (torch.float32, 2e-3)):
+        y = torch.full((M, N), float("nan"), device="cuda", dtype=out_dtype)
+        G.gemm(G.operand(x, K, M), G.operand(w, K, N), y, M, N, K, bias=bias,
+               epilogue=G.EPI_RELU if relu else G.EPI_NONE, impl=impl)
+        ref = x.float() @ w.float().t() + bias
+        if relu:
+            ref = ref.relu()
+        assert torch.isfinite(y.float()).all()
+        assert rel_err(y, ref) < tol, (impl, out_dtype, rel_err(y, ref))
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+@pytest.mark.parametrize("B,T,Cin,Cout,k", [(3, 200, 256, 1024, 9), (2, 77, 256, 256, 3),
+                                            (2, 130, 512, 512, 5), (2, 130, 80, 512, 5),
+                                            (2, 130, 512, 80, 5), (5, 40, 1024, 256, 1)])
+def test_conv1d_channels_last(impl, B, T, Cin, Cout, k):
+    torch.manual_seed(B * T + Cin + k)
+    x = rnd(B, T, Cin)
+    w = (torch.randn(Cout, Cin, k, device="cuda") * (Cin * k) ** -0.5).to(torch.bfloat16)
+    bias = torch.randn(Cout, device="cuda")
+    cpad = ((Cin + 63) // 64) * 64
+    wp = torch.zeros(Cout, k, cpad, device="cuda", dtype=torch.bfloat16)
+    wp[:, :, :Cin] = w.permute(0, 2, 1)
+    y = torch.full((B, T, Cout), float("nan"), device="cuda", dtype=torch.bfloat16)
+    G.gemm(G.operand(x, Cin, T, B), G.operand(wp, k * cpad, Cout), y, T, Cout, Cin, Z=B, taps=k,
+           tap_shift0=-((k - 1) // 2), b_tap_kstride=cpad, bias=bias, d_zdiv=1,
+           d_zdiv_stride=T * Cout, impl=impl)
+    ref = torch.nn.functional.conv1d(x.float().transpose(1, 2), w.float(), bias,
+                                     padding=(k - 1) // 2).transpose(1, 2)
+    assert torch.isfinite(y.float()).all()
+    assert rel_err(y, ref) < 1e-2, rel_err(y, ref)
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+@pytest.mark.parametrize("B,T,H", [(2, 200, 2), (3, 77, 2), (1, 850, 2)])
+def test_attention_bmms(impl, B, T, H):
+    """QK^T from the fused [B,T,3*H*dk] buffer, then P.V with V as an MN-major operand."""
+    dk = 128
+    torch.manual_seed(T)
+    C = 3 * H * dk
+    qkv = rnd(B, T, C)
+    Tp = ((T + 63) // 64) * 64
+    s = torch.full((B * H, T, Tp), float("nan"), device="cuda")
+    a = G.operand(qkv, C, T, B, inner_base=0, zdiv=H, zmod_stride=dk)
+    b = G.operand(qkv, C, T, B, inner_base=H * dk, zdiv=H, zmod_stride=dk)
+    G.gemm(a, b, s, T, T, dk, Z=B * H, ldd=Tp, alpha=dk ** -0.5, d_zdiv=1, d_zdiv_stride=T * Tp,
+           impl=impl)
+    q = qkv[..., : H * dk].float().view(B, T, H, dk).permute(0, 2, 1, 3)
+    kk = qkv[..., H * dk: 2 * H * dk].float().view(B, T, H, dk).permute(0, 2, 1, 3)
+    v = qkv[..., 2 * H * dk:].float().view(B, T, H, dk).permute(0, 2, 1, 3)
+    sref = (q @ kk.transpose(-1, -2)) * dk ** -0.5  # [B,H,T,T]; z = b*H + h
+    assert rel_err(s[:, :, :T].reshape(B, H, T, T), sref) < 2e-3
+    p = torch.zeros(B * H, T, Tp, device="cuda", dtype=torch.bfloat16)
+    p[:, :, :T] = torch.softmax(sref, -1).reshape(B * H, T, T).to(torch.bfloat16)
+    o = torch.full((B, T, H * dk), float("nan"), device="cuda", dtype=torch.bfloat16)
+    pa = G.operand(p, Tp, T, B * H)
+    vb = G.operand(qkv, C, T, B, mn_major=True, inner_base=2 * H * dk, zdiv=H, zmod_stride=dk)
+    G.gemm(pa, vb, o, T, dk, T, Z=B * H, ldd=H * dk, d_zdiv=H, d_zdiv_stride=T * H * dk,
+           d_zmod_stride=dk, impl=impl)
+    oref = (p[:, :, :T].float().reshape(B, H, T, T) @ v).permute(0, 2, 1, 3).reshape(B, T, H * dk)
+    assert torch.isfinite(o.float()).all()
+    assert rel_err(o, oref) < 1e-2, rel_err(o, oref)
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+def test_mn_major_both(impl):
+    """dK = dS^T Q : A = dS^T (MN-major), B = Q^T (MN-major), batched."""
+    torch.manual_seed(5)
+    Z, Tq, Tk, dk = 4, 150, 150, 128
+    Tp = 192
+    ds = torch.zeros(Z, Tq, Tp, device="cuda", dtype=torch.bfloat16)
+    ds[:, :, :Tk] = rnd(Z, Tq, Tk)
+    q = rnd(Z, Tq, dk)
+    out = torch.full((Z, Tk, dk), float("nan"), device="cuda", dtype=torch.bfloat16)
+    a = G.operand(ds, Tk, Tq, Z, ld=Tp, batch_stride=Tq * Tp, mn_major=True)
+    b = G.operand(q, dk, Tq, Z, mn_major=True)
+    G.gemm(a, b, out, Tk, dk, Tq, Z=Z, ldd=dk, d_zdiv=1, d_zdiv_stride=Tk * dk, impl=impl)
+    ref = ds[:, :, :Tk].float().transpose(1, 2) @ q.float()
+    assert rel_err(out, ref) < 1e-2, rel_err(out, ref)
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+@pytest.mark.parametrize("epi", ["relu_bwd", "add_aux"])
+def test_aux_epilogues(impl, epi):
+    torch.manual_seed(9)
+    M, N, K = 333, 1024, 256
+    x, w = rnd(M, K), rnd(N, K, scale=K ** -0.5)
+    aux = rnd(M, N)
+    y = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    G.gemm(G.operand(x, K, M), G.operand(w, K, N), y, M, N, K, aux=aux, ld_aux=N,
+           epilogue=G.EPI_RELU_BWD if epi == "relu_bwd" else G.EPI_ADD_AUX, impl=impl)
+    ref = x.float() @ w.float().t()
+    ref = ref * (aux.float() > 0) if epi == "relu_bwd" else ref + aux.float()
+    assert rel_err(y, ref) < 1e-2, rel_err(y, ref)
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+@pytest.mark.parametrize("M,N,K,splits", [(1000, 768, 256, 1), (1000, 768, 256, 5), (3000, 256, 1024, 7),
+                                          (500, 80, 256, 3)])
+def test_wgrad_linear(impl, M, N, K, splits):
+    """dW[N,K] = dY^T X, accumulated on top of existing contents."""
+    torch.manual_seed(M)
+    dy, x = rnd(M, N), rnd(M, K)
+    dw = torch.ones(N, K, device="cuda")
+    G.wgrad(G.operand(dy, N, M, mn_major=True), G.operand(x, K, M, mn_major=True), dw, N, K,
+            splits=splits, impl=impl)
+    ref = dy.float().t() @ x.float() + 1.0
+    assert rel_err(dw, ref) < 2e-3, rel_err(dw, ref)
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+@pytest.mark.parametrize("B,T,Cin,Cout,k,splits", [(3, 200, 256, 1024, 9, 2), (2, 77, 256, 256, 3, 1),
+                                                   (2, 130, 80, 512, 5, 3), (2, 130, 512, 80, 5, 2)])
+def test_wgrad_conv(impl, B, T, Cin, Cout, k, splits):
+    """dW[co][ci][tap] written straight in the reference parameter layout (Conv1d.weight)."""
+    torch.manual_seed(T)
+    x = rnd(B, T, Cin).float().requires_grad_()
+    w = torch.zeros(Cout, Cin, k, device="cuda", requires_grad=True)
+    dy = rnd(B, T, Cout)
+    y = torch.nn.functional.conv1d(x.transpose(1, 2), w, None, padding=(k - 1) // 2).transpose(1, 2)
+    y.backward(dy.float())
+    dw = torch.zeros(Cout, Cin, k, device="cuda")
+    xb = x.detach().to(torch.bfloat16)
+    G.wgrad(G.operand(dy, Cout, T, B, mn_major=True), G.operand(xb, Cin, T, B, mn_major=True), dw,
+            Cout, Cin, taps=k, tap_shift0=-((k - 1) // 2), ldd=Cin * k, d_col_stride=k,
+            d_tap_stride=1, splits=splits, impl=impl)
+    assert rel_err(dw, w.grad) < 2e-3, rel_err(dw, w.grad)

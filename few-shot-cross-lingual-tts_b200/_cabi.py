@@ -63,21 +63,45 @@ def check(rc, what):
         raise Fs2Error("%s failed (rc=%d): %s" % (what, rc, lib().fs2_last_error().decode()))
 
 
+_CTYPE = {"int": ctypes.c_int, "int32_t": c_i32, "int64_t": c_i64, "uint64_t": ctypes.c_uint64,
+          "float": c_f32}
+
+
+def header_path():
+    return os.path.join(os.path.dirname(_HERE), "include", "fs2b200.h")
+
+
+def parse_header(path=None):
+    """{name: (restype, [argtypes])} for every function declared in include/fs2b200.h.
+
+    The header is the single source of truth for the ABI; the ctypes prototypes are derived from it.
+    """
+    import re
+
+    text = open(path or header_path()).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    protos = {}
+    for m in re.finditer(r"\b(int|int64_t|const char\*)\s+(fs2_\w+)\s*\(([^;{]*?)\)\s*;", text, flags=re.S):
+        ret, name, args = m.group(1), m.group(2), m.group(3).strip()
+        argtypes = []
+        if args and args != "void":
+            for a in args.split(","):
+                a = " ".join(a.split())
+                if "*" in a:
+                    argtypes.append(c_vp)
+                else:
+                    argtypes.append(_CTYPE[a.replace("const ", "").split(" ")[0]])
+        restype = {"int": ctypes.c_int, "int64_t": c_i64, "const char*": ctypes.c_char_p}[ret]
+        protos[name] = (restype, argtypes)
+    return protos
+
+
 def _declare(L):
-    L.fs2_version.restype = ctypes.c_int
-    L.fs2_last_error.restype = ctypes.c_char_p
-    L.fs2_launch_count.restype = c_i64
-    L.fs2_gemm_bf16.argtypes = [ctypes.POINTER(Gemm), ctypes.c_int, c_vp]
-    L.fs2_gemm_bf16.restype = ctypes.c_int
-    for name, argtypes in _PROTOS.items():
-        fn = getattr(L, name)
+    for name, (restype, argtypes) in parse_header().items():
+        fn = getattr(L, name)  # AttributeError here = header and library disagree: fail loudly
+        fn.restype = restype
         fn.argtypes = argtypes
-        fn.restype = ctypes.c_int
-
-
-# name -> argtypes for every int-returning kernel entry point (filled by the op sections below;
-# tests/test_abi.py checks this table against include/fs2b200.h).
-_PROTOS = {}
+    L.fs2_gemm_bf16.argtypes = [ctypes.POINTER(Gemm), ctypes.c_int, c_vp]
 
 
 def launch_count():

@@ -1,0 +1,291 @@
+// PostNet BatchNorm1d (training mode) + tanh + dropout, forward and backward, channels-last.
+//
+// Replaces transformer/Layers.py:129-137: for each of the five blocks
+//     x = F.dropout(torch.tanh(BatchNorm1d(conv(x))), 0.5, training)      (no tanh on the last)
+// and `postnet(output) + output` (lightning/model/fastspeech2m.py:145) for the last block.
+// Statistics are taken over ALL B*T rows, padded frames included, exactly like nn.BatchNorm1d on
+// the reference's [B, C, T] tensor; running_mean / running_var use
+// momentum 0.1 and the unbiased variance; eps = 1e-5.
+// Kernels: column statistics (sum, sum of squares) -> apply; backward: column reductions
+// (dbeta = sum g, dgamma = sum g*yhat) -> apply.  All HBM-bound (one read of y per kernel).
+#include "common.h"
+#include "util.cuh"
+
+namespace fs2 {
+
+constexpr float kBnEps = 1e-5f;
+
+struct BnArgs {
+  const __nv_bfloat16* y;  // conv output [M][C]
+  long long M;
+  int C;
+  float* stats;        // [2][C]: sum, sumsq (forward)   |  backward: [2][C] dbeta, dgamma
+  const float* fstats; // forward stats (read-only in apply / backward)
+  const float* gamma;
+  const float* beta;
+  int act_tanh;
+  float p_drop;
+  uint64_t seed;
+  const uint64_t* seed_dev;
+  // forward outputs
+  __nv_bfloat16* out_bf16;
+  float* out_f32;
+  const float* res_f32;
+  // backward
+  const void* dout;
+  int dout_is_f32;
+  __nv_bfloat16* dy;
+  int rows_per_block;
+};
+
+__device__ __forceinline__ void load_vec8(const __nv_bfloat16* p, float (&f)[8]) { unpack8(ld8(p), f); }
+
+// mean / rstd of 8 consecutive channels from the raw sums
+__device__ __forceinline__ void col_stats8(const float* fstats, int C, int c, float invM, float (&mean)[8],
+                                           float (&rstd)[8]) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float m = fstats[c + j] * invM;
+    const float var = fmaxf(fstats[C + c + j] * invM - m * m, 0.f);
+    mean[j] = m;
+    rstd[j] = rsqrtf(var + kBnEps);
+  }
+}
+
+__global__ void __launch_bounds__(256) bn_stats_kernel(const BnArgs a) {
+  extern __shared__ float sh[];  // [2][C]
+  const int vpr = a.C / 8, rs = 256 / vpr;
+  for (int i = threadIdx.x; i < 2 * a.C; i += 256) sh[i] = 0.f;
+  __syncthreads();
+  const int v = threadIdx.x % vpr, ro = threadIdx.x / vpr;
+  if (ro < rs) {
+    float s[8], q[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.f;
+    const long long r0 = (long long)blockIdx.x * a.rows_per_block;
+    const long long r1 = min(r0 + a.rows_per_block, a.M);
+    for (long long r = r0 + ro; r < r1; r += rs) {
+      float f[8];
+      load_vec8(a.y + r * a.C + v * 8, f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        s[j] += f[j];
+        q[j] += f[j] * f[j];
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      atomicAdd(&sh[v * 8 + j], s[j]);
+      atomicAdd(&sh[a.C + v * 8 + j], q[j]);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * a.C; i += 256) atomicAdd(a.stats + i, sh[i]);
+}
+
+__global__ void __launch_bounds__(256) bn_apply_kernel(const BnArgs a) {
+  const int vpr = a.C / 8;
+  const float invM = 1.f / (float)a.M;
+  const uint32_t thresh = dropout_thresh(a.p_drop);
+  const float keep_scale = a.p_drop > 0.f ? 1.f / (1.f - a.p_drop) : 1.f;
+  const long long n_vec = a.M * vpr;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / vpr;
+    const int c = (i - r * vpr) * 8;
+    float f[8], mean[8], rstd[8];
+    load_vec8(a.y + r * a.C + c, f);
+    col_stats8(a.fstats, a.C, c, invM, mean, rstd);
+    const uint32_t keep = thresh ? dropout_keep8(mix_seed(a.seed_dev, a.seed), (uint64_t)r * a.C + c, thresh) : 0xFFu;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float z = (f[j] - mean[j]) * rstd[j] * a.gamma[c + j] + a.beta[c + j];
+      if (a.act_tanh) z = tanhf(z);
+      f[j] = (keep >> j) & 1u ? z * keep_scale : 0.f;
+    }
+    if (a.out_f32) {
+      float* o = a.out_f32 + r * a.C + c;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = f[j] + (a.res_f32 ? a.res_f32[r * a.C + c + j] : 0.f);
+    } else {
+      st8(a.out_bf16 + r * a.C + c, pack8(f));
+    }
+  }
+}
+
+// g = dout * dropout_mask * (1 - tanh(z)^2); returns yhat in `yh`
+__device__ __forceinline__ void bn_bwd_g(const BnArgs& a, long long r, int c, float invM, uint32_t thresh,
+                                         float keep_scale, float (&g)[8], float (&yh)[8],
+                                         float (&rstd)[8]) {
+  float f[8], mean[8];
+  load_vec8(a.y + r * a.C + c, f);
+  col_stats8(a.fstats, a.C, c, invM, mean, rstd);
+  if (a.dout_is_f32) {
+    const float* d = static_cast<const float*>(a.dout) + r * a.C + c;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) g[j] = d[j];
+  } else {
+    load_vec8(static_cast<const __nv_bfloat16*>(a.dout) + r * a.C + c, g);
+  }
+  const uint32_t keep = thresh ? dropout_keep8(mix_seed(a.seed_dev, a.seed), (uint64_t)r * a.C + c, thresh) : 0xFFu;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    yh[j] = (f[j] - mean[j]) * rstd[j];
+    g[j] = (keep >> j) & 1u ? g[j] * keep_scale : 0.f;
+    if (a.act_tanh) {
+      const float t = tanhf(yh[j] * a.gamma[c + j] + a.beta[c + j]);
+      g[j] *= 1.f - t * t;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const BnArgs a) {
+  extern __shared__ float sh[];  // [2][C]
+  const int vpr = a.C / 8, rs = 256 / vpr;
+  const float invM = 1.f / (float)a.M;
+  const uint32_t thresh = dropout_thresh(a.p_drop);
+  const float keep_scale = a.p_drop > 0.f ? 1.f / (1.f - a.p_drop) : 1.f;
+  for (int i = threadIdx.x; i < 2 * a.C; i += 256) sh[i] = 0.f;
+  __syncthreads();
+  const int v = threadIdx.x % vpr, ro = threadIdx.x / vpr;
+  if (ro < rs) {
+    float sb[8], sg[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sb[j] = sg[j] = 0.f;
+    const long long r0 = (long long)blockIdx.x * a.rows_per_block;
+    const long long r1 = min(r0 + a.rows_per_block, a.M);
+    for (long long r = r0 + ro; r < r1; r += rs) {
+      float g[8], yh[8], rstd[8];
+      bn_bwd_g(a, r, v * 8, invM, thresh, keep_scale, g, yh, rstd);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        sb[j] += g[j];
+        sg[j] += g[j] * yh[j];
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      atomicAdd(&sh[v * 8 + j], sb[j]);
+      atomicAdd(&sh[a.C + v * 8 + j], sg[j]);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * a.C; i += 256) atomicAdd(a.stats + i, sh[i]);
+}
+
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BnArgs a) {
+  const int vpr = a.C / 8;
+  const float invM = 1.f / (float)a.M;
+  const uint32_t thresh = dropout_thresh(a.p_drop);
+  const float keep_scale = a.p_drop > 0.f ? 1.f / (1.f - a.p_drop) : 1.f;
+  const long long n_vec = a.M * vpr;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / vpr;
+    const int c = (i - r * vpr) * 8;
+    float g[8], yh[8], rstd[8], o[8];
+    bn_bwd_g(a, r, c, invM, thresh, keep_scale, g, yh, rstd);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float db = a.stats[c + j] * invM, dg = a.stats[a.C + c + j] * invM;
+      o[j] = a.gamma[c + j] * rstd[j] * (g[j] - db - yh[j] * dg);
+    }
+    st8(a.dy + r * a.C + c, pack8(o));
+  }
+}
+
+__global__ void bn_running_kernel(const float* __restrict__ fstats, long long M, int C, float momentum,
+                                  float* running_mean, float* running_var, int64_t* num_batches) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c == 0 && num_batches) *num_batches += 1;
+  if (c >= C) return;
+  const float invM = 1.f / (float)M;
+  const float m = fstats[c] * invM;
+  const float var = fmaxf(fstats[C + c] * invM - m * m, 0.f);
+  const float unbiased = M > 1 ? var * ((float)M / (float)(M - 1)) : var;
+  running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * m;
+  running_var[c] = (1.f - momentum) * running_var[c] + momentum * unbiased;
+}
+
+static int bn_check(long long M, int C) {
+  if (C % 8 || C > 2048 || C / 8 > 256) return set_error("batchnorm: C must be a multiple of 8, <= 2048");
+  if (M <= 0) return set_error("batchnorm: empty batch");
+  return 0;
+}
+static int rows_per_block_for(long long M) {
+  long long rpb = (M + 148 * 4 - 1) / (148 * 4);
+  if (rpb < 32) rpb = 32;
+  return (int)rpb;
+}
+static unsigned ew_grid(long long n_vec) {
+  long long g = (n_vec + 255) / 256;
+  if (g > 148 * 16) g = 148 * 16;
+  return (unsigned)(g < 1 ? 1 : g);
+}
+
+}  // namespace fs2
+
+extern "C" {
+
+// stats f32 [2][C] must be zero on entry (sum, sum of squares are accumulated with atomics).
+int fs2_bn_stats_bf16(const void* y, int64_t M, int C, float* stats, void* stream) {
+  if (int rc = fs2::bn_check(M, C)) return rc;
+  fs2::BnArgs a{};
+  a.y = static_cast<const __nv_bfloat16*>(y);
+  a.M = M; a.C = C; a.stats = stats;
+  a.rows_per_block = fs2::rows_per_block_for(M);
+  const unsigned grid = (unsigned)((M + a.rows_per_block - 1) / a.rows_per_block);
+  fs2::bn_stats_kernel<<<grid, 256, 2 * C * sizeof(float), static_cast<cudaStream_t>(stream)>>>(a);
+  fs2::count_launch();
+  return fs2::check_launch("bn_stats_kernel");
+}
+
+// out = dropout(act(bn(y)));  exactly one of out_bf16 / out_f32 is non-NULL; res_f32 (optional) is
+// added to the f32 output (the postnet residual).
+int fs2_bn_apply_fwd(const void* y, const float* stats, const float* gamma, const float* beta, int64_t M,
+                     int C, int act_tanh, float p_drop, uint64_t seed, const uint64_t* seed_dev,
+                     void* out_bf16, float* out_f32, const float* res_f32, void* stream) {
+  if (int rc = fs2::bn_check(M, C)) return rc;
+  if ((out_bf16 == nullptr) == (out_f32 == nullptr)) return fs2::set_error("bn_apply: one output");
+  fs2::BnArgs a{};
+  a.y = static_cast<const __nv_bfloat16*>(y);
+  a.M = M; a.C = C; a.fstats = stats; a.gamma = gamma; a.beta = beta;
+  a.act_tanh = act_tanh; a.p_drop = p_drop; a.seed = seed; a.seed_dev = seed_dev;
+  a.out_bf16 = static_cast<__nv_bfloat16*>(out_bf16); a.out_f32 = out_f32; a.res_f32 = res_f32;
+  fs2::bn_apply_kernel<<<fs2::ew_grid(M * (C / 8)), 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
+  fs2::count_launch();
+  return fs2::check_launch("bn_apply_kernel");
+}
+
+int fs2_bn_update_running(const float* stats, int64_t M, int C, float momentum, float* running_mean,
+                          float* running_var, int64_t* num_batches_tracked, void* stream) {
+  if (int rc = fs2::bn_check(M, C)) return rc;
+  fs2::bn_running_kernel<<<(C + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      stats, M, C, momentum, running_mean, running_var, num_batches_tracked);
+  fs2::count_launch();
+  return fs2::check_launch("bn_running_kernel");
+}
+
+// dstats f32 [2][C] must be zero on entry; on exit dstats[0][c] = dbeta, dstats[1][c] = dgamma.
+// dout is bf16 [M][C] (dout_is_f32 = 0) or f32.
+int fs2_bn_bwd(const void* dout, int dout_is_f32, const void* y, const float* stats, const float* gamma,
+               const float* beta, int64_t M, int C, int act_tanh, float p_drop, uint64_t seed,
+               const uint64_t* seed_dev, float* dstats, void* dy, void* stream) {
+  if (int rc = fs2::bn_check(M, C)) return rc;
+  fs2::BnArgs a{};
+  a.y = static_cast<const __nv_bfloat16*>(y);
+  a.M = M; a.C = C; a.fstats = stats; a.gamma = gamma; a.beta = beta;
+  a.act_tanh = act_tanh; a.p_drop = p_drop; a.seed = seed; a.seed_dev = seed_dev;
+  a.dout = dout; a.dout_is_f32 = dout_is_f32; a.stats = dstats;
+  a.dy = static_cast<__nv_bfloat16*>(dy);
+  a.rows_per_block = fs2::rows_per_block_for(M);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const unsigned grid = (unsigned)((M + a.rows_per_block - 1) / a.rows_per_block);
+  fs2::bn_bwd_reduce_kernel<<<grid, 256, 2 * C * sizeof(float), s>>>(a);
+  fs2::count_launch();
+  if (int rc = fs2::check_launch("bn_bwd_reduce_kernel")) return rc;
+  fs2::bn_bwd_apply_kernel<<<fs2::ew_grid(M * (C / 8)), 256, 0, s>>>(a);
+  fs2::count_launch();
+  return fs2::check_launch("bn_bwd_apply_kernel");
+}
+}

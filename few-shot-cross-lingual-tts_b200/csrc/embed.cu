@@ -1,0 +1,136 @@
+// Embedding-shaped ops of the variance adaptor and the phoneme front-end.
+//
+//  * fs2_bucket_embed_add_bf16: y = x + table[bucketize(target, bins)]
+//      replaces lightning/model/modules.py:82-102,119-128 (`torch.bucketize(target, bins)` with the
+//      default right=False -> index = #{bins < v}, `nn.Embedding(n_bins, d)`, `x = x + embedding`).
+//      Targets may be f32 or f64 (energies can arrive as f64, collates/utils.py:82): the comparison is
+//      done in double in both cases, which equals torch's type-promoted comparison.
+//  * fs2_embedding_fwd_bf16 / fs2_embedding_bwd_f32: row gather and scatter-add
+//      replaces F.embedding (lightning/systems/language/embeddings.py:25-31) and the backward of both
+//      embeddings above (fp32 atomics into the [rows][C] table gradient; order is non-deterministic
+//      at the 1e-7 level, like torch's own embedding_dense_backward on CUDA).
+#include "common.h"
+#include "util.cuh"
+
+namespace fs2 {
+
+template <typename TgtT>
+__global__ void __launch_bounds__(256)
+bucket_embed_add_kernel(const __nv_bfloat16* __restrict__ x, const TgtT* __restrict__ target,
+                        const float* __restrict__ bins, int nb, const float* __restrict__ table,
+                        long long rows, int C, __nv_bfloat16* __restrict__ y,
+                        int32_t* __restrict__ idx_out) {
+  extern __shared__ float s_bins[];
+  for (int i = threadIdx.x; i < nb; i += blockDim.x) s_bins[i] = bins[i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const double v = static_cast<double>(target[row]);
+  int lo = 0, hi = nb;  // first i with bins[i] >= v  (== count of bins < v)
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (static_cast<double>(s_bins[mid]) < v) lo = mid + 1; else hi = mid;
+  }
+  if (lane == 0) idx_out[row] = lo;
+  const float* e = table + (long long)lo * C;
+  for (int c = lane * 8; c < C; c += 256) {
+    float f[8];
+    unpack8(ld8(x + row * C + c), f);
+    const float4 e0 = *reinterpret_cast<const float4*>(e + c);
+    const float4 e1 = *reinterpret_cast<const float4*>(e + c + 4);
+    f[0] += e0.x; f[1] += e0.y; f[2] += e0.z; f[3] += e0.w;
+    f[4] += e1.x; f[5] += e1.y; f[6] += e1.z; f[7] += e1.w;
+    st8(y + row * C + c, pack8(f));
+  }
+}
+
+__global__ void __launch_bounds__(256)
+embedding_fwd_kernel(const int64_t* __restrict__ ids, const float* __restrict__ table, long long rows,
+                     int C, int n_rows_table, int pad_idx, __nv_bfloat16* __restrict__ y) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  long long id = ids[row];
+  if (id < 0 || id >= n_rows_table) id = pad_idx >= 0 ? pad_idx : 0;
+  const float* e = table + id * C;
+  for (int c = lane * 8; c < C; c += 256) {
+    const float4 e0 = *reinterpret_cast<const float4*>(e + c);
+    const float4 e1 = *reinterpret_cast<const float4*>(e + c + 4);
+    const float f[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
+    st8(y + row * C + c, pack8(f));
+  }
+}
+
+template <typename IdxT>
+__global__ void __launch_bounds__(256)
+embedding_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const IdxT* __restrict__ ids,
+                     long long rows, int C, int n_rows_table, int pad_idx,
+                     float* __restrict__ dtable) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const long long id = static_cast<long long>(ids[row]);
+  if (id < 0 || id >= n_rows_table || id == pad_idx) return;  // padding_idx rows get no gradient
+  float* g = dtable + id * C;
+  for (int c = lane * 8; c < C; c += 256) {
+    float f[8];
+    unpack8(ld8(dy + row * C + c), f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) atomicAdd(g + c + j, f[j]);
+  }
+}
+
+}  // namespace fs2
+
+extern "C" {
+
+int fs2_bucket_embed_add_bf16(const void* x, const void* target, int target_is_f64, const float* bins,
+                              int n_bins_minus_1, const float* table, int64_t rows, int C, void* y,
+                              int32_t* idx_out, void* stream) {
+  if (C % 8) return fs2::set_error("bucket_embed_add: C must be a multiple of 8");
+  if (rows <= 0) return 0;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const unsigned grid = (unsigned)((rows + 7) / 8);
+  const size_t smem = (size_t)n_bins_minus_1 * sizeof(float);
+  if (target_is_f64)
+    fs2::bucket_embed_add_kernel<double><<<grid, 256, smem, s>>>(
+        static_cast<const __nv_bfloat16*>(x), static_cast<const double*>(target), bins,
+        n_bins_minus_1, table, rows, C, static_cast<__nv_bfloat16*>(y), idx_out);
+  else
+    fs2::bucket_embed_add_kernel<float><<<grid, 256, smem, s>>>(
+        static_cast<const __nv_bfloat16*>(x), static_cast<const float*>(target), bins, n_bins_minus_1,
+        table, rows, C, static_cast<__nv_bfloat16*>(y), idx_out);
+  fs2::count_launch();
+  return fs2::check_launch("bucket_embed_add_kernel");
+}
+
+int fs2_embedding_fwd_bf16(const int64_t* ids, const float* table, int64_t rows, int C,
+                           int n_rows_table, int pad_idx, void* y, void* stream) {
+  if (C % 8) return fs2::set_error("embedding_fwd: C must be a multiple of 8");
+  if (rows <= 0) return 0;
+  fs2::embedding_fwd_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      ids, table, rows, C, n_rows_table, pad_idx, static_cast<__nv_bfloat16*>(y));
+  fs2::count_launch();
+  return fs2::check_launch("embedding_fwd_kernel");
+}
+
+// ids: int32 (ids_is_i64 = 0, the bucket indices saved by the forward) or int64.
+int fs2_embedding_bwd_f32(const void* dy, const void* ids, int ids_is_i64, int64_t rows, int C,
+                          int n_rows_table, int pad_idx, float* dtable, void* stream) {
+  if (C % 8) return fs2::set_error("embedding_bwd: C must be a multiple of 8");
+  if (rows <= 0) return 0;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const unsigned grid = (unsigned)((rows + 7) / 8);
+  if (ids_is_i64)
+    fs2::embedding_bwd_kernel<int64_t><<<grid, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(dy),
+                                                            static_cast<const int64_t*>(ids), rows, C,
+                                                            n_rows_table, pad_idx, dtable);
+  else
+    fs2::embedding_bwd_kernel<int32_t><<<grid, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(dy),
+                                                            static_cast<const int32_t*>(ids), rows, C,
+                                                            n_rows_table, pad_idx, dtable);
+  fs2::count_launch();
+  return fs2::check_launch("embedding_bwd_kernel");
+}
+}

@@ -66,7 +66,7 @@ __global__ void gemm_simt_normal(const SimtP sp) {
       if (!g.b.mn_major)
         b = fetch(g.b, zb, n, ib + (long long)tap * g.b_tap_kstride + k);
       else
-        b = fetch(g.b, zb, k, ib + n);
+        b = fetch(g.b, zb, k, ib + (long long)tap * g.b_tap_kstride + n);
       acc += a * b;
     }
   }

@@ -154,7 +154,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             } else {
 #pragma unroll
               for (int h = 0; h < BN / 64; ++h)
-                tma_load_3d(sb + h * kChunkBytes, &tmB, full_bar(s), ib + n0 + h * 64, k0, zb);
+                tma_load_3d(sb + h * kChunkBytes, &tmB, full_bar(s),
+                            ib + tap * p.b_tap_kstride + n0 + h * 64, k0, zb);
             }
           } else {
             const int g = t.kb0 + kb;
@@ -480,6 +481,14 @@ int gemm_tc_launch(const fs2_gemm& g, cudaStream_t stream) {
     return set_error("gemm: unknown mode");
   }
   if (g.d_atomic && !g.d_f32) return set_error("atomic accumulation needs an f32 output");
+  if (kp.d_col_stride == 1 && !g.d_atomic) {
+    const long long al = g.d_f32 ? 4 : 8;  // vector stores: 16-byte aligned rows
+    if ((reinterpret_cast<uintptr_t>(g.d) & 15) || (g.ldd % al) || (g.d_zdiv_stride % al) ||
+        (g.d_zmod_stride % al) || (g.d_tap_stride % al))
+      return set_error("gemm: output rows must be 16-byte aligned (ldd / strides)");
+  }
+  if (g.aux && ((reinterpret_cast<uintptr_t>(g.aux) & 15) || (g.ld_aux & 7) || (g.aux_batch_stride & 7)))
+    return set_error("gemm: aux rows must be 16-byte aligned");
   if ((g.epilogue == FS2_EPI_RELU_BWD || g.epilogue == FS2_EPI_ADD_AUX) && !g.aux)
     return set_error("epilogue needs aux");
 

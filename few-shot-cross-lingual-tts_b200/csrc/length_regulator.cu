@@ -1,0 +1,229 @@
+// LengthRegulator as an integer inclusive cumsum + a vectorised row gather (forward) and a
+// contiguous segment sum (backward).
+//
+// Replaces lightning/model/modules.py:169-196 (python double loop with one `.item()` host sync per
+// phoneme, `vec.expand`, `torch.cat`) and `pad` (lightning/utils/tool.py:168-186).  Semantics kept:
+//   * each duration goes through max(int(d), 0) (modules.py:188-189) -- int() truncates toward 0;
+//   * out[b, t] = x[b, i] where i = #{j : cum[b, j] <= t}, zero rows for t >= cum[b, Ts-1];
+//   * max_len smaller than the expansion CROPS (negative F.pad), larger zero-pads;
+//   * mel_len[b] = sum_i max(int(d[b,i]),0) (NOT cropped).
+// The gather is a pure copy, so the output is bit-exact for any element type.  Optional fused adds
+// (speaker row, sinusoid table row: fastspeech2m.py:132-136, transformer/Models.py:224-226) are only
+// used by the fused FastSpeech2 forward, never by the stand-alone LengthRegulator module.
+// HBM-bound: algorithmic bytes = (B*Ts + B*max_len) * C * sizeof(elt) + 8*B*Ts.
+#include "common.h"
+#include "util.cuh"
+
+namespace fs2 {
+
+// One block per utterance: clamp + inclusive scan of durations, then idx for every output frame.
+template <typename DurT>
+__global__ void __launch_bounds__(256)
+lr_index_kernel(const DurT* __restrict__ dur, int Ts, int max_len, int64_t* __restrict__ cum,
+                int32_t* __restrict__ idx, int64_t* __restrict__ mel_len) {
+  extern __shared__ long long s_cum[];  // Ts entries
+  __shared__ long long s_warp[8];
+  __shared__ long long s_carry;
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) s_carry = 0;
+  __syncthreads();
+  for (int base = 0; base < Ts; base += 256) {
+    const int i = base + tid;
+    long long v = 0;
+    if (i < Ts) {
+      const DurT d = dur[(long long)b * Ts + i];
+      v = static_cast<long long>(d);  // float -> truncation toward zero == python int()
+      if (v < 0) v = 0;
+    }
+    long long x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const long long y = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane >= o) x += y;
+    }
+    if (lane == 31) s_warp[warp] = x;
+    __syncthreads();
+    long long off = s_carry;
+    for (int w = 0; w < warp; ++w) off += s_warp[w];
+    if (i < Ts) {
+      s_cum[i] = x + off;
+      cum[(long long)b * Ts + i] = x + off;
+    }
+    __syncthreads();
+    if (tid == 255) s_carry = x + off;
+    __syncthreads();
+  }
+  const long long total = Ts > 0 ? s_carry : 0;
+  if (tid == 0) mel_len[b] = total;
+  for (int t = tid; t < max_len; t += 256) {
+    int r = -1;
+    if (t < total) {
+      int lo = 0, hi = Ts;  // first i with cum[i] > t
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (s_cum[mid] <= t) lo = mid + 1; else hi = mid;
+      }
+      r = lo;
+    }
+    idx[(long long)b * max_len + t] = r;
+  }
+}
+
+// One warp per output row; VEC 16-byte vectors per row are spread over the lanes.
+__global__ void __launch_bounds__(256)
+lr_gather_kernel(const uint4* __restrict__ x, const int32_t* __restrict__ idx, int B, int Ts,
+                 int max_len, int out_len, int vec_per_row, uint4* __restrict__ out) {
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= (long long)B * out_len) return;
+  const int lane = threadIdx.x & 31;
+  const int b = row / out_len, t = row - (long long)b * out_len;
+  const int i = idx[(long long)b * max_len + t];
+  const uint4* src = i >= 0 ? x + ((long long)b * Ts + i) * vec_per_row : nullptr;
+  uint4* dst = out + row * vec_per_row;
+  for (int v = lane; v < vec_per_row; v += 32) dst[v] = src ? __ldg(src + v) : make_uint4(0, 0, 0, 0);
+}
+
+// bf16 gather fused with "+ speaker row + sinusoid row" (decoder input of the fused forward).
+__global__ void __launch_bounds__(256)
+lr_gather_fused_kernel(const __nv_bfloat16* __restrict__ x, const int32_t* __restrict__ idx,
+                       const float* __restrict__ spk, const float* __restrict__ pe, int B, int Ts,
+                       int max_len, int out_len, int C, __nv_bfloat16* __restrict__ out) {
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= (long long)B * out_len) return;
+  const int lane = threadIdx.x & 31;
+  const int b = row / out_len, t = row - (long long)b * out_len;
+  const int i = idx[(long long)b * max_len + t];
+  for (int c = lane * 8; c < C; c += 256) {
+    float f[8];
+    if (i >= 0) {
+      unpack8(ld8(x + ((long long)b * Ts + i) * C + c), f);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = 0.f;
+    }
+    if (spk) {
+      // the reference adds in two rounded steps (x + spk, then + pe), each in fp32
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] += spk[(long long)b * C + c + j];
+    }
+    if (pe) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] += pe[(long long)t * C + c + j];
+    }
+    st8(out + row * C + c, pack8(f));
+  }
+}
+
+// dx[b,i,:] = sum_{t in [cum[i-1], min(cum[i], n_rows))} dout[b,t,:]   (contiguous, deterministic)
+__global__ void __launch_bounds__(256)
+lr_bwd_kernel(const __nv_bfloat16* __restrict__ dout, const int64_t* __restrict__ cum, int B, int Ts,
+              int n_rows, int C, __nv_bfloat16* __restrict__ dx) {
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= (long long)B * Ts) return;
+  const int lane = threadIdx.x & 31;
+  const int b = row / Ts, i = row - (long long)b * Ts;
+  long long t0 = i > 0 ? cum[row - 1] : 0, t1 = cum[row];
+  if (t1 > n_rows) t1 = n_rows;
+  for (int c = lane * 8; c < C; c += 256) {
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    for (long long t = t0; t < t1; ++t) {
+      float f[8];
+      unpack8(ld8(dout + ((long long)b * n_rows + t) * C + c), f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += f[j];
+    }
+    st8(dx + row * C + c, pack8(acc));
+  }
+}
+
+__global__ void __launch_bounds__(256)
+lr_bwd_f32_kernel(const float* __restrict__ dout, const int64_t* __restrict__ cum, int B, int Ts,
+                  int n_rows, int C, float* __restrict__ dx) {
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= (long long)B * Ts) return;
+  const int lane = threadIdx.x & 31;
+  const int b = row / Ts, i = row - (long long)b * Ts;
+  long long t0 = i > 0 ? cum[row - 1] : 0, t1 = cum[row];
+  if (t1 > n_rows) t1 = n_rows;
+  for (int c = lane; c < C; c += 32) {
+    float acc = 0.f;
+    for (long long t = t0; t < t1; ++t) acc += dout[((long long)b * n_rows + t) * C + c];
+    dx[row * C + c] = acc;
+  }
+}
+
+}  // namespace fs2
+
+extern "C" {
+
+// dur: int64 [B][Ts] (dur_is_f32 = 0) or f32 (inference path, modules.py:133-139).
+// Outputs: cum int64 [B][Ts] (inclusive clamped cumsum), idx int32 [B][max_len] (-1 = zero row),
+// mel_len int64 [B].
+int fs2_lr_index(const void* dur, int dur_is_f32, int B, int Ts, int max_len, int64_t* cum,
+                 int32_t* idx, int64_t* mel_len, void* stream) {
+  if (B <= 0) return 0;
+  if (Ts > 12000) return fs2::set_error("lr_index: Ts too large for the shared-memory scan");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const size_t smem = (size_t)(Ts > 0 ? Ts : 1) * sizeof(long long);
+  if (dur_is_f32)
+    fs2::lr_index_kernel<float><<<B, 256, smem, s>>>(static_cast<const float*>(dur), Ts, max_len, cum,
+                                                     idx, mel_len);
+  else
+    fs2::lr_index_kernel<int64_t><<<B, 256, smem, s>>>(static_cast<const int64_t*>(dur), Ts, max_len,
+                                                       cum, idx, mel_len);
+  fs2::count_launch();
+  return fs2::check_launch("lr_index_kernel");
+}
+
+// Pure copy gather; row_bytes = C * sizeof(element) must be a multiple of 16.
+// out: [B][out_len][C] with out_len <= max_len (the decoder truncates to max_seq_len).
+int fs2_lr_gather(const void* x, const int32_t* idx, int B, int Ts, int max_len, int out_len,
+                  int row_bytes, void* out, void* stream) {
+  if (row_bytes % 16) return fs2::set_error("lr_gather: row bytes must be a multiple of 16");
+  const long long rows = (long long)B * out_len;
+  if (rows <= 0) return 0;
+  fs2::lr_gather_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const uint4*>(x), idx, B, Ts, max_len, out_len, row_bytes / 16,
+      static_cast<uint4*>(out));
+  fs2::count_launch();
+  return fs2::check_launch("lr_gather_kernel");
+}
+
+// bf16 gather + optional f32 speaker row [B][C] + optional f32 position table [>=out_len][C].
+int fs2_lr_gather_fused_bf16(const void* x, const int32_t* idx, const float* spk, const float* pe,
+                             int B, int Ts, int max_len, int out_len, int C, void* out, void* stream) {
+  if (C % 8) return fs2::set_error("lr_gather_fused: C must be a multiple of 8");
+  const long long rows = (long long)B * out_len;
+  if (rows <= 0) return 0;
+  fs2::lr_gather_fused_kernel<<<(unsigned)((rows + 7) / 8), 256, 0,
+                                static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(x), idx, spk, pe, B, Ts, max_len, out_len, C,
+      static_cast<__nv_bfloat16*>(out));
+  fs2::count_launch();
+  return fs2::check_launch("lr_gather_fused_kernel");
+}
+
+// dout: bf16 [B][n_rows][C] (n_rows = rows that exist in the forward output) -> dx bf16 [B][Ts][C].
+int fs2_lr_bwd_bf16(const void* dout, const int64_t* cum, int B, int Ts, int n_rows, int C, void* dx,
+                    void* stream) {
+  if (C % 8) return fs2::set_error("lr_bwd: C must be a multiple of 8");
+  const long long rows = (long long)B * Ts;
+  if (rows <= 0) return 0;
+  fs2::lr_bwd_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(dout), cum, B, Ts, n_rows, C, static_cast<__nv_bfloat16*>(dx));
+  fs2::count_launch();
+  return fs2::check_launch("lr_bwd_kernel");
+}
+
+int fs2_lr_bwd_f32(const float* dout, const int64_t* cum, int B, int Ts, int n_rows, int C, float* dx,
+                   void* stream) {
+  const long long rows = (long long)B * Ts;
+  if (rows <= 0) return 0;
+  fs2::lr_bwd_f32_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      dout, cum, B, Ts, n_rows, C, dx);
+  fs2::count_launch();
+  return fs2::check_launch("lr_bwd_f32_kernel");
+}
+}

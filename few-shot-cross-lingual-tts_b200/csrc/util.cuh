@@ -1,0 +1,93 @@
+// Device helpers shared by the memory-bound kernels: 16-byte bf16 vectors, warp/block reductions,
+// Philox4x32-10 counter RNG for dropout (regenerated, never stored, in the backward kernels).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+namespace fs2 {
+
+constexpr int kWarp = 32;
+
+struct alignas(16) bf16x8 {
+  __nv_bfloat162 v[4];
+};
+
+__device__ __forceinline__ void unpack8(const bf16x8& p, float (&f)[8]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 t = __bfloat1622float2(p.v[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+__device__ __forceinline__ bf16x8 pack8(const float (&f)[8]) {
+  bf16x8 p;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) p.v[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+  return p;
+}
+__device__ __forceinline__ bf16x8 ld8(const __nv_bfloat16* p) {
+  return *reinterpret_cast<const bf16x8*>(p);
+}
+__device__ __forceinline__ void st8(__nv_bfloat16* p, const bf16x8& v) {
+  *reinterpret_cast<bf16x8*>(p) = v;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// ---- Philox4x32-10 (Salmon et al.), one call -> 4 x 32 random bits --------------------------------
+__device__ __forceinline__ uint4 philox4x32(uint64_t seed, uint64_t ctr) {
+  uint32_t k0 = static_cast<uint32_t>(seed), k1 = static_cast<uint32_t>(seed >> 32);
+  uint32_t c0 = static_cast<uint32_t>(ctr), c1 = static_cast<uint32_t>(ctr >> 32), c2 = 0x243F6A88u,
+           c3 = 0x85A308D3u;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+    c0 = n0;
+    c1 = lo1;
+    c2 = n2;
+    c3 = lo0;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  return make_uint4(c0, c1, c2, c3);
+}
+
+// Dropout keep-mask for 8 consecutive elements starting at linear index `elem0` (multiple of 8).
+// bit i of the result = keep element elem0+i.  `thresh` = p * 2^16 (16 random bits per element).
+__device__ __forceinline__ uint32_t dropout_keep8(uint64_t seed, uint64_t elem0, uint32_t thresh) {
+  const uint4 r = philox4x32(seed, elem0 >> 3);
+  const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+  uint32_t m = 0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    m |= ((w[i] & 0xFFFFu) >= thresh ? 1u : 0u) << (2 * i);
+    m |= ((w[i] >> 16) >= thresh ? 1u : 0u) << (2 * i + 1);
+  }
+  return m;
+}
+// Per-step seed: a device-resident counter (so that a replayed CUDA graph draws fresh masks every
+// step) mixed with a per-call-site salt.
+__device__ __forceinline__ uint64_t mix_seed(const uint64_t* seed_dev, uint64_t salt) {
+  const uint64_t s = seed_dev ? *seed_dev : 0ull;
+  return s * 0x9E3779B97F4A7C15ull + salt;
+}
+__host__ __device__ __forceinline__ uint32_t dropout_thresh(float p) {
+  float t = p * 65536.f;
+  return t <= 0.f ? 0u : (t >= 65536.f ? 65536u : static_cast<uint32_t>(t));
+}
+
+}  // namespace fs2

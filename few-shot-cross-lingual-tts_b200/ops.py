@@ -1,0 +1,744 @@
+"""Autograd-level operators of the B200 FastSpeech2 path.
+
+Each `torch.autograd.Function` here is one reference *module* worth of math (a multi-head-attention
+sub-layer, a conv-FFN sub-layer, a variance predictor, the PostNet, the loss ...) whose forward and
+hand-written backward are sequences of calls into libfs2b200.so.  PyTorch provides device memory,
+streams and the autograd tape; every FLOP and every byte moved on the hot path is ours.
+
+Activations are bf16 [B, T, C] channels-last; parameters stay fp32 `nn.Parameter`s in the reference's
+layout (state_dict parity) and are cast / packed to bf16 inside the step.  Weight gradients are fp32
+and are accumulated either into fresh tensors (returned to autograd) or, when a parameter carries a
+`main_grad` view of the flat data-parallel bucket (runtime/dp.py), straight into that view.
+"""
+import math
+
+import torch
+
+from . import _cabi
+from . import gemm as G
+
+BF16 = torch.bfloat16
+F32 = torch.float32
+
+
+def _st():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _L():
+    return _cabi.lib()
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def _ck(rc, what):
+    _cabi.check(rc, what)
+
+
+def _roundup(x, m):
+    return (x + m - 1) // m * m
+
+
+# --------------------------------------------------------------------------------------------------
+# dropout RNG state: a device-resident step counter (CUDA-graph friendly) + per-call-site salts
+# --------------------------------------------------------------------------------------------------
+class _Rng:
+    seed_dev = None
+    salt = 0
+
+    @classmethod
+    def tensor(cls, device):
+        if cls.seed_dev is None or cls.seed_dev.device != device:
+            cls.seed_dev = torch.zeros(1, dtype=torch.int64, device=device)
+        return cls.seed_dev
+
+    @classmethod
+    def next_salt(cls):
+        cls.salt = (cls.salt * 6364136223846793005 + 1442695040888963407) & 0x7FFFFFFFFFFFFFFF
+        return cls.salt
+
+
+def manual_seed(seed, device="cuda"):
+    """Seed the dropout stream of the CUDA path (independent of torch's generators)."""
+    _Rng.tensor(torch.device(device) if not isinstance(device, torch.device) else device).fill_(int(seed))
+    _Rng.salt = int(seed) & 0xFFFF
+
+
+def advance_rng():
+    """Advance the device-side dropout counter by one step (captured inside the step graph)."""
+    if _Rng.seed_dev is not None:
+        _Rng.seed_dev.add_(1)
+
+
+# --------------------------------------------------------------------------------------------------
+# weight preparation and gradient buffers
+# --------------------------------------------------------------------------------------------------
+def cast_bf16(w, out=None):
+    w = w.detach()
+    assert w.dtype == F32 and w.is_contiguous()
+    if out is None:
+        out = torch.empty(w.shape, dtype=BF16, device=w.device)
+    _ck(_L().fs2_cast_f32_bf16(_p(w), w.numel(), _p(out), _st()), "cast_f32_bf16")
+    return out
+
+
+def cast_f32(x):
+    out = torch.empty(x.shape, dtype=F32, device=x.device)
+    _ck(_L().fs2_cast_bf16_f32(_p(x), x.numel(), _p(out), _st()), "cast_bf16_f32")
+    return out
+
+
+def pack_conv(w):
+    """Conv1d.weight [Co, Ci, k] fp32 -> [Co, k, Cpad] bf16 (Cpad = Ci rounded up to 64, zero filled)."""
+    w = w.detach()
+    Co, Ci, k = w.shape
+    cpad = _roundup(Ci, 64)
+    out = torch.empty(Co, k, cpad, dtype=BF16, device=w.device)
+    _ck(_L().fs2_pack_conv_weight(_p(w.contiguous()), Co, Ci, k, cpad, _p(out), _st()), "pack_conv_weight")
+    return out
+
+
+def grad_target(param):
+    """(buffer to accumulate into, value to hand back to autograd)."""
+    mg = getattr(param, "main_grad", None)
+    if mg is not None:
+        return mg, None
+    g = torch.zeros(param.shape, dtype=F32, device=param.device)
+    return g, g
+
+
+def _splits(m_out, n_out, taps, red_blocks):
+    tiles = ((m_out + 127) // 128) * taps * ((n_out + 255) // 256 if n_out > 128 else 1)
+    s = max(1, min(148 // max(tiles, 1), red_blocks, 64))
+    return s
+
+
+# --------------------------------------------------------------------------------------------------
+# raw kernels wrappers (no autograd)
+# --------------------------------------------------------------------------------------------------
+def linear_fwd(x2d, w_bf, bias, out_dtype=BF16, relu=False):
+    M, K = x2d.shape
+    N = w_bf.shape[0]
+    y = torch.empty(M, N, dtype=out_dtype, device=x2d.device)
+    G.gemm(G.operand(x2d, K, M), G.operand(w_bf, K, N), y, M, N, K, bias=bias,
+           epilogue=G.EPI_RELU if relu else G.EPI_NONE)
+    return y
+
+
+def linear_dgrad(dy2d, w_bf, epilogue=G.EPI_NONE, aux=None):
+    """dx[M,K] = dy[M,N] @ W[N,K]  (W read as an MN-major B operand: no transposed copy)."""
+    M, N = dy2d.shape
+    K = w_bf.shape[1]
+    dx = torch.empty(M, K, dtype=BF16, device=dy2d.device)
+    G.gemm(G.operand(dy2d, N, M), G.operand(w_bf, K, N, mn_major=True), dx, M, K, N,
+           epilogue=epilogue, aux=aux, ld_aux=K)
+    return dx
+
+
+def linear_wgrad(dy2d, x2d, dw, row0=0, rows=None):
+    """dw[rows, K] += dy[:, row0:row0+rows]^T @ x"""
+    M, N = dy2d.shape
+    K = x2d.shape[1]
+    rows = N if rows is None else rows
+    a = G.operand(dy2d, N, M, mn_major=True, inner_base=row0)
+    b = G.operand(x2d, K, M, mn_major=True)
+    G.wgrad(a, b, dw, rows, K, splits=_splits(rows, K, 1, (M + 63) // 64))
+
+
+def colsum(x2d, out, col0=0, cols=None):
+    """out[cols] += column sums of x2d[:, col0:col0+cols] (bias gradients)."""
+    M, N = x2d.shape
+    cols = N if cols is None else cols
+    ptr = x2d.data_ptr() + 2 * col0
+    _ck(_L().fs2_colsum_bf16(ptr, N, 1, M, cols, _p(out), _st()), "colsum")
+
+
+def conv_fwd(x, wp, bias, relu=False):
+    B, T, Ci = x.shape
+    Co, k, cpad = wp.shape
+    y = torch.empty(B, T, Co, dtype=BF16, device=x.device)
+    G.gemm(G.operand(x, Ci, T, B), G.operand(wp, k * cpad, Co), y, T, Co, Ci, Z=B, taps=k,
+           tap_shift0=-((k - 1) // 2), b_tap_kstride=cpad, bias=bias,
+           epilogue=G.EPI_RELU if relu else G.EPI_NONE, d_zdiv=1, d_zdiv_stride=T * Co)
+    return y
+
+
+def conv_dgrad(dy, wp, Ci, epilogue=G.EPI_NONE, aux=None):
+    """Input gradient of the channels-last Conv1d: the same implicit GEMM with flipped taps, reading the
+    forward-packed weights [Co][k][Cpad] as an MN-major operand (negative tap stride)."""
+    B, T, Co = dy.shape
+    _, k, cpad = wp.shape
+    dx = torch.empty(B, T, Ci, dtype=BF16, device=dy.device)
+    b = G.operand(wp, k * cpad, Co, mn_major=True, inner_base=(k - 1) * cpad)
+    G.gemm(G.operand(dy, Co, T, B), b, dx, T, Ci, Co, Z=B, taps=k, tap_shift0=-((k - 1) // 2),
+           b_tap_kstride=-cpad, epilogue=epilogue, aux=aux, ld_aux=Ci, aux_batch_stride=T * Ci,
+           d_zdiv=1, d_zdiv_stride=T * Ci)
+    return dx
+
+
+def conv_wgrad(dy, x, dw):
+    """dw[Co, Ci, k] (reference Conv1d.weight layout, fp32) += correlation of dy with x."""
+    B, T, Co = dy.shape
+    Ci = x.shape[2]
+    k = dw.shape[2]
+    G.wgrad(G.operand(dy, Co, T, B, mn_major=True), G.operand(x, Ci, T, B, mn_major=True), dw, Co, Ci,
+            taps=k, tap_shift0=-((k - 1) // 2), ldd=Ci * k, d_col_stride=k, d_tap_stride=1,
+            splits=_splits(Co, Ci, k, B * ((T + 63) // 64)))
+
+
+def ln_fwd(x, res, gamma, beta, lens, p, mode, salt):
+    B, T, C = x.shape
+    y = torch.empty_like(x)
+    mean = torch.empty(B * T, dtype=F32, device=x.device)
+    rstd = torch.empty(B * T, dtype=F32, device=x.device)
+    seed_dev = _Rng.tensor(x.device) if p > 0 else None
+    _ck(_L().fs2_ln_fwd_bf16(_p(x), _p(res), _p(gamma), _p(beta), _p(lens), B, T, C, p, mode, salt,
+                             _p(seed_dev), _p(y), _p(mean), _p(rstd), _st()), "ln_fwd")
+    return y, mean, rstd
+
+
+def ln_bwd(dy, x, res, gamma, mean, rstd, lens, p, mode, salt, dgamma, dbeta, want_dres, relu_x=False):
+    B, T, C = x.shape
+    dx = torch.empty_like(x)
+    dres = torch.empty_like(x) if want_dres and p > 0 and mode == 1 else None
+    seed_dev = _Rng.tensor(x.device) if p > 0 else None
+    _ck(_L().fs2_ln_bwd_bf16(_p(dy), _p(x), _p(res), _p(gamma), _p(mean), _p(rstd), _p(lens), B, T, C, p,
+                             mode, 1 if relu_x else 0, salt, _p(seed_dev), _p(dx), _p(dres), _p(dgamma),
+                             _p(dbeta), _st()), "ln_bwd")
+    if want_dres and dres is None:
+        dres = dx  # without pre-LN dropout the two gradients are the same tensor
+    return dx, dres
+
+
+def _contig(dy):
+    return dy if dy.is_contiguous() else dy.contiguous()
+
+
+# --------------------------------------------------------------------------------------------------
+# sinusoid add
+# --------------------------------------------------------------------------------------------------
+class PosEncAdd(torch.autograd.Function):
+    """bf16(x[:, :T_out] + position_enc[:, :T_out])   (transformer/Models.py:155-157, 220-226)."""
+
+    @staticmethod
+    def forward(ctx, x, pe, t_out):
+        B, T, C = x.shape
+        x = x.contiguous()
+        y = torch.empty(B, t_out, C, dtype=BF16, device=x.device)
+        pe2 = pe.detach().reshape(-1, C)
+        assert pe2.shape[0] >= t_out and pe2.dtype == F32
+        _ck(_L().fs2_posenc_add(_p(x), 1 if x.dtype == F32 else 0, T * C, _p(pe2), B, t_out, C, _p(y),
+                                _st()), "posenc_add")
+        ctx.meta = (x.dtype, T, t_out)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        dtype, T, t_out = ctx.meta
+        dy = _contig(dy)
+        dx = cast_f32(dy) if dtype == F32 else dy
+        if t_out < T:
+            full = torch.zeros(dx.shape[0], T, dx.shape[2], dtype=dx.dtype, device=dx.device)
+            full[:, :t_out] = dx
+            dx = full
+        return dx, None, None
+
+
+# --------------------------------------------------------------------------------------------------
+# multi-head self-attention sub-layer
+# --------------------------------------------------------------------------------------------------
+class MHASublayer(torch.autograd.Function):
+    """LN(dropout(fc(attention(x))) + x) [+ zero padded rows]  -- transformer/SubLayers.py:29-57,
+    transformer/Modules.py:14-25, transformer/Layers.py:22-25."""
+
+    @staticmethod
+    def forward(ctx, x, lens, wq, bq, wk, bk, wv, bv, wo, bo, gamma, beta, n_head, p_drop, zero_pad):
+        B, T, D = x.shape
+        x = x.contiguous()
+        H = n_head
+        dk = wq.shape[0] // H
+        assert dk % 64 == 0 and wq.shape[0] == wk.shape[0] == wv.shape[0] and D % 8 == 0
+        HD = H * dk
+        dev = x.device
+        wqkv = torch.empty(3 * HD, D, dtype=BF16, device=dev)
+        for i, w in enumerate((wq, wk, wv)):
+            cast_bf16(w, wqkv[i * HD:(i + 1) * HD])
+        bqkv = torch.cat([bq.detach(), bk.detach(), bv.detach()])
+        x2 = x.view(B * T, D)
+        qkv = linear_fwd(x2, wqkv, bqkv)  # [B*T, 3*HD], head h of Q = cols [h*dk, (h+1)*dk)
+        Tp = _roundup(T, 128)
+        Z = B * H
+        C3 = 3 * HD
+        S = torch.empty(Z, T, Tp, dtype=F32, device=dev)
+        G.gemm(G.operand(qkv, C3, T, B, zdiv=H, zmod_stride=dk),
+               G.operand(qkv, C3, T, B, inner_base=HD, zdiv=H, zmod_stride=dk), S, T, T, dk, Z=Z, ldd=Tp,
+               alpha=1.0 / math.sqrt(dk), d_zdiv=1, d_zdiv_stride=T * Tp)
+        P = torch.empty(Z, T, Tp, dtype=BF16, device=dev)
+        _ck(_L().fs2_softmax_fwd(_p(S), _p(lens), Z, H, T, Tp, _p(P), _st()), "softmax_fwd")
+        del S
+        attn = torch.empty(B * T, HD, dtype=BF16, device=dev)
+        G.gemm(G.operand(P, Tp, T, Z),
+               G.operand(qkv, C3, T, B, mn_major=True, inner_base=2 * HD, zdiv=H, zmod_stride=dk), attn, T,
+               dk, T, Z=Z, ldd=HD, d_zdiv=H, d_zdiv_stride=T * HD, d_zmod_stride=dk)
+        wo_bf = cast_bf16(wo)
+        o = linear_fwd(attn, wo_bf, bo.detach())
+        salt = _Rng.next_salt()
+        y, mean, rstd = ln_fwd(o.view(B, T, D), x, gamma.detach(), beta.detach(), lens if zero_pad else None,
+                               p_drop, 1, salt)
+        ctx.save_for_backward(x, lens, qkv, P, attn, o, mean, rstd, wqkv, wo_bf, gamma)
+        ctx.params = (wq, bq, wk, bk, wv, bv, wo, bo, gamma, beta)
+        ctx.cfg = (H, dk, p_drop, zero_pad, salt, Tp)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, lens, qkv, P, attn, o, mean, rstd, wqkv, wo_bf, gamma_t = ctx.saved_tensors
+        wq, bq, wk, bk, wv, bv, wo, bo, gamma, beta = ctx.params
+        H, dk, p_drop, zero_pad, salt, Tp = ctx.cfg
+        B, T, D = x.shape
+        HD, C3, Z, M = H * dk, 3 * H * dk, B * H, B * T
+        dev = x.device
+        dy = _contig(dy)
+        gbuf = [grad_target(p) for p in (wq, bq, wk, bk, wv, bv, wo, bo, gamma, beta)]
+        do, dres = ln_bwd(dy, o.view(B, T, D), x, gamma_t, mean, rstd, lens if zero_pad else None, p_drop, 1,
+                          salt, gbuf[8][0], gbuf[9][0], want_dres=True)
+        do2 = do.view(M, D)
+        # output projection
+        dattn = linear_dgrad(do2, wo_bf)
+        linear_wgrad(do2, attn, gbuf[6][0])
+        colsum(do2, gbuf[7][0])
+        # attention core: dP = dO V^T ; dS = softmax'(P, dP) ; dQ = dS K ; dK = dS^T Q ; dV = P^T dO
+        dP = torch.empty(Z, T, Tp, dtype=F32, device=dev)
+        G.gemm(G.operand(dattn, HD, T, B, zdiv=H, zmod_stride=dk),
+               G.operand(qkv, C3, T, B, inner_base=2 * HD, zdiv=H, zmod_stride=dk), dP, T, T, dk, Z=Z,
+               ldd=Tp, d_zdiv=1, d_zdiv_stride=T * Tp)
+        dS = torch.empty(Z, T, Tp, dtype=BF16, device=dev)
+        _ck(_L().fs2_softmax_bwd(_p(P), _p(dP), _p(lens), Z, H, T, Tp, 1.0 / math.sqrt(dk), _p(dS), _st()),
+            "softmax_bwd")
+        del dP
+        dqkv = torch.empty(M, C3, dtype=BF16, device=dev)
+        out_kw = dict(Z=Z, ldd=C3, d_zdiv=H, d_zdiv_stride=T * C3, d_zmod_stride=dk)
+        G.gemm(G.operand(dS, Tp, T, Z),
+               G.operand(qkv, C3, T, B, mn_major=True, inner_base=HD, zdiv=H, zmod_stride=dk),
+               dqkv[:, 0:HD], T, dk, T, **out_kw)
+        G.gemm(G.operand(dS, T, T, Z, ld=Tp, batch_stride=T * Tp, mn_major=True),
+               G.operand(qkv, C3, T, B, mn_major=True, inner_base=0, zdiv=H, zmod_stride=dk),
+               dqkv[:, HD:2 * HD], T, dk, T, **out_kw)
+        G.gemm(G.operand(P, T, T, Z, ld=Tp, batch_stride=T * Tp, mn_major=True),
+               G.operand(dattn, HD, T, B, mn_major=True, inner_base=0, zdiv=H, zmod_stride=dk),
+               dqkv[:, 2 * HD:], T, dk, T, **out_kw)
+        # fused QKV projection
+        x2 = x.view(M, D)
+        dx = linear_dgrad(dqkv, wqkv, epilogue=G.EPI_ADD_AUX, aux=dres.view(M, D))
+        for i in range(3):
+            linear_wgrad(dqkv, x2, gbuf[2 * i][0], row0=i * HD, rows=HD)
+            colsum(dqkv, gbuf[2 * i + 1][0], col0=i * HD, cols=HD)
+        return (dx.view(B, T, D), None) + tuple(g[1] for g in gbuf) + (None, None, None)
+
+
+# --------------------------------------------------------------------------------------------------
+# conv feed-forward sub-layer
+# --------------------------------------------------------------------------------------------------
+class FFNSublayer(torch.autograd.Function):
+    """LN(dropout(w_2(relu(w_1(x)))) + x) [+ zero padded rows] -- transformer/SubLayers.py:85-93,
+    transformer/Layers.py:27-28; both Conv1d run channels-last as implicit GEMMs (no transposes)."""
+
+    @staticmethod
+    def forward(ctx, x, lens, w1, b1, w2, b2, gamma, beta, p_drop, zero_pad):
+        B, T, D = x.shape
+        x = x.contiguous()
+        w1p, w2p = pack_conv(w1), pack_conv(w2)
+        h = conv_fwd(x, w1p, b1.detach(), relu=True)
+        f = conv_fwd(h, w2p, b2.detach())
+        salt = _Rng.next_salt()
+        y, mean, rstd = ln_fwd(f, x, gamma.detach(), beta.detach(), lens if zero_pad else None, p_drop, 1,
+                               salt)
+        ctx.save_for_backward(x, lens, h, f, mean, rstd, w1p, w2p, gamma)
+        ctx.params = (w1, b1, w2, b2, gamma, beta)
+        ctx.cfg = (p_drop, zero_pad, salt)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, lens, h, f, mean, rstd, w1p, w2p, gamma_t = ctx.saved_tensors
+        w1, b1, w2, b2, gamma, beta = ctx.params
+        p_drop, zero_pad, salt = ctx.cfg
+        B, T, D = x.shape
+        Dh = h.shape[2]
+        dy = _contig(dy)
+        gbuf = [grad_target(p) for p in (w1, b1, w2, b2, gamma, beta)]
+        df, dres = ln_bwd(dy, f, x, gamma_t, mean, rstd, lens if zero_pad else None, p_drop, 1, salt,
+                          gbuf[4][0], gbuf[5][0], want_dres=True)
+        dh = conv_dgrad(df, w2p, Dh, epilogue=G.EPI_RELU_BWD, aux=h)
+        conv_wgrad(df, h, gbuf[2][0])
+        colsum(df.view(B * T, D), gbuf[3][0])
+        dx = conv_dgrad(dh, w1p, D, epilogue=G.EPI_ADD_AUX, aux=dres)
+        conv_wgrad(dh, x, gbuf[0][0])
+        colsum(dh.view(B * T, Dh), gbuf[1][0])
+        return (dx, None) + tuple(g[1] for g in gbuf) + (None, None)
+
+
+# --------------------------------------------------------------------------------------------------
+# variance predictor
+# --------------------------------------------------------------------------------------------------
+class VariancePredictorFn(torch.autograd.Function):
+    """[Conv1d k -> ReLU -> LayerNorm -> Dropout] x2 -> Linear(F -> 1) -> squeeze -> masked_fill(0)
+    -- lightning/model/modules.py:199-252 (conv1d_2 keeps its literal padding=1, modules.py:232)."""
+
+    @staticmethod
+    def forward(ctx, x, lens, c1w, c1b, g1, be1, c2w, c2b, g2, be2, lw, lb, p_drop, use_mask):
+        B, T, D = x.shape
+        x = x.contiguous()
+        assert c2w.shape[2] == 3, "conv1d_2 has literal padding=1: only kernel 3 keeps the length"
+        c1p, c2p = pack_conv(c1w), pack_conv(c2w)
+        a1 = conv_fwd(x, c1p, c1b.detach(), relu=True)
+        s1, s2 = _Rng.next_salt(), _Rng.next_salt()
+        n1, m1, r1 = ln_fwd(a1, None, g1.detach(), be1.detach(), None, p_drop, 2, s1)
+        a2 = conv_fwd(n1, c2p, c2b.detach(), relu=True)
+        n2, m2, r2 = ln_fwd(a2, None, g2.detach(), be2.detach(), None, p_drop, 2, s2)
+        F_ = n2.shape[2]
+        out = torch.empty(B, T, dtype=F32, device=x.device)
+        lw2 = lw.detach().reshape(-1).contiguous()
+        _ck(_L().fs2_rowdot_fwd(_p(n2), _p(lw2), _p(lb.detach()), _p(lens if use_mask else None), B, T, F_,
+                                _p(out), _st()), "rowdot_fwd")
+        ctx.save_for_backward(x, lens, a1, n1, a2, n2, m1, r1, m2, r2, c1p, c2p, g1, g2, lw2)
+        ctx.params = (c1w, c1b, g1, be1, c2w, c2b, g2, be2, lw, lb)
+        ctx.cfg = (p_drop, use_mask, s1, s2)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, lens, a1, n1, a2, n2, m1, r1, m2, r2, c1p, c2p, g1t, g2t, lw2 = ctx.saved_tensors
+        c1w, c1b, g1, be1, c2w, c2b, g2, be2, lw, lb = ctx.params
+        p_drop, use_mask, s1, s2 = ctx.cfg
+        B, T, D = x.shape
+        F_ = n2.shape[2]
+        gbuf = [grad_target(p) for p in (c1w, c1b, g1, be1, c2w, c2b, g2, be2, lw, lb)]
+        dout = _contig(dout.to(F32))
+        dn2 = torch.empty_like(n2)
+        _ck(_L().fs2_rowdot_bwd(_p(dout), _p(n2), _p(lw2), _p(lens if use_mask else None), B, T, F_, _p(dn2),
+                                _p(gbuf[8][0]), _p(gbuf[9][0]), _st()), "rowdot_bwd")
+        da2, _ = ln_bwd(dn2, a2, None, g2t, m2, r2, None, p_drop, 2, s2, gbuf[6][0], gbuf[7][0],
+                        want_dres=False, relu_x=True)
+        dn1 = conv_dgrad(da2, c2p, n1.shape[2])
+        conv_wgrad(da2, n1, gbuf[4][0])
+        colsum(da2.view(B * T, -1), gbuf[5][0])
+        da1, _ = ln_bwd(dn1, a1, None, g1t, m1, r1, None, p_drop, 2, s1, gbuf[2][0], gbuf[3][0],
+                        want_dres=False, relu_x=True)
+        dx = conv_dgrad(da1, c1p, D)
+        conv_wgrad(da1, x, gbuf[0][0])
+        colsum(da1.view(B * T, -1), gbuf[1][0])
+        return (dx, None) + tuple(g[1] for g in gbuf) + (None, None)
+
+
+# --------------------------------------------------------------------------------------------------
+# embeddings
+# --------------------------------------------------------------------------------------------------
+class BucketEmbedAdd(torch.autograd.Function):
+    """x + Embedding(bucketize(target, bins)) -- lightning/model/modules.py:82-102,119-128."""
+
+    @staticmethod
+    def forward(ctx, x, target, bins, table):
+        B, T, C = x.shape
+        x = x.contiguous()
+        target = target.contiguous()
+        assert target.dtype in (F32, torch.float64) and target.shape == (B, T)
+        y = torch.empty_like(x)
+        idx = torch.empty(B * T, dtype=torch.int32, device=x.device)
+        tb = table.detach()
+        _ck(_L().fs2_bucket_embed_add_bf16(_p(x), _p(target), 1 if target.dtype == torch.float64 else 0,
+                                           _p(bins.detach()), bins.numel(), _p(tb), B * T, C, _p(y), _p(idx),
+                                           _st()), "bucket_embed_add")
+        ctx.save_for_backward(idx)
+        ctx.table = table
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (idx,) = ctx.saved_tensors
+        table = ctx.table
+        dy = _contig(dy)
+        buf, ret = grad_target(table)
+        C = dy.shape[-1]
+        _ck(_L().fs2_embedding_bwd_f32(_p(dy), _p(idx), 0, idx.numel(), C, table.shape[0], -1, _p(buf), _st()),
+            "embedding_bwd")
+        return dy, None, None, ret
+
+
+class EmbeddingFn(torch.autograd.Function):
+    """F.embedding(ids, table, padding_idx) -> bf16 -- lightning/systems/language/embeddings.py:25-31."""
+
+    @staticmethod
+    def forward(ctx, ids, table, pad_idx):
+        ids = ids.contiguous()
+        C = table.shape[1]
+        y = torch.empty(ids.shape + (C,), dtype=BF16, device=table.device)
+        tb = table.detach().contiguous()
+        _ck(_L().fs2_embedding_fwd_bf16(_p(ids), _p(tb), ids.numel(), C, table.shape[0],
+                                        -1 if pad_idx is None else pad_idx, _p(y), _st()), "embedding_fwd")
+        ctx.save_for_backward(ids)
+        ctx.meta = (table.shape, pad_idx)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (ids,) = ctx.saved_tensors
+        shape, pad_idx = ctx.meta
+        dy = _contig(dy)
+        g = torch.zeros(shape, dtype=F32, device=dy.device)
+        _ck(_L().fs2_embedding_bwd_f32(_p(dy), _p(ids), 1, ids.numel(), shape[1], shape[0],
+                                       -1 if pad_idx is None else pad_idx, _p(g), _st()), "embedding_bwd")
+        return None, g, None
+
+
+class AddRowVec(torch.autograd.Function):
+    """x + e[:, None, :] with e fp32 [B, C] -- fastspeech2m.py:84-101 (speaker / language rows)."""
+
+    @staticmethod
+    def forward(ctx, x, e):
+        B, T, C = x.shape
+        x = x.contiguous()
+        e = e.contiguous().to(F32)
+        y = torch.empty_like(x)
+        _ck(_L().fs2_add_rowvec_bf16(_p(x), _p(e), B, T, C, _p(y), _st()), "add_rowvec")
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        dy = _contig(dy)
+        B, T, C = dy.shape
+        de = torch.zeros(B, C, dtype=F32, device=dy.device)
+        _ck(_L().fs2_colsum_bf16(_p(dy), C, B, T, C, _p(de), _st()), "colsum(rowvec)")
+        return dy, de
+
+
+# --------------------------------------------------------------------------------------------------
+# length regulator
+# --------------------------------------------------------------------------------------------------
+def lr_index(duration, max_len):
+    """(cum int64 [B,Ts], idx int32 [B,max_len], mel_len int64 [B]) on the device, no host sync."""
+    B, Ts = duration.shape
+    duration = duration.contiguous()
+    if duration.dtype == torch.int64:
+        is_f32 = 0
+    else:
+        duration = duration.to(F32)
+        is_f32 = 1
+    dev = duration.device
+    cum = torch.empty(B, Ts, dtype=torch.int64, device=dev)
+    idx = torch.empty(B, max_len, dtype=torch.int32, device=dev)
+    mel_len = torch.empty(B, dtype=torch.int64, device=dev)
+    _ck(_L().fs2_lr_index(_p(duration), is_f32, B, Ts, max_len, _p(cum), _p(idx), _p(mel_len), _st()),
+        "lr_index")
+    return cum, idx, mel_len
+
+
+class LengthRegulate(torch.autograd.Function):
+    """Expand phoneme rows by their durations (lightning/model/modules.py:169-196), optionally fused with
+    the `+ speaker row` and `+ sinusoid row` that follow it in the model (fastspeech2m.py:132-136,
+    transformer/Models.py:224-226).  `out_len <= max_len` lets the caller skip frames the decoder would
+    truncate anyway."""
+
+    @staticmethod
+    def forward(ctx, x, cum, idx, max_len, out_len, spk, pe):
+        B, Ts, C = x.shape
+        x = x.contiguous()
+        out = torch.empty(B, out_len, C, dtype=x.dtype, device=x.device)
+        if spk is None and pe is None:
+            _ck(_L().fs2_lr_gather(_p(x), _p(idx), B, Ts, max_len, out_len, C * x.element_size(), _p(out),
+                                   _st()), "lr_gather")
+        else:
+            assert x.dtype == BF16
+            spk_c = None if spk is None else spk.detach().contiguous().to(F32)
+            pe_c = None if pe is None else pe.detach().reshape(-1, C)
+            _ck(_L().fs2_lr_gather_fused_bf16(_p(x), _p(idx), _p(spk_c), _p(pe_c), B, Ts, max_len, out_len, C,
+                                              _p(out), _st()), "lr_gather_fused")
+        ctx.save_for_backward(cum)
+        ctx.meta = (Ts, out_len, spk is not None, x.dtype)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        (cum,) = ctx.saved_tensors
+        Ts, out_len, has_spk, dtype = ctx.meta
+        dout = _contig(dout)
+        B, _, C = dout.shape
+        dx = torch.empty(B, Ts, C, dtype=dtype, device=dout.device)
+        if dtype == BF16:
+            _ck(_L().fs2_lr_bwd_bf16(_p(dout), _p(cum), B, Ts, out_len, C, _p(dx), _st()), "lr_bwd")
+        else:
+            assert dtype == F32
+            _ck(_L().fs2_lr_bwd_f32(_p(dout), _p(cum), B, Ts, out_len, C, _p(dx), _st()), "lr_bwd_f32")
+        dspk = None
+        if has_spk:
+            dspk = torch.zeros(B, C, dtype=F32, device=dout.device)
+            _ck(_L().fs2_colsum_bf16(_p(dout), C, B, out_len, C, _p(dspk), _st()), "colsum(spk)")
+        return dx, None, None, None, None, dspk, None
+
+
+# --------------------------------------------------------------------------------------------------
+# mel projection (fp32 output) and the PostNet
+# --------------------------------------------------------------------------------------------------
+class LinearF32Out(torch.autograd.Function):
+    """nn.Linear on bf16 activations with an fp32 result -- mel_linear, fastspeech2m.py:143."""
+
+    @staticmethod
+    def forward(ctx, x, w, b):
+        B, T, D = x.shape
+        x = x.contiguous()
+        w_bf = cast_bf16(w)
+        y = linear_fwd(x.view(B * T, D), w_bf, b.detach(), out_dtype=F32)
+        ctx.save_for_backward(x, w_bf)
+        ctx.params = (w, b)
+        return y.view(B, T, -1)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w_bf = ctx.saved_tensors
+        w, b = ctx.params
+        B, T, D = x.shape
+        N = w.shape[0]
+        dy = _contig(dy.to(F32)).view(B * T, N)
+        dy_bf = torch.empty(B * T, N, dtype=BF16, device=dy.device)
+        _ck(_L().fs2_cast_f32_bf16(_p(dy), dy.numel(), _p(dy_bf), _st()), "cast(dmel)")
+        (gw, rw), (gb, rb) = grad_target(w), grad_target(b)
+        dx = linear_dgrad(dy_bf, w_bf)
+        linear_wgrad(dy_bf, x.view(B * T, D), gw)
+        _ck(_L().fs2_colsum_f32(_p(dy), N, B * T, N, _p(gb), _st()), "colsum_f32")
+        return dx.view(B, T, D), rw, rb
+
+
+class PostNetFn(torch.autograd.Function):
+    """postnet(mel) + mel: 5 x [Conv1d k5 -> BatchNorm1d -> tanh (not last) -> dropout 0.5]
+    -- transformer/Layers.py:67-137, fastspeech2m.py:145.  Batch statistics include padded frames."""
+
+    @staticmethod
+    def forward(ctx, mel, training, p_drop, n_layers, *tensors):
+        # tensors: per layer (conv_w, conv_b, bn_w, bn_b, running_mean, running_var, num_batches)
+        B, T, n_mel = mel.shape
+        mel = mel.contiguous()
+        dev = mel.device
+        M = B * T
+        x = torch.empty(B, T, n_mel, dtype=BF16, device=dev)
+        _ck(_L().fs2_cast_f32_bf16(_p(mel), mel.numel(), _p(x), _st()), "cast(mel)")
+        saved, salts, params = [], [], []
+        out = None
+        p = p_drop if training else 0.0
+        for i in range(n_layers):
+            cw, cb, bw, bb, rm, rv, nb = tensors[7 * i:7 * i + 7]
+            last = i == n_layers - 1
+            wp = pack_conv(cw)
+            y = conv_fwd(x, wp, cb.detach())
+            Co = y.shape[2]
+            if training:
+                stats = torch.zeros(2, Co, dtype=F32, device=dev)
+                _ck(_L().fs2_bn_stats_bf16(_p(y), M, Co, _p(stats), _st()), "bn_stats")
+                _ck(_L().fs2_bn_update_running(_p(stats), M, Co, 0.1, _p(rm), _p(rv), _p(nb), _st()),
+                    "bn_update_running")
+            else:  # eval: express the running statistics as (sum, sum of squares)
+                stats = torch.stack([rm * M, (rv + rm * rm) * M]).to(F32).contiguous()
+            salt = _Rng.next_salt()
+            seed_dev = _Rng.tensor(dev) if p > 0 else None
+            if last:
+                out = torch.empty(B, T, Co, dtype=F32, device=dev)
+                _ck(_L().fs2_bn_apply_fwd(_p(y), _p(stats), _p(bw.detach()), _p(bb.detach()), M, Co, 0, p, salt,
+                                          _p(seed_dev), None, _p(out), _p(mel), _st()), "bn_apply(last)")
+                nx = None
+            else:
+                nx = torch.empty(B, T, Co, dtype=BF16, device=dev)
+                _ck(_L().fs2_bn_apply_fwd(_p(y), _p(stats), _p(bw.detach()), _p(bb.detach()), M, Co, 1, p, salt,
+                                          _p(seed_dev), _p(nx), None, None, _st()), "bn_apply")
+            saved += [x, y, stats, wp]
+            salts.append(salt)
+            params.append((cw, cb, bw, bb))
+            x = nx
+        ctx.save_for_backward(*saved)
+        ctx.params = params
+        ctx.cfg = (p, n_layers, salts, training)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        saved = ctx.saved_tensors
+        p, n_layers, salts, training = ctx.cfg
+        assert training, "PostNet backward is implemented for train-mode BatchNorm only"
+        dout = _contig(dout.to(F32))
+        B, T, n_mel = dout.shape
+        M = B * T
+        dev = dout.device
+        grads = [None] * (7 * n_layers)
+        d, d_is_f32 = dout, 1
+        seed_dev = _Rng.tensor(dev) if p > 0 else None
+        for i in reversed(range(n_layers)):
+            x, y, stats, wp = saved[4 * i:4 * i + 4]
+            cw, cb, bw, bb = ctx.params[i]
+            Co = y.shape[2]
+            dstats = torch.zeros(2, Co, dtype=F32, device=dev)
+            dy = torch.empty_like(y)
+            _ck(_L().fs2_bn_bwd(_p(d), d_is_f32, _p(y), _p(stats), _p(bw.detach()), _p(bb.detach()), M, Co,
+                                0 if i == n_layers - 1 else 1, p, salts[i], _p(seed_dev), _p(dstats), _p(dy),
+                                _st()), "bn_bwd")
+            (gcw, rcw), (gcb, rcb), (gbw, rbw), (gbb, rbb) = (grad_target(t) for t in (cw, cb, bw, bb))
+            gbb.add_(dstats[0])  # dbeta / dgamma come back as [2][C]; tiny adds
+            gbw.add_(dstats[1])
+            conv_wgrad(dy, x, gcw)
+            colsum(dy.view(M, Co), gcb)
+            d, d_is_f32 = conv_dgrad(dy, wp, x.shape[2]), 0
+            grads[7 * i:7 * i + 4] = [rcw, rcb, rbw, rbb]
+        dmel = torch.empty(B, T, n_mel, dtype=F32, device=dev)
+        _ck(_L().fs2_add_f32_bf16(_p(dout), _p(d), dout.numel(), _p(dmel), _st()), "add_f32_bf16")
+        return (dmel, None, None, None) + tuple(grads)
+
+
+# --------------------------------------------------------------------------------------------------
+# loss
+# --------------------------------------------------------------------------------------------------
+class FastSpeech2LossFn(torch.autograd.Function):
+    """lightning/model/loss.py:15-89 in two kernels forward, one backward."""
+
+    @staticmethod
+    def forward(ctx, mel, post, p_pred, e_pred, d_pred, mel_tgt, p_tgt, e_tgt, d_tgt, src_lens, mel_lens):
+        B, Tm, n_mel = mel.shape
+        Ts = p_pred.shape[1]
+        dev = mel.device
+        mel, post = mel.contiguous(), post.contiguous()
+        p_pred, e_pred, d_pred = (t.contiguous().to(F32) for t in (p_pred, e_pred, d_pred))
+        mel_tgt = mel_tgt.contiguous().to(F32)
+        p_tgt = p_tgt.contiguous().to(F32)  # loss.py:73 `.float()`
+        e_tgt = e_tgt.contiguous()
+        if e_tgt.dtype not in (F32, torch.float64):
+            e_tgt = e_tgt.to(F32)
+        d_tgt = d_tgt.contiguous().to(torch.int64)
+        src_lens = src_lens.contiguous().to(torch.int64)
+        mel_lens = mel_lens.contiguous().to(torch.int64)
+        Tm_t = mel_tgt.shape[1]
+        nws = _L().fs2_loss_workspace_floats(B, Ts, Tm, n_mel)
+        if nws < 0:
+            _ck(1, "loss_workspace")
+        ws = torch.empty(nws, dtype=F32, device=dev)
+        out8 = torch.empty(8, dtype=F32, device=dev)
+        e64 = 1 if e_tgt.dtype == torch.float64 else 0
+        _ck(_L().fs2_loss_fwd(_p(mel), _p(post), _p(mel_tgt), _p(p_pred), _p(p_tgt), _p(e_pred), _p(e_tgt), e64,
+                              _p(d_pred), _p(d_tgt), _p(src_lens), _p(mel_lens), B, Ts, Tm, Tm_t, n_mel, _p(ws),
+                              _p(out8), _st()), "loss_fwd")
+        ctx.save_for_backward(out8, mel, post, mel_tgt, p_pred, p_tgt, e_pred, e_tgt, d_pred, d_tgt, src_lens,
+                              mel_lens)
+        ctx.meta = (B, Ts, Tm, Tm_t, n_mel, e64)
+        return tuple(out8[i] for i in range(6))
+
+    @staticmethod
+    def backward(ctx, *gouts):
+        (out8, mel, post, mel_tgt, p_pred, p_tgt, e_pred, e_tgt, d_pred, d_tgt, src_lens,
+         mel_lens) = ctx.saved_tensors
+        B, Ts, Tm, Tm_t, n_mel, e64 = ctx.meta
+        dev = mel.device
+        g6 = torch.stack([torch.zeros((), dtype=F32, device=dev) if g is None else g.to(F32).reshape(())
+                          for g in gouts])
+        d_mel, d_post = torch.empty_like(mel), torch.empty_like(post)
+        d_p, d_e, d_d = torch.empty_like(p_pred), torch.empty_like(e_pred), torch.empty_like(d_pred)
+        _ck(_L().fs2_loss_bwd(_p(g6), _p(out8), _p(mel), _p(post), _p(mel_tgt), _p(p_pred), _p(p_tgt), _p(e_pred),
+                              _p(e_tgt), e64, _p(d_pred), _p(d_tgt), _p(src_lens), _p(mel_lens), B, Ts, Tm, Tm_t,
+                              n_mel, _p(d_mel), _p(d_post), _p(d_p), _p(d_e), _p(d_d), _st()), "loss_bwd")
+        return d_mel, d_post, d_p, d_e, d_d, None, None, None, None, None, None

@@ -95,6 +95,114 @@ typedef struct fs2_gemm {
 /* impl: 0 = tcgen05 (product path), 1 = plain CUDA-core kernel (debug cross-check only). */
 int fs2_gemm_bf16(const fs2_gemm* g, int impl, void* stream);
 
+
+/* ------------------------------------------------------------------------------------------ */
+/* Fused (dropout +) residual + LayerNorm (+ dropout) + padding-row zeroing                    */
+/*   transformer/SubLayers.py:54-55,90-91; transformer/Layers.py:25,28;                        */
+/*   lightning/model/modules.py:222-225,234-237                                                */
+/*   x,res,y,dy,dx,dres: bf16 [B][T][C], C in {256,512,1024}; mean,rstd: f32 [B*T];           */
+/*   lens: int64 [B] or NULL (rows t >= lens[b] are zeroed); drop_mode 1: LN(drop(x)+res),      */
+/*   2: drop(LN(x+res)); the mask is regenerated in the backward (Philox4x32-10) from         */
+/*   seed_dev[0] (device step counter, may be NULL) mixed with the call-site salt `seed`.      */
+/*   dgamma/dbeta: f32 [C], accumulated with atomics (zero them first).                        */
+/* ------------------------------------------------------------------------------------------ */
+int fs2_ln_fwd_bf16(const void* x, const void* res, const float* gamma, const float* beta,
+                    const int64_t* lens, int B, int T, int C, float p_drop, int drop_mode,
+                    uint64_t seed, const uint64_t* seed_dev, void* y, float* mean, float* rstd,
+                    void* stream);
+int fs2_ln_bwd_bf16(const void* dy, const void* x, const void* res, const float* gamma,
+                    const float* mean, const float* rstd, const int64_t* lens, int B, int T, int C,
+                    float p_drop, int drop_mode, int relu_x, uint64_t seed, const uint64_t* seed_dev,
+                    void* dx, void* dres, float* dgamma, float* dbeta, void* stream);
+
+/* ------------------------------------------------------------------------------------------ */
+/* Key-padding-masked softmax (transformer/Modules.py:17-22), z = b*H + h                      */
+/*   S,dP: f32 [Z][T][Tp]; P,dS: bf16 [Z][T][Tp]; lens: int64 [Z/H]; Tp % 128 == 0, <= 2048     */
+/* ------------------------------------------------------------------------------------------ */
+int fs2_softmax_fwd(const float* S, const int64_t* lens, int Z, int H, int T, int Tp, void* P,
+                    void* stream);
+int fs2_softmax_bwd(const void* P, const float* dP, const int64_t* lens, int Z, int H, int T, int Tp,
+                    float alpha, void* dS, void* stream);
+
+/* ------------------------------------------------------------------------------------------ */
+/* LengthRegulator (lightning/model/modules.py:169-196, lightning/utils/tool.py:168-186)       */
+/*   integer cumsum + vectorised gather; bit-exact copy semantics; see csrc/length_regulator.cu */
+/* ------------------------------------------------------------------------------------------ */
+int fs2_lr_index(const void* dur, int dur_is_f32, int B, int Ts, int max_len, int64_t* cum,
+                 int32_t* idx, int64_t* mel_len, void* stream);
+int fs2_lr_gather(const void* x, const int32_t* idx, int B, int Ts, int max_len, int out_len,
+                  int row_bytes, void* out, void* stream);
+int fs2_lr_gather_fused_bf16(const void* x, const int32_t* idx, const float* spk, const float* pe,
+                             int B, int Ts, int max_len, int out_len, int C, void* out, void* stream);
+int fs2_lr_bwd_bf16(const void* dout, const int64_t* cum, int B, int Ts, int n_rows, int C, void* dx,
+                    void* stream);
+int fs2_lr_bwd_f32(const float* dout, const int64_t* cum, int B, int Ts, int n_rows, int C, float* dx,
+                   void* stream);
+
+/* ------------------------------------------------------------------------------------------ */
+/* bucketize + embedding (+ add) and plain embedding (modules.py:82-102,119-128;               */
+/*   lightning/systems/language/embeddings.py:25-31); tables are the f32 master parameters     */
+/* ------------------------------------------------------------------------------------------ */
+int fs2_bucket_embed_add_bf16(const void* x, const void* target, int target_is_f64, const float* bins,
+                              int n_bins_minus_1, const float* table, int64_t rows, int C, void* y,
+                              int32_t* idx_out, void* stream);
+int fs2_embedding_fwd_bf16(const int64_t* ids, const float* table, int64_t rows, int C,
+                           int n_rows_table, int pad_idx, void* y, void* stream);
+int fs2_embedding_bwd_f32(const void* dy, const void* ids, int ids_is_i64, int64_t rows, int C,
+                          int n_rows_table, int pad_idx, float* dtable, void* stream);
+
+/* ------------------------------------------------------------------------------------------ */
+/* Small helpers: sinusoid add (transformer/Models.py:155-157,224-226), casts, Conv1d weight   */
+/* packing [Co][Ci][k] f32 -> [Co][k][Cpad] bf16, broadcast row add (fastspeech2m.py:89,101,   */
+/* 136), column sums (bias / speaker-row gradients), the 256->1 predictor head                 */
+/* (modules.py:242,246-252)                                                                    */
+/* ------------------------------------------------------------------------------------------ */
+int fs2_posenc_add(const void* x, int x_is_f32, int64_t x_batch_stride, const float* pe, int B, int T,
+                   int C, void* y, void* stream);
+int fs2_cast_f32_bf16(const float* x, int64_t n, void* y, void* stream);
+int fs2_cast_bf16_f32(const void* x, int64_t n, float* y, void* stream);
+int fs2_pack_conv_weight(const float* w, int Co, int Ci, int k, int Cpad, void* wp, void* stream);
+int fs2_add_rowvec_bf16(const void* x, const float* e, int B, int T, int C, void* y, void* stream);
+int fs2_add_f32_bf16(const float* a, const void* b, int64_t n, float* out, void* stream);
+int fs2_colsum_bf16(const void* x, int64_t ld, int groups, int rows_per_group, int C, float* out,
+                    void* stream);
+int fs2_colsum_f32(const float* x, int64_t ld, int rows, int C, float* out, void* stream);
+int fs2_rowdot_fwd(const void* x, const float* w, const float* bias, const int64_t* lens, int B, int T,
+                   int C, float* out, void* stream);
+int fs2_rowdot_bwd(const float* dout, const void* x, const float* w, const int64_t* lens, int B, int T,
+                   int C, void* dx, float* dw, float* db, void* stream);
+
+/* ------------------------------------------------------------------------------------------ */
+/* FastSpeech2Loss (lightning/model/loss.py:15-89): out8 = total, mel, postnet, pitch, energy, */
+/* duration, N_mel, N_src.  partials: f32 workspace of fs2_loss_workspace_floats() elements.   */
+/* ------------------------------------------------------------------------------------------ */
+int64_t fs2_loss_workspace_floats(int B, int Ts, int Tm, int n_mel);
+int fs2_loss_fwd(const float* mel_pred, const float* post_pred, const float* mel_tgt,
+                 const float* p_pred, const float* p_tgt, const float* e_pred, const void* e_tgt,
+                 int e_tgt_is_f64, const float* d_pred, const int64_t* d_tgt, const int64_t* src_lens,
+                 const int64_t* mel_lens, int B, int Ts, int Tm, int Tm_tgt, int n_mel, float* partials,
+                 float* out8, void* stream);
+int fs2_loss_bwd(const float* gout6, const float* out8, const float* mel_pred, const float* post_pred,
+                 const float* mel_tgt, const float* p_pred, const float* p_tgt, const float* e_pred,
+                 const void* e_tgt, int e_tgt_is_f64, const float* d_pred, const int64_t* d_tgt,
+                 const int64_t* src_lens, const int64_t* mel_lens, int B, int Ts, int Tm, int Tm_tgt,
+                 int n_mel, float* d_mel, float* d_post, float* d_p, float* d_e, float* d_d,
+                 void* stream);
+
+/* ------------------------------------------------------------------------------------------ */
+/* PostNet BatchNorm1d(train) + tanh + dropout (transformer/Layers.py:129-137,                 */
+/* fastspeech2m.py:145); y: bf16 [M][C] conv output; stats: f32 [2][C] (sum, sum of squares)   */
+/* ------------------------------------------------------------------------------------------ */
+int fs2_bn_stats_bf16(const void* y, int64_t M, int C, float* stats, void* stream);
+int fs2_bn_apply_fwd(const void* y, const float* stats, const float* gamma, const float* beta, int64_t M,
+                     int C, int act_tanh, float p_drop, uint64_t seed, const uint64_t* seed_dev,
+                     void* out_bf16, float* out_f32, const float* res_f32, void* stream);
+int fs2_bn_update_running(const float* stats, int64_t M, int C, float momentum, float* running_mean,
+                          float* running_var, int64_t* num_batches_tracked, void* stream);
+int fs2_bn_bwd(const void* dout, int dout_is_f32, const void* y, const float* stats, const float* gamma,
+               const float* beta, int64_t M, int C, int act_tanh, float p_drop, uint64_t seed,
+               const uint64_t* seed_dev, float* dstats, void* dy, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -109,6 +109,20 @@ def grad_target(param):
     return g, g
 
 
+_grad_listener = None
+
+
+def set_grad_listener(fn):
+    """runtime/dp.py registers a callback that learns which parameters' gradients are final."""
+    global _grad_listener
+    _grad_listener = fn
+
+
+def grads_done(params):
+    if _grad_listener is not None:
+        _grad_listener(params)
+
+
 def _splits(m_out, n_out, taps, red_blocks):
     tiles = ((m_out + 127) // 128) * taps * ((n_out + 255) // 256 if n_out > 128 else 1)
     s = max(1, min(148 // max(tiles, 1), red_blocks, 64))
@@ -335,6 +349,7 @@ class MHASublayer(torch.autograd.Function):
         for i in range(3):
             linear_wgrad(dqkv, x2, gbuf[2 * i][0], row0=i * HD, rows=HD)
             colsum(dqkv, gbuf[2 * i + 1][0], col0=i * HD, cols=HD)
+        grads_done((wq, bq, wk, bk, wv, bv, wo, bo, gamma, beta))
         return (dx.view(B, T, D), None) + tuple(g[1] for g in gbuf) + (None, None, None)
 
 
@@ -377,6 +392,7 @@ class FFNSublayer(torch.autograd.Function):
         dx = conv_dgrad(dh, w1p, D, epilogue=G.EPI_ADD_AUX, aux=dres)
         conv_wgrad(dh, x, gbuf[0][0])
         colsum(dh.view(B * T, Dh), gbuf[1][0])
+        grads_done((w1, b1, w2, b2, gamma, beta))
         return (dx, None) + tuple(g[1] for g in gbuf) + (None, None)
 
 
@@ -430,6 +446,7 @@ class VariancePredictorFn(torch.autograd.Function):
         dx = conv_dgrad(da1, c1p, D)
         conv_wgrad(da1, x, gbuf[0][0])
         colsum(da1.view(B * T, -1), gbuf[1][0])
+        grads_done((c1w, c1b, g1, be1, c2w, c2b, g2, be2, lw, lb))
         return (dx, None) + tuple(g[1] for g in gbuf) + (None, None)
 
 
@@ -464,6 +481,7 @@ class BucketEmbedAdd(torch.autograd.Function):
         C = dy.shape[-1]
         _ck(_L().fs2_embedding_bwd_f32(_p(dy), _p(idx), 0, idx.numel(), C, table.shape[0], -1, _p(buf), _st()),
             "embedding_bwd")
+        grads_done((table,))
         return dy, None, None, ret
 
 
@@ -607,6 +625,7 @@ class LinearF32Out(torch.autograd.Function):
         dx = linear_dgrad(dy_bf, w_bf)
         linear_wgrad(dy_bf, x.view(B * T, D), gw)
         _ck(_L().fs2_colsum_f32(_p(dy), N, B * T, N, _p(gb), _st()), "colsum_f32")
+        grads_done((w, b))
         return dx.view(B, T, D), rw, rb
 
 
@@ -687,6 +706,7 @@ class PostNetFn(torch.autograd.Function):
             colsum(dy.view(M, Co), gcb)
             d, d_is_f32 = conv_dgrad(dy, wp, x.shape[2]), 0
             grads[7 * i:7 * i + 4] = [rcw, rcb, rbw, rbb]
+            grads_done((cw, cb, bw, bb))
         dmel = torch.empty(B, T, n_mel, dtype=F32, device=dev)
         _ck(_L().fs2_add_f32_bf16(_p(dout), _p(d), dout.numel(), _p(dmel), _st()), "add_f32_bf16")
         return (dmel, None, None, None) + tuple(grads)

@@ -1,0 +1,96 @@
+"""Data-parallel gradient plumbing: one flat fp32 gradient buffer, bucketed in reverse execution
+order, each bucket all-reduced (NCCL over NVLink / NVSwitch on the box, gloo in the CPU tests) on a
+side stream as soon as the backward pass has produced its last gradient.
+
+The reference gets this from pytorch_lightning's `strategy="ddp"` (main.py:34-40): gradients are
+averaged over ranks, losses are normalised per rank (mean of means), BatchNorm statistics and dropout
+streams stay per rank.  Here the weight-gradient kernels write straight into the flat buffer
+(`param.main_grad` views, see ops.grad_target), so a bucket is ready for the wire without a copy.
+"""
+import torch
+import torch.distributed as dist
+
+
+class GradBuckets:
+    def __init__(self, params, bucket_bytes=32 << 20, process_group=None, device=None):
+        self.params = [p for p in params if p.requires_grad]
+        self.group = process_group
+        self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
+        device = device or self.params[0].device
+        # reverse registration order ~ the order in which backward produces gradients
+        order = list(reversed(self.params))
+        total = sum(p.numel() for p in order)
+        self.flat = torch.zeros(total, dtype=torch.float32, device=device)
+        self.buckets = []  # (start, end) element ranges of self.flat
+        self._bucket_of = {}
+        self._pending0 = []
+        off, bstart, bcount = 0, 0, 0
+        for p in order:
+            n = p.numel()
+            view = self.flat[off:off + n].view(p.shape)
+            p.main_grad = view
+            p.grad = view  # autograd-produced gradients (embeddings) accumulate in place as well
+            self._bucket_of[id(p)] = len(self.buckets)
+            bcount += 1
+            off += n
+            if (off - bstart) * 4 >= bucket_bytes:
+                self.buckets.append((bstart, off))
+                self._pending0.append(bcount)
+                bstart, bcount = off, 0
+        if off > bstart:
+            self.buckets.append((bstart, off))
+            self._pending0.append(bcount)
+        self._pending = list(self._pending0)
+        self._launched = [False] * len(self.buckets)
+        self.comm_stream = torch.cuda.Stream(device) if device.type == "cuda" else None
+        self.overlap = True
+
+    # -- per-step protocol ---------------------------------------------------------------------------
+    def zero(self):
+        self.flat.zero_()
+        self._pending = list(self._pending0)
+        self._launched = [False] * len(self.buckets)
+
+    def _all_reduce(self, b):
+        s, e = self.buckets[b]
+        chunk = self.flat[s:e]
+        if self.world > 1:
+            dist.all_reduce(chunk, op=dist.ReduceOp.SUM, group=self.group)
+            chunk.div_(self.world)
+        self._launched[b] = True
+
+    def _launch(self, b):
+        if self.comm_stream is not None:
+            self.comm_stream.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(self.comm_stream):
+                self._all_reduce(b)
+        else:
+            self._all_reduce(b)
+
+    def notify(self, params):
+        """Called by the backward functions when the gradients of `params` are final."""
+        if self.world == 1 or not self.overlap:
+            return
+        for p in params:
+            b = self._bucket_of.get(id(p))
+            if b is None:
+                continue
+            self._pending[b] -= 1
+            if self._pending[b] == 0 and not self._launched[b]:
+                self._launch(b)
+
+    def finish(self):
+        """Reduce whatever has not been sent yet and join the side stream."""
+        if self.world > 1:
+            for b in range(len(self.buckets)):
+                if not self._launched[b]:
+                    self._launch(b)
+            if self.comm_stream is not None:
+                torch.cuda.current_stream().wait_stream(self.comm_stream)
+
+    def reduce_scalars(self, t):
+        """Mean over ranks of a small tensor (the six logged losses: FastSpeech2.py:89 sync_dist=True)."""
+        if self.world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+            t.div_(self.world)
+        return t

@@ -1,0 +1,89 @@
+"""One FastSpeech2 training step (forward + loss + backward [+ gradient all-reduce]) as a replayable
+CUDA graph with static device buffers -- the B200-native stand-in for what pytorch_lightning does
+around `BaselineSystem.training_step` (lightning/systems/language/FastSpeech2.py:53-90, main.py:34-40).
+
+The graph is keyed by the padded batch shape (B, Ts, Tm): lengths, durations and all tensor contents
+are device data, so one capture serves every batch of that shape; dropout masks change per replay
+through a device-side step counter (ops.advance_rng).
+"""
+import torch
+
+from .. import ops
+from .dp import GradBuckets
+
+# batch tuple slots that are device tensors (lightning/collates/utils.py:70-85)
+_TENSOR_SLOTS = (2, 3, 4, 6, 7, 9, 10, 11, 12)
+
+
+class TrainStep:
+    def __init__(self, model, loss_fn, example_batch, use_graph=True, buckets=None, device=None):
+        self.model, self.loss_fn = model, loss_fn
+        self.device = device or next(model.parameters()).device
+        self.buckets = buckets or GradBuckets(model.parameters(), device=self.device)
+        ops.set_grad_listener(self.buckets.notify)
+        self.static = list(example_batch)
+        self.host = {}
+        for i in _TENSOR_SLOTS:
+            t = example_batch[i]
+            self.static[i] = t.to(self.device).clone()
+            self.host[i] = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+            self.host[i].copy_(t)
+        self.losses = torch.zeros(6, dtype=torch.float32, device=self.device)
+        self.losses_host = torch.empty(6, dtype=torch.float32, pin_memory=True)
+        self.h2d_bytes = sum(t.numel() * t.element_size() for t in self.host.values())
+        self.d2h_bytes = self.losses_host.numel() * 4
+        self.graph = None
+        self.use_graph = use_graph
+        if use_graph:
+            self._capture()
+
+    # ---------------------------------------------------------------------------------------------
+    def _body(self):
+        b = self.static
+        self.buckets.zero()
+        out = self.model(b[2], b[3], *b[4:12], lang_args=b[12])
+        losses = self.loss_fn(tuple(b[:12]), out)
+        losses[0].backward()
+        self.buckets.finish()
+        self.losses.copy_(torch.stack([l.detach() for l in losses]))
+        self.buckets.reduce_scalars(self.losses)
+        ops.advance_rng()
+
+    def _capture(self):
+        s = torch.cuda.Stream(self.device)
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(2):  # warm-up outside capture (allocator, lazy inits, NCCL communicators)
+                self._body()
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self._body()
+
+    # ---------------------------------------------------------------------------------------------
+    def load_batch(self, batch=None):
+        """Host -> device copy of one batch (pinned staging buffers, same padded shape)."""
+        if batch is not None:
+            for i in _TENSOR_SLOTS:
+                self.host[i].copy_(batch[i])
+        for i in _TENSOR_SLOTS:
+            self.static[i].copy_(self.host[i], non_blocking=True)
+
+    def run(self):
+        """Device-resident step: inputs are whatever load_batch() last put in the static buffers."""
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            self._body()
+
+    def read_losses(self):
+        self.losses_host.copy_(self.losses, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return self.losses_host
+
+    def step_e2e(self, batch=None):
+        """What a user calls: H2D of the batch, the step, D2H of the six losses."""
+        self.load_batch(batch)
+        self.run()
+        return self.read_losses()

@@ -1,0 +1,67 @@
+"""The oracle restatement (oracle/fs2_oracle.py) against the fixtures produced by the UNMODIFIED
+reference (oracle/make_golden.py), and -- where /root/reference exists -- against the reference live.
+CPU only."""
+import os
+
+import pytest
+import torch
+
+from oracle import fs2_oracle, ref_loader, synth
+from tests.util_parity import load_golden
+
+
+def _template_state_dict(cfg, spk_config):
+    # keys / shapes of the state_dict come from the boundary package (pure nn.Module containers on CPU)
+    from fs2b200 import sub
+
+    M = sub("lightning.model")
+    m = M.FastSpeech2(cfg, spk_config=spk_config) if spk_config else M.FastSpeech2(cfg)
+    return m.state_dict()
+
+
+@pytest.mark.parametrize("case", ["small", "spk_lang", "truncate", "f64_energy"])
+def test_oracle_matches_golden(case):
+    fx = load_golden("model_%s.pt" % case)
+    sd = synth.init_state_dict(_template_state_dict(fx["cfg"], fx["spk_config"]), fx["weight_seed"])
+    out, losses, grads = fs2_oracle.step(sd, fx["cfg"], fx["batch"])
+    ref = fx["out"]
+    for n, o in zip(("mel", "post", "pitch", "energy", "log_d"), out[:5]):
+        assert torch.allclose(o, ref[n], atol=2e-5, rtol=1e-4), n
+    assert torch.equal(out[9], ref["mel_len"])
+    assert out[7].shape[1] == ref["mel_mask_len"]
+    assert torch.allclose(torch.stack(losses), fx["losses"], atol=1e-5, rtol=1e-5)
+    for k, (norm, head) in fx["grad_digest"].items():
+        assert abs(float(grads[k].norm()) - norm) <= 1e-4 * max(norm, 1e-3), k
+        assert torch.allclose(grads[k].flatten()[:8], head, atol=1e-5, rtol=1e-3), k
+    for k, g in fx["grad_full"].items():
+        assert torch.allclose(grads[k], g, atol=1e-5, rtol=1e-3), k
+
+
+def test_length_regulator_oracle_matches_golden():
+    for c in load_golden("length_regulator.pt"):
+        out, mel_len = fs2_oracle.length_regulate(c["x"], c["dur"], c["max_len"])
+        assert torch.equal(out, c["out"]), c["name"]
+        assert torch.equal(mel_len, c["mel_len"]), c["name"]
+
+
+def test_mask_definition():
+    # lightning/utils/tool.py:63-74: ids >= lengths
+    m = fs2_oracle.mask_from_lengths(torch.tensor([0, 2, 5]), 5)
+    assert m.tolist() == [[True] * 5, [False, False, True, True, True], [False] * 5]
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason="/root/reference only exists in the build container")
+def test_oracle_matches_reference_live():
+    cfg = synth.model_cfg(encoder_layer=2, decoder_layer=2)
+    model, loss_fn = ref_loader.build_reference_model(cfg)
+    sd = synth.init_state_dict(model.state_dict(), 3)
+    model.load_state_dict(sd)
+    batch = synth.make_batch(B=2, src_len=(6, 15), dur=synth.uniform_dur(0, 5), seed=77)
+    with ref_loader.no_functional_dropout():
+        out = model(batch[2], batch[3], *batch[4:12])
+        losses = loss_fn(batch[:-1], out)
+    o_out = fs2_oracle.forward({k: v.clone() for k, v in sd.items()}, cfg, batch[2], batch[3], *batch[4:12])
+    o_losses = fs2_oracle.loss(batch[:12], o_out)
+    for a, b in zip(out[:5], o_out[:5]):
+        assert torch.allclose(a, b, atol=1e-6)
+    assert torch.allclose(torch.stack(list(losses)), torch.stack(list(o_losses)), atol=1e-6)

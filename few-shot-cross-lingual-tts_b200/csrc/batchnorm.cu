@@ -40,16 +40,25 @@ struct BnArgs {
 
 __device__ __forceinline__ void load_vec8(const __nv_bfloat16* p, float (&f)[8]) { unpack8(ld8(p), f); }
 
-// mean / rstd of 8 consecutive channels from the raw sums
-__device__ __forceinline__ void col_stats8(const float* fstats, int C, int c, float invM, float (&mean)[8],
-                                           float (&rstd)[8]) {
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const float m = fstats[c + j] * invM;
-    const float var = fmaxf(fstats[C + c + j] * invM - m * m, 0.f);
-    mean[j] = m;
-    rstd[j] = rsqrtf(var + kBnEps);
+__device__ __forceinline__ float fast_tanh(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));  // rel. error ~2^-11: below bf16 output precision
+  return y;
+}
+
+// Per-channel affine form of the normalisation, computed once per block into shared memory:
+//   yhat = y * rs[c] + sh[c]            (rs = rstd, sh = -mean * rstd)
+//   z    = yhat * gamma[c] + beta[c]
+__device__ __forceinline__ void bn_channel_params(const BnArgs& a, float* s_rs, float* s_sh) {
+  const float invM = 1.f / (float)a.M;
+  for (int c = threadIdx.x; c < a.C; c += blockDim.x) {
+    const float m = a.fstats[c] * invM;
+    const float var = fmaxf(a.fstats[a.C + c] * invM - m * m, 0.f);
+    const float r = rsqrtf(var + kBnEps);
+    s_rs[c] = r;
+    s_sh[c] = -m * r;
   }
+  __syncthreads();
 }
 
 __global__ void __launch_bounds__(256) bn_stats_kernel(const BnArgs a) {
@@ -84,23 +93,26 @@ __global__ void __launch_bounds__(256) bn_stats_kernel(const BnArgs a) {
 }
 
 __global__ void __launch_bounds__(256) bn_apply_kernel(const BnArgs a) {
+  extern __shared__ float sh[];  // [2][C]: rstd, shift
+  float* s_rs = sh;
+  float* s_sh = sh + a.C;
+  bn_channel_params(a, s_rs, s_sh);
   const int vpr = a.C / 8;
-  const float invM = 1.f / (float)a.M;
   const uint32_t thresh = dropout_thresh(a.p_drop);
   const float keep_scale = a.p_drop > 0.f ? 1.f / (1.f - a.p_drop) : 1.f;
+  const uint64_t seed = mix_seed(a.seed_dev, a.seed);
   const long long n_vec = a.M * vpr;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec;
        i += (long long)gridDim.x * blockDim.x) {
     const long long r = i / vpr;
     const int c = (i - r * vpr) * 8;
-    float f[8], mean[8], rstd[8];
+    float f[8];
     load_vec8(a.y + r * a.C + c, f);
-    col_stats8(a.fstats, a.C, c, invM, mean, rstd);
-    const uint32_t keep = thresh ? dropout_keep8(mix_seed(a.seed_dev, a.seed), (uint64_t)r * a.C + c, thresh) : 0xFFu;
+    const uint32_t keep = thresh ? dropout_keep8(seed, (uint64_t)r * a.C + c, thresh) : 0xFFu;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      float z = (f[j] - mean[j]) * rstd[j] * a.gamma[c + j] + a.beta[c + j];
-      if (a.act_tanh) z = tanhf(z);
+      float z = (f[j] * s_rs[c + j] + s_sh[c + j]) * a.gamma[c + j] + a.beta[c + j];
+      if (a.act_tanh) z = fast_tanh(z);
       f[j] = (keep >> j) & 1u ? z * keep_scale : 0.f;
     }
     if (a.out_f32) {
@@ -114,39 +126,42 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const BnArgs a) {
 }
 
 // g = dout * dropout_mask * (1 - tanh(z)^2); returns yhat in `yh`
-__device__ __forceinline__ void bn_bwd_g(const BnArgs& a, long long r, int c, float invM, uint32_t thresh,
-                                         float keep_scale, float (&g)[8], float (&yh)[8],
-                                         float (&rstd)[8]) {
-  float f[8], mean[8];
+__device__ __forceinline__ void bn_bwd_g(const BnArgs& a, const float* s_rs, const float* s_sh, long long r,
+                                         int c, uint64_t seed, uint32_t thresh, float keep_scale, float (&g)[8],
+                                         float (&yh)[8]) {
+  float f[8];
   load_vec8(a.y + r * a.C + c, f);
-  col_stats8(a.fstats, a.C, c, invM, mean, rstd);
   if (a.dout_is_f32) {
-    const float* d = static_cast<const float*>(a.dout) + r * a.C + c;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) g[j] = d[j];
+    const float4* d = reinterpret_cast<const float4*>(static_cast<const float*>(a.dout) + r * a.C + c);
+    const float4 d0 = d[0], d1 = d[1];
+    g[0] = d0.x; g[1] = d0.y; g[2] = d0.z; g[3] = d0.w;
+    g[4] = d1.x; g[5] = d1.y; g[6] = d1.z; g[7] = d1.w;
   } else {
     load_vec8(static_cast<const __nv_bfloat16*>(a.dout) + r * a.C + c, g);
   }
-  const uint32_t keep = thresh ? dropout_keep8(mix_seed(a.seed_dev, a.seed), (uint64_t)r * a.C + c, thresh) : 0xFFu;
+  const uint32_t keep = thresh ? dropout_keep8(seed, (uint64_t)r * a.C + c, thresh) : 0xFFu;
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    yh[j] = (f[j] - mean[j]) * rstd[j];
+    yh[j] = f[j] * s_rs[c + j] + s_sh[c + j];
     g[j] = (keep >> j) & 1u ? g[j] * keep_scale : 0.f;
     if (a.act_tanh) {
-      const float t = tanhf(yh[j] * a.gamma[c + j] + a.beta[c + j]);
+      const float t = fast_tanh(yh[j] * a.gamma[c + j] + a.beta[c + j]);
       g[j] *= 1.f - t * t;
     }
   }
 }
 
 __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const BnArgs a) {
-  extern __shared__ float sh[];  // [2][C]
+  extern __shared__ float sh[];  // [4][C]: rstd, shift, sum g, sum g*yhat
+  float* s_rs = sh;
+  float* s_sh = sh + a.C;
+  float* s_acc = sh + 2 * a.C;
   const int vpr = a.C / 8, rs = 256 / vpr;
-  const float invM = 1.f / (float)a.M;
   const uint32_t thresh = dropout_thresh(a.p_drop);
   const float keep_scale = a.p_drop > 0.f ? 1.f / (1.f - a.p_drop) : 1.f;
-  for (int i = threadIdx.x; i < 2 * a.C; i += 256) sh[i] = 0.f;
-  __syncthreads();
+  const uint64_t seed = mix_seed(a.seed_dev, a.seed);
+  for (int i = threadIdx.x; i < 2 * a.C; i += 256) s_acc[i] = 0.f;
+  bn_channel_params(a, s_rs, s_sh);
   const int v = threadIdx.x % vpr, ro = threadIdx.x / vpr;
   if (ro < rs) {
     float sb[8], sg[8];
@@ -155,8 +170,8 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const BnArgs a) {
     const long long r0 = (long long)blockIdx.x * a.rows_per_block;
     const long long r1 = min(r0 + a.rows_per_block, a.M);
     for (long long r = r0 + ro; r < r1; r += rs) {
-      float g[8], yh[8], rstd[8];
-      bn_bwd_g(a, r, v * 8, invM, thresh, keep_scale, g, yh, rstd);
+      float g[8], yh[8];
+      bn_bwd_g(a, s_rs, s_sh, r, v * 8, seed, thresh, keep_scale, g, yh);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         sb[j] += g[j];
@@ -165,30 +180,35 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const BnArgs a) {
     }
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      atomicAdd(&sh[v * 8 + j], sb[j]);
-      atomicAdd(&sh[a.C + v * 8 + j], sg[j]);
+      atomicAdd(&s_acc[v * 8 + j], sb[j]);
+      atomicAdd(&s_acc[a.C + v * 8 + j], sg[j]);
     }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < 2 * a.C; i += 256) atomicAdd(a.stats + i, sh[i]);
+  for (int i = threadIdx.x; i < 2 * a.C; i += 256) atomicAdd(a.stats + i, s_acc[i]);
 }
 
 __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BnArgs a) {
+  extern __shared__ float sh[];  // [2][C]
+  float* s_rs = sh;
+  float* s_sh = sh + a.C;
+  bn_channel_params(a, s_rs, s_sh);
   const int vpr = a.C / 8;
   const float invM = 1.f / (float)a.M;
   const uint32_t thresh = dropout_thresh(a.p_drop);
   const float keep_scale = a.p_drop > 0.f ? 1.f / (1.f - a.p_drop) : 1.f;
+  const uint64_t seed = mix_seed(a.seed_dev, a.seed);
   const long long n_vec = a.M * vpr;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec;
        i += (long long)gridDim.x * blockDim.x) {
     const long long r = i / vpr;
     const int c = (i - r * vpr) * 8;
-    float g[8], yh[8], rstd[8], o[8];
-    bn_bwd_g(a, r, c, invM, thresh, keep_scale, g, yh, rstd);
+    float g[8], yh[8], o[8];
+    bn_bwd_g(a, s_rs, s_sh, r, c, seed, thresh, keep_scale, g, yh);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const float db = a.stats[c + j] * invM, dg = a.stats[a.C + c + j] * invM;
-      o[j] = a.gamma[c + j] * rstd[j] * (g[j] - db - yh[j] * dg);
+      o[j] = a.gamma[c + j] * s_rs[c + j] * (g[j] - db - yh[j] * dg);
     }
     st8(a.dy + r * a.C + c, pack8(o));
   }
@@ -219,7 +239,7 @@ static int rows_per_block_for(long long M) {
 }
 static unsigned ew_grid(long long n_vec) {
   long long g = (n_vec + 255) / 256;
-  if (g > 148 * 16) g = 148 * 16;
+  if (g > 148 * 8) g = 148 * 8;
   return (unsigned)(g < 1 ? 1 : g);
 }
 
@@ -252,7 +272,8 @@ int fs2_bn_apply_fwd(const void* y, const float* stats, const float* gamma, cons
   a.M = M; a.C = C; a.fstats = stats; a.gamma = gamma; a.beta = beta;
   a.act_tanh = act_tanh; a.p_drop = p_drop; a.seed = seed; a.seed_dev = seed_dev;
   a.out_bf16 = static_cast<__nv_bfloat16*>(out_bf16); a.out_f32 = out_f32; a.res_f32 = res_f32;
-  fs2::bn_apply_kernel<<<fs2::ew_grid(M * (C / 8)), 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
+  fs2::bn_apply_kernel<<<fs2::ew_grid(M * (C / 8)), 256, 2 * C * sizeof(float),
+                         static_cast<cudaStream_t>(stream)>>>(a);
   fs2::count_launch();
   return fs2::check_launch("bn_apply_kernel");
 }
@@ -281,10 +302,10 @@ int fs2_bn_bwd(const void* dout, int dout_is_f32, const void* y, const float* st
   a.rows_per_block = fs2::rows_per_block_for(M);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const unsigned grid = (unsigned)((M + a.rows_per_block - 1) / a.rows_per_block);
-  fs2::bn_bwd_reduce_kernel<<<grid, 256, 2 * C * sizeof(float), s>>>(a);
+  fs2::bn_bwd_reduce_kernel<<<grid, 256, 4 * C * sizeof(float), s>>>(a);
   fs2::count_launch();
   if (int rc = fs2::check_launch("bn_bwd_reduce_kernel")) return rc;
-  fs2::bn_bwd_apply_kernel<<<fs2::ew_grid(M * (C / 8)), 256, 0, s>>>(a);
+  fs2::bn_bwd_apply_kernel<<<fs2::ew_grid(M * (C / 8)), 256, 2 * C * sizeof(float), s>>>(a);
   fs2::count_launch();
   return fs2::check_launch("bn_bwd_apply_kernel");
 }

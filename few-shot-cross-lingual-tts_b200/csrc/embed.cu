@@ -62,22 +62,49 @@ embedding_fwd_kernel(const int64_t* __restrict__ ids, const float* __restrict__ 
   }
 }
 
+// Each warp walks a contiguous run of rows and keeps a running sum while the table index stays the
+// same (padded positions all bucketise to one bin and are contiguous), flushing with atomics only
+// when the index changes: removes the same-address atomic storm of the naive scatter-add.
+constexpr int kEmbRowsPerWarp = 16;
+
 template <typename IdxT>
 __global__ void __launch_bounds__(256)
 embedding_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const IdxT* __restrict__ ids,
                      long long rows, int C, int n_rows_table, int pad_idx,
                      float* __restrict__ dtable) {
   const int lane = threadIdx.x & 31;
-  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (row >= rows) return;
-  const long long id = static_cast<long long>(ids[row]);
-  if (id < 0 || id >= n_rows_table || id == pad_idx) return;  // padding_idx rows get no gradient
-  float* g = dtable + id * C;
+  const long long w = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long long r0 = w * kEmbRowsPerWarp;
+  if (r0 >= rows) return;
+  const long long r1 = min(r0 + (long long)kEmbRowsPerWarp, rows);
   for (int c = lane * 8; c < C; c += 256) {
-    float f[8];
-    unpack8(ld8(dy + row * C + c), f);
+    float acc[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) atomicAdd(g + c + j, f[j]);
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    long long cur = -1;
+    for (long long r = r0; r < r1; ++r) {
+      long long id = static_cast<long long>(ids[r]);
+      if (id < 0 || id >= n_rows_table || id == pad_idx) id = -1;  // padding_idx rows get no gradient
+      if (id != cur) {
+        if (cur >= 0) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) atomicAdd(dtable + cur * C + c + j, acc[j]);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+        cur = id;
+      }
+      if (id >= 0) {
+        float f[8];
+        unpack8(ld8(dy + r * C + c), f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] += f[j];
+      }
+    }
+    if (cur >= 0) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) atomicAdd(dtable + cur * C + c + j, acc[j]);
+    }
   }
 }
 
@@ -121,7 +148,7 @@ int fs2_embedding_bwd_f32(const void* dy, const void* ids, int ids_is_i64, int64
   if (C % 8) return fs2::set_error("embedding_bwd: C must be a multiple of 8");
   if (rows <= 0) return 0;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  const unsigned grid = (unsigned)((rows + 7) / 8);
+  const unsigned grid = (unsigned)((rows + 8 * fs2::kEmbRowsPerWarp - 1) / (8 * fs2::kEmbRowsPerWarp));
   if (ids_is_i64)
     fs2::embedding_bwd_kernel<int64_t><<<grid, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(dy),
                                                             static_cast<const int64_t*>(ids), rows, C,

@@ -71,12 +71,136 @@ struct SmemLayout {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
+  static constexpr int STAGING_OFF = STAGES * STAGE_BYTES;  // 4 epilogue warps x (32 rows x 128 B)
+  static constexpr int STAGING_BYTES = 4 * 32 * 128;
+  static constexpr int BAR_OFF = STAGING_OFF + STAGING_BYTES;
   static constexpr int NUM_BARS = 2 * STAGES + 4;
   static constexpr int TMEM_PTR_OFF = BAR_OFF + NUM_BARS * 8;
   static constexpr int TOTAL = TMEM_PTR_OFF + 16;
   static constexpr int DYN_BYTES = TOTAL + 1024;  // slack for manual 1024-B alignment
 };
+
+// ------------------------------------------------------------------------------------------------
+// Epilogue of one [32 rows x 128 B] output chunk of one warp: TMEM -> registers -> math -> this warp's
+// 4 KiB staging area (16-byte chunks XOR-swizzled by row, conflict free both ways) -> global memory
+// with 8 lanes covering one full 128-byte line per row (coalesced), instead of every thread dribbling
+// 16-byte pieces of its own row.  The optional aux tile (ReLU-backward mask / residual add) is read
+// through the same staging area with the same coalesced pattern.
+// ------------------------------------------------------------------------------------------------
+template <bool F32OUT>
+__device__ __forceinline__ void epilogue_chunk(const GemmKP& p, uint32_t taddr, uint8_t* stg, int lane,
+                                               int m_w0, int n0, int nlimit, long long base_off,
+                                               const __nv_bfloat16* aux_base, bool tile_ok) {
+  constexpr int NC = F32OUT ? 32 : 64;  // accumulator columns per 128-byte output row segment
+  float f[NC];
+  {
+    uint32_t v[32];
+    tmem_ld32(taddr, v);
+    if constexpr (!F32OUT) {
+      uint32_t v2[32];
+      tmem_ld32(taddr + 32, v2);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) f[32 + j] = __uint_as_float(v2[j]) * p.alpha;
+    } else {
+      tmem_ld_wait();
+    }
+#pragma unroll
+    for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * p.alpha;
+  }
+  const int sw = lane & 7;
+  uint8_t* my_row = stg + lane * 128;
+  if (p.bias) {
+#pragma unroll
+    for (int j = 0; j < NC; ++j)
+      if (n0 + j < nlimit) f[j] += __ldg(p.bias + n0 + j);
+  }
+  if (p.epilogue == FS2_EPI_RELU) {
+#pragma unroll
+    for (int j = 0; j < NC; ++j) f[j] = fmaxf(f[j], 0.f);
+  }
+  if constexpr (!F32OUT) {
+    if (aux_base) {  // bf16 aux tile, 64 columns = 128 B per row
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const int r = it * 4 + (lane >> 3), ch = lane & 7;
+        const int gm = m_w0 + r, col = n0 + ch * 8;
+        uint4 val = make_uint4(0u, 0u, 0u, 0u);
+        if (gm < p.M && col < nlimit)
+          val = __ldg(reinterpret_cast<const uint4*>(aux_base + (long long)gm * p.ld_aux + col));
+        *reinterpret_cast<uint4*>(stg + r * 128 + ((ch ^ (r & 7)) << 4)) = val;
+      }
+      __syncwarp();
+      const bool bwd = p.epilogue == FS2_EPI_RELU_BWD;
+#pragma unroll
+      for (int ch = 0; ch < 8; ++ch) {
+        const uint4 u = *reinterpret_cast<const uint4*>(my_row + ((ch ^ sw) << 4));
+        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+          const float lo = __uint_as_float(w[h] << 16), hi = __uint_as_float(w[h] & 0xFFFF0000u);
+          float& f0 = f[ch * 8 + 2 * h];
+          float& f1 = f[ch * 8 + 2 * h + 1];
+          if (bwd) {
+            f0 = lo > 0.f ? f0 : 0.f;
+            f1 = hi > 0.f ? f1 : 0.f;
+          } else {
+            f0 += lo;
+            f1 += hi;
+          }
+        }
+      }
+      __syncwarp();
+    }
+  }
+  // own row -> staging
+#pragma unroll
+  for (int ch = 0; ch < 8; ++ch) {
+    uint4 val;
+    if constexpr (F32OUT) {
+      val = make_uint4(__float_as_uint(f[4 * ch]), __float_as_uint(f[4 * ch + 1]),
+                       __float_as_uint(f[4 * ch + 2]), __float_as_uint(f[4 * ch + 3]));
+    } else {
+      uint32_t w[4];
+#pragma unroll
+      for (int h = 0; h < 4; ++h) {
+        __nv_bfloat162 b2 = __floats2bfloat162_rn(f[ch * 8 + 2 * h], f[ch * 8 + 2 * h + 1]);
+        w[h] = *reinterpret_cast<uint32_t*>(&b2);
+      }
+      val = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+    *reinterpret_cast<uint4*>(my_row + ((ch ^ sw) << 4)) = val;
+  }
+  __syncwarp();
+  // staging -> global: 8 lanes per row, 4 rows per instruction
+  constexpr int EPV = F32OUT ? 4 : 8;  // elements per 16-byte vector
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const int r = it * 4 + (lane >> 3), ch = lane & 7;
+    const int gm = m_w0 + r, col = n0 + ch * EPV;
+    if (tile_ok && gm < p.M && col < nlimit) {
+      const uint4 val = *reinterpret_cast<const uint4*>(stg + r * 128 + ((ch ^ (r & 7)) << 4));
+      const long long off = base_off + (long long)gm * p.ldd + col;
+      if (col + EPV <= nlimit) {
+        if constexpr (F32OUT)
+          *reinterpret_cast<uint4*>(static_cast<float*>(p.d) + off) = val;
+        else
+          *reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.d) + off) = val;
+      } else {  // ragged last vector of the row
+        const uint32_t w[4] = {val.x, val.y, val.z, val.w};
+        for (int e = 0; e < EPV && col + e < nlimit; ++e) {
+          if constexpr (F32OUT) {
+            static_cast<float*>(p.d)[off + e] = __uint_as_float(w[e]);
+          } else {
+            const uint16_t h = (e & 1) ? (uint16_t)(w[e >> 1] >> 16) : (uint16_t)(w[e >> 1] & 0xFFFFu);
+            reinterpret_cast<uint16_t*>(p.d)[off + e] = h;
+          }
+        }
+      }
+    }
+  }
+  __syncwarp();
+}
 
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -245,6 +369,27 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const long long row_off = base_off + (long long)m * p.ldd;
       const __nv_bfloat16* aux_row =
           p.aux ? p.aux + (long long)t.z * p.aux_batch_stride + (long long)m * p.ld_aux : nullptr;
+      if (p.d_col_stride == 1 && !p.d_atomic) {
+        // coalesced path (every NORMAL-mode output)
+        uint8_t* stg = sgen + L::STAGING_OFF + q * 4096;
+        const __nv_bfloat16* aux_base = p.aux ? p.aux + (long long)t.z * p.aux_batch_stride : nullptr;
+        const int m_w0 = t.tm * BM + q * 32;
+        if (p.d_f32) {
+#pragma unroll 1
+          for (int c0 = 0; c0 < BN; c0 += 32) {
+            if (ncol0 + c0 >= nlimit) break;  // warp-uniform
+            epilogue_chunk<true>(p, taddr + c0, stg, lane, m_w0, ncol0 + c0, nlimit, base_off, nullptr,
+                                 t.nkb > 0);
+          }
+        } else {
+#pragma unroll 1
+          for (int c0 = 0; c0 < BN; c0 += 64) {
+            if (ncol0 + c0 >= nlimit) break;
+            epilogue_chunk<false>(p, taddr + c0, stg, lane, m_w0, ncol0 + c0, nlimit, base_off, aux_base,
+                                  t.nkb > 0);
+          }
+        }
+      } else
 #pragma unroll 1
       for (int c = 0; c < BN / 32; ++c) {
         const int n0 = ncol0 + c * 32;
@@ -487,6 +632,7 @@ int gemm_tc_launch(const fs2_gemm& g, cudaStream_t stream) {
         (g.d_zmod_stride % al) || (g.d_tap_stride % al))
       return set_error("gemm: output rows must be 16-byte aligned (ldd / strides)");
   }
+  if (g.aux && (g.d_f32 || (g.N & 7))) return set_error("gemm: aux epilogues need a bf16 output and N % 8 == 0");
   if (g.aux && ((reinterpret_cast<uintptr_t>(g.aux) & 15) || (g.ld_aux & 7) || (g.aux_batch_stride & 7)))
     return set_error("gemm: aux rows must be 16-byte aligned");
   if ((g.epilogue == FS2_EPI_RELU_BWD || g.epilogue == FS2_EPI_ADD_AUX) && !g.aux)

@@ -98,29 +98,48 @@ add_f32_bf16_kernel(const float* __restrict__ a, const __nv_bfloat16* __restrict
 }
 
 // out[g, c] += sum_{r in group g} x[g*rows_per_group + r, c]     (bias grads: groups = 1;
-// speaker-embedding grads: groups = B, rows_per_group = T).  x bf16 with row stride ld.
+// speaker-embedding grads: groups = B, rows_per_group = T).  x bf16 with row stride ld (C % 8 == 0).
+// Each thread owns 8 consecutive channels (one 16-byte load per row), 4 independent rows in flight.
 __global__ void __launch_bounds__(256)
 colsum_kernel(const __nv_bfloat16* __restrict__ x, long long ld, int rows_per_group, int C,
               int rows_per_block, float* __restrict__ out) {
+  extern __shared__ float s_acc[];  // [C]
   const int g = blockIdx.y;
-  const int r0 = blockIdx.x * rows_per_block;
-  const int r1 = min(r0 + rows_per_block, rows_per_group);
-  for (int c = threadIdx.x * 2; c < C; c += blockDim.x * 2) {
-    float s0 = 0.f, s1 = 0.f;
-    const __nv_bfloat16* p = x + ((long long)g * rows_per_group + r0) * ld + c;
-    if (c + 1 < C) {
-      for (int r = r0; r < r1; ++r, p += ld) {
-        const float2 t = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(p));
-        s0 += t.x;
-        s1 += t.y;
+  const int vpr = C / 8, rs = 256 / vpr;
+  for (int i = threadIdx.x; i < C; i += 256) s_acc[i] = 0.f;
+  __syncthreads();
+  const int v = threadIdx.x % vpr, ro = threadIdx.x / vpr;
+  if (ro < rs) {
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    const int r0 = blockIdx.x * rows_per_block;
+    const int r1 = min(r0 + rows_per_block, rows_per_group);
+    const __nv_bfloat16* base = x + (long long)g * rows_per_group * ld + v * 8;
+    int r = r0 + ro;
+    for (; r + 3 * rs < r1; r += 4 * rs) {
+      bf16x8 t[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) t[u] = ld8(base + (long long)(r + u * rs) * ld);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        float f[8];
+        unpack8(t[u], f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] += f[j];
       }
-      atomicAdd(out + (long long)g * C + c, s0);
-      atomicAdd(out + (long long)g * C + c + 1, s1);
-    } else {
-      for (int r = r0; r < r1; ++r, p += ld) s0 += __bfloat162float(*p);
-      atomicAdd(out + (long long)g * C + c, s0);
     }
+    for (; r < r1; r += rs) {
+      float f[8];
+      unpack8(ld8(base + (long long)r * ld), f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += f[j];
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) atomicAdd(&s_acc[v * 8 + j], acc[j]);
   }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C; i += 256) atomicAdd(out + (long long)g * C + i, s_acc[i]);
 }
 
 // same for fp32 input (mel-space gradients)
@@ -286,10 +305,12 @@ int fs2_add_rowvec_bf16(const void* x, const float* e, int B, int T, int C, void
 int fs2_colsum_bf16(const void* x, int64_t ld, int groups, int rows_per_group, int C, float* out,
                     void* stream) {
   if (groups <= 0 || rows_per_group <= 0) return 0;
-  if (ld % 2) return fs2::set_error("colsum: ld must be even");
-  const int rpb = 64;
+  if ((ld % 8) || (C % 8) || C / 8 > 256 || (reinterpret_cast<uintptr_t>(x) & 15))
+    return fs2::set_error("colsum: ld and C must be multiples of 8 (16-byte aligned rows), C <= 2048");
+  int rpb = (rows_per_group * groups + 148 * 4 - 1) / (148 * 4);
+  if (rpb < 64) rpb = 64;
   dim3 grid((rows_per_group + rpb - 1) / rpb, groups);
-  fs2::colsum_kernel<<<grid, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+  fs2::colsum_kernel<<<grid, 256, C * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __nv_bfloat16*>(x), ld, rows_per_group, C, rpb, out);
   fs2::count_launch();
   return fs2::check_launch("colsum_kernel");

@@ -125,8 +125,9 @@ def grads_done(params):
 
 def _splits(m_out, n_out, taps, red_blocks):
     tiles = ((m_out + 127) // 128) * taps * ((n_out + 255) // 256 if n_out > 128 else 1)
-    s = max(1, min(148 // max(tiles, 1), red_blocks, 64))
-    return s
+    # enough CTAs to fill the 148 SMs, but never less than ~32 reduction blocks (2048 rows) per CTA:
+    # short split-K slices are all prologue + fp32 atomics
+    return max(1, min(148 // max(tiles, 1), red_blocks // 32))
 
 
 # --------------------------------------------------------------------------------------------------

@@ -100,9 +100,10 @@ def test_against_oracle(name, over, bkw):
     model, loss_fn = build(cfg, spk)
     batch = synth.make_batch(**bkw)
     out, losses = run_step(model, loss_fn, batch)
-    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
-    o_out, o_losses, o_grads = fs2_oracle.step(sd, cfg, cuda_batch(batch))
-    assert torch.equal(out[9], o_out[9])
+    # the oracle runs on the host CPU (fp32): it is the checker, not the thing measured
+    sd = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
+    o_out, o_losses, o_grads = fs2_oracle.step(sd, cfg, batch)
+    assert torch.equal(out[9].cpu(), o_out[9])
     errs = {n: rel_err(o, r) for n, o, r in zip(("mel", "post", "pitch", "energy", "log_d"), out[:5], o_out[:5])}
     lerr = [abs(float(l) - float(r)) / abs(float(r)) for l, r in zip(losses, o_losses)]
     print(name, errs, "loss rel-err", max(lerr))

@@ -1,0 +1,298 @@
+"""Per-kernel parity tests (CUDA path through the C ABI vs golden fixtures / a plain PyTorch fp32
+reference of the same op).  Integer / index work is bit-exact; floating point tolerances are stated."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from fs2b200 import sub
+from oracle import fs2_oracle
+from tests.util_parity import load_golden, rel_err
+
+pytestmark = pytest.mark.gpu
+BF16 = torch.bfloat16
+
+
+def setup_module(module):
+    global ops, MODS
+    ops = sub("ops")
+    MODS = sub("lightning.model.modules")
+
+
+# ------------------------------------------------------------------------------------------------------
+# LengthRegulator: bit-exact against the fixtures written by the unmodified reference
+# ------------------------------------------------------------------------------------------------------
+def test_length_regulator_bit_exact_vs_reference_golden():
+    lr = MODS.LengthRegulator()
+    for c in load_golden("length_regulator.pt"):
+        out, mel_len = lr(c["x"].cuda(), c["dur"].cuda(), c["max_len"])
+        assert torch.equal(out.cpu(), c["out"]), c["name"]
+        assert torch.equal(mel_len.cpu(), c["mel_len"]), c["name"]
+        assert mel_len.dtype == torch.int64
+
+
+@pytest.mark.parametrize("B,Ts,C,dmax,seed", [(4, 220, 256, 120, 4), (64, 200, 256, 11, 2), (3, 1, 256, 7, 9),
+                                             (2, 1500, 256, 3, 5)])
+def test_length_regulator_bit_exact_vs_oracle_and_index_map(B, Ts, C, dmax, seed):
+    g = torch.Generator().manual_seed(seed)
+    dur = torch.randint(0, dmax + 1, (B, Ts), generator=g)
+    dur[torch.rand(B, Ts, generator=g) < 0.3] = 0  # plenty of zero durations
+    x = torch.randn(B, Ts, C, generator=g)
+    for max_len in (None, int(dur.sum(1).max()) + 13, max(int(dur.sum(1).max()) // 2, 1)):
+        ref, ref_len = fs2_oracle.length_regulate(x, dur, max_len)
+        for dtype in (torch.float32, BF16):
+            out, mel_len = MODS.LengthRegulator()(x.to(dtype).cuda(), dur.cuda(), max_len)
+            assert torch.equal(out.cpu(), ref.to(dtype)), (max_len, dtype)
+            assert torch.equal(mel_len.cpu(), ref_len)
+        # the implied index map: idx[b,t] = searchsorted(cumsum(d[b]), t, right=True)
+        L = ref.shape[1]
+        cum, idx, _ = ops.lr_index(dur.cuda(), L)
+        exp = torch.searchsorted(torch.cumsum(dur, 1), torch.arange(L).expand(B, L).contiguous(), right=True)
+        exp = torch.where(torch.arange(L)[None, :] < dur.sum(1, keepdim=True), exp, torch.full_like(exp, -1))
+        assert torch.equal(idx.cpu().long(), exp)
+        assert torch.equal(cum.cpu(), torch.cumsum(dur, 1))
+
+
+def test_length_regulator_backward_is_segment_sum():
+    g = torch.Generator().manual_seed(3)
+    dur = torch.randint(0, 6, (3, 17), generator=g)
+    x = torch.randn(3, 17, 256, generator=g)
+    xr = x.clone().requires_grad_()
+    ref, _ = fs2_oracle.length_regulate(xr, dur, 60)
+    w = torch.randn(ref.shape, generator=g)
+    (ref * w).sum().backward()
+    xc = x.clone().cuda().requires_grad_()
+    out, _ = MODS.LengthRegulator()(xc, dur.cuda(), 60)
+    (out * w.cuda()).sum().backward()
+    assert torch.allclose(xc.grad.cpu(), xr.grad, atol=1e-5)  # fp32 summation order only
+
+
+# ------------------------------------------------------------------------------------------------------
+# bucketize + embedding
+# ------------------------------------------------------------------------------------------------------
+def test_bucketize_semantics_and_embedding_add():
+    fx = load_golden("misc.pt")
+    bins, xs, ref_idx = fx["bins"].cuda(), fx["bucket_x"], fx["bucket_idx"]
+    table = torch.randn(6, 256, device="cuda")
+    x = torch.zeros(1, xs.numel(), 256, device="cuda", dtype=BF16)
+    for dtype in (torch.float32, torch.float64):
+        y = ops.BucketEmbedAdd.apply(x, xs.to(dtype).cuda()[None], bins, table)
+        assert torch.equal(y[0].float(), table[ref_idx.cuda()].to(BF16).float())
+    # 255 edges, values on / between edges, fp32 targets
+    edges = torch.linspace(-2.8, 16.6, 255)
+    t = torch.cat([edges[::7], edges[::7] + 1e-3, torch.randn(300) * 4])[None]
+    tab = torch.randn(256, 256, device="cuda")
+    y = ops.BucketEmbedAdd.apply(torch.zeros(1, t.shape[1], 256, device="cuda", dtype=BF16), t.cuda(), edges.cuda(), tab)
+    assert torch.equal(y[0].float(), tab[torch.bucketize(t[0], edges).cuda()].to(BF16).float())
+
+
+def test_embedding_backward_scatter_add():
+    torch.manual_seed(0)
+    B, T, C = 4, 50, 256
+    target = torch.randn(B, T, device="cuda")
+    target[:, 30:] = 0  # long runs of equal buckets (padding)
+    bins = torch.linspace(-2, 2, 255, device="cuda")
+    table = torch.randn(256, C, device="cuda", requires_grad=True)
+    x = torch.randn(B, T, C, device="cuda").to(BF16).requires_grad_()
+    w = torch.randn(B, T, C, device="cuda").to(BF16)
+    (ops.BucketEmbedAdd.apply(x, target, bins, table).float() * w.float()).sum().backward()
+    ref = torch.zeros(256, C, device="cuda").index_add_(0, torch.bucketize(target, bins).flatten(),
+                                                        w.float().view(-1, C))
+    assert rel_err(table.grad, ref) < 1e-5
+    assert torch.equal(x.grad, w)
+
+
+# ------------------------------------------------------------------------------------------------------
+# fused LayerNorm
+# ------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("with_res,with_lens", [(True, True), (False, False)])
+def test_layernorm_fwd_bwd(with_res, with_lens):
+    torch.manual_seed(1)
+    B, T, C = 3, 37, 256
+    x = torch.randn(B, T, C, device="cuda").to(BF16)
+    res = torch.randn(B, T, C, device="cuda").to(BF16) if with_res else None
+    g, b = torch.randn(C, device="cuda"), torch.randn(C, device="cuda")
+    lens = torch.tensor([37, 5, 20], device="cuda") if with_lens else None
+    y, mean, rstd = ops.ln_fwd(x, res, g, b, lens, 0.0, 1, 0)
+    pre = (x.float() + (res.float() if with_res else 0)).requires_grad_()
+    gr, br = g.clone().requires_grad_(), b.clone().requires_grad_()
+    ref = F.layer_norm(pre, (C,), gr, br)
+    if with_lens:
+        mask = torch.arange(T, device="cuda")[None, :] >= lens[:, None]
+        ref = ref.masked_fill(mask[..., None], 0)
+    assert rel_err(y, ref) < 5e-3  # bf16 output rounding
+    dy = torch.randn(B, T, C, device="cuda").to(BF16)
+    ref.backward(dy.float())
+    dg, db = torch.zeros(C, device="cuda"), torch.zeros(C, device="cuda")
+    dx, dres = ops.ln_bwd(dy, x, res, g, mean, rstd, lens, 0.0, 1, 0, dg, db, want_dres=True)
+    assert rel_err(dx, pre.grad) < 5e-3
+    assert rel_err(dg, gr.grad) < 2e-3 and rel_err(db, br.grad) < 2e-3
+
+
+@pytest.mark.parametrize("mode", [1, 2])
+def test_layernorm_dropout_statistics_and_backward_consistency(mode):
+    """keep-rate, 1/(1-p) scaling, and forward/backward use the same regenerated mask."""
+    torch.manual_seed(2)
+    B, T, C, p = 8, 64, 256, 0.5
+    ops.manual_seed(77)
+    x = torch.ones(B, T, C, device="cuda").to(BF16) * 3
+    g, b = torch.ones(C, device="cuda"), torch.zeros(C, device="cuda")
+    if mode == 2:  # drop(LN(x)): use a non-constant input so that LN(x) != 0
+        x = torch.randn(B, T, C, device="cuda").to(BF16)
+    y, mean, rstd = ops.ln_fwd(x, None, g, b, None, p, mode, 1234)
+    if mode == 2:
+        keep = (y != 0).float().mean().item()
+        assert abs(keep - (1 - p)) < 0.01
+        ln = F.layer_norm(x.float(), (C,))
+        kept = y.float() != 0
+        assert rel_err(y.float()[kept], (ln / (1 - p))[kept]) < 1e-2
+    dy = torch.ones(B, T, C, device="cuda").to(BF16)
+    dg, db = torch.zeros(C, device="cuda"), torch.zeros(C, device="cuda")
+    dx, _ = ops.ln_bwd(dy, x, None, g, mean, rstd, None, p, mode, 1234, dg, db, want_dres=False)
+    if mode == 2:
+        # dbeta = sum over rows of the masked, rescaled dy: same mask as the forward
+        assert torch.allclose(db, ((y != 0).float() / (1 - p)).sum((0, 1)), rtol=1e-3)
+    else:
+        # pre-LN dropout: dx is zero exactly where the input element was dropped
+        y2, _, _ = ops.ln_fwd(x, None, g, b, None, p, mode, 1234)
+        assert torch.equal(y, y2)  # same seed, same mask
+        assert abs((dx == 0).float().mean().item() - p) < 0.02
+
+
+# ------------------------------------------------------------------------------------------------------
+# masked softmax
+# ------------------------------------------------------------------------------------------------------
+def test_softmax_fwd_bwd_masked():
+    torch.manual_seed(3)
+    B, H, T = 3, 2, 70
+    Tp = 128
+    lens = torch.tensor([70, 33, 1], device="cuda")
+    S = torch.full((B * H, T, Tp), float("nan"), device="cuda")
+    S[:, :, :T] = torch.randn(B * H, T, T, device="cuda") * 3
+    P = torch.empty(B * H, T, Tp, device="cuda", dtype=BF16)
+    L = ops._L()
+    ops._ck(L.fs2_softmax_fwd(S.data_ptr(), lens.data_ptr(), B * H, H, T, Tp, P.data_ptr(), ops._st()), "sm")
+    key_mask = (torch.arange(T, device="cuda")[None, :] >= lens[:, None]).repeat_interleave(H, 0)  # z = b*H+h
+    Sr = S[:, :, :T].clone().requires_grad_()
+    ref = torch.softmax(Sr.masked_fill(key_mask[:, None, :], float("-inf")), -1)
+    qvalid = ~key_mask  # query rows beyond the length are padding: P = 0 there by contract
+    assert torch.isfinite(P.float()).all()
+    assert rel_err(P[:, :, :T][qvalid], ref[qvalid]) < 5e-3
+    assert P[:, :, :T][~qvalid].abs().sum() == 0 and P[:, :, T:].abs().sum() == 0
+    dP = torch.full((B * H, T, Tp), float("nan"), device="cuda")
+    dP[:, :, :T] = torch.randn(B * H, T, T, device="cuda")
+    dS = torch.empty_like(P)
+    ops._ck(L.fs2_softmax_bwd(P.data_ptr(), dP.data_ptr(), lens.data_ptr(), B * H, H, T, Tp, 0.5, dS.data_ptr(),
+                              ops._st()), "smb")
+    (ref * qvalid[..., None]).backward(dP[:, :, :T])
+    assert torch.isfinite(dS.float()).all()
+    assert rel_err(dS[:, :, :T], 0.5 * Sr.grad) < 1.5e-2  # P is stored in bf16
+
+
+# ------------------------------------------------------------------------------------------------------
+# loss
+# ------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("Tm_t,e64", [(50, False), (61, True)])
+def test_loss_fwd_bwd(Tm_t, e64):
+    torch.manual_seed(4)
+    B, Ts, Tm, n_mel = 5, 23, 50, 80
+    src_lens = torch.tensor([23, 1, 10, 17, 5], device="cuda")
+    mel_lens = torch.tensor([50, 3, 77, 20, 49], device="cuda")  # 77 > Tm: decoder truncation case
+    mel = torch.randn(B, Tm, n_mel, device="cuda", requires_grad=True)
+    post = torch.randn(B, Tm, n_mel, device="cuda", requires_grad=True)
+    pp, ep, dp = (torch.randn(B, Ts, device="cuda", requires_grad=True) for _ in range(3))
+    mel_t = torch.randn(B, Tm_t, n_mel, device="cuda")
+    pt = torch.randn(B, Ts, device="cuda")
+    et = torch.randn(B, Ts, device="cuda", dtype=torch.float64 if e64 else torch.float32)
+    dt = torch.randint(0, 9, (B, Ts), device="cuda")
+    out = ops.FastSpeech2LossFn.apply(mel, post, pp, ep, dp, mel_t, pt, et, dt, src_lens, mel_lens)
+    sm = torch.arange(Ts, device="cuda")[None, :] >= src_lens[:, None]
+    mm = torch.arange(Tm, device="cuda")[None, :] >= mel_lens[:, None]
+    leaves = [t.detach().clone().requires_grad_() for t in (mel, post, pp, ep, dp)]
+    ref = fs2_oracle.loss((None,) * 6 + (mel_t, None, None, pt, et, dt),
+                          (*leaves, None, sm, mm, src_lens, mel_lens))
+    for a, b in zip(out, ref):
+        assert abs(float(a) - float(b)) <= 2e-6 * max(1.0, abs(float(b)))
+    (out[0] * 1.5 + out[3] * 0.25).backward()
+    (ref[0] * 1.5 + ref[3] * 0.25).backward()
+    for a, b in zip((mel, post, pp, ep, dp), leaves):
+        assert torch.allclose(a.grad, b.grad, atol=1e-7, rtol=1e-5)
+
+
+# ------------------------------------------------------------------------------------------------------
+# PostNet (conv + train-mode BatchNorm over padded frames + tanh), running statistics
+# ------------------------------------------------------------------------------------------------------
+def test_postnet_against_torch_reference_and_running_stats():
+    torch.manual_seed(5)
+    L = sub("transformer.Layers")
+    pn = L.PostNet().cuda().train()
+    pn.p_dropout = 0.0
+    for blk in pn.convolutions:
+        blk[1].weight.data.normal_(1, 0.1)
+        blk[1].bias.data.normal_(0, 0.1)
+    sd = {"postnet." + k: v.detach().clone() for k, v in pn.state_dict().items()}
+    x = torch.randn(3, 41, 80, device="cuda")
+    xr = x.clone().requires_grad_()
+    ref = fs2_oracle.postnet(sd, "postnet.", xr, running=sd) + xr
+    xc = x.clone().requires_grad_()
+    out = pn.forward_residual(xc)
+    assert rel_err(out, ref) < 2e-2
+    w = torch.randn_like(out)
+    (out * w).sum().backward()
+    (ref * w).sum().backward()
+    assert rel_err(xc.grad, xr.grad) < 3e-2
+    for i in range(5):
+        bn = pn.convolutions[i][1]
+        assert int(bn.num_batches_tracked) == 1
+        assert rel_err(bn.running_mean, sd["postnet.convolutions.%d.1.running_mean" % i]) < 2e-2
+        assert rel_err(bn.running_var, sd["postnet.convolutions.%d.1.running_var" % i]) < 2e-2
+
+
+def test_postnet_dropout_keep_rate():
+    L = sub("transformer.Layers")
+    pn = L.PostNet().cuda().train()
+    ops.manual_seed(5)
+    x = torch.randn(4, 100, 80, device="cuda")
+    out = pn.forward_residual(x) - x  # last block: dropout(bn(conv)) -> exact zeros where dropped
+    keep = (out != 0).float().mean().item()
+    assert abs(keep - 0.5) < 0.02
+
+
+# ------------------------------------------------------------------------------------------------------
+# variance predictor and FFT block against the oracle functions
+# ------------------------------------------------------------------------------------------------------
+def test_variance_predictor_matches_oracle():
+    torch.manual_seed(6)
+    synth = sub("synthetic")
+    vp = MODS.VariancePredictor(synth.model_cfg()).cuda().train()
+    vp.dropout = 0.0
+    sd = {"vp." + k: v.detach() for k, v in vp.state_dict().items()}
+    x = torch.randn(2, 19, 256, device="cuda")
+    lens = torch.tensor([19, 7], device="cuda")
+    mask = torch.arange(19, device="cuda")[None, :] >= lens[:, None]
+    xr = x.clone().requires_grad_()
+    ref = fs2_oracle.variance_predictor(sd, "vp.", xr, mask)
+    xc = x.clone().requires_grad_()
+    out = vp(xc, mask)
+    assert out.dtype == torch.float32 and rel_err(out, ref) < 2e-2
+    assert out[1, 7:].abs().sum() == 0
+    w = torch.randn_like(ref)
+    (out * w).sum().backward()
+    (ref * w).sum().backward()
+    assert rel_err(xc.grad, xr.grad) < 3e-2
+
+
+def test_fft_block_matches_oracle_and_zeroes_padding():
+    torch.manual_seed(7)
+    L = sub("transformer.Layers")
+    blk = L.FFTBlock(256, 2, 128, 128, 1024, [9, 1], dropout=0.0).cuda().train()
+    sd = {"layer_stack.0." + k: v.detach() for k, v in blk.state_dict().items()}
+    x = torch.randn(3, 45, 256, device="cuda")
+    lens = torch.tensor([45, 12, 30], device="cuda")
+    mask = torch.arange(45, device="cuda")[None, :] >= lens[:, None]
+    ref = fs2_oracle.fft_stack(sd, "", x, mask, 1, 2)
+    out, attn = blk(x, mask=mask, slf_attn_mask=mask[:, None, :].expand(-1, 45, -1))
+    assert out.dtype == torch.float32 and attn is None
+    assert rel_err(out, ref) < 1.5e-2
+    assert out[1, 12:].abs().sum() == 0

@@ -198,6 +198,11 @@ def dominant_kernel_roofline(B, Tm, bf16_peak):
             "avg_launch_ms": ms, "flops_per_launch": fl}
 
 
+def dbg(msg):
+    if os.environ.get("FS2_DEBUG"):
+        print("[rank %s %.1f] %s" % (os.environ.get("RANK", "0"), time.time() % 1000, msg), file=sys.stderr, flush=True)
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -234,9 +239,11 @@ def run_ours(args):
     B, Ts, Tm = base[3].shape[0], int(base[5]), int(base[8])
     frames = synth.count_real_frames(base, cfg["max_seq_len"])
 
+    dbg("model built, B=%d Ts=%d Tm=%d" % (B, Ts, Tm))
     n0 = cabi.launch_count()
     step = rt.TrainStep(model, loss_fn, base, use_graph=not args.no_graph, device=dev)
     launches_total = cabi.launch_count() - n0
+    dbg("TrainStep ready")
     launches_per_step = launches_total // 3 if not args.no_graph else None  # 2 warm-up bodies + 1 captured
 
     # three host variants of the batch with the same padded shape (utterance order permuted)
@@ -278,10 +285,12 @@ def run_ours(args):
     load(0)
     for i in range(max(args.warmup, 3)):
         step.run()
+    dbg("warm-up done")
     clocks = Clocks(local) if rank == 0 else None
     n_before = cabi.launch_count()
     dev_ms, wall_ms = timed(lambda i: step.run(), args.steps)
     eager_launches = cabi.launch_count() - n_before
+    dbg("timed loop done %.2f ms" % dev_ms)
 
     def e2e_iter(i):
         load(i)
@@ -341,7 +350,13 @@ def run_ours(args):
                                         "sample": "failed: %r" % (e,)}
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # Captured NCCL kernels keep the communicator busy; tearing the process group down after graph
+        # capture can block (observed on 2xB200, torch 2.11 / NCCL 2.28).  Everything is flushed and
+        # synchronised, so leave without the destructor.
+        barrier()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":

@@ -52,14 +52,21 @@ class TrainStep:
     def _capture(self):
         s = torch.cuda.Stream(self.device)
         s.wait_stream(torch.cuda.current_stream())
+        import os
+        import sys
+        dbg = (lambda m: print("[step] " + m, file=sys.stderr, flush=True)) if os.environ.get("FS2_DEBUG") \
+            else (lambda m: None)
         with torch.cuda.stream(s):
-            for _ in range(2):  # warm-up outside capture (allocator, lazy inits, NCCL communicators)
+            for i in range(2):  # warm-up outside capture (allocator, lazy inits, NCCL communicators)
                 self._body()
+                torch.cuda.synchronize()
+                dbg("warm-up body %d done" % i)
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             self._body()
+        dbg("captured")
 
     # ---------------------------------------------------------------------------------------------
     def load_batch(self, batch=None):

@@ -1,0 +1,534 @@
+// Fused attention backward for sm_100a (d_k = 128): two tcgen05 kernels + a row-dot prologue.
+//
+// Replaces autograd through transformer/Modules.py:14-25 (bmm, /sqrt(dk), masked softmax, bmm):
+//   D_q   = sum_d dO[q,d] * O[q,d]                                   (attn_bwd_prep_kernel)
+//   P     = exp2(S*c - lse2_q),  S = Q K^T       (recomputed, never stored)
+//   dP    = dO V^T ;  dS = P o (dP - D_q) / sqrt(dk)
+//   dV_j += P^T dO ; dK_j += dS^T Q                (attn_bwd_dkv_kernel: CTA = (z, 128-key tile), loops q)
+//   dQ_i += dS K                                    (attn_bwd_dq_kernel : CTA = (z, 128-query tile), loops k)
+// The dkv kernel works on TRANSPOSED scores (S^T = K Q^T: TMEM lane = key), so that P^T / dS^T leave the
+// softmax warps already K-major for the dV / dK MMAs; per-query statistics (lse2, D) are then per-column
+// broadcast loads and no row reduction is needed anywhere in the backward.  dQ gets its own kernel
+// (S and dP recomputed once more: 7 instead of 5 MMAs per tile pair) instead of fp32 atomics.
+// All operand tiles are [rows][64 bf16] swizzle-128B blocks; one tile serves both as a K-major operand
+// (S / dP MMAs) and as an MN-major operand (dV / dK / dQ MMAs) -- same bytes, different descriptor.
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include "common.h"
+#include "ptx.cuh"
+#include "tmap.h"
+#include "util.cuh"
+
+namespace fs2 {
+
+namespace ab {
+constexpr int DK = 128;
+constexpr int BLK128 = 128 * 128;  // [128 rows x 64 cols] bf16 block = 16 KiB
+constexpr int BLK64 = 64 * 128;    // [ 64 rows x 64 cols] bf16 block =  8 KiB
+}  // namespace ab
+
+struct AttnBwdP {
+  const int64_t* lens;
+  const float* lse2;  // [Z][T]
+  const float* dsum;  // [Z][T]  D_q
+  int B, T, H, n_outer, n_inner;
+  float scale, scale_log2;
+  __nv_bfloat16* dqkv;  // [B][T][3*H*dk]
+};
+
+// ------------------------------------------------------------------------------------------------
+// D = rowsum(dO o O) per (b, head, q); one warp per (b, q) row, both heads
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+attn_bwd_prep_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ d_o, int B, int T,
+                     int H, float* __restrict__ dsum) {
+  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= (long long)B * T) return;
+  const int lane = threadIdx.x & 31;
+  const int b = row / T, t = row - (long long)b * T;
+  const int HD = H * ab::DK;
+  for (int h = 0; h < H; ++h) {
+    float s = 0.f;
+    const int c = h * ab::DK + lane * 4;
+    const uint2 a = *reinterpret_cast<const uint2*>(o + row * HD + c);
+    const uint2 g = *reinterpret_cast<const uint2*>(d_o + row * HD + c);
+    const float2 a0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&a.x));
+    const float2 a1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&a.y));
+    const float2 g0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&g.x));
+    const float2 g1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&g.y));
+    s = a0.x * g0.x + a0.y * g0.y + a1.x * g1.x + a1.y * g1.y;
+    s = warp_sum(s);
+    if (lane == 0) dsum[((long long)b * H + h) * T + t] = s;
+  }
+}
+
+// write 32 fp32 values (already final) as bf16 into this thread's 128-byte swizzled smem row, 16-byte
+// chunks [chunk0, chunk0+4)
+__device__ __forceinline__ void store_row_chunks(uint8_t* row_ptr, int sw, int chunk0, const float (&f)[32]) {
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    uint32_t w[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      __nv_bfloat162 b2 = __floats2bfloat162_rn(f[g * 8 + 2 * t], f[g * 8 + 2 * t + 1]);
+      w[t] = *reinterpret_cast<uint32_t*>(&b2);
+    }
+    *reinterpret_cast<uint4*>(row_ptr + (((chunk0 + g) ^ sw) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+}
+
+// TMEM accumulator [128 lanes x 128 cols] -> bf16 -> per-warp staging -> coalesced global rows
+__device__ __forceinline__ void store_acc_128x128(uint32_t tacc, uint32_t lane_base, uint8_t* stg, int warp,
+                                                  int lane, __nv_bfloat16* gbase, long long g_ld, int row0,
+                                                  int row_limit) {
+  uint8_t* my = stg + lane * 128;
+  const int lsw = lane & 7;
+#pragma unroll 1
+  for (int half = 0; half < 2; ++half) {
+    float f[64];
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      uint32_t v[32];
+      tmem_ld32(tacc + lane_base + half * 64 + c * 32, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 32; ++i) f[c * 32 + i] = __uint_as_float(v[i]);
+    }
+#pragma unroll
+    for (int ch = 0; ch < 8; ++ch) {
+      uint32_t w[4];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        __nv_bfloat162 b2 = __floats2bfloat162_rn(f[ch * 8 + 2 * t], f[ch * 8 + 2 * t + 1]);
+        w[t] = *reinterpret_cast<uint32_t*>(&b2);
+      }
+      *reinterpret_cast<uint4*>(my + ((ch ^ lsw) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int r = it * 4 + (lane >> 3), ch = lane & 7;
+      const int grow = row0 + warp * 32 + r;
+      if (grow < row_limit) {
+        const uint4 val = *reinterpret_cast<const uint4*>(stg + r * 128 + ((ch ^ (r & 7)) << 4));
+        *reinterpret_cast<uint4*>(gbase + (long long)grow * g_ld + half * 64 + ch * 8) = val;
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// ================================================================================================
+// dK / dV kernel
+// ================================================================================================
+namespace dkv {
+using namespace ab;
+constexpr int OFF_K = 0;                       // [128 keys x 128 d]  32 KiB
+constexpr int OFF_V = OFF_K + 2 * BLK128;      // 32 KiB
+constexpr int OFF_Q = OFF_V + 2 * BLK128;      // 2 stages x [64 q x 128 d] 16 KiB
+constexpr int OFF_DO = OFF_Q + 2 * 2 * BLK64;  // 2 stages x 16 KiB
+constexpr int OFF_PT = OFF_DO + 2 * 2 * BLK64; // P^T  [128 keys x 64 q] 16 KiB
+constexpr int OFF_DST = OFF_PT + BLK128;       // dS^T 16 KiB
+constexpr int OFF_BAR = OFF_DST + BLK128;
+constexpr int OFF_TMEM = OFF_BAR + 16 * 8;
+constexpr int SMEM_BYTES = OFF_TMEM + 16 + 1024;
+enum { KV_FULL = 0, QDO_FULL = 1, QDO_EMPTY = 3, SP_FULL = 5, SP_EMPTY = 7, PDS_FULL = 9, PDS_EMPTY = 10,
+       ACC_FULL = 11 };
+}  // namespace dkv
+
+__global__ void __launch_bounds__(192, 1)
+attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmKV,   // qkv, box 64 x 128 rows
+                    const __grid_constant__ CUtensorMap tmQ,    // qkv, box 64 x 64 rows
+                    const __grid_constant__ CUtensorMap tmDO,   // dO,  box 64 x 64 rows
+                    const __grid_constant__ AttnBwdP p) {
+  using namespace dkv;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* sgen = smem_raw + (sbase - smem_u32(smem_raw));
+  auto bar = [&](int i) { return sbase + OFF_BAR + 8u * i; };
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int jt = blockIdx.x % p.n_outer, z = blockIdx.x / p.n_outer;
+  const int b = z / p.H, h = z % p.H;
+  const int k0 = jt * 128;
+  const int HD = p.H * DK;
+  const int n = p.n_inner;  // 64-query tiles
+
+  if (threadIdx.x == 0) {
+    mbar_init(bar(KV_FULL), 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(bar(QDO_FULL + s), 1);
+      mbar_init(bar(QDO_EMPTY + s), 1);
+      mbar_init(bar(SP_FULL + s), 1);
+      mbar_init(bar(SP_EMPTY + s), 4);
+    }
+    mbar_init(bar(PDS_FULL), 4);
+    mbar_init(bar(PDS_EMPTY), 1);
+    mbar_init(bar(ACC_FULL), 1);
+    fence_mbar_init();
+  }
+  if (warp == 5) {
+    tmem_alloc(sbase + OFF_TMEM, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(sgen + OFF_TMEM);
+  const uint32_t tSt = tmem_base, tdPt = tmem_base + 128, tdV = tmem_base + 256, tdK = tmem_base + 384;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(bar(KV_FULL), 4 * BLK128);
+      for (int kb = 0; kb < 2; ++kb) {
+        tma_load_3d(sbase + OFF_K + kb * BLK128, &tmKV, bar(KV_FULL), HD + h * DK + kb * 64, k0, b);
+        tma_load_3d(sbase + OFF_V + kb * BLK128, &tmKV, bar(KV_FULL), 2 * HD + h * DK + kb * 64, k0, b);
+      }
+      for (int i = 0; i < n; ++i) {
+        const int s = i & 1;
+        mbar_wait(bar(QDO_EMPTY + s), ((i >> 1) & 1) ^ 1u);
+        mbar_arrive_expect_tx(bar(QDO_FULL + s), 4 * BLK64);
+        for (int kb = 0; kb < 2; ++kb) {
+          tma_load_3d(sbase + OFF_Q + s * 2 * BLK64 + kb * BLK64, &tmQ, bar(QDO_FULL + s), h * DK + kb * 64,
+                      i * 64, b);
+          tma_load_3d(sbase + OFF_DO + s * 2 * BLK64 + kb * BLK64, &tmDO, bar(QDO_FULL + s), h * DK + kb * 64,
+                      i * 64, b);
+        }
+      }
+    }
+  } else if (warp == 5) {
+    if (lane == 0) {
+      const uint32_t idesc_s = make_idesc_bf16(128, 64, 0, 0);    // S^T / dP^T: [128 keys x 64 q]
+      const uint32_t idesc_a = make_idesc_bf16(128, 128, 0, 1);   // dV / dK: B operand MN-major
+      auto issue_sp = [&](int i) {
+        const int s = i & 1;
+        mbar_wait(bar(QDO_FULL + s), (i >> 1) & 1);
+        mbar_wait(bar(SP_EMPTY + s), ((i >> 1) & 1) ^ 1u);
+        tc_fence_after();
+        const uint32_t sq = sbase + OFF_Q + s * 2 * BLK64, sdo = sbase + OFF_DO + s * 2 * BLK64;
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+          const uint32_t offa = (t >> 2) * BLK128 + (t & 3) * 32, offb = (t >> 2) * BLK64 + (t & 3) * 32;
+          umma_f16(tSt + s * 64, make_smem_desc(sbase + OFF_K + offa, 16, 1024),
+                   make_smem_desc(sq + offb, 16, 1024), idesc_s, t > 0);
+        }
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+          const uint32_t offa = (t >> 2) * BLK128 + (t & 3) * 32, offb = (t >> 2) * BLK64 + (t & 3) * 32;
+          umma_f16(tdPt + s * 64, make_smem_desc(sbase + OFF_V + offa, 16, 1024),
+                   make_smem_desc(sdo + offb, 16, 1024), idesc_s, t > 0);
+        }
+        umma_commit(bar(SP_FULL + s));
+      };
+      mbar_wait(bar(KV_FULL), 0);
+      issue_sp(0);
+      for (int i = 0; i < n; ++i) {
+        const int s = i & 1;
+        if (i + 1 < n) issue_sp(i + 1);
+        mbar_wait(bar(PDS_FULL), i & 1);
+        tc_fence_after();
+        const uint32_t sq = sbase + OFF_Q + s * 2 * BLK64, sdo = sbase + OFF_DO + s * 2 * BLK64;
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {  // K = 64 queries, 16 per step
+          umma_f16(tdV, make_smem_desc(sbase + OFF_PT + t * 32, 16, 1024),
+                   make_smem_desc(sdo + t * 2048, BLK64, 1024), idesc_a, (i > 0 || t > 0) ? 1u : 0u);
+        }
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          umma_f16(tdK, make_smem_desc(sbase + OFF_DST + t * 32, 16, 1024),
+                   make_smem_desc(sq + t * 2048, BLK64, 1024), idesc_a, (i > 0 || t > 0) ? 1u : 0u);
+        }
+        umma_commit(bar(QDO_EMPTY + s));
+        umma_commit(bar(PDS_EMPTY));
+        if (i == n - 1) umma_commit(bar(ACC_FULL));
+      }
+    }
+  } else {
+    // softmax warps: thread = key row
+    const int row = warp * 32 + lane;
+    const int key = k0 + row;
+    const int len = min((int)p.lens[b], p.T);
+    const bool key_valid = key < len;
+    const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
+    uint8_t* pt_row = sgen + OFF_PT + row * 128;
+    uint8_t* dst_row = sgen + OFF_DST + row * 128;
+    const int sw = row & 7;
+    const float* lse2 = p.lse2 + (long long)z * p.T;
+    const float* dsum = p.dsum + (long long)z * p.T;
+    for (int i = 0; i < n; ++i) {
+      const int s = i & 1;
+      mbar_wait(bar(SP_FULL + s), (i >> 1) & 1);
+      tc_fence_after();
+      mbar_wait(bar(PDS_EMPTY), (i & 1) ^ 1u);
+#pragma unroll 1
+      for (int c = 0; c < 2; ++c) {
+        uint32_t vs[32], vd[32];
+        tmem_ld32(tSt + s * 64 + lane_base + c * 32, vs);
+        tmem_ld32(tdPt + s * 64 + lane_base + c * 32, vd);
+        tmem_ld_wait();
+        float pf[32], df[32];
+        const int qb = i * 64 + c * 32;
+#pragma unroll
+        for (int t = 0; t < 32; ++t) {
+          const int q = qb + t;
+          float pr = 0.f, ds = 0.f;
+          if (key_valid && q < p.T) {
+            const float l2 = __ldg(lse2 + q);
+            pr = exp2f(__uint_as_float(vs[t]) * p.scale_log2 - l2);  // lse2 = +inf on padded queries -> 0
+            ds = pr * (__uint_as_float(vd[t]) - __ldg(dsum + q)) * p.scale;
+          }
+          pf[t] = pr;
+          df[t] = ds;
+        }
+        store_row_chunks(pt_row, sw, c * 4, pf);
+        store_row_chunks(dst_row, sw, c * 4, df);
+      }
+      tc_fence_before();
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(bar(SP_EMPTY + s));
+        mbar_arrive(bar(PDS_FULL));
+      }
+    }
+    mbar_wait(bar(ACC_FULL), 0);
+    tc_fence_after();
+    uint8_t* stg = sgen + OFF_PT + warp * 4096;  // P^T tile is free now
+    __nv_bfloat16* gb = p.dqkv + (long long)b * p.T * 3 * HD;
+    store_acc_128x128(tdV, lane_base, stg, warp, lane, gb + 2 * HD + h * DK, 3 * HD, k0, p.T);
+    store_acc_128x128(tdK, lane_base, stg, warp, lane, gb + HD + h * DK, 3 * HD, k0, p.T);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ================================================================================================
+// dQ kernel
+// ================================================================================================
+namespace dq {
+using namespace ab;
+constexpr int OFF_Q = 0;                       // [128 q x 128 d] 32 KiB
+constexpr int OFF_DO = OFF_Q + 2 * BLK128;     // 32 KiB
+constexpr int OFF_K = OFF_DO + 2 * BLK128;     // 2 stages x [64 keys x 128 d] 16 KiB
+constexpr int OFF_V = OFF_K + 2 * 2 * BLK64;   // 2 stages x 16 KiB
+constexpr int OFF_DS = OFF_V + 2 * 2 * BLK64;  // dS [128 q x 64 keys] 16 KiB
+constexpr int OFF_STG = OFF_DS + BLK128;       // epilogue staging 16 KiB
+constexpr int OFF_BAR = OFF_STG + BLK128;
+constexpr int OFF_TMEM = OFF_BAR + 16 * 8;
+constexpr int SMEM_BYTES = OFF_TMEM + 16 + 1024;
+enum { QDO_FULL = 0, KV_FULL = 1, KV_EMPTY = 3, SP_FULL = 5, SP_EMPTY = 7, DS_FULL = 9, DS_EMPTY = 10,
+       ACC_FULL = 11 };
+}  // namespace dq
+
+__global__ void __launch_bounds__(192, 1)
+attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ128,  // qkv, box 64 x 128 rows
+                   const __grid_constant__ CUtensorMap tmKV64,  // qkv, box 64 x 64 rows
+                   const __grid_constant__ CUtensorMap tmDO128, // dO,  box 64 x 128 rows
+                   const __grid_constant__ AttnBwdP p) {
+  using namespace dq;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* sgen = smem_raw + (sbase - smem_u32(smem_raw));
+  auto bar = [&](int i) { return sbase + OFF_BAR + 8u * i; };
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int it = blockIdx.x % p.n_outer, z = blockIdx.x / p.n_outer;
+  const int b = z / p.H, h = z % p.H;
+  const int q0 = it * 128;
+  const int HD = p.H * DK;
+  const int n = p.n_inner;  // 64-key tiles
+
+  if (threadIdx.x == 0) {
+    mbar_init(bar(QDO_FULL), 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(bar(KV_FULL + s), 1);
+      mbar_init(bar(KV_EMPTY + s), 1);
+      mbar_init(bar(SP_FULL + s), 1);
+      mbar_init(bar(SP_EMPTY + s), 4);
+    }
+    mbar_init(bar(DS_FULL), 4);
+    mbar_init(bar(DS_EMPTY), 1);
+    mbar_init(bar(ACC_FULL), 1);
+    fence_mbar_init();
+  }
+  if (warp == 5) {
+    tmem_alloc(sbase + OFF_TMEM, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(sgen + OFF_TMEM);
+  const uint32_t tS = tmem_base, tdP = tmem_base + 128, tdQ = tmem_base + 256;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(bar(QDO_FULL), 4 * BLK128);
+      for (int kb = 0; kb < 2; ++kb) {
+        tma_load_3d(sbase + OFF_Q + kb * BLK128, &tmQ128, bar(QDO_FULL), h * DK + kb * 64, q0, b);
+        tma_load_3d(sbase + OFF_DO + kb * BLK128, &tmDO128, bar(QDO_FULL), h * DK + kb * 64, q0, b);
+      }
+      for (int j = 0; j < n; ++j) {
+        const int s = j & 1;
+        mbar_wait(bar(KV_EMPTY + s), ((j >> 1) & 1) ^ 1u);
+        mbar_arrive_expect_tx(bar(KV_FULL + s), 4 * BLK64);
+        for (int kb = 0; kb < 2; ++kb) {
+          tma_load_3d(sbase + OFF_K + s * 2 * BLK64 + kb * BLK64, &tmKV64, bar(KV_FULL + s),
+                      HD + h * DK + kb * 64, j * 64, b);
+          tma_load_3d(sbase + OFF_V + s * 2 * BLK64 + kb * BLK64, &tmKV64, bar(KV_FULL + s),
+                      2 * HD + h * DK + kb * 64, j * 64, b);
+        }
+      }
+    }
+  } else if (warp == 5) {
+    if (lane == 0) {
+      const uint32_t idesc_s = make_idesc_bf16(128, 64, 0, 0);   // S / dP: [128 q x 64 keys]
+      const uint32_t idesc_q = make_idesc_bf16(128, 128, 0, 1);  // dQ += dS K (K tile as MN-major B)
+      auto issue_sp = [&](int j) {
+        const int s = j & 1;
+        mbar_wait(bar(KV_FULL + s), (j >> 1) & 1);
+        mbar_wait(bar(SP_EMPTY + s), ((j >> 1) & 1) ^ 1u);
+        tc_fence_after();
+        const uint32_t sk = sbase + OFF_K + s * 2 * BLK64, sv = sbase + OFF_V + s * 2 * BLK64;
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+          const uint32_t offa = (t >> 2) * BLK128 + (t & 3) * 32, offb = (t >> 2) * BLK64 + (t & 3) * 32;
+          umma_f16(tS + s * 64, make_smem_desc(sbase + OFF_Q + offa, 16, 1024),
+                   make_smem_desc(sk + offb, 16, 1024), idesc_s, t > 0);
+        }
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+          const uint32_t offa = (t >> 2) * BLK128 + (t & 3) * 32, offb = (t >> 2) * BLK64 + (t & 3) * 32;
+          umma_f16(tdP + s * 64, make_smem_desc(sbase + OFF_DO + offa, 16, 1024),
+                   make_smem_desc(sv + offb, 16, 1024), idesc_s, t > 0);
+        }
+        umma_commit(bar(SP_FULL + s));
+      };
+      mbar_wait(bar(QDO_FULL), 0);
+      issue_sp(0);
+      for (int j = 0; j < n; ++j) {
+        const int s = j & 1;
+        if (j + 1 < n) issue_sp(j + 1);
+        mbar_wait(bar(DS_FULL), j & 1);
+        tc_fence_after();
+        const uint32_t sk = sbase + OFF_K + s * 2 * BLK64;
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {  // K = 64 keys, 16 per step
+          umma_f16(tdQ, make_smem_desc(sbase + OFF_DS + t * 32, 16, 1024),
+                   make_smem_desc(sk + t * 2048, BLK64, 1024), idesc_q, (j > 0 || t > 0) ? 1u : 0u);
+        }
+        umma_commit(bar(KV_EMPTY + s));
+        umma_commit(bar(DS_EMPTY));
+        if (j == n - 1) umma_commit(bar(ACC_FULL));
+      }
+    }
+  } else {
+    // softmax warps: thread = query row
+    const int row = warp * 32 + lane;
+    const int q = q0 + row;
+    const int len = min((int)p.lens[b], p.T);
+    const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
+    uint8_t* ds_row = sgen + OFF_DS + row * 128;
+    const int sw = row & 7;
+    const bool q_ok = q < len;
+    const float l2 = q_ok ? p.lse2[(long long)z * p.T + q] : INFINITY;
+    const float dq_sum = q_ok ? p.dsum[(long long)z * p.T + q] : 0.f;
+    for (int j = 0; j < n; ++j) {
+      const int s = j & 1;
+      mbar_wait(bar(SP_FULL + s), (j >> 1) & 1);
+      tc_fence_after();
+      mbar_wait(bar(DS_EMPTY), (j & 1) ^ 1u);
+#pragma unroll 1
+      for (int c = 0; c < 2; ++c) {
+        uint32_t vs[32], vd[32];
+        tmem_ld32(tS + s * 64 + lane_base + c * 32, vs);
+        tmem_ld32(tdP + s * 64 + lane_base + c * 32, vd);
+        tmem_ld_wait();
+        float df[32];
+        const int kb = j * 64 + c * 32;
+#pragma unroll
+        for (int t = 0; t < 32; ++t) {
+          float ds = 0.f;
+          if (q_ok && kb + t < len) {
+            const float pr = exp2f(__uint_as_float(vs[t]) * p.scale_log2 - l2);
+            ds = pr * (__uint_as_float(vd[t]) - dq_sum) * p.scale;
+          }
+          df[t] = ds;
+        }
+        store_row_chunks(ds_row, sw, c * 4, df);
+      }
+      tc_fence_before();
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(bar(SP_EMPTY + s));
+        mbar_arrive(bar(DS_FULL));
+      }
+    }
+    mbar_wait(bar(ACC_FULL), 0);
+    tc_fence_after();
+    uint8_t* stg = sgen + OFF_STG + warp * 4096;
+    __nv_bfloat16* gb = p.dqkv + (long long)b * p.T * 3 * HD;
+    store_acc_128x128(tdQ, lane_base, stg, warp, lane, gb + h * DK, 3 * HD, q0, p.T);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+}  // namespace fs2
+
+extern "C" {
+
+// qkv: bf16 [B][T][3*H*128]; o, d_o: bf16 [B][T][H*128]; lse2: f32 [B*H][T] from the forward;
+// dsum: f32 [B*H][T] workspace; dqkv: bf16 [B][T][3*H*128] (every element is written).
+int fs2_attn_bwd_bf16(const void* qkv, const void* o, const void* d_o, const float* lse2, const int64_t* lens,
+                      int B, int T, int H, int dk, float* dsum, void* dqkv, void* stream) {
+  using namespace fs2;
+  if (dk != ab::DK) return set_error("attn_bwd: d_k must be 128");
+  if (B <= 0 || T <= 0) return 0;
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(attn_bwd_dkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         dkv::SMEM_BYTES);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(attn_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dq::SMEM_BYTES);
+    if (e != cudaSuccess) return set_cuda_error("cudaFuncSetAttribute(attn_bwd)", e);
+    attr = true;
+  }
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int C3 = 3 * H * dk, HD = H * dk;
+  const long long rows = (long long)B * T;
+  attn_bwd_prep_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, s>>>(static_cast<const __nv_bfloat16*>(o),
+                                                                 static_cast<const __nv_bfloat16*>(d_o), B, T, H,
+                                                                 dsum);
+  count_launch();
+  if (int rc = check_launch("attn_bwd_prep_kernel")) return rc;
+  CUtensorMap tm128, tm64, tmdo128, tmdo64;
+  if (int rc = make_tmap_bf16_3d(&tm128, qkv, C3, T, B, C3, (long long)T * C3, 64, 128)) return rc;
+  if (int rc = make_tmap_bf16_3d(&tm64, qkv, C3, T, B, C3, (long long)T * C3, 64, 64)) return rc;
+  if (int rc = make_tmap_bf16_3d(&tmdo128, d_o, HD, T, B, HD, (long long)T * HD, 64, 128)) return rc;
+  if (int rc = make_tmap_bf16_3d(&tmdo64, d_o, HD, T, B, HD, (long long)T * HD, 64, 64)) return rc;
+  AttnBwdP p{};
+  p.lens = lens; p.lse2 = lse2; p.dsum = dsum;
+  p.B = B; p.T = T; p.H = H;
+  p.scale = 1.f / sqrtf((float)dk);
+  p.scale_log2 = 1.4426950408889634f * p.scale;
+  p.dqkv = static_cast<__nv_bfloat16*>(dqkv);
+  p.n_outer = (T + 127) / 128;
+  p.n_inner = (T + 63) / 64;
+  const unsigned grid = (unsigned)(p.n_outer * B * H);
+  attn_bwd_dkv_kernel<<<grid, 192, dkv::SMEM_BYTES, s>>>(tm128, tm64, tmdo64, p);
+  count_launch();
+  if (int rc = check_launch("attn_bwd_dkv_kernel")) return rc;
+  attn_bwd_dq_kernel<<<grid, 192, dq::SMEM_BYTES, s>>>(tm128, tm64, tmdo128, p);
+  count_launch();
+  return check_launch("attn_bwd_dq_kernel");
+}
+}

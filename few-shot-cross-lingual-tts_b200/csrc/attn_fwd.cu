@@ -1,0 +1,304 @@
+// Fused key-padding-masked softmax attention, forward, for sm_100a (d_k = 128).
+//
+// Replaces transformer/Modules.py:14-25 + the head split / merge of transformer/SubLayers.py:39-52:
+//     attn = softmax(mask(Q K^T / sqrt(d_k))) ; out = attn V
+// without ever writing the [H*B, T, T] score / probability tensors to HBM.  Q, K, V are read straight
+// out of the fused projection buffer [B][T][3*H*dk] by TMA (head = a column offset), the two GEMMs
+// run on tcgen05 with S and O accumulators in TMEM, P goes registers -> swizzled smem -> tcgen05.
+//
+// One CTA = one (batch*head z, 128-query tile).  Exact two-pass softmax:
+//   pass A: S_j = Q K_j^T for every 128-key tile j, row max m                (no exp, no P)
+//   pass B: S_j again, P_j = exp2(S_j*c - m*c) (masked keys -> 0), l += rowsum, O += P_j V_j
+// (QK^T is recomputed instead of rescaling O in TMEM: +50 % of the cheap GEMM, no correction step and
+//  no dependence of the PV pipeline on the running max).  Epilogue: O / l -> bf16, and
+//  lse2 = m*c + log2(l) per row for the backward kernels (+inf for padded / empty rows => P = 0).
+//
+// Warp roles (192 threads): warps 0-3 softmax + epilogue (thread = query row = TMEM lane),
+// warp 4 TMA producer, warp 5 MMA issuer (+ TMEM alloc).
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include "common.h"
+#include "ptx.cuh"
+#include "tmap.h"
+
+namespace fs2 {
+
+namespace af {
+constexpr int DK = 128, BQ = 128, BKV = 128;
+constexpr int TILE_BYTES = 128 * 128 * 2;  // 32 KiB: two [128 x 64] bf16 swizzle-128B blocks
+constexpr int BLK = 16384;                 // one [128 rows x 64 cols] block
+constexpr int OFF_Q = 0;
+constexpr int OFF_K = OFF_Q + TILE_BYTES;      // 2 stages
+constexpr int OFF_V = OFF_K + 2 * TILE_BYTES;  // 2 stages
+constexpr int OFF_P = OFF_V + 2 * TILE_BYTES;
+constexpr int OFF_BAR = OFF_P + TILE_BYTES;
+constexpr int NUM_BARS = 16;
+constexpr int OFF_TMEM = OFF_BAR + NUM_BARS * 8;
+constexpr int SMEM_BYTES = OFF_TMEM + 16 + 1024;
+enum { Q_FULL = 0, K_FULL = 1, K_EMPTY = 3, V_FULL = 5, V_EMPTY = 7, S_FULL = 9, S_EMPTY = 11, P_FULL = 13,
+       P_EMPTY = 14, O_FULL = 15 };
+}  // namespace af
+
+struct AttnFwdP {
+  const int64_t* lens;
+  int B, T, H, nq, nkv;
+  float scale_log2;
+  __nv_bfloat16* out;  // [B][T][H*dk]
+  float* lse2;         // [B*H][T]
+};
+
+__global__ void __launch_bounds__(192, 1)
+attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constant__ CUtensorMap tmV,
+                const __grid_constant__ AttnFwdP p) {
+  using namespace af;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* sgen = smem_raw + (sbase - smem_u32(smem_raw));
+  auto bar = [&](int i) { return sbase + OFF_BAR + 8u * i; };
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int qt = blockIdx.x % p.nq, z = blockIdx.x / p.nq;
+  const int b = z / p.H, h = z % p.H;
+  const int q0 = qt * BQ;
+  const int HD = p.H * DK;
+  const int n = p.nkv;  // key tiles
+
+  if (threadIdx.x == 0) {
+    mbar_init(bar(Q_FULL), 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(bar(K_FULL + s), 1);
+      mbar_init(bar(K_EMPTY + s), 1);
+      mbar_init(bar(V_FULL + s), 1);
+      mbar_init(bar(V_EMPTY + s), 1);
+      mbar_init(bar(S_FULL + s), 1);
+      mbar_init(bar(S_EMPTY + s), 4);
+    }
+    mbar_init(bar(P_FULL), 4);
+    mbar_init(bar(P_EMPTY), 1);
+    mbar_init(bar(O_FULL), 1);
+    fence_mbar_init();
+  }
+  if (warp == 5) {
+    tmem_alloc(sbase + OFF_TMEM, 512);
+    tmem_relinquish();
+  }
+  if (warp == 4 && lane == 0) {
+    tma_prefetch_desc(&tmQK);
+    tma_prefetch_desc(&tmV);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(sgen + OFF_TMEM);
+  const uint32_t tS0 = tmem_base, tO = tmem_base + 256;
+
+  if (warp == 4) {
+    // ============================== TMA producer ==============================
+    if (lane == 0) {
+      mbar_arrive_expect_tx(bar(Q_FULL), TILE_BYTES);
+      for (int kb = 0; kb < 2; ++kb)
+        tma_load_3d(sbase + OFF_Q + kb * BLK, &tmQK, bar(Q_FULL), h * DK + kb * 64, q0, b);
+      for (int u = 0; u < 2 * n; ++u) {
+        const int j = u % n, s = u & 1;
+        mbar_wait(bar(K_EMPTY + s), ((u >> 1) & 1) ^ 1u);
+        mbar_arrive_expect_tx(bar(K_FULL + s), TILE_BYTES);
+        for (int kb = 0; kb < 2; ++kb)
+          tma_load_3d(sbase + OFF_K + s * TILE_BYTES + kb * BLK, &tmQK, bar(K_FULL + s),
+                      HD + h * DK + kb * 64, j * BKV, b);
+        if (u >= n) {
+          const int vs = j & 1;
+          mbar_wait(bar(V_EMPTY + vs), ((j >> 1) & 1) ^ 1u);
+          mbar_arrive_expect_tx(bar(V_FULL + vs), TILE_BYTES);
+          for (int dh = 0; dh < 2; ++dh)
+            for (int kh = 0; kh < 2; ++kh)
+              tma_load_3d(sbase + OFF_V + vs * TILE_BYTES + dh * BLK + kh * 8192, &tmV, bar(V_FULL + vs),
+                          2 * HD + h * DK + dh * 64, j * BKV + kh * 64, b);
+        }
+      }
+    }
+  } else if (warp == 5) {
+    // ============================== MMA issuer ==============================
+    if (lane == 0) {
+      const uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);  // S = Q K^T   (both K-major)
+      const uint32_t idesc_o = make_idesc_bf16(128, 128, 0, 1);  // O += P V    (V is MN-major)
+      auto issue_s = [&](int u) {
+        const int s = u & 1;
+        mbar_wait(bar(K_FULL + s), (u >> 1) & 1);
+        mbar_wait(bar(S_EMPTY + s), ((u >> 1) & 1) ^ 1u);
+        tc_fence_after();
+        const uint32_t sq = sbase + OFF_Q, sk = sbase + OFF_K + s * TILE_BYTES;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const uint32_t off = (i >> 2) * BLK + (i & 3) * 32;
+          umma_f16(tS0 + s * 128, make_smem_desc(sq + off, 16, 1024), make_smem_desc(sk + off, 16, 1024),
+                   idesc_s, i > 0);
+        }
+        umma_commit(bar(K_EMPTY + s));
+        umma_commit(bar(S_FULL + s));
+      };
+      mbar_wait(bar(Q_FULL), 0);
+      issue_s(0);
+      for (int u = 0; u < 2 * n; ++u) {
+        if (u + 1 < 2 * n) issue_s(u + 1);
+        if (u >= n) {
+          const int j = u - n, vs = j & 1;
+          mbar_wait(bar(P_FULL), j & 1);
+          mbar_wait(bar(V_FULL + vs), (j >> 1) & 1);
+          tc_fence_after();
+          const uint32_t sp = sbase + OFF_P, sv = sbase + OFF_V + vs * TILE_BYTES;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            // A = P: K-major over keys (two 64-key blocks); B = V: MN-major, 16 key rows per step
+            const uint64_t ad = make_smem_desc(sp + (i >> 2) * BLK + (i & 3) * 32, 16, 1024);
+            const uint64_t bd = make_smem_desc(sv + i * 2048, BLK, 1024);
+            umma_f16(tO, ad, bd, idesc_o, (j > 0 || i > 0) ? 1u : 0u);
+          }
+          umma_commit(bar(V_EMPTY + vs));
+          umma_commit(bar(P_EMPTY));
+          if (j == n - 1) umma_commit(bar(O_FULL));
+        }
+      }
+    }
+  } else {
+    // ============================== softmax + epilogue warps ==============================
+    const int row = warp * 32 + lane;
+    const int q = q0 + row;
+    const int len = min((int)p.lens[b], p.T);
+    const bool row_valid = q < len;
+    const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
+    uint8_t* sp_row = sgen + OFF_P + row * 128;
+    const int sw = row & 7;
+    float mx = -INFINITY, m2 = 0.f, l = 0.f;
+    for (int u = 0; u < 2 * n; ++u) {
+      const int j = u % n, s = u & 1;
+      const bool pass_b = u >= n;
+      if (u == n) m2 = (mx == -INFINITY) ? 0.f : mx * p.scale_log2;
+      mbar_wait(bar(S_FULL + s), (u >> 1) & 1);
+      tc_fence_after();
+      if (pass_b) mbar_wait(bar(P_EMPTY), (((u - n) & 1)) ^ 1u);  // previous P consumed by the PV MMA
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t v[32];
+        tmem_ld32(tS0 + s * 128 + lane_base + c * 32, v);
+        tmem_ld_wait();
+        const int k0 = j * BKV + c * 32;
+        if (!pass_b) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (k0 + i < len) mx = fmaxf(mx, __uint_as_float(v[i]));
+        } else {
+          float pv[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float e = exp2f(__uint_as_float(v[i]) * p.scale_log2 - m2);
+            pv[i] = (row_valid && k0 + i < len) ? e : 0.f;
+            l += pv[i];
+          }
+          uint8_t* blk = sp_row + (c >> 1) * BLK;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            uint32_t w[4];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              __nv_bfloat162 b2 = __floats2bfloat162_rn(pv[g * 8 + 2 * t], pv[g * 8 + 2 * t + 1]);
+              w[t] = *reinterpret_cast<uint32_t*>(&b2);
+            }
+            const int ch = (c & 1) * 4 + g;
+            *reinterpret_cast<uint4*>(blk + ((ch ^ sw) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+          }
+        }
+      }
+      tc_fence_before();
+      if (pass_b) fence_proxy_async_smem();  // P (generic-proxy stores) must be visible to the MMA
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(bar(S_EMPTY + s));
+        if (pass_b) mbar_arrive(bar(P_FULL));
+      }
+    }
+    // ---- epilogue: O / l -> bf16 -> staging (the P tile is free now) -> coalesced global store
+    mbar_wait(bar(O_FULL), 0);
+    tc_fence_after();
+    const float inv = l > 0.f ? 1.f / l : 0.f;
+    if (q < p.T) p.lse2[(long long)z * p.T + q] = l > 0.f ? m2 + log2f(l) : INFINITY;
+    uint8_t* stg = sgen + OFF_P + warp * 4096;
+    uint8_t* my = stg + lane * 128;
+    const int lsw = lane & 7;
+#pragma unroll 1
+    for (int half = 0; half < 2; ++half) {  // 64 output columns (128 B) per pass
+      float f[64];
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t v[32];
+        tmem_ld32(tO + lane_base + half * 64 + c * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) f[c * 32 + i] = __uint_as_float(v[i]) * inv;
+      }
+#pragma unroll
+      for (int ch = 0; ch < 8; ++ch) {
+        uint32_t w[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          __nv_bfloat162 b2 = __floats2bfloat162_rn(f[ch * 8 + 2 * t], f[ch * 8 + 2 * t + 1]);
+          w[t] = *reinterpret_cast<uint32_t*>(&b2);
+        }
+        *reinterpret_cast<uint4*>(my + ((ch ^ lsw) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+      }
+      __syncwarp();
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const int r = it * 4 + (lane >> 3), ch = lane & 7;
+        const int gq = q0 + warp * 32 + r;
+        if (gq < p.T) {
+          const uint4 val = *reinterpret_cast<const uint4*>(stg + r * 128 + ((ch ^ (r & 7)) << 4));
+          *reinterpret_cast<uint4*>(p.out + ((long long)b * p.T + gq) * HD + h * DK + half * 64 + ch * 8) = val;
+        }
+      }
+      __syncwarp();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+}  // namespace fs2
+
+extern "C" {
+
+// qkv: bf16 [B][T][3*H*128] (Q | K | V, head h = columns [h*128, (h+1)*128) of each third);
+// lens: int64 [B]; out: bf16 [B][T][H*128]; lse2: f32 [B*H][T] (log2-domain log-sum-exp of the scaled
+// scores; +inf on padded rows).  scale = 1/sqrt(dk) is applied inside.
+int fs2_attn_fwd_bf16(const void* qkv, const int64_t* lens, int B, int T, int H, int dk, void* out,
+                      float* lse2, void* stream) {
+  using namespace fs2;
+  if (dk != af::DK) return set_error("attn_fwd: d_k must be 128");
+  if (B <= 0 || T <= 0) return 0;
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         af::SMEM_BYTES);
+    if (e != cudaSuccess) return set_cuda_error("cudaFuncSetAttribute(attn_fwd)", e);
+    attr = true;
+  }
+  const int C3 = 3 * H * dk;
+  CUtensorMap tmQK, tmV;
+  if (int rc = make_tmap_bf16_3d(&tmQK, qkv, C3, T, B, C3, (long long)T * C3, 64, 128)) return rc;
+  if (int rc = make_tmap_bf16_3d(&tmV, qkv, C3, T, B, C3, (long long)T * C3, 64, 64)) return rc;
+  AttnFwdP p{};
+  p.lens = lens;
+  p.B = B; p.T = T; p.H = H;
+  p.nq = (T + af::BQ - 1) / af::BQ;
+  p.nkv = (T + af::BKV - 1) / af::BKV;
+  p.scale_log2 = 1.4426950408889634f / sqrtf((float)dk);
+  p.out = static_cast<__nv_bfloat16*>(out);
+  p.lse2 = lse2;
+  attn_fwd_kernel<<<p.nq * B * H, 192, af::SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(tmQK, tmV, p);
+  count_launch();
+  return check_launch("attn_fwd_kernel");
+}
+}

@@ -15,6 +15,7 @@
 
 #include "common.h"
 #include "ptx.cuh"
+#include "tmap.h"
 
 namespace fs2 {
 
@@ -498,44 +499,42 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // ------------------------------------------------------------------------------------------------
 // Host side
 // ------------------------------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
-                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
-                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn get_encode_fn() {
-  static EncodeTiledFn fn = nullptr;
-  if (!fn) {
+int make_tmap_bf16_3d(CUtensorMap* map, const void* ptr, long long inner, long long rows, long long batches,
+                      long long ld, long long batch_stride, int box_inner, int box_rows) {
+  typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                    CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                    CUtensorMapFloatOOBfill);
+  static EncodeTiledFn enc = nullptr;
+  if (!enc) {
     void* sym = nullptr;
     cudaDriverEntryPointQueryResult qres;
     cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres);
-    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !sym) return nullptr;
-    fn = reinterpret_cast<EncodeTiledFn>(sym);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !sym)
+      return set_error("cuTensorMapEncodeTiled driver entry point not available");
+    enc = reinterpret_cast<EncodeTiledFn>(sym);
   }
-  return fn;
-}
-
-static int make_tmap(CUtensorMap* map, const fs2_operand& o, int box_inner, int box_rows) {
-  EncodeTiledFn enc = get_encode_fn();
-  if (!enc) return set_error("cuTensorMapEncodeTiled driver entry point not available");
-  if ((reinterpret_cast<uintptr_t>(o.ptr) & 15) || (o.ld & 7) || (o.batch_stride & 7))
-    return set_error("gemm operand must be 16-byte aligned with ld / batch_stride multiples of 8");
-  cuuint64_t dims[3] = {(cuuint64_t)o.inner, (cuuint64_t)o.rows, (cuuint64_t)o.batches};
-  cuuint64_t bs = o.batches > 1 ? (cuuint64_t)o.batch_stride : (cuuint64_t)o.ld * o.rows;
-  cuuint64_t strides[2] = {(cuuint64_t)o.ld * 2, bs * 2};
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (ld & 7) || (batch_stride & 7))
+    return set_error("TMA operand must be 16-byte aligned with ld / batch_stride multiples of 8 elements");
+  cuuint64_t dims[3] = {(cuuint64_t)inner, (cuuint64_t)rows, (cuuint64_t)batches};
+  cuuint64_t bs = batches > 1 ? (cuuint64_t)batch_stride : (cuuint64_t)ld * rows;
+  cuuint64_t strides[2] = {(cuuint64_t)ld * 2, bs * 2};
   cuuint32_t box[3] = {(cuuint32_t)box_inner, (cuuint32_t)box_rows, 1};
   cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(o.ptr), dims,
-                   strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     char buf[256];
-    snprintf(buf, sizeof buf,
-             "cuTensorMapEncodeTiled failed (%d): inner=%d rows=%d batches=%d ld=%lld bs=%lld", (int)r,
-             o.inner, o.rows, o.batches, (long long)o.ld, (long long)o.batch_stride);
+    snprintf(buf, sizeof buf, "cuTensorMapEncodeTiled failed (%d): inner=%lld rows=%lld batches=%lld ld=%lld bs=%lld",
+             (int)r, inner, rows, batches, ld, batch_stride);
     return set_error(buf);
   }
   return 0;
+}
+
+static int make_tmap(CUtensorMap* map, const fs2_operand& o, int box_inner, int box_rows) {
+  return make_tmap_bf16_3d(map, o.ptr, o.inner, o.rows, o.batches, o.ld, o.batch_stride, box_inner, box_rows);
 }
 
 static int g_num_sms = 0;

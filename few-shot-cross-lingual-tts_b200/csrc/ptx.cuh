@@ -3,6 +3,7 @@
 // Everything here is device-only and header-only.
 #pragma once
 #include <cstdint>
+#include <cstdio>
 #include <cuda_runtime.h>
 
 namespace fs2 {

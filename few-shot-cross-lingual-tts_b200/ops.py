@@ -227,6 +227,35 @@ def ln_bwd(dy, x, res, gamma, mean, rstd, lens, p, mode, salt, dgamma, dbeta, wa
     return dx, dres
 
 
+def attn_fwd(qkv, lens, H, dk):
+    """Fused masked-softmax attention forward on the packed [B, T, 3*H*dk] projection.
+    Returns (out bf16 [B, T, H*dk], lse2 f32 [B*H, T])."""
+    B, T, C3 = qkv.shape
+    assert C3 == 3 * H * dk and qkv.is_contiguous()
+    out = torch.empty(B, T, H * dk, dtype=BF16, device=qkv.device)
+    lse2 = torch.empty(B * H, T, dtype=F32, device=qkv.device)
+    _ck(_L().fs2_attn_fwd_bf16(_p(qkv), _p(lens), B, T, H, dk, _p(out), _p(lse2), _st()), "attn_fwd")
+    return out, lse2
+
+
+def attn_bwd(qkv, out, d_out, lse2, lens, H, dk):
+    """Fused attention backward: returns dqkv bf16 [B, T, 3*H*dk]."""
+    B, T, C3 = qkv.shape
+    dqkv = torch.empty_like(qkv)
+    dsum = torch.empty(B * H, T, dtype=F32, device=qkv.device)
+    _ck(_L().fs2_attn_bwd_bf16(_p(qkv), _p(out), _p(d_out), _p(lse2), _p(lens), B, T, H, dk, _p(dsum), _p(dqkv),
+                               _st()), "attn_bwd")
+    return dqkv
+
+
+def fused_attention_enabled(dk):
+    """The fused tcgen05 attention kernels cover d_k = 128 (every reference config); FS2_ATTN=unfused
+    selects the older GEMM -> softmax -> GEMM composition (kept as a cross-check)."""
+    import os
+
+    return dk == 128 and os.environ.get("FS2_ATTN", "fused") != "unfused"
+
+
 def _contig(dy):
     return dy if dy.is_contiguous() else dy.contiguous()
 
@@ -286,6 +315,19 @@ class MHASublayer(torch.autograd.Function):
         Tp = _roundup(T, 128)
         Z = B * H
         C3 = 3 * HD
+        fused = fused_attention_enabled(dk)
+        if fused:
+            attn3, lse2 = attn_fwd(qkv.view(B, T, C3), lens, H, dk)
+            attn = attn3.view(B * T, HD)
+            wo_bf = cast_bf16(wo)
+            o = linear_fwd(attn, wo_bf, bo.detach())
+            salt = _Rng.next_salt()
+            y, mean, rstd = ln_fwd(o.view(B, T, D), x, gamma.detach(), beta.detach(),
+                                   lens if zero_pad else None, p_drop, 1, salt)
+            ctx.save_for_backward(x, lens, qkv, lse2, attn, o, mean, rstd, wqkv, wo_bf, gamma)
+            ctx.params = (wq, bq, wk, bk, wv, bv, wo, bo, gamma, beta)
+            ctx.cfg = (H, dk, p_drop, zero_pad, salt, Tp, True)
+            return y
         S = torch.empty(Z, T, Tp, dtype=F32, device=dev)
         G.gemm(G.operand(qkv, C3, T, B, zdiv=H, zmod_stride=dk),
                G.operand(qkv, C3, T, B, inner_base=HD, zdiv=H, zmod_stride=dk), S, T, T, dk, Z=Z, ldd=Tp,
@@ -304,14 +346,14 @@ class MHASublayer(torch.autograd.Function):
                                p_drop, 1, salt)
         ctx.save_for_backward(x, lens, qkv, P, attn, o, mean, rstd, wqkv, wo_bf, gamma)
         ctx.params = (wq, bq, wk, bk, wv, bv, wo, bo, gamma, beta)
-        ctx.cfg = (H, dk, p_drop, zero_pad, salt, Tp)
+        ctx.cfg = (H, dk, p_drop, zero_pad, salt, Tp, False)
         return y
 
     @staticmethod
     def backward(ctx, dy):
         x, lens, qkv, P, attn, o, mean, rstd, wqkv, wo_bf, gamma_t = ctx.saved_tensors
         wq, bq, wk, bk, wv, bv, wo, bo, gamma, beta = ctx.params
-        H, dk, p_drop, zero_pad, salt, Tp = ctx.cfg
+        H, dk, p_drop, zero_pad, salt, Tp, fused = ctx.cfg
         B, T, D = x.shape
         HD, C3, Z, M = H * dk, 3 * H * dk, B * H, B * T
         dev = x.device
@@ -324,6 +366,16 @@ class MHASublayer(torch.autograd.Function):
         dattn = linear_dgrad(do2, wo_bf)
         linear_wgrad(do2, attn, gbuf[6][0])
         colsum(do2, gbuf[7][0])
+        if fused:  # `P` slot of the saved tensors holds lse2; S / P / dS never touch HBM
+            dqkv = attn_bwd(qkv.view(B, T, C3), attn.view(B, T, HD), dattn.view(B, T, HD), P, lens, H,
+                            dk).view(M, C3)
+            x2 = x.view(M, D)
+            dx = linear_dgrad(dqkv, wqkv, epilogue=G.EPI_ADD_AUX, aux=dres.view(M, D))
+            for i in range(3):
+                linear_wgrad(dqkv, x2, gbuf[2 * i][0], row0=i * HD, rows=HD)
+                colsum(dqkv, gbuf[2 * i + 1][0], col0=i * HD, cols=HD)
+            grads_done((wq, bq, wk, bk, wv, bv, wo, bo, gamma, beta))
+            return (dx.view(B, T, D), None) + tuple(g[1] for g in gbuf) + (None, None, None)
         # attention core: dP = dO V^T ; dS = softmax'(P, dP) ; dQ = dS K ; dK = dS^T Q ; dV = P^T dO
         dP = torch.empty(Z, T, Tp, dtype=F32, device=dev)
         G.gemm(G.operand(dattn, HD, T, B, zdiv=H, zmod_stride=dk),

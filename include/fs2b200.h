@@ -125,6 +125,17 @@ int fs2_softmax_bwd(const void* P, const float* dP, const int64_t* lens, int Z, 
                     float alpha, void* dS, void* stream);
 
 /* ------------------------------------------------------------------------------------------ */
+/* Fused masked-softmax attention, d_k = 128 (transformer/Modules.py:14-25 + the head split /   */
+/* merge of transformer/SubLayers.py:39-52).  qkv: bf16 [B][T][3*H*dk]; out: bf16 [B][T][H*dk]; */
+/* lse2: f32 [B*H][T] log2-domain log-sum-exp of the scaled scores (+inf on padded rows).       */
+/* ------------------------------------------------------------------------------------------ */
+int fs2_attn_fwd_bf16(const void* qkv, const int64_t* lens, int B, int T, int H, int dk, void* out,
+                      float* lse2, void* stream);
+/* backward: o, d_o: bf16 [B][T][H*dk]; dsum: f32 [B*H][T] workspace; dqkv: bf16 [B][T][3*H*dk]   */
+int fs2_attn_bwd_bf16(const void* qkv, const void* o, const void* d_o, const float* lse2, const int64_t* lens,
+                      int B, int T, int H, int dk, float* dsum, void* dqkv, void* stream);
+
+/* ------------------------------------------------------------------------------------------ */
 /* LengthRegulator (lightning/model/modules.py:169-196, lightning/utils/tool.py:168-186)       */
 /*   integer cumsum + vectorised gather; bit-exact copy semantics; see csrc/length_regulator.cu */
 /* ------------------------------------------------------------------------------------------ */

@@ -42,7 +42,7 @@ struct AttnBwdP {
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 attn_bwd_prep_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ d_o, int B, int T,
-                     int H, float* __restrict__ dsum) {
+                     int H, float scale, float* __restrict__ dsum) {
   const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= (long long)B * T) return;
   const int lane = threadIdx.x & 31;
@@ -59,9 +59,16 @@ attn_bwd_prep_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* _
     const float2 g1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&g.y));
     s = a0.x * g0.x + a0.y * g0.y + a1.x * g1.x + a1.y * g1.y;
     s = warp_sum(s);
-    if (lane == 0) dsum[((long long)b * H + h) * T + t] = s;
+    if (lane == 0) dsum[((long long)b * H + h) * T + t] = s * scale;  // pre-scaled: dS = P*(dP*c - D*c)
   }
 }
+
+__device__ __forceinline__ float ex2_fast(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ void softmax_bar_sync_bwd() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 // write 32 fp32 values (already final) as bf16 into this thread's 128-byte swizzled smem row, 16-byte
 // chunks [chunk0, chunk0+4)
@@ -78,45 +85,43 @@ __device__ __forceinline__ void store_row_chunks(uint8_t* row_ptr, int sw, int c
   }
 }
 
-// TMEM accumulator [128 lanes x 128 cols] -> bf16 -> per-warp staging -> coalesced global rows
-__device__ __forceinline__ void store_acc_128x128(uint32_t tacc, uint32_t lane_base, uint8_t* stg, int warp,
-                                                  int lane, __nv_bfloat16* gbase, long long g_ld, int row0,
-                                                  int row_limit) {
+// 64 columns [half*64, half*64+64) of a TMEM accumulator [128 lanes x 128 cols] -> bf16 -> this warp's
+// staging tile -> coalesced global rows (warp = lane quarter q4, rows row0 + q4*32 ...)
+__device__ __forceinline__ void store_acc_half(uint32_t tacc, uint32_t lane_base, uint8_t* stg, int q4, int lane,
+                                               int half, __nv_bfloat16* gbase, long long g_ld, int row0,
+                                               int row_limit) {
   uint8_t* my = stg + lane * 128;
   const int lsw = lane & 7;
-#pragma unroll 1
-  for (int half = 0; half < 2; ++half) {
-    float f[64];
+  float f[64];
 #pragma unroll
-    for (int c = 0; c < 2; ++c) {
-      uint32_t v[32];
-      tmem_ld32(tacc + lane_base + half * 64 + c * 32, v);
-      tmem_ld_wait();
+  for (int c = 0; c < 2; ++c) {
+    uint32_t v[32];
+    tmem_ld32(tacc + lane_base + half * 64 + c * 32, v);
+    tmem_ld_wait();
 #pragma unroll
-      for (int i = 0; i < 32; ++i) f[c * 32 + i] = __uint_as_float(v[i]);
-    }
-#pragma unroll
-    for (int ch = 0; ch < 8; ++ch) {
-      uint32_t w[4];
-#pragma unroll
-      for (int t = 0; t < 4; ++t) {
-        __nv_bfloat162 b2 = __floats2bfloat162_rn(f[ch * 8 + 2 * t], f[ch * 8 + 2 * t + 1]);
-        w[t] = *reinterpret_cast<uint32_t*>(&b2);
-      }
-      *reinterpret_cast<uint4*>(my + ((ch ^ lsw) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
-    }
-    __syncwarp();
-#pragma unroll
-    for (int it = 0; it < 8; ++it) {
-      const int r = it * 4 + (lane >> 3), ch = lane & 7;
-      const int grow = row0 + warp * 32 + r;
-      if (grow < row_limit) {
-        const uint4 val = *reinterpret_cast<const uint4*>(stg + r * 128 + ((ch ^ (r & 7)) << 4));
-        *reinterpret_cast<uint4*>(gbase + (long long)grow * g_ld + half * 64 + ch * 8) = val;
-      }
-    }
-    __syncwarp();
+    for (int i = 0; i < 32; ++i) f[c * 32 + i] = __uint_as_float(v[i]);
   }
+#pragma unroll
+  for (int ch = 0; ch < 8; ++ch) {
+    uint32_t w[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      __nv_bfloat162 b2 = __floats2bfloat162_rn(f[ch * 8 + 2 * t], f[ch * 8 + 2 * t + 1]);
+      w[t] = *reinterpret_cast<uint32_t*>(&b2);
+    }
+    *reinterpret_cast<uint4*>(my + ((ch ^ lsw) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+  __syncwarp();
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const int r = it * 4 + (lane >> 3), ch = lane & 7;
+    const int grow = row0 + q4 * 32 + r;
+    if (grow < row_limit) {
+      const uint4 val = *reinterpret_cast<const uint4*>(stg + r * 128 + ((ch ^ (r & 7)) << 4));
+      *reinterpret_cast<uint4*>(gbase + (long long)grow * g_ld + half * 64 + ch * 8) = val;
+    }
+  }
+  __syncwarp();
 }
 
 // ================================================================================================
@@ -128,16 +133,17 @@ constexpr int OFF_K = 0;                       // [128 keys x 128 d]  32 KiB
 constexpr int OFF_V = OFF_K + 2 * BLK128;      // 32 KiB
 constexpr int OFF_Q = OFF_V + 2 * BLK128;      // 2 stages x [64 q x 128 d] 16 KiB
 constexpr int OFF_DO = OFF_Q + 2 * 2 * BLK64;  // 2 stages x 16 KiB
-constexpr int OFF_PT = OFF_DO + 2 * 2 * BLK64; // P^T  [128 keys x 64 q] 16 KiB
-constexpr int OFF_DST = OFF_PT + BLK128;       // dS^T 16 KiB
-constexpr int OFF_BAR = OFF_DST + BLK128;
+constexpr int OFF_PT = OFF_DO + 2 * 2 * BLK64; // 2 x P^T  [128 keys x 64 q] 16 KiB
+constexpr int OFF_DST = OFF_PT + 2 * BLK128;   // 2 x dS^T 16 KiB
+constexpr int OFF_STAT = OFF_DST + 2 * BLK128; // [2 parities][lse2 | dsum][64] f32
+constexpr int OFF_BAR = OFF_STAT + 2 * 2 * 64 * 4;
 constexpr int OFF_TMEM = OFF_BAR + 16 * 8;
 constexpr int SMEM_BYTES = OFF_TMEM + 16 + 1024;
-enum { KV_FULL = 0, QDO_FULL = 1, QDO_EMPTY = 3, SP_FULL = 5, SP_EMPTY = 7, PDS_FULL = 9, PDS_EMPTY = 10,
-       ACC_FULL = 11 };
+enum { KV_FULL = 0, QDO_FULL = 1, QDO_EMPTY = 3, SP_FULL = 5, SP_EMPTY = 7, PDS_FULL = 9, PDS_EMPTY = 11,
+       ACC_FULL = 13 };
 }  // namespace dkv
 
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(320, 1)
 attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmKV,   // qkv, box 64 x 128 rows
                     const __grid_constant__ CUtensorMap tmQ,    // qkv, box 64 x 64 rows
                     const __grid_constant__ CUtensorMap tmDO,   // dO,  box 64 x 64 rows
@@ -160,14 +166,14 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmKV,   // qkv, box 64 x
       mbar_init(bar(QDO_FULL + s), 1);
       mbar_init(bar(QDO_EMPTY + s), 1);
       mbar_init(bar(SP_FULL + s), 1);
-      mbar_init(bar(SP_EMPTY + s), 4);
+      mbar_init(bar(SP_EMPTY + s), 8);
+      mbar_init(bar(PDS_FULL + s), 8);
+      mbar_init(bar(PDS_EMPTY + s), 1);
     }
-    mbar_init(bar(PDS_FULL), 4);
-    mbar_init(bar(PDS_EMPTY), 1);
     mbar_init(bar(ACC_FULL), 1);
     fence_mbar_init();
   }
-  if (warp == 5) {
+  if (warp == 9) {
     tmem_alloc(sbase + OFF_TMEM, 512);
     tmem_relinquish();
   }
@@ -177,7 +183,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmKV,   // qkv, box 64 x
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(sgen + OFF_TMEM);
   const uint32_t tSt = tmem_base, tdPt = tmem_base + 128, tdV = tmem_base + 256, tdK = tmem_base + 384;
 
-  if (warp == 4) {
+  if (warp == 8) {
     if (lane == 0) {
       mbar_arrive_expect_tx(bar(KV_FULL), 4 * BLK128);
       for (int kb = 0; kb < 2; ++kb) {
@@ -196,7 +202,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmKV,   // qkv, box 64 x
         }
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == 9) {
     if (lane == 0) {
       const uint32_t idesc_s = make_idesc_bf16(128, 64, 0, 0);    // S^T / dP^T: [128 keys x 64 q]
       const uint32_t idesc_a = make_idesc_bf16(128, 128, 0, 1);   // dV / dK: B operand MN-major
@@ -225,82 +231,94 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmKV,   // qkv, box 64 x
       for (int i = 0; i < n; ++i) {
         const int s = i & 1;
         if (i + 1 < n) issue_sp(i + 1);
-        mbar_wait(bar(PDS_FULL), i & 1);
+        mbar_wait(bar(PDS_FULL + s), (i >> 1) & 1);
         tc_fence_after();
         const uint32_t sq = sbase + OFF_Q + s * 2 * BLK64, sdo = sbase + OFF_DO + s * 2 * BLK64;
 #pragma unroll
         for (int t = 0; t < 4; ++t) {  // K = 64 queries, 16 per step
-          umma_f16(tdV, make_smem_desc(sbase + OFF_PT + t * 32, 16, 1024),
+          umma_f16(tdV, make_smem_desc(sbase + OFF_PT + s * BLK128 + t * 32, 16, 1024),
                    make_smem_desc(sdo + t * 2048, BLK64, 1024), idesc_a, (i > 0 || t > 0) ? 1u : 0u);
         }
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
-          umma_f16(tdK, make_smem_desc(sbase + OFF_DST + t * 32, 16, 1024),
+          umma_f16(tdK, make_smem_desc(sbase + OFF_DST + s * BLK128 + t * 32, 16, 1024),
                    make_smem_desc(sq + t * 2048, BLK64, 1024), idesc_a, (i > 0 || t > 0) ? 1u : 0u);
         }
         umma_commit(bar(QDO_EMPTY + s));
-        umma_commit(bar(PDS_EMPTY));
+        umma_commit(bar(PDS_EMPTY + s));
         if (i == n - 1) umma_commit(bar(ACC_FULL));
       }
     }
   } else {
-    // softmax warps: thread = key row
-    const int row = warp * 32 + lane;
+    // softmax warps: thread = key row; warps w / w+4 take the query columns [0,32) / [32,64) of the tile
+    const int q4 = warp & 3, half = warp >> 2;
+    const int row = q4 * 32 + lane;
     const int key = k0 + row;
     const int len = min((int)p.lens[b], p.T);
     const bool key_valid = key < len;
-    const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
+    const uint32_t lane_base = static_cast<uint32_t>(q4 * 32) << 16;
     uint8_t* pt_row = sgen + OFF_PT + row * 128;
     uint8_t* dst_row = sgen + OFF_DST + row * 128;
+    float* s_stat = reinterpret_cast<float*>(sgen + OFF_STAT);
     const int sw = row & 7;
+    const int tid = threadIdx.x;  // 0..255 here
     const float* lse2 = p.lse2 + (long long)z * p.T;
     const float* dsum = p.dsum + (long long)z * p.T;
     for (int i = 0; i < n; ++i) {
       const int s = i & 1;
+      // per-query statistics of this 64-query tile -> smem (double buffered by tile parity)
+      if (tid < 128) {
+        const int qq = i * 64 + (tid & 63);
+        float val;
+        if (tid < 64) val = qq < p.T ? __ldg(lse2 + qq) : INFINITY;  // +inf => P = 0 (padded queries too)
+        else val = qq < p.T ? __ldg(dsum + qq) : 0.f;
+        s_stat[s * 128 + tid] = val;
+      }
+      softmax_bar_sync_bwd();
       mbar_wait(bar(SP_FULL + s), (i >> 1) & 1);
       tc_fence_after();
-      mbar_wait(bar(PDS_EMPTY), (i & 1) ^ 1u);
-#pragma unroll 1
-      for (int c = 0; c < 2; ++c) {
-        uint32_t vs[32], vd[32];
-        tmem_ld32(tSt + s * 64 + lane_base + c * 32, vs);
-        tmem_ld32(tdPt + s * 64 + lane_base + c * 32, vd);
-        tmem_ld_wait();
-        float pf[32], df[32];
-        const int qb = i * 64 + c * 32;
+      uint32_t vs[32], vd[32];
+      tmem_ld32(tSt + s * 64 + lane_base + half * 32, vs);
+      tmem_ld32(tdPt + s * 64 + lane_base + half * 32, vd);
+      tmem_ld_wait();
+      float pf[32], df[32];
+      const float4* st_l = reinterpret_cast<const float4*>(s_stat + s * 128 + half * 32);
+      const float4* st_d = st_l + 16;
+      // invalid key rows (beyond the utterance) get P = dS = 0 through an infinite "lse" offset
+      const float kill = key_valid ? 0.f : INFINITY;
 #pragma unroll
-        for (int t = 0; t < 32; ++t) {
-          const int q = qb + t;
-          float pr = 0.f, ds = 0.f;
-          if (key_valid && q < p.T) {
-            const float l2 = __ldg(lse2 + q);
-            pr = exp2f(__uint_as_float(vs[t]) * p.scale_log2 - l2);  // lse2 = +inf on padded queries -> 0
-            ds = pr * (__uint_as_float(vd[t]) - __ldg(dsum + q)) * p.scale;
-          }
+      for (int t4 = 0; t4 < 8; ++t4) {
+        const float4 l4 = st_l[t4], d4 = st_d[t4];
+        const float lv[4] = {l4.x, l4.y, l4.z, l4.w}, dv[4] = {d4.x, d4.y, d4.z, d4.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int t = t4 * 4 + e;
+          const float pr = ex2_fast(fmaf(__uint_as_float(vs[t]), p.scale_log2, -(lv[e] + kill)));
           pf[t] = pr;
-          df[t] = ds;
+          df[t] = pr * fmaf(__uint_as_float(vd[t]), p.scale, -dv[e]);
         }
-        store_row_chunks(pt_row, sw, c * 4, pf);
-        store_row_chunks(dst_row, sw, c * 4, df);
       }
+      mbar_wait(bar(PDS_EMPTY + s), ((i >> 1) & 1) ^ 1u);  // dV / dK MMAs of tile i-2 consumed this buffer
+      store_row_chunks(pt_row + s * BLK128, sw, half * 4, pf);
+      store_row_chunks(dst_row + s * BLK128, sw, half * 4, df);
       tc_fence_before();
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) {
         mbar_arrive(bar(SP_EMPTY + s));
-        mbar_arrive(bar(PDS_FULL));
+        mbar_arrive(bar(PDS_FULL + s));
       }
     }
     mbar_wait(bar(ACC_FULL), 0);
     tc_fence_after();
-    uint8_t* stg = sgen + OFF_PT + warp * 4096;  // P^T tile is free now
+    uint8_t* stg = sgen + OFF_PT + warp * 4096;  // P^T / dS^T tiles (32 KiB) are free now
     __nv_bfloat16* gb = p.dqkv + (long long)b * p.T * 3 * HD;
-    store_acc_128x128(tdV, lane_base, stg, warp, lane, gb + 2 * HD + h * DK, 3 * HD, k0, p.T);
-    store_acc_128x128(tdK, lane_base, stg, warp, lane, gb + HD + h * DK, 3 * HD, k0, p.T);
+    store_acc_half(tdV, lane_base, stg, q4, lane, half, gb + 2 * HD + h * DK, 3 * HD, k0, p.T);
+    store_acc_half(tdK, lane_base, stg, q4, lane, half, gb + HD + h * DK, 3 * HD, k0, p.T);
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) {
+  if (warp == 9) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }
@@ -315,16 +333,16 @@ constexpr int OFF_Q = 0;                       // [128 q x 128 d] 32 KiB
 constexpr int OFF_DO = OFF_Q + 2 * BLK128;     // 32 KiB
 constexpr int OFF_K = OFF_DO + 2 * BLK128;     // 2 stages x [64 keys x 128 d] 16 KiB
 constexpr int OFF_V = OFF_K + 2 * 2 * BLK64;   // 2 stages x 16 KiB
-constexpr int OFF_DS = OFF_V + 2 * 2 * BLK64;  // dS [128 q x 64 keys] 16 KiB
-constexpr int OFF_STG = OFF_DS + BLK128;       // epilogue staging 16 KiB
-constexpr int OFF_BAR = OFF_STG + BLK128;
+constexpr int OFF_DS = OFF_V + 2 * 2 * BLK64;  // 2 x dS [128 q x 64 keys] 16 KiB (also the epilogue staging)
+constexpr int OFF_STG = OFF_DS;
+constexpr int OFF_BAR = OFF_DS + 2 * BLK128;
 constexpr int OFF_TMEM = OFF_BAR + 16 * 8;
 constexpr int SMEM_BYTES = OFF_TMEM + 16 + 1024;
-enum { QDO_FULL = 0, KV_FULL = 1, KV_EMPTY = 3, SP_FULL = 5, SP_EMPTY = 7, DS_FULL = 9, DS_EMPTY = 10,
-       ACC_FULL = 11 };
+enum { QDO_FULL = 0, KV_FULL = 1, KV_EMPTY = 3, SP_FULL = 5, SP_EMPTY = 7, DS_FULL = 9, DS_EMPTY = 11,
+       ACC_FULL = 13 };
 }  // namespace dq
 
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(320, 1)
 attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ128,  // qkv, box 64 x 128 rows
                    const __grid_constant__ CUtensorMap tmKV64,  // qkv, box 64 x 64 rows
                    const __grid_constant__ CUtensorMap tmDO128, // dO,  box 64 x 128 rows
@@ -347,14 +365,14 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ128,  // qkv, box 64 x
       mbar_init(bar(KV_FULL + s), 1);
       mbar_init(bar(KV_EMPTY + s), 1);
       mbar_init(bar(SP_FULL + s), 1);
-      mbar_init(bar(SP_EMPTY + s), 4);
+      mbar_init(bar(SP_EMPTY + s), 8);
+      mbar_init(bar(DS_FULL + s), 8);
+      mbar_init(bar(DS_EMPTY + s), 1);
     }
-    mbar_init(bar(DS_FULL), 4);
-    mbar_init(bar(DS_EMPTY), 1);
     mbar_init(bar(ACC_FULL), 1);
     fence_mbar_init();
   }
-  if (warp == 5) {
+  if (warp == 9) {
     tmem_alloc(sbase + OFF_TMEM, 512);
     tmem_relinquish();
   }
@@ -364,7 +382,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ128,  // qkv, box 64 x
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(sgen + OFF_TMEM);
   const uint32_t tS = tmem_base, tdP = tmem_base + 128, tdQ = tmem_base + 256;
 
-  if (warp == 4) {
+  if (warp == 8) {
     if (lane == 0) {
       mbar_arrive_expect_tx(bar(QDO_FULL), 4 * BLK128);
       for (int kb = 0; kb < 2; ++kb) {
@@ -383,7 +401,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ128,  // qkv, box 64 x
         }
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == 9) {
     if (lane == 0) {
       const uint32_t idesc_s = make_idesc_bf16(128, 64, 0, 0);   // S / dP: [128 q x 64 keys]
       const uint32_t idesc_q = make_idesc_bf16(128, 128, 0, 1);  // dQ += dS K (K tile as MN-major B)
@@ -412,71 +430,74 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ128,  // qkv, box 64 x
       for (int j = 0; j < n; ++j) {
         const int s = j & 1;
         if (j + 1 < n) issue_sp(j + 1);
-        mbar_wait(bar(DS_FULL), j & 1);
+        mbar_wait(bar(DS_FULL + s), (j >> 1) & 1);
         tc_fence_after();
         const uint32_t sk = sbase + OFF_K + s * 2 * BLK64;
 #pragma unroll
         for (int t = 0; t < 4; ++t) {  // K = 64 keys, 16 per step
-          umma_f16(tdQ, make_smem_desc(sbase + OFF_DS + t * 32, 16, 1024),
+          umma_f16(tdQ, make_smem_desc(sbase + OFF_DS + s * BLK128 + t * 32, 16, 1024),
                    make_smem_desc(sk + t * 2048, BLK64, 1024), idesc_q, (j > 0 || t > 0) ? 1u : 0u);
         }
         umma_commit(bar(KV_EMPTY + s));
-        umma_commit(bar(DS_EMPTY));
+        umma_commit(bar(DS_EMPTY + s));
         if (j == n - 1) umma_commit(bar(ACC_FULL));
       }
     }
   } else {
-    // softmax warps: thread = query row
-    const int row = warp * 32 + lane;
+    // softmax warps: thread = query row; warps w / w+4 take the key columns [0,32) / [32,64) of the tile
+    const int q4 = warp & 3, half = warp >> 2;
+    const int row = q4 * 32 + lane;
     const int q = q0 + row;
     const int len = min((int)p.lens[b], p.T);
-    const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
+    const uint32_t lane_base = static_cast<uint32_t>(q4 * 32) << 16;
     uint8_t* ds_row = sgen + OFF_DS + row * 128;
     const int sw = row & 7;
     const bool q_ok = q < len;
-    const float l2 = q_ok ? p.lse2[(long long)z * p.T + q] : INFINITY;
+    const float l2 = q_ok ? p.lse2[(long long)z * p.T + q] : INFINITY;  // +inf => P = 0
     const float dq_sum = q_ok ? p.dsum[(long long)z * p.T + q] : 0.f;
     for (int j = 0; j < n; ++j) {
       const int s = j & 1;
       mbar_wait(bar(SP_FULL + s), (j >> 1) & 1);
       tc_fence_after();
-      mbar_wait(bar(DS_EMPTY), (j & 1) ^ 1u);
-#pragma unroll 1
-      for (int c = 0; c < 2; ++c) {
-        uint32_t vs[32], vd[32];
-        tmem_ld32(tS + s * 64 + lane_base + c * 32, vs);
-        tmem_ld32(tdP + s * 64 + lane_base + c * 32, vd);
-        tmem_ld_wait();
-        float df[32];
-        const int kb = j * 64 + c * 32;
+      uint32_t vs[32], vd[32];
+      tmem_ld32(tS + s * 64 + lane_base + half * 32, vs);
+      tmem_ld32(tdP + s * 64 + lane_base + half * 32, vd);
+      tmem_ld_wait();
+      float df[32];
+      const int kb = j * 64 + half * 32;
+      if (kb + 32 <= len) {  // warp-uniform fast path: every key of this slice is valid
 #pragma unroll
         for (int t = 0; t < 32; ++t) {
-          float ds = 0.f;
-          if (q_ok && kb + t < len) {
-            const float pr = exp2f(__uint_as_float(vs[t]) * p.scale_log2 - l2);
-            ds = pr * (__uint_as_float(vd[t]) - dq_sum) * p.scale;
-          }
-          df[t] = ds;
+          const float pr = ex2_fast(fmaf(__uint_as_float(vs[t]), p.scale_log2, -l2));
+          df[t] = pr * fmaf(__uint_as_float(vd[t]), p.scale, -dq_sum);
         }
-        store_row_chunks(ds_row, sw, c * 4, df);
+      } else {
+#pragma unroll
+        for (int t = 0; t < 32; ++t) {
+          const float pr = ex2_fast(fmaf(__uint_as_float(vs[t]), p.scale_log2, -l2));
+          const float ds = pr * fmaf(__uint_as_float(vd[t]), p.scale, -dq_sum);
+          df[t] = (kb + t < len) ? ds : 0.f;
+        }
       }
+      mbar_wait(bar(DS_EMPTY + s), ((j >> 1) & 1) ^ 1u);  // the dQ MMA of tile j-2 has consumed this buffer
+      store_row_chunks(ds_row + s * BLK128, sw, half * 4, df);
       tc_fence_before();
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) {
         mbar_arrive(bar(SP_EMPTY + s));
-        mbar_arrive(bar(DS_FULL));
+        mbar_arrive(bar(DS_FULL + s));
       }
     }
     mbar_wait(bar(ACC_FULL), 0);
     tc_fence_after();
     uint8_t* stg = sgen + OFF_STG + warp * 4096;
     __nv_bfloat16* gb = p.dqkv + (long long)b * p.T * 3 * HD;
-    store_acc_128x128(tdQ, lane_base, stg, warp, lane, gb + h * DK, 3 * HD, q0, p.T);
+    store_acc_half(tdQ, lane_base, stg, q4, lane, half, gb + h * DK, 3 * HD, q0, p.T);
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) {
+  if (warp == 9) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }
@@ -507,7 +528,7 @@ int fs2_attn_bwd_bf16(const void* qkv, const void* o, const void* d_o, const flo
   const long long rows = (long long)B * T;
   attn_bwd_prep_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, s>>>(static_cast<const __nv_bfloat16*>(o),
                                                                  static_cast<const __nv_bfloat16*>(d_o), B, T, H,
-                                                                 dsum);
+                                                                 1.f / sqrtf((float)dk), dsum);
   count_launch();
   if (int rc = check_launch("attn_bwd_prep_kernel")) return rc;
   CUtensorMap tm128, tm64, tmdo128, tmdo64;
@@ -524,10 +545,10 @@ int fs2_attn_bwd_bf16(const void* qkv, const void* o, const void* d_o, const flo
   p.n_outer = (T + 127) / 128;
   p.n_inner = (T + 63) / 64;
   const unsigned grid = (unsigned)(p.n_outer * B * H);
-  attn_bwd_dkv_kernel<<<grid, 192, dkv::SMEM_BYTES, s>>>(tm128, tm64, tmdo64, p);
+  attn_bwd_dkv_kernel<<<grid, 320, dkv::SMEM_BYTES, s>>>(tm128, tm64, tmdo64, p);
   count_launch();
   if (int rc = check_launch("attn_bwd_dkv_kernel")) return rc;
-  attn_bwd_dq_kernel<<<grid, 192, dq::SMEM_BYTES, s>>>(tm128, tm64, tmdo128, p);
+  attn_bwd_dq_kernel<<<grid, 320, dq::SMEM_BYTES, s>>>(tm128, tm64, tmdo128, p);
   count_launch();
   return check_launch("attn_bwd_dq_kernel");
 }

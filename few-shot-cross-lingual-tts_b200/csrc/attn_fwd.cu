@@ -13,8 +13,10 @@
 //  no dependence of the PV pipeline on the running max).  Epilogue: O / l -> bf16, and
 //  lse2 = m*c + log2(l) per row for the backward kernels (+inf for padded / empty rows => P = 0).
 //
-// Warp roles (192 threads): warps 0-3 softmax + epilogue (thread = query row = TMEM lane),
-// warp 4 TMA producer, warp 5 MMA issuer (+ TMEM alloc).
+// Warp roles (320 threads): warps 0-7 softmax + epilogue (thread = query row = TMEM lane; warps w and
+// w+4 share the 32 rows of lane quarter w%4 and split the key / output columns in halves, so every SM
+// sub-partition always has two softmax warps to interleave), warp 8 TMA producer, warp 9 MMA issuer
+// (+ TMEM alloc).  Row max and row sum are combined across the two halves once per pass.
 #include <cuda.h>
 #include <cuda_bf16.h>
 
@@ -32,12 +34,13 @@ constexpr int OFF_Q = 0;
 constexpr int OFF_K = OFF_Q + TILE_BYTES;      // 2 stages
 constexpr int OFF_V = OFF_K + 2 * TILE_BYTES;  // 2 stages
 constexpr int OFF_P = OFF_V + 2 * TILE_BYTES;
-constexpr int OFF_BAR = OFF_P + TILE_BYTES;
-constexpr int NUM_BARS = 16;
+constexpr int OFF_RED = OFF_P + 2 * TILE_BYTES;  // P is double buffered  // [2 halves][128 rows] f32 exchange of max / sum
+constexpr int OFF_BAR = OFF_RED + 2 * 128 * 4;
+constexpr int NUM_BARS = 18;
 constexpr int OFF_TMEM = OFF_BAR + NUM_BARS * 8;
 constexpr int SMEM_BYTES = OFF_TMEM + 16 + 1024;
 enum { Q_FULL = 0, K_FULL = 1, K_EMPTY = 3, V_FULL = 5, V_EMPTY = 7, S_FULL = 9, S_EMPTY = 11, P_FULL = 13,
-       P_EMPTY = 14, O_FULL = 15 };
+       P_EMPTY = 15, O_FULL = 17 };
 }  // namespace af
 
 struct AttnFwdP {
@@ -48,7 +51,14 @@ struct AttnFwdP {
   float* lse2;         // [B*H][T]
 };
 
-__global__ void __launch_bounds__(192, 1)
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ void softmax_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+__global__ void __launch_bounds__(320, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constant__ CUtensorMap tmV,
                 const __grid_constant__ AttnFwdP p) {
   using namespace af;
@@ -71,18 +81,18 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constant_
       mbar_init(bar(V_FULL + s), 1);
       mbar_init(bar(V_EMPTY + s), 1);
       mbar_init(bar(S_FULL + s), 1);
-      mbar_init(bar(S_EMPTY + s), 4);
+      mbar_init(bar(S_EMPTY + s), 8);
+      mbar_init(bar(P_FULL + s), 8);
+      mbar_init(bar(P_EMPTY + s), 1);
     }
-    mbar_init(bar(P_FULL), 4);
-    mbar_init(bar(P_EMPTY), 1);
     mbar_init(bar(O_FULL), 1);
     fence_mbar_init();
   }
-  if (warp == 5) {
+  if (warp == 9) {
     tmem_alloc(sbase + OFF_TMEM, 512);
     tmem_relinquish();
   }
-  if (warp == 4 && lane == 0) {
+  if (warp == 8 && lane == 0) {
     tma_prefetch_desc(&tmQK);
     tma_prefetch_desc(&tmV);
   }
@@ -92,7 +102,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constant_
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(sgen + OFF_TMEM);
   const uint32_t tS0 = tmem_base, tO = tmem_base + 256;
 
-  if (warp == 4) {
+  if (warp == 8) {
     // ============================== TMA producer ==============================
     if (lane == 0) {
       mbar_arrive_expect_tx(bar(Q_FULL), TILE_BYTES);
@@ -116,7 +126,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constant_
         }
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == 9) {
     // ============================== MMA issuer ==============================
     if (lane == 0) {
       const uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);  // S = Q K^T   (both K-major)
@@ -142,10 +152,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constant_
         if (u + 1 < 2 * n) issue_s(u + 1);
         if (u >= n) {
           const int j = u - n, vs = j & 1;
-          mbar_wait(bar(P_FULL), j & 1);
+          mbar_wait(bar(P_FULL + (j & 1)), (j >> 1) & 1);
           mbar_wait(bar(V_FULL + vs), (j >> 1) & 1);
           tc_fence_after();
-          const uint32_t sp = sbase + OFF_P, sv = sbase + OFF_V + vs * TILE_BYTES;
+          const uint32_t sp = sbase + OFF_P + (j & 1) * TILE_BYTES, sv = sbase + OFF_V + vs * TILE_BYTES;
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             // A = P: K-major over keys (two 64-key blocks); B = V: MN-major, 16 key rows per step
@@ -154,58 +164,67 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constant_
             umma_f16(tO, ad, bd, idesc_o, (j > 0 || i > 0) ? 1u : 0u);
           }
           umma_commit(bar(V_EMPTY + vs));
-          umma_commit(bar(P_EMPTY));
+          umma_commit(bar(P_EMPTY + (j & 1)));
           if (j == n - 1) umma_commit(bar(O_FULL));
         }
       }
     }
   } else {
     // ============================== softmax + epilogue warps ==============================
-    const int row = warp * 32 + lane;
+    const int q4 = warp & 3, half = warp >> 2;  // TMEM lane quarter, column half
+    const int row = q4 * 32 + lane;
     const int q = q0 + row;
     const int len = min((int)p.lens[b], p.T);
     const bool row_valid = q < len;
-    const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
-    uint8_t* sp_row = sgen + OFF_P + row * 128;
+    const uint32_t lane_base = static_cast<uint32_t>(q4 * 32) << 16;
+    uint8_t* sp_row0 = sgen + OFF_P + half * BLK + row * 128;  // this half's 64-key block of the P tile
+    float* s_red = reinterpret_cast<float*>(sgen + OFF_RED);
     const int sw = row & 7;
     float mx = -INFINITY, m2 = 0.f, l = 0.f;
     for (int u = 0; u < 2 * n; ++u) {
       const int j = u % n, s = u & 1;
       const bool pass_b = u >= n;
-      if (u == n) m2 = (mx == -INFINITY) ? 0.f : mx * p.scale_log2;
+      if (u == n) {  // combine the row maxima of the two column halves (once per CTA)
+        s_red[half * 128 + row] = mx;
+        softmax_bar_sync();
+        const float m = fmaxf(s_red[row], s_red[128 + row]);
+        m2 = (m == -INFINITY) ? 0.f : m * p.scale_log2;
+        softmax_bar_sync();
+      }
       mbar_wait(bar(S_FULL + s), (u >> 1) & 1);
       tc_fence_after();
-      if (pass_b) mbar_wait(bar(P_EMPTY), (((u - n) & 1)) ^ 1u);  // previous P consumed by the PV MMA
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
+      float pv[64];
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
         uint32_t v[32];
-        tmem_ld32(tS0 + s * 128 + lane_base + c * 32, v);
+        tmem_ld32(tS0 + s * 128 + lane_base + half * 64 + c * 32, v);
         tmem_ld_wait();
-        const int k0 = j * BKV + c * 32;
+        const int k0 = j * BKV + half * 64 + c * 32;
         if (!pass_b) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (k0 + i < len) mx = fmaxf(mx, __uint_as_float(v[i]));
+          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, (k0 + i < len) ? __uint_as_float(v[i]) : -INFINITY);
         } else {
-          float pv[32];
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
-            const float e = exp2f(__uint_as_float(v[i]) * p.scale_log2 - m2);
-            pv[i] = (row_valid && k0 + i < len) ? e : 0.f;
-            l += pv[i];
+            const float e = ex2_approx(fmaf(__uint_as_float(v[i]), p.scale_log2, -m2));
+            pv[c * 32 + i] = (row_valid && k0 + i < len) ? e : 0.f;
+            l += pv[c * 32 + i];
           }
-          uint8_t* blk = sp_row + (c >> 1) * BLK;
+        }
+      }
+      if (pass_b) {
+        const int jb = u - n;
+        uint8_t* sp_row = sp_row0 + (jb & 1) * TILE_BYTES;
+        mbar_wait(bar(P_EMPTY + (jb & 1)), ((jb >> 1) & 1) ^ 1u);  // PV MMA of tile jb-2 has consumed this buffer
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            uint32_t w[4];
+        for (int g = 0; g < 8; ++g) {
+          uint32_t w[4];
 #pragma unroll
-            for (int t = 0; t < 4; ++t) {
-              __nv_bfloat162 b2 = __floats2bfloat162_rn(pv[g * 8 + 2 * t], pv[g * 8 + 2 * t + 1]);
-              w[t] = *reinterpret_cast<uint32_t*>(&b2);
-            }
-            const int ch = (c & 1) * 4 + g;
-            *reinterpret_cast<uint4*>(blk + ((ch ^ sw) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+          for (int t = 0; t < 4; ++t) {
+            __nv_bfloat162 b2 = __floats2bfloat162_rn(pv[g * 8 + 2 * t], pv[g * 8 + 2 * t + 1]);
+            w[t] = *reinterpret_cast<uint32_t*>(&b2);
           }
+          *reinterpret_cast<uint4*>(sp_row + ((g ^ sw) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
         }
       }
       tc_fence_before();
@@ -213,19 +232,22 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constant_
       __syncwarp();
       if (lane == 0) {
         mbar_arrive(bar(S_EMPTY + s));
-        if (pass_b) mbar_arrive(bar(P_FULL));
+        if (pass_b) mbar_arrive(bar(P_FULL + ((u - n) & 1)));
       }
     }
-    // ---- epilogue: O / l -> bf16 -> staging (the P tile is free now) -> coalesced global store
+    // ---- combine the row sums, then epilogue: O / l -> bf16 -> staging (the P tile is free once the
+    //      last PV MMA has retired) -> coalesced global store; each half stores 64 output columns
+    s_red[half * 128 + row] = l;
+    softmax_bar_sync();
+    l = s_red[row] + s_red[128 + row];
     mbar_wait(bar(O_FULL), 0);
     tc_fence_after();
     const float inv = l > 0.f ? 1.f / l : 0.f;
-    if (q < p.T) p.lse2[(long long)z * p.T + q] = l > 0.f ? m2 + log2f(l) : INFINITY;
+    if (half == 0 && q < p.T) p.lse2[(long long)z * p.T + q] = l > 0.f ? m2 + log2f(l) : INFINITY;
     uint8_t* stg = sgen + OFF_P + warp * 4096;
     uint8_t* my = stg + lane * 128;
     const int lsw = lane & 7;
-#pragma unroll 1
-    for (int half = 0; half < 2; ++half) {  // 64 output columns (128 B) per pass
+    {
       float f[64];
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
@@ -249,18 +271,17 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constant_
 #pragma unroll
       for (int it = 0; it < 8; ++it) {
         const int r = it * 4 + (lane >> 3), ch = lane & 7;
-        const int gq = q0 + warp * 32 + r;
+        const int gq = q0 + q4 * 32 + r;
         if (gq < p.T) {
           const uint4 val = *reinterpret_cast<const uint4*>(stg + r * 128 + ((ch ^ (r & 7)) << 4));
           *reinterpret_cast<uint4*>(p.out + ((long long)b * p.T + gq) * HD + h * DK + half * 64 + ch * 8) = val;
         }
       }
-      __syncwarp();
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) {
+  if (warp == 9) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }
@@ -297,7 +318,7 @@ int fs2_attn_fwd_bf16(const void* qkv, const int64_t* lens, int B, int T, int H,
   p.scale_log2 = 1.4426950408889634f / sqrtf((float)dk);
   p.out = static_cast<__nv_bfloat16*>(out);
   p.lse2 = lse2;
-  attn_fwd_kernel<<<p.nq * B * H, 192, af::SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(tmQK, tmV, p);
+  attn_fwd_kernel<<<p.nq * B * H, 320, af::SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(tmQK, tmV, p);
   count_launch();
   return check_launch("attn_fwd_kernel");
 }

@@ -21,7 +21,7 @@ namespace fs2 {
 
 constexpr int BM = 128;
 constexpr int BK = 64;
-constexpr int kThreads = 256;
+constexpr int kThreads = 384;  // 4 control warps (TMA, MMA, TMEM alloc, spare) + 8 epilogue warps
 constexpr int kChunkBytes = 64 * 64 * 2;  // one 64x64 bf16 swizzle-128B box (MN-major operands)
 
 struct GemmKP {
@@ -72,8 +72,8 @@ struct SmemLayout {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGING_OFF = STAGES * STAGE_BYTES;  // 4 epilogue warps x (32 rows x 128 B)
-  static constexpr int STAGING_BYTES = 4 * 32 * 128;
+  static constexpr int STAGING_OFF = STAGES * STAGE_BYTES;  // 8 epilogue warps x (32 rows x 128 B)
+  static constexpr int STAGING_BYTES = 8 * 32 * 128;
   static constexpr int BAR_OFF = STAGING_OFF + STAGING_BYTES;
   static constexpr int NUM_BARS = 2 * STAGES + 4;
   static constexpr int TMEM_PTR_OFF = BAR_OFF + NUM_BARS * 8;
@@ -102,19 +102,35 @@ __device__ __forceinline__ void epilogue_chunk(const GemmKP& p, uint32_t taddr, 
       tmem_ld32(taddr + 32, v2);
       tmem_ld_wait();
 #pragma unroll
-      for (int j = 0; j < 32; ++j) f[32 + j] = __uint_as_float(v2[j]) * p.alpha;
+      for (int j = 0; j < 32; ++j) f[32 + j] = __uint_as_float(v2[j]);
     } else {
       tmem_ld_wait();
     }
 #pragma unroll
-    for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * p.alpha;
+    for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+    if (p.alpha != 1.f) {
+#pragma unroll
+      for (int j = 0; j < NC; ++j) f[j] *= p.alpha;
+    }
   }
   const int sw = lane & 7;
   uint8_t* my_row = stg + lane * 128;
   if (p.bias) {
+    if (n0 + NC <= nlimit) {  // warp-uniform: whole chunk in range -> 16-byte broadcast loads
+      const float4* b4 = reinterpret_cast<const float4*>(p.bias + n0);
 #pragma unroll
-    for (int j = 0; j < NC; ++j)
-      if (n0 + j < nlimit) f[j] += __ldg(p.bias + n0 + j);
+      for (int j = 0; j < NC / 4; ++j) {
+        const float4 bv = __ldg(b4 + j);
+        f[4 * j] += bv.x;
+        f[4 * j + 1] += bv.y;
+        f[4 * j + 2] += bv.z;
+        f[4 * j + 3] += bv.w;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < NC; ++j)
+        if (n0 + j < nlimit) f[j] += __ldg(p.bias + n0 + j);
+    }
   }
   if (p.epilogue == FS2_EPI_RELU) {
 #pragma unroll
@@ -233,7 +249,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), 1);
-      mbar_init(tempty_bar(s), 4);  // one arrive per epilogue warp
+      mbar_init(tempty_bar(s), 8);  // one arrive per epilogue warp
     }
     fence_mbar_init();
   }
@@ -342,8 +358,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   } else if (warp >= 4) {
-    // ======================= epilogue (4 warps, one TMEM lane = one row per thread) ===========
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    // ======================= epilogue (8 warps, one TMEM lane = one row per thread; warps w and
+    // w+4 share a lane quarter and split the tile's columns in halves) ===========
+    const int q = warp & 3;            // TMEM lane quarter this warp may access
+    const int chalf = (warp - 4) >> 2;  // column half of the tile
     const int row = q * 32 + lane;
     int as = 0;
     uint32_t aph = 0;
@@ -372,19 +390,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           p.aux ? p.aux + (long long)t.z * p.aux_batch_stride + (long long)m * p.ld_aux : nullptr;
       if (p.d_col_stride == 1 && !p.d_atomic) {
         // coalesced path (every NORMAL-mode output)
-        uint8_t* stg = sgen + L::STAGING_OFF + q * 4096;
+        uint8_t* stg = sgen + L::STAGING_OFF + (warp - 4) * 4096;
         const __nv_bfloat16* aux_base = p.aux ? p.aux + (long long)t.z * p.aux_batch_stride : nullptr;
         const int m_w0 = t.tm * BM + q * 32;
         if (p.d_f32) {
 #pragma unroll 1
-          for (int c0 = 0; c0 < BN; c0 += 32) {
+          for (int c0 = chalf * (BN / 2); c0 < (chalf + 1) * (BN / 2); c0 += 32) {
             if (ncol0 + c0 >= nlimit) break;  // warp-uniform
             epilogue_chunk<true>(p, taddr + c0, stg, lane, m_w0, ncol0 + c0, nlimit, base_off, nullptr,
                                  t.nkb > 0);
           }
         } else {
 #pragma unroll 1
-          for (int c0 = 0; c0 < BN; c0 += 64) {
+          for (int c0 = chalf * (BN / 2); c0 < (chalf + 1) * (BN / 2); c0 += 64) {
             if (ncol0 + c0 >= nlimit) break;
             epilogue_chunk<false>(p, taddr + c0, stg, lane, m_w0, ncol0 + c0, nlimit, base_off, aux_base,
                                   t.nkb > 0);
@@ -392,7 +410,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       } else
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = chalf * (BN / 64); c < (chalf + 1) * (BN / 64); ++c) {
         const int n0 = ncol0 + c * 32;
         if (n0 >= nlimit) break;  // warp-uniform
         uint32_t v[32];

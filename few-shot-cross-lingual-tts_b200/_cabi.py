@@ -28,6 +28,7 @@ class Gemm(ctypes.Structure):
         ("d_zdiv", c_i32), ("alpha", c_f32), ("d", c_vp), ("ldd", c_i64), ("d_col_stride", c_i64),
         ("d_tap_stride", c_i64), ("d_zdiv_stride", c_i64), ("d_zmod_stride", c_i64),
         ("bias", c_vp), ("aux", c_vp), ("ld_aux", c_i64), ("aux_batch_stride", c_i64),
+        ("d_seg_rows", c_i32), ("d_seg_pad", c_i32), ("d_seg", c_vp * 4),
     ]
 
 

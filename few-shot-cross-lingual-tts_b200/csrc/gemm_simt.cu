@@ -31,7 +31,12 @@ __device__ __forceinline__ void epilogue_store(const fs2_gemm& g, float acc, int
     acc = g.epilogue == FS2_EPI_RELU_BWD ? (a > 0.f ? acc : 0.f) : acc + a;
   }
   if (g.d_f32) {
-    float* dp = static_cast<float*>(g.d) + off;
+    float* dbase = static_cast<float*>(g.d);
+    if (g.d_seg_rows > 0) {  // off = m*ldd + ...: move the row into its segment
+      dbase = static_cast<float*>(g.d_seg[m / g.d_seg_rows]);
+      off -= (long long)(m / g.d_seg_rows) * g.d_seg_rows * g.ldd;
+    }
+    float* dp = dbase + off;
     if (g.d_atomic)
       atomicAdd(dp, acc);
     else

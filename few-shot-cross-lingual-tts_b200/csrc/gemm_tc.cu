@@ -43,6 +43,8 @@ struct GemmKP {
   const float* bias;
   const __nv_bfloat16* aux;
   long long ld_aux, aux_batch_stride;
+  int seg_rows;
+  void* seg[4];
 };
 
 struct TileCoord {
@@ -88,7 +90,7 @@ struct SmemLayout {
 // 16-byte pieces of its own row.  The optional aux tile (ReLU-backward mask / residual add) is read
 // through the same staging area with the same coalesced pattern.
 // ------------------------------------------------------------------------------------------------
-template <bool F32OUT>
+template <bool F32OUT, bool ATOMIC = false>
 __device__ __forceinline__ void epilogue_chunk(const GemmKP& p, uint32_t taddr, uint8_t* stg, int lane,
                                                int m_w0, int n0, int nlimit, long long base_off,
                                                const __nv_bfloat16* aux_base, bool tile_ok) {
@@ -197,7 +199,24 @@ __device__ __forceinline__ void epilogue_chunk(const GemmKP& p, uint32_t taddr, 
     const int gm = m_w0 + r, col = n0 + ch * EPV;
     if (tile_ok && gm < p.M && col < nlimit) {
       const uint4 val = *reinterpret_cast<const uint4*>(stg + r * 128 + ((ch ^ (r & 7)) << 4));
-      const long long off = base_off + (long long)gm * p.ldd + col;
+      long long off = base_off + (long long)gm * p.ldd + col;
+      if constexpr (ATOMIC) {  // split-K accumulation: one 16-byte vector reduction per lane (coalesced)
+        float* dbase = static_cast<float*>(p.d);
+        if (p.seg_rows > 0) {
+          const int sg = gm / p.seg_rows;
+          dbase = static_cast<float*>(p.seg[sg]);
+          off -= (long long)sg * p.seg_rows * p.ldd;
+        }
+        float* dp = dbase + off;
+        if (col + 4 <= nlimit) {
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dp), "f"(__uint_as_float(val.x)),
+                       "f"(__uint_as_float(val.y)), "f"(__uint_as_float(val.z)), "f"(__uint_as_float(val.w))
+                       : "memory");
+        } else {
+          const uint32_t w[4] = {val.x, val.y, val.z, val.w};
+          for (int e = 0; e < 4 && col + e < nlimit; ++e) atomicAdd(dp + e, __uint_as_float(w[e]));
+        }
+      } else
       if (col + EPV <= nlimit) {
         if constexpr (F32OUT)
           *reinterpret_cast<uint4*>(static_cast<float*>(p.d) + off) = val;
@@ -388,7 +407,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const long long row_off = base_off + (long long)m * p.ldd;
       const __nv_bfloat16* aux_row =
           p.aux ? p.aux + (long long)t.z * p.aux_batch_stride + (long long)m * p.ld_aux : nullptr;
-      if (p.d_col_stride == 1 && !p.d_atomic) {
+      if (p.d_col_stride == 1 && p.d_atomic) {
+        // split-K weight gradients with unit column stride: coalesced vector reductions
+        uint8_t* stg = sgen + L::STAGING_OFF + (warp - 4) * 4096;
+        const int m_w0 = t.tm * BM + q * 32;
+#pragma unroll 1
+        for (int c0 = chalf * (BN / 2); c0 < (chalf + 1) * (BN / 2); c0 += 32) {
+          if (ncol0 + c0 >= nlimit) break;  // warp-uniform
+          epilogue_chunk<true, true>(p, taddr + c0, stg, lane, m_w0, ncol0 + c0, nlimit, base_off, nullptr,
+                                     t.nkb > 0);
+        }
+      } else if (p.d_col_stride == 1 && !p.d_atomic) {
         // coalesced path (every NORMAL-mode output)
         uint8_t* stg = sgen + L::STAGING_OFF + (warp - 4) * 4096;
         const __nv_bfloat16* aux_base = p.aux ? p.aux + (long long)t.z * p.aux_batch_stride : nullptr;
@@ -619,6 +648,8 @@ int gemm_tc_launch(const fs2_gemm& g, cudaStream_t stream) {
   kp.aux = static_cast<const __nv_bfloat16*>(g.aux);
   kp.ld_aux = g.ld_aux;
   kp.aux_batch_stride = g.aux_batch_stride;
+  kp.seg_rows = g.d_seg_rows;
+  for (int i = 0; i < 4; ++i) kp.seg[i] = g.d_seg[i];
   const int taps = g.taps > 0 ? g.taps : 1;
   if (g.mode == FS2_GEMM_NORMAL) {
     if (g.a.mn_major && taps != 1) return set_error("conv taps need a K-major A operand");
@@ -643,8 +674,11 @@ int gemm_tc_launch(const fs2_gemm& g, cudaStream_t stream) {
     return set_error("gemm: unknown mode");
   }
   if (g.d_atomic && !g.d_f32) return set_error("atomic accumulation needs an f32 output");
-  if (kp.d_col_stride == 1 && !g.d_atomic) {
-    const long long al = g.d_f32 ? 4 : 8;  // vector stores: 16-byte aligned rows
+  if (g.d_seg_rows > 0 && !(g.mode == FS2_GEMM_WGRAD && kp.d_col_stride == 1 && g.d_atomic))
+    return set_error("gemm: row segments are supported for unit-stride atomic WGRAD outputs only");
+  if (g.d_seg_rows > 0 && (g.M + g.d_seg_rows - 1) / g.d_seg_rows > 4) return set_error("gemm: at most 4 segments");
+  if (kp.d_col_stride == 1) {
+    const long long al = g.d_f32 ? 4 : 8;  // vector stores / reductions: 16-byte aligned rows
     if ((reinterpret_cast<uintptr_t>(g.d) & 15) || (g.ldd % al) || (g.d_zdiv_stride % al) ||
         (g.d_zmod_stride % al) || (g.d_tap_stride % al))
       return set_error("gemm: output rows must be 16-byte aligned (ldd / strides)");

@@ -142,6 +142,19 @@ colsum_kernel(const __nv_bfloat16* __restrict__ x, long long ld, int rows_per_gr
   for (int i = threadIdx.x; i < C; i += 256) atomicAdd(out + (long long)g * C + i, s_acc[i]);
 }
 
+// grad[co][ci][tap] += packed[co][tap][ci]
+__global__ void __launch_bounds__(256)
+unpack_add_conv_grad_kernel(const float* __restrict__ packed, int Co, int Ci, int k, float* __restrict__ grad) {
+  const long long n = (long long)Co * Ci * k;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int tap = i % k;
+    const int ci = (i / k) % Ci;
+    const long long co = i / ((long long)k * Ci);
+    grad[i] += packed[(co * k + tap) * Ci + ci];
+  }
+}
+
 // same for fp32 input (mel-space gradients)
 __global__ void __launch_bounds__(256)
 colsum_f32_kernel(const float* __restrict__ x, long long ld, int rows, int C, int rows_per_block,
@@ -314,6 +327,25 @@ int fs2_colsum_bf16(const void* x, int64_t ld, int groups, int rows_per_group, i
       static_cast<const __nv_bfloat16*>(x), ld, rows_per_group, C, rpb, out);
   fs2::count_launch();
   return fs2::check_launch("colsum_kernel");
+}
+
+int fs2_colsum3_bf16(const void* x, int64_t ld, int rows, int seg_cols, float* out0, float* out1, float* out2,
+                     void* stream) {
+  float* outs[3] = {out0, out1, out2};
+  for (int i = 0; i < 3; ++i) {
+    const __nv_bfloat16* xi = static_cast<const __nv_bfloat16*>(x) + (long long)i * seg_cols;
+    if (int rc = fs2_colsum_bf16(xi, ld, 1, rows, seg_cols, outs[i], stream)) return rc;
+  }
+  return 0;
+}
+
+int fs2_unpack_add_conv_grad(const float* packed, int Co, int Ci, int k, float* grad, void* stream) {
+  const long long n = (long long)Co * Ci * k;
+  if (n <= 0) return 0;
+  fs2::unpack_add_conv_grad_kernel<<<fs2::grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      packed, Co, Ci, k, grad);
+  fs2::count_launch();
+  return fs2::check_launch("unpack_add_conv_grad_kernel");
 }
 
 int fs2_colsum_f32(const float* x, int64_t ld, int rows, int C, float* out, void* stream) {

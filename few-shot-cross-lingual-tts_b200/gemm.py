@@ -70,8 +70,10 @@ def gemm(a, b, d, M, N, K, Z=1, taps=1, tap_shift0=0, b_tap_kstride=0, ldd=None,
 
 
 def wgrad(a, b, d, M, N, taps=1, tap_shift0=0, ldd=None, d_col_stride=1, d_tap_stride=0, splits=1,
-          accumulate=True, impl=None):
+          accumulate=True, impl=None, segments=None):
     """D[m][tap][n] (+)= sum_{z,r} A[z][r][m] * B[z][r+shift+tap][n]; D is fp32."""
+    if segments is not None:  # (rows_per_segment, [tensor, ...]): row block i of D lives in tensors[i]
+        d = segments[1][0]
     assert d.dtype == torch.float32
     g = Gemm()
     g.a, g.b = a, b
@@ -90,4 +92,9 @@ def wgrad(a, b, d, M, N, taps=1, tap_shift0=0, ldd=None, d_col_stride=1, d_tap_s
     g.bias = None
     g.aux = None
     g.ld_aux = g.aux_batch_stride = 0
+    if segments is not None:
+        g.d_seg_rows = int(segments[0])
+        for i, t in enumerate(segments[1]):
+            assert t.dtype == torch.float32 and t.is_contiguous()
+            g.d_seg[i] = t.data_ptr()
     run(g, impl)

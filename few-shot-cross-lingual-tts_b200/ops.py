@@ -162,6 +162,17 @@ def linear_wgrad(dy2d, x2d, dw, row0=0, rows=None):
     G.wgrad(a, b, dw, rows, K, splits=_splits(rows, K, 1, (M + 63) // 64))
 
 
+def qkv_param_grads(dqkv, x2d, gbuf, HD):
+    """Weight / bias gradients of the fused Q|K|V projection in ONE weight-gradient GEMM and one column
+    sum pass; row block i of the [3*HD, D] result lands directly in the i-th parameter's gradient."""
+    M, C3 = dqkv.shape
+    D = x2d.shape[1]
+    G.wgrad(G.operand(dqkv, C3, M, mn_major=True), G.operand(x2d, D, M, mn_major=True), None, C3, D,
+            splits=_splits(C3, D, 1, (M + 63) // 64), segments=(HD, [gbuf[0][0], gbuf[2][0], gbuf[4][0]]))
+    _ck(_L().fs2_colsum3_bf16(_p(dqkv), C3, M, HD, _p(gbuf[1][0]), _p(gbuf[3][0]), _p(gbuf[5][0]), _st()),
+        "colsum3")
+
+
 def colsum(x2d, out, col0=0, cols=None):
     """out[cols] += column sums of x2d[:, col0:col0+cols] (bias gradients)."""
     M, N = x2d.shape
@@ -194,13 +205,29 @@ def conv_dgrad(dy, wp, Ci, epilogue=G.EPI_NONE, aux=None):
 
 
 def conv_wgrad(dy, x, dw):
-    """dw[Co, Ci, k] (reference Conv1d.weight layout, fp32) += correlation of dy with x."""
+    """dw[Co, Ci, k] (reference Conv1d.weight layout, fp32) += correlation of dy with x.
+
+    k == 1 is a plain unit-stride weight gradient.  For k > 1 the split-K partial sums are reduced with
+    coalesced 16-byte vector atomics into a [Co][k][Ci] scratch (the GEMM's natural N order) and then
+    folded into the reference layout by one small kernel -- strided scalar atomics straight into
+    [Co][Ci][k] cost more than the extra 2 x 9 MB of traffic."""
     B, T, Co = dy.shape
     Ci = x.shape[2]
     k = dw.shape[2]
-    G.wgrad(G.operand(dy, Co, T, B, mn_major=True), G.operand(x, Ci, T, B, mn_major=True), dw, Co, Ci,
-            taps=k, tap_shift0=-((k - 1) // 2), ldd=Ci * k, d_col_stride=k, d_tap_stride=1,
-            splits=_splits(Co, Ci, k, B * ((T + 63) // 64)))
+    a = G.operand(dy, Co, T, B, mn_major=True)
+    b = G.operand(x, Ci, T, B, mn_major=True)
+    splits = _splits(Co, Ci, k, B * ((T + 63) // 64))
+    if k == 1:
+        G.wgrad(a, b, dw, Co, Ci, splits=splits)
+        return
+    if Ci % 4:
+        G.wgrad(a, b, dw, Co, Ci, taps=k, tap_shift0=-((k - 1) // 2), ldd=Ci * k, d_col_stride=k, d_tap_stride=1,
+                splits=splits)
+        return
+    scratch = torch.zeros(Co, k, Ci, dtype=F32, device=dy.device)
+    G.wgrad(a, b, scratch, Co, Ci, taps=k, tap_shift0=-((k - 1) // 2), ldd=Ci * k, d_col_stride=1,
+            d_tap_stride=Ci, splits=splits)
+    _ck(_L().fs2_unpack_add_conv_grad(_p(scratch), Co, Ci, k, _p(dw), _st()), "unpack_add_conv_grad")
 
 
 def ln_fwd(x, res, gamma, beta, lens, p, mode, salt):
@@ -371,9 +398,7 @@ class MHASublayer(torch.autograd.Function):
                             dk).view(M, C3)
             x2 = x.view(M, D)
             dx = linear_dgrad(dqkv, wqkv, epilogue=G.EPI_ADD_AUX, aux=dres.view(M, D))
-            for i in range(3):
-                linear_wgrad(dqkv, x2, gbuf[2 * i][0], row0=i * HD, rows=HD)
-                colsum(dqkv, gbuf[2 * i + 1][0], col0=i * HD, cols=HD)
+            qkv_param_grads(dqkv, x2, gbuf, HD)
             grads_done((wq, bq, wk, bk, wv, bv, wo, bo, gamma, beta))
             return (dx.view(B, T, D), None) + tuple(g[1] for g in gbuf) + (None, None, None)
         # attention core: dP = dO V^T ; dS = softmax'(P, dP) ; dQ = dS K ; dK = dS^T Q ; dV = P^T dO
@@ -399,9 +424,7 @@ class MHASublayer(torch.autograd.Function):
         # fused QKV projection
         x2 = x.view(M, D)
         dx = linear_dgrad(dqkv, wqkv, epilogue=G.EPI_ADD_AUX, aux=dres.view(M, D))
-        for i in range(3):
-            linear_wgrad(dqkv, x2, gbuf[2 * i][0], row0=i * HD, rows=HD)
-            colsum(dqkv, gbuf[2 * i + 1][0], col0=i * HD, cols=HD)
+        qkv_param_grads(dqkv, x2, gbuf, HD)
         grads_done((wq, bq, wk, bk, wv, bv, wo, bo, gamma, beta))
         return (dx.view(B, T, D), None) + tuple(g[1] for g in gbuf) + (None, None, None)
 

@@ -19,7 +19,9 @@ class GradBuckets:
         device = device or self.params[0].device
         # reverse registration order ~ the order in which backward produces gradients
         order = list(reversed(self.params))
-        total = sum(p.numel() for p in order)
+        # every gradient starts on a 16-byte boundary (vector reductions / TMA-friendly), so sizes are
+        # rounded up to 4 floats; the few padding elements stay zero and ride along in the all-reduce
+        total = sum((p.numel() + 3) // 4 * 4 for p in order)
         self.flat = torch.zeros(total, dtype=torch.float32, device=device)
         self.buckets = []  # (start, end) element ranges of self.flat
         self._bucket_of = {}
@@ -32,7 +34,7 @@ class GradBuckets:
             p.grad = view  # autograd-produced gradients (embeddings) accumulate in place as well
             self._bucket_of[id(p)] = len(self.buckets)
             bcount += 1
-            off += n
+            off += (n + 3) // 4 * 4
             if (off - bstart) * 4 >= bucket_bytes:
                 self.buckets.append((bstart, off))
                 self._pending0.append(bcount)

@@ -90,6 +90,11 @@ typedef struct fs2_gemm {
   const void* aux;      /* bf16 [Z][M][ld_aux] or NULL */
   int64_t ld_aux;
   int64_t aux_batch_stride;
+  /* optional row segmentation of D (fused Q|K|V weight gradients land in three separate tensors):
+     row m goes to d_seg[m / d_seg_rows] + (m % d_seg_rows) * ldd; d_seg_rows = 0 disables it. */
+  int32_t d_seg_rows;
+  int32_t d_seg_pad;
+  void* d_seg[4];
 } fs2_gemm;
 
 /* impl: 0 = tcgen05 (product path), 1 = plain CUDA-core kernel (debug cross-check only). */
@@ -178,6 +183,11 @@ int fs2_add_f32_bf16(const float* a, const void* b, int64_t n, float* out, void*
 int fs2_colsum_bf16(const void* x, int64_t ld, int groups, int rows_per_group, int C, float* out,
                     void* stream);
 int fs2_colsum_f32(const float* x, int64_t ld, int rows, int C, float* out, void* stream);
+/* column sums of x[:, 0:3*seg_cols] split into three outputs (fused Q|K|V bias gradients) */
+int fs2_colsum3_bf16(const void* x, int64_t ld, int rows, int seg_cols, float* out0, float* out1, float* out2,
+                     void* stream);
+/* grad[co][ci][tap] += packed[co][tap][ci]  (Conv1d weight gradient accumulated in the GEMM-friendly layout) */
+int fs2_unpack_add_conv_grad(const float* packed, int Co, int Ci, int k, float* grad, void* stream);
 int fs2_rowdot_fwd(const void* x, const float* w, const float* bias, const int64_t* lens, int B, int T,
                    int C, float* out, void* stream);
 int fs2_rowdot_bwd(const float* dout, const void* x, const float* w, const int64_t* lens, int B, int T,

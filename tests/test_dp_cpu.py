@@ -86,13 +86,14 @@ def test_bucket_views_alias_flat_buffer_in_reverse_order():
     m = _model()
     b = dp.GradBuckets(m.parameters(), bucket_bytes=128, device=torch.device("cpu"))
     params = list(m.parameters())
-    assert b.flat.numel() == sum(p.numel() for p in params)
+    assert b.flat.numel() == sum((p.numel() + 3) // 4 * 4 for p in params)
+    assert all(p.main_grad.data_ptr() % 16 == 0 for p in params)
     # reverse registration order: the last parameter sits first in the flat buffer
     assert params[-1].main_grad.data_ptr() == b.flat.data_ptr()
     for p in params:
         assert p.grad.data_ptr() == p.main_grad.data_ptr()
         p.main_grad.fill_(1.0)
-    assert float(b.flat.sum()) == b.flat.numel()
+    assert float(b.flat.sum()) == sum(p.numel() for p in params)
     covered = sorted(b.buckets)
     assert covered[0][0] == 0 and covered[-1][1] == b.flat.numel()
     assert all(covered[i][1] == covered[i + 1][0] for i in range(len(covered) - 1))

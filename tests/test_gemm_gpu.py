@@ -165,3 +165,31 @@ def test_wgrad_conv(impl, B, T, Cin, Cout, k, splits):
             Cout, Cin, taps=k, tap_shift0=-((k - 1) // 2), ldd=Cin * k, d_col_stride=k,
             d_tap_stride=1, splits=splits, impl=impl)
     assert rel_err(dw, w.grad) < 2e-3, rel_err(dw, w.grad)
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+def test_wgrad_row_segments(impl):
+    """Fused Q|K|V weight gradient: row blocks of one [3*HD, D] result land in three tensors."""
+    torch.manual_seed(11)
+    M, HD, D = 1500, 256, 256
+    dy, x = rnd(M, 3 * HD), rnd(M, D)
+    outs = [torch.full((HD, D), float(i), device="cuda") for i in range(3)]
+    G.wgrad(G.operand(dy, 3 * HD, M, mn_major=True), G.operand(x, D, M, mn_major=True), None, 3 * HD, D, splits=3,
+            segments=(HD, outs), impl=impl)
+    ref = dy.float().t() @ x.float()
+    for i in range(3):
+        assert rel_err(outs[i], ref[i * HD:(i + 1) * HD] + float(i)) < 2e-3
+
+
+@pytest.mark.parametrize("B,T,Cin,Cout,k", [(3, 200, 256, 1024, 9), (2, 130, 80, 512, 5), (2, 77, 1024, 256, 1)])
+def test_ops_conv_wgrad_reference_layout(B, T, Cin, Cout, k):
+    ops = sub("ops")
+    torch.manual_seed(T)
+    x = rnd(B, T, Cin)
+    dy = rnd(B, T, Cout)
+    w = torch.zeros(Cout, Cin, k, device="cuda", requires_grad=True)
+    y = torch.nn.functional.conv1d(x.float().transpose(1, 2), w, None, padding=(k - 1) // 2).transpose(1, 2)
+    y.backward(dy.float())
+    dw = torch.ones(Cout, Cin, k, device="cuda")
+    ops.conv_wgrad(dy, x, dw)
+    assert rel_err(dw, w.grad + 1.0) < 2e-3

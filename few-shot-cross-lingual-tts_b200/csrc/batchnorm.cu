@@ -46,21 +46,6 @@ __device__ __forceinline__ float fast_tanh(float x) {
   return y;
 }
 
-// Per-channel affine form of the normalisation, computed once per block into shared memory:
-//   yhat = y * rs[c] + sh[c]            (rs = rstd, sh = -mean * rstd)
-//   z    = yhat * gamma[c] + beta[c]
-__device__ __forceinline__ void bn_channel_params(const BnArgs& a, float* s_rs, float* s_sh) {
-  const float invM = 1.f / (float)a.M;
-  for (int c = threadIdx.x; c < a.C; c += blockDim.x) {
-    const float m = a.fstats[c] * invM;
-    const float var = fmaxf(a.fstats[a.C + c] * invM - m * m, 0.f);
-    const float r = rsqrtf(var + kBnEps);
-    s_rs[c] = r;
-    s_sh[c] = -m * r;
-  }
-  __syncthreads();
-}
-
 __global__ void __launch_bounds__(256) bn_stats_kernel(const BnArgs a) {
   extern __shared__ float sh[];  // [2][C]
   const int vpr = a.C / 8, rs = 256 / vpr;
@@ -92,96 +77,111 @@ __global__ void __launch_bounds__(256) bn_stats_kernel(const BnArgs a) {
   for (int i = threadIdx.x; i < 2 * a.C; i += 256) atomicAdd(a.stats + i, sh[i]);
 }
 
+// Thread = one 8-channel column vector (fixed for the whole kernel) x a strided set of rows, so the
+// per-channel affine parameters live in registers; 64 consecutive threads cover one 1 KiB row (C=512).
 __global__ void __launch_bounds__(256) bn_apply_kernel(const BnArgs a) {
-  extern __shared__ float sh[];  // [2][C]: rstd, shift
-  float* s_rs = sh;
-  float* s_sh = sh + a.C;
-  bn_channel_params(a, s_rs, s_sh);
-  const int vpr = a.C / 8;
+  const int vpr = a.C / 8, rs = 256 / vpr;
+  const int v = threadIdx.x % vpr, ro = threadIdx.x / vpr;
+  if (ro >= rs) return;
+  const int c = v * 8;
+  const float invM = 1.f / (float)a.M;
+  float A[8], Bc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float m = a.fstats[c + j] * invM;
+    const float var = fmaxf(a.fstats[a.C + c + j] * invM - m * m, 0.f);
+    const float r = rsqrtf(var + kBnEps) * a.gamma[c + j];
+    A[j] = r;
+    Bc[j] = a.beta[c + j] - m * r;
+  }
   const uint32_t thresh = dropout_thresh(a.p_drop);
   const float keep_scale = a.p_drop > 0.f ? 1.f / (1.f - a.p_drop) : 1.f;
   const uint64_t seed = mix_seed(a.seed_dev, a.seed);
-  const long long n_vec = a.M * vpr;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec;
-       i += (long long)gridDim.x * blockDim.x) {
-    const long long r = i / vpr;
-    const int c = (i - r * vpr) * 8;
-    float f[8];
-    load_vec8(a.y + r * a.C + c, f);
-    const uint32_t keep = thresh ? dropout_keep8(seed, (uint64_t)r * a.C + c, thresh) : 0xFFu;
+  const long long r0 = (long long)blockIdx.x * a.rows_per_block;
+  const long long r1 = min(r0 + a.rows_per_block, a.M);
+  for (long long r = r0 + ro; r < r1; r += 2 * rs) {
+    const bool two = r + rs < r1;
+    float f0[8], f1[8];
+    load_vec8(a.y + r * a.C + c, f0);
+    if (two) load_vec8(a.y + (r + rs) * a.C + c, f1);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float z = (f[j] * s_rs[c + j] + s_sh[c + j]) * a.gamma[c + j] + a.beta[c + j];
-      if (a.act_tanh) z = fast_tanh(z);
-      f[j] = (keep >> j) & 1u ? z * keep_scale : 0.f;
-    }
-    if (a.out_f32) {
-      float* o = a.out_f32 + r * a.C + c;
+    for (int u = 0; u < 2; ++u) {
+      if (u == 1 && !two) break;
+      float (&f)[8] = u == 0 ? f0 : f1;
+      const long long rr = r + u * rs;
+      const uint32_t keep = thresh ? dropout_keep8(seed, (uint64_t)rr * a.C + c, thresh) : 0xFFu;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) o[j] = f[j] + (a.res_f32 ? a.res_f32[r * a.C + c + j] : 0.f);
-    } else {
-      st8(a.out_bf16 + r * a.C + c, pack8(f));
-    }
-  }
-}
-
-// g = dout * dropout_mask * (1 - tanh(z)^2); returns yhat in `yh`
-__device__ __forceinline__ void bn_bwd_g(const BnArgs& a, const float* s_rs, const float* s_sh, long long r,
-                                         int c, uint64_t seed, uint32_t thresh, float keep_scale, float (&g)[8],
-                                         float (&yh)[8]) {
-  float f[8];
-  load_vec8(a.y + r * a.C + c, f);
-  if (a.dout_is_f32) {
-    const float4* d = reinterpret_cast<const float4*>(static_cast<const float*>(a.dout) + r * a.C + c);
-    const float4 d0 = d[0], d1 = d[1];
-    g[0] = d0.x; g[1] = d0.y; g[2] = d0.z; g[3] = d0.w;
-    g[4] = d1.x; g[5] = d1.y; g[6] = d1.z; g[7] = d1.w;
-  } else {
-    load_vec8(static_cast<const __nv_bfloat16*>(a.dout) + r * a.C + c, g);
-  }
-  const uint32_t keep = thresh ? dropout_keep8(seed, (uint64_t)r * a.C + c, thresh) : 0xFFu;
+      for (int j = 0; j < 8; ++j) {
+        float z = fmaf(f[j], A[j], Bc[j]);
+        if (a.act_tanh) z = fast_tanh(z);
+        f[j] = (keep >> j) & 1u ? z * keep_scale : 0.f;
+      }
+      if (a.out_f32) {
+        float* o = a.out_f32 + rr * a.C + c;
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    yh[j] = f[j] * s_rs[c + j] + s_sh[c + j];
-    g[j] = (keep >> j) & 1u ? g[j] * keep_scale : 0.f;
-    if (a.act_tanh) {
-      const float t = fast_tanh(yh[j] * a.gamma[c + j] + a.beta[c + j]);
-      g[j] *= 1.f - t * t;
+        for (int j = 0; j < 8; ++j) o[j] = f[j] + (a.res_f32 ? a.res_f32[rr * a.C + c + j] : 0.f);
+      } else {
+        st8(a.out_bf16 + rr * a.C + c, pack8(f));
+      }
     }
   }
 }
 
 __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const BnArgs a) {
-  extern __shared__ float sh[];  // [4][C]: rstd, shift, sum g, sum g*yhat
-  float* s_rs = sh;
-  float* s_sh = sh + a.C;
-  float* s_acc = sh + 2 * a.C;
+  extern __shared__ float s_acc[];  // [2][C]: sum g, sum g*yhat
   const int vpr = a.C / 8, rs = 256 / vpr;
-  const uint32_t thresh = dropout_thresh(a.p_drop);
-  const float keep_scale = a.p_drop > 0.f ? 1.f / (1.f - a.p_drop) : 1.f;
-  const uint64_t seed = mix_seed(a.seed_dev, a.seed);
   for (int i = threadIdx.x; i < 2 * a.C; i += 256) s_acc[i] = 0.f;
-  bn_channel_params(a, s_rs, s_sh);
+  __syncthreads();
   const int v = threadIdx.x % vpr, ro = threadIdx.x / vpr;
   if (ro < rs) {
+    const int c = v * 8;
+    const float invM = 1.f / (float)a.M;
+    float rsd[8], sh[8], gam[8], bet[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float m = a.fstats[c + j] * invM;
+      const float var = fmaxf(a.fstats[a.C + c + j] * invM - m * m, 0.f);
+      rsd[j] = rsqrtf(var + kBnEps);
+      sh[j] = -m * rsd[j];
+      gam[j] = a.gamma[c + j];
+      bet[j] = a.beta[c + j];
+    }
+    const uint32_t thresh = dropout_thresh(a.p_drop);
+    const float keep_scale = a.p_drop > 0.f ? 1.f / (1.f - a.p_drop) : 1.f;
+    const uint64_t seed = mix_seed(a.seed_dev, a.seed);
     float sb[8], sg[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) sb[j] = sg[j] = 0.f;
     const long long r0 = (long long)blockIdx.x * a.rows_per_block;
     const long long r1 = min(r0 + a.rows_per_block, a.M);
     for (long long r = r0 + ro; r < r1; r += rs) {
-      float g[8], yh[8];
-      bn_bwd_g(a, s_rs, s_sh, r, v * 8, seed, thresh, keep_scale, g, yh);
+      float f[8], g[8];
+      load_vec8(a.y + r * a.C + c, f);
+      if (a.dout_is_f32) {
+        const float4* d = reinterpret_cast<const float4*>(static_cast<const float*>(a.dout) + r * a.C + c);
+        const float4 d0 = d[0], d1 = d[1];
+        g[0] = d0.x; g[1] = d0.y; g[2] = d0.z; g[3] = d0.w;
+        g[4] = d1.x; g[5] = d1.y; g[6] = d1.z; g[7] = d1.w;
+      } else {
+        load_vec8(static_cast<const __nv_bfloat16*>(a.dout) + r * a.C + c, g);
+      }
+      const uint32_t keep = thresh ? dropout_keep8(seed, (uint64_t)r * a.C + c, thresh) : 0xFFu;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        sb[j] += g[j];
-        sg[j] += g[j] * yh[j];
+        const float yh = fmaf(f[j], rsd[j], sh[j]);
+        float gg = (keep >> j) & 1u ? g[j] * keep_scale : 0.f;
+        if (a.act_tanh) {
+          const float t = fast_tanh(fmaf(yh, gam[j], bet[j]));
+          gg *= 1.f - t * t;
+        }
+        sb[j] += gg;
+        sg[j] += gg * yh;
       }
     }
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      atomicAdd(&s_acc[v * 8 + j], sb[j]);
-      atomicAdd(&s_acc[a.C + v * 8 + j], sg[j]);
+      atomicAdd(&s_acc[c + j], sb[j]);
+      atomicAdd(&s_acc[a.C + c + j], sg[j]);
     }
   }
   __syncthreads();
@@ -189,26 +189,49 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const BnArgs a) {
 }
 
 __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BnArgs a) {
-  extern __shared__ float sh[];  // [2][C]
-  float* s_rs = sh;
-  float* s_sh = sh + a.C;
-  bn_channel_params(a, s_rs, s_sh);
-  const int vpr = a.C / 8;
+  const int vpr = a.C / 8, rs = 256 / vpr;
+  const int v = threadIdx.x % vpr, ro = threadIdx.x / vpr;
+  if (ro >= rs) return;
+  const int c = v * 8;
   const float invM = 1.f / (float)a.M;
+  float rsd[8], sh[8], gam[8], bet[8], db[8], dg[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float m = a.fstats[c + j] * invM;
+    const float var = fmaxf(a.fstats[a.C + c + j] * invM - m * m, 0.f);
+    rsd[j] = rsqrtf(var + kBnEps);
+    sh[j] = -m * rsd[j];
+    gam[j] = a.gamma[c + j];
+    bet[j] = a.beta[c + j];
+    db[j] = a.stats[c + j] * invM;
+    dg[j] = a.stats[a.C + c + j] * invM;
+  }
   const uint32_t thresh = dropout_thresh(a.p_drop);
   const float keep_scale = a.p_drop > 0.f ? 1.f / (1.f - a.p_drop) : 1.f;
   const uint64_t seed = mix_seed(a.seed_dev, a.seed);
-  const long long n_vec = a.M * vpr;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec;
-       i += (long long)gridDim.x * blockDim.x) {
-    const long long r = i / vpr;
-    const int c = (i - r * vpr) * 8;
-    float g[8], yh[8], o[8];
-    bn_bwd_g(a, s_rs, s_sh, r, c, seed, thresh, keep_scale, g, yh);
+  const long long r0 = (long long)blockIdx.x * a.rows_per_block;
+  const long long r1 = min(r0 + a.rows_per_block, a.M);
+  for (long long r = r0 + ro; r < r1; r += rs) {
+    float f[8], g[8], o[8];
+    load_vec8(a.y + r * a.C + c, f);
+    if (a.dout_is_f32) {
+      const float4* d = reinterpret_cast<const float4*>(static_cast<const float*>(a.dout) + r * a.C + c);
+      const float4 d0 = d[0], d1 = d[1];
+      g[0] = d0.x; g[1] = d0.y; g[2] = d0.z; g[3] = d0.w;
+      g[4] = d1.x; g[5] = d1.y; g[6] = d1.z; g[7] = d1.w;
+    } else {
+      load_vec8(static_cast<const __nv_bfloat16*>(a.dout) + r * a.C + c, g);
+    }
+    const uint32_t keep = thresh ? dropout_keep8(seed, (uint64_t)r * a.C + c, thresh) : 0xFFu;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const float db = a.stats[c + j] * invM, dg = a.stats[a.C + c + j] * invM;
-      o[j] = a.gamma[c + j] * s_rs[c + j] * (g[j] - db - yh[j] * dg);
+      const float yh = fmaf(f[j], rsd[j], sh[j]);
+      float gg = (keep >> j) & 1u ? g[j] * keep_scale : 0.f;
+      if (a.act_tanh) {
+        const float t = fast_tanh(fmaf(yh, gam[j], bet[j]));
+        gg *= 1.f - t * t;
+      }
+      o[j] = gam[j] * rsd[j] * (gg - db[j] - yh * dg[j]);
     }
     st8(a.dy + r * a.C + c, pack8(o));
   }
@@ -233,7 +256,7 @@ static int bn_check(long long M, int C) {
   return 0;
 }
 static int rows_per_block_for(long long M) {
-  long long rpb = (M + 148 * 4 - 1) / (148 * 4);
+  long long rpb = (M + 148 * 8 - 1) / (148 * 8);
   if (rpb < 32) rpb = 32;
   return (int)rpb;
 }
@@ -272,7 +295,8 @@ int fs2_bn_apply_fwd(const void* y, const float* stats, const float* gamma, cons
   a.M = M; a.C = C; a.fstats = stats; a.gamma = gamma; a.beta = beta;
   a.act_tanh = act_tanh; a.p_drop = p_drop; a.seed = seed; a.seed_dev = seed_dev;
   a.out_bf16 = static_cast<__nv_bfloat16*>(out_bf16); a.out_f32 = out_f32; a.res_f32 = res_f32;
-  fs2::bn_apply_kernel<<<fs2::ew_grid(M * (C / 8)), 256, 2 * C * sizeof(float),
+  a.rows_per_block = fs2::rows_per_block_for(M);
+  fs2::bn_apply_kernel<<<(unsigned)((M + a.rows_per_block - 1) / a.rows_per_block), 256, 0,
                          static_cast<cudaStream_t>(stream)>>>(a);
   fs2::count_launch();
   return fs2::check_launch("bn_apply_kernel");
@@ -302,10 +326,10 @@ int fs2_bn_bwd(const void* dout, int dout_is_f32, const void* y, const float* st
   a.rows_per_block = fs2::rows_per_block_for(M);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const unsigned grid = (unsigned)((M + a.rows_per_block - 1) / a.rows_per_block);
-  fs2::bn_bwd_reduce_kernel<<<grid, 256, 4 * C * sizeof(float), s>>>(a);
+  fs2::bn_bwd_reduce_kernel<<<grid, 256, 2 * C * sizeof(float), s>>>(a);
   fs2::count_launch();
   if (int rc = fs2::check_launch("bn_bwd_reduce_kernel")) return rc;
-  fs2::bn_bwd_apply_kernel<<<fs2::ew_grid(M * (C / 8)), 256, 2 * C * sizeof(float), s>>>(a);
+  fs2::bn_bwd_apply_kernel<<<grid, 256, 0, s>>>(a);
   fs2::count_launch();
   return fs2::check_launch("bn_bwd_apply_kernel");
 }

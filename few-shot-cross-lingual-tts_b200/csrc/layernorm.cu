@@ -45,16 +45,39 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const LnArgs a) {
   const uint32_t thresh = dropout_thresh(a.p_drop);
   const float keep_scale = a.p_drop > 0.f ? 1.f / (1.f - a.p_drop) : 1.f;
   const uint64_t seed = mix_seed(a.seed_dev, a.seed);
-  for (long long row = (long long)blockIdx.x * warps_per_block + (threadIdx.x >> 5); row < a.rows;
-       row += (long long)gridDim.x * warps_per_block) {
+  const long long stride = (long long)gridDim.x * warps_per_block;
+  long long row = (long long)blockIdx.x * warps_per_block + (threadIdx.x >> 5);
+  // software pipeline: the next row's 16-byte vectors are in flight while this row is reduced
+  bf16x8 nx[NV], nr[NV];
+  if (row < a.rows) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      nx[i] = ld8(a.x + row * C + i * 256 + lane * 8);
+      if (a.res) nr[i] = ld8(a.res + row * C + i * 256 + lane * 8);
+    }
+  }
+  for (; row < a.rows; row += stride) {
     const int b = row / a.T, t = row - (long long)b * a.T;
     const bool masked = a.lens && t >= a.lens[b];
+    bf16x8 cx[NV], cr[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      cx[i] = nx[i];
+      cr[i] = nr[i];
+    }
+    if (row + stride < a.rows) {
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        nx[i] = ld8(a.x + (row + stride) * C + i * 256 + lane * 8);
+        if (a.res) nr[i] = ld8(a.res + (row + stride) * C + i * 256 + lane * 8);
+      }
+    }
     float v[NV][8];
     float s = 0.f;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const int col = i * 256 + lane * 8;
-      unpack8(ld8(a.x + row * C + col), v[i]);
+      unpack8(cx[i], v[i]);
       if (a.drop_mode == 1 && thresh) {
         const uint32_t keep = dropout_keep8(seed, (uint64_t)row * C + col, thresh);
 #pragma unroll
@@ -62,7 +85,7 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const LnArgs a) {
       }
       if (a.res) {
         float r[8];
-        unpack8(ld8(a.res + row * C + col), r);
+        unpack8(cr[i], r);
 #pragma unroll
         for (int j = 0; j < 8; ++j) v[i][j] += r[j];
       }
@@ -125,10 +148,35 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const LnArgs a) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc_g[i][j] = acc_b[i][j] = 0.f;
 
-  for (long long row = (long long)blockIdx.x * warps_per_block + warp; row < a.rows;
-       row += (long long)gridDim.x * warps_per_block) {
+  const long long stride = (long long)gridDim.x * warps_per_block;
+  long long row = (long long)blockIdx.x * warps_per_block + warp;
+  bf16x8 nx[NV], nd[NV], nr[NV];
+  if (row < a.rows) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      nx[i] = ld8(a.x + row * C + i * 256 + lane * 8);
+      nd[i] = ld8(a.dy + row * C + i * 256 + lane * 8);
+      if (a.res) nr[i] = ld8(a.res + row * C + i * 256 + lane * 8);
+    }
+  }
+  for (; row < a.rows; row += stride) {
     const int b = row / a.T, t = row - (long long)b * a.T;
     const bool masked = a.lens && t >= a.lens[b];
+    bf16x8 cx[NV], cd[NV], cr[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      cx[i] = nx[i];
+      cd[i] = nd[i];
+      cr[i] = nr[i];
+    }
+    if (row + stride < a.rows) {
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        nx[i] = ld8(a.x + (row + stride) * C + i * 256 + lane * 8);
+        nd[i] = ld8(a.dy + (row + stride) * C + i * 256 + lane * 8);
+        if (a.res) nr[i] = ld8(a.res + (row + stride) * C + i * 256 + lane * 8);
+      }
+    }
     if (masked) {
       const bf16x8 z = {};
 #pragma unroll
@@ -147,8 +195,8 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const LnArgs a) {
     for (int i = 0; i < NV; ++i) {
       const int col = i * 256 + lane * 8;
       float xv[8], dyv[8];
-      unpack8(ld8(a.x + row * C + col), xv);
-      unpack8(ld8(a.dy + row * C + col), dyv);
+      unpack8(cx[i], xv);
+      unpack8(cd[i], dyv);
       uint32_t pos = 0xFFu;
       if (a.relu_x) {
         pos = 0;
@@ -167,7 +215,7 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const LnArgs a) {
       }
       if (a.res) {
         float r[8];
-        unpack8(ld8(a.res + row * C + col), r);
+        unpack8(cr[i], r);
 #pragma unroll
         for (int j = 0; j < 8; ++j) xv[j] += r[j];
       }

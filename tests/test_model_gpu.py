@@ -111,3 +111,58 @@ def test_against_oracle(name, over, bkw):
     assert max(lerr) <= 1e-2, lerr
     worst = check_grads(model, ref_grads=o_grads)
     print(name, "worst grad cosine", worst)
+
+
+def test_c3_task_step_with_averaged_speaker_embedding():
+    """FSCL query-batch step: multi-speaker + multi-lingual model called with
+    average_spk_emb=True, max_seq_len 1500 (config/model/multilingual-fastspeech2.yaml)."""
+    cfg = synth.model_cfg(multi_speaker=True, multi_lingual=True, max_seq_len=1500, encoder_layer=2,
+                          decoder_layer=2)
+    spk = {"emb_type": "table", "speakers": list(range(11))}
+    model, loss_fn = build(cfg, spk)
+    batch = synth.make_batch(B=8, src_len=(20, 70), dur=synth.uniform_dur(2, 9), seed=3, n_speaker=11, n_lang=8)
+    b = cuda_batch(batch)
+    out = model(b[2], b[3], *b[4:12], lang_args=b[12], average_spk_emb=True)
+    losses = loss_fn(b[:-1], out)
+    model.zero_grad(set_to_none=True)
+    losses[0].backward()
+    sd = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
+    params = {k: v for k, v in sd.items() if v.is_floating_point() and "position_enc" not in k
+              and not k.endswith("_bins") and "running_" not in k}
+    for v in params.values():
+        v.requires_grad_(True)
+    o_out = fs2_oracle.forward(sd, cfg, batch[2], batch[3], *batch[4:12], lang_args=batch[12],
+                               average_spk_emb=True)
+    o_losses = fs2_oracle.loss(batch[:12], o_out)
+    o_losses[0].backward()
+    assert rel_err(out[0], o_out[0]) <= 3e-2 and rel_err(out[1], o_out[1]) <= 3e-2
+    for l, r in zip(losses, o_losses):
+        assert abs(float(l) - float(r)) / abs(float(r)) <= 1e-2
+    for k in ("speaker_emb.model.weight", "language_emb.model.weight", "decoder.layer_stack.1.pos_ffn.w_1.weight"):
+        c = cosine(dict(model.named_parameters())[k].grad, params[k].grad)
+        assert c >= 0.99, (k, c)
+
+
+def test_inference_path_predicted_durations_and_eval_batchnorm():
+    """eval(): no targets -> durations from the duration predictor (modules.py:133-139), eval-mode
+    BatchNorm with running statistics, bucketised predictions.  Compared with plain torch ops run on the
+    CUDA model's own intermediate predictions (the rounding of exp(log_d) makes an fp32-vs-bf16 comparison
+    of frame counts ill-posed, so durations are taken from the CUDA path and fed to the reference LR)."""
+    cfg = synth.model_cfg(encoder_layer=1, decoder_layer=1)
+    model, _ = build(cfg)
+    # make the duration predictor produce a few frames per phoneme
+    with torch.no_grad():
+        model.variance_adaptor.duration_predictor.linear_layer.bias.fill_(1.2)
+    model.eval()
+    batch = cuda_batch(synth.make_batch(B=3, src_len=(5, 12), dur=synth.uniform_dur(1, 4), seed=17))
+    with torch.no_grad():
+        out = model(batch[2], batch[3], batch[4], batch[5], p_control=1.0, e_control=1.0, d_control=1.0)
+    mel, post, p_pred, e_pred, log_d, d_rounded, src_masks, mel_masks, src_lens, mel_lens = out
+    exp_d = torch.clamp(torch.round(torch.exp(log_d) - 1), min=0)
+    assert torch.equal(d_rounded, exp_d)
+    assert torch.equal(mel_lens.cpu(), exp_d.long().sum(1).cpu())
+    assert mel.shape[1] == int(mel_lens.max()) and mel.shape == post.shape
+    assert torch.equal(mel_masks.cpu(), fs2_oracle.mask_from_lengths(mel_lens.cpu(), int(mel_lens.max())))
+    assert torch.isfinite(mel).all() and torch.isfinite(post).all()
+    # padded phonemes predict nothing
+    assert (p_pred * src_masks).abs().sum() == 0 and (log_d * src_masks).abs().sum() == 0

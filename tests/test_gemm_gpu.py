@@ -152,19 +152,19 @@ def test_wgrad_linear(impl, M, N, K, splits):
 @pytest.mark.parametrize("B,T,Cin,Cout,k,splits", [(3, 200, 256, 1024, 9, 2), (2, 77, 256, 256, 3, 1),
                                                    (2, 130, 80, 512, 5, 3), (2, 130, 512, 80, 5, 2)])
 def test_wgrad_conv(impl, B, T, Cin, Cout, k, splits):
-    """dW[co][ci][tap] written straight in the reference parameter layout (Conv1d.weight)."""
+    """dW accumulated in the GEMM-friendly [co][tap][ci] layout (unit column stride, vector atomics)."""
     torch.manual_seed(T)
     x = rnd(B, T, Cin).float().requires_grad_()
     w = torch.zeros(Cout, Cin, k, device="cuda", requires_grad=True)
     dy = rnd(B, T, Cout)
     y = torch.nn.functional.conv1d(x.transpose(1, 2), w, None, padding=(k - 1) // 2).transpose(1, 2)
     y.backward(dy.float())
-    dw = torch.zeros(Cout, Cin, k, device="cuda")
+    dw = torch.zeros(Cout, k, Cin, device="cuda")
     xb = x.detach().to(torch.bfloat16)
     G.wgrad(G.operand(dy, Cout, T, B, mn_major=True), G.operand(xb, Cin, T, B, mn_major=True), dw,
-            Cout, Cin, taps=k, tap_shift0=-((k - 1) // 2), ldd=Cin * k, d_col_stride=k,
-            d_tap_stride=1, splits=splits, impl=impl)
-    assert rel_err(dw, w.grad) < 2e-3, rel_err(dw, w.grad)
+            Cout, Cin, taps=k, tap_shift0=-((k - 1) // 2), ldd=Cin * k, d_col_stride=1,
+            d_tap_stride=Cin, splits=splits, impl=impl)
+    assert rel_err(dw, w.grad.permute(0, 2, 1)) < 2e-3, rel_err(dw, w.grad.permute(0, 2, 1))
 
 
 @pytest.mark.parametrize("impl", IMPLS)

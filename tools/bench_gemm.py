@@ -33,7 +33,7 @@ def rnd(*s):
 
 
 def main():
-    B, T = 16, 850
+    B, T = (int(sys.argv[1]) if len(sys.argv) > 1 else 16), (int(sys.argv[2]) if len(sys.argv) > 2 else 850)
     M = B * T
     rows = []
     # linear shapes
@@ -53,11 +53,11 @@ def main():
     rows.append(("conv_k9_fwd", ms, 2.0 * M * 1024 * 2304 / ms / 1e9))
     # conv k9 wgrad
     dy = rnd(B, T, 1024)
-    dw = torch.zeros(1024, 256, 9, device="cuda")
+    dw = torch.zeros(1024, 9, 256, device="cuda")
     for splits in (1, 2, 4):
         ms = timeit(lambda: G.wgrad(G.operand(dy, 1024, T, B, mn_major=True),
                                     G.operand(x, 256, T, B, mn_major=True), dw, 1024, 256, taps=9,
-                                    tap_shift0=-4, ldd=2304, d_col_stride=9, d_tap_stride=1,
+                                    tap_shift0=-4, ldd=2304, d_col_stride=1, d_tap_stride=256,
                                     splits=splits))
         rows.append(("conv_k9_wgrad_s%d" % splits, ms, 2.0 * M * 1024 * 2304 / ms / 1e9))
     # attention bmm QK^T

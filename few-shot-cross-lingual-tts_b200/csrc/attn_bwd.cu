@@ -158,7 +158,18 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmKV,   // qkv, box 64 x
   const int b = z / p.H, h = z % p.H;
   const int k0 = jt * 128;
   const int HD = p.H * DK;
-  const int n = p.n_inner;  // 64-query tiles
+  const int len = min((int)p.lens[b], p.T);
+  if (k0 >= len) {  // a key tile of padded frames only (CTA-uniform): dK = dV = 0, no MMAs
+    __nv_bfloat16* gb = p.dqkv + (long long)b * p.T * 3 * HD;
+    for (int i = threadIdx.x; i < 128 * 32; i += blockDim.x) {
+      const int r = i >> 5, c = i & 31;  // 32 x 16-byte vectors per row: 16 for dK, 16 for dV
+      if (k0 + r < p.T)
+        *reinterpret_cast<uint4*>(gb + (long long)(k0 + r) * 3 * HD + (1 + (c >> 4)) * HD + h * DK + (c & 15) * 8) =
+            make_uint4(0u, 0u, 0u, 0u);
+    }
+    return;
+  }
+  const int n = min(p.n_inner, (len + 63) / 64);  // 64-query tiles with at least one valid query
 
   if (threadIdx.x == 0) {
     mbar_init(bar(KV_FULL), 1);
@@ -254,7 +265,6 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmKV,   // qkv, box 64 x
     const int q4 = warp & 3, half = warp >> 2;
     const int row = q4 * 32 + lane;
     const int key = k0 + row;
-    const int len = min((int)p.lens[b], p.T);
     const bool key_valid = key < len;
     const uint32_t lane_base = static_cast<uint32_t>(q4 * 32) << 16;
     uint8_t* pt_row = sgen + OFF_PT + row * 128;
@@ -357,7 +367,17 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ128,  // qkv, box 64 x
   const int b = z / p.H, h = z % p.H;
   const int q0 = it * 128;
   const int HD = p.H * DK;
-  const int n = p.n_inner;  // 64-key tiles
+  const int len = min((int)p.lens[b], p.T);
+  if (q0 >= len) {  // a query tile of padded frames only (CTA-uniform): dQ = 0, no MMAs
+    __nv_bfloat16* gb = p.dqkv + (long long)b * p.T * 3 * HD;
+    for (int i = threadIdx.x; i < 128 * 16; i += blockDim.x) {
+      const int r = i >> 4, c = i & 15;
+      if (q0 + r < p.T)
+        *reinterpret_cast<uint4*>(gb + (long long)(q0 + r) * 3 * HD + h * DK + c * 8) = make_uint4(0u, 0u, 0u, 0u);
+    }
+    return;
+  }
+  const int n = min(p.n_inner, (len + 63) / 64);  // 64-key tiles with at least one valid key
 
   if (threadIdx.x == 0) {
     mbar_init(bar(QDO_FULL), 1);
@@ -448,7 +468,6 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ128,  // qkv, box 64 x
     const int q4 = warp & 3, half = warp >> 2;
     const int row = q4 * 32 + lane;
     const int q = q0 + row;
-    const int len = min((int)p.lens[b], p.T);
     const uint32_t lane_base = static_cast<uint32_t>(q4 * 32) << 16;
     uint8_t* ds_row = sgen + OFF_DS + row * 128;
     const int sw = row & 7;

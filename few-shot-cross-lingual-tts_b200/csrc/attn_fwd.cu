@@ -71,7 +71,19 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constant_
   const int b = z / p.H, h = z % p.H;
   const int q0 = qt * BQ;
   const int HD = p.H * DK;
-  const int n = p.nkv;  // key tiles
+  const int len = min((int)p.lens[b], p.T);
+  if (q0 >= len) {  // a query tile of padded frames only (CTA-uniform): out = 0, lse2 = +inf, no MMAs
+    for (int i = threadIdx.x; i < BQ * 16; i += blockDim.x) {
+      const int r = i >> 4, c = i & 15;
+      if (q0 + r < p.T)
+        *reinterpret_cast<uint4*>(p.out + ((long long)b * p.T + q0 + r) * HD + h * DK + c * 8) =
+            make_uint4(0u, 0u, 0u, 0u);
+    }
+    for (int r = threadIdx.x; r < BQ; r += blockDim.x)
+      if (q0 + r < p.T) p.lse2[(long long)z * p.T + q0 + r] = INFINITY;
+    return;
+  }
+  const int n = min(p.nkv, (len + BKV - 1) / BKV);  // key tiles that hold at least one valid key
 
   if (threadIdx.x == 0) {
     mbar_init(bar(Q_FULL), 1);
@@ -174,7 +186,6 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constant_
     const int q4 = warp & 3, half = warp >> 2;  // TMEM lane quarter, column half
     const int row = q4 * 32 + lane;
     const int q = q0 + row;
-    const int len = min((int)p.lens[b], p.T);
     const bool row_valid = q < len;
     const uint32_t lane_base = static_cast<uint32_t>(q4 * 32) << 16;
     uint8_t* sp_row0 = sgen + OFF_P + half * BLK + row * 128;  // this half's 64-key block of the P tile

@@ -38,26 +38,121 @@ struct GemmKP {
   long long ld_aux, aux_batch_stride;
   int seg_rows;
   void* seg[4];
+  // ragged rows (fs2_gemm::row_lens): padded rows are zero / skipped
+  const long long* row_lens;
+  int lens_zdiv;
+  int ragged;      // 1: compact schedule over the prefix table (sched_n <= kMaxRaggedZ entries)
+  int sched_n;     // table entries: NORMAL batches Z, WGRAD reduction batches
+  int unit_rows;   // rows per schedule unit: NORMAL BM (1-CTA) / 2*BM (CTA pair); WGRAD BK
+  int units_max;   // units per entry when nothing is padded
+  int row_extent;  // rows per entry (NORMAL: M, WGRAD: a.rows)
 };
+
+constexpr int kMaxRaggedZ = 256;  // prefix table lives in the ~1.9 KiB of shared memory left by the smem ring
+
+// cum[z] = inclusive prefix sum of the schedule units (row tiles / reduction blocks) that contain at least one
+// valid row of entry z.  One warp builds it with shuffles.
+__device__ __forceinline__ void build_ragged_table(const GemmKP& p, int* cum, int lane) {
+  int carry = 0;
+  for (int z0 = 0; z0 < p.sched_n; z0 += 32) {
+    const int z = z0 + lane;
+    int u = 0;
+    if (z < p.sched_n) {
+      long long len = p.row_lens[z / p.lens_zdiv];
+      len = len < 0 ? 0 : (len > p.row_extent ? p.row_extent : len);
+      u = (int)((len + p.unit_rows - 1) / p.unit_rows);
+      if (u > p.units_max) u = p.units_max;
+    }
+    int v = u;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, v, o);
+      if (lane >= o) v += t;
+    }
+    if (z < p.sched_n) cum[z] = carry + v;
+    carry += __shfl_sync(0xffffffffu, v, 31);
+  }
+}
+
+// first entry z with cum[z] > r  (r < cum[n-1])
+__device__ __forceinline__ int ragged_find(const int* cum, int n, int r) {
+  int lo = 0, hi = n - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (cum[mid] > r) hi = mid; else lo = mid + 1;
+  }
+  return lo;
+}
+
+// number of tiles of the persistent loop (1-CTA: 128-row tiles; pair kernel: pair tiles, `dense` = its dense count)
+__device__ __forceinline__ int sched_total(const GemmKP& p, const int* cum, int dense) {
+  if (p.ragged && p.mode == FS2_GEMM_NORMAL) return cum[p.sched_n - 1] * p.tiles_n;
+  return dense;
+}
+
+// WGRAD split-K range [kb0, kb0 + nkb) of split `z` over the (compacted) list of reduction blocks
+__device__ __forceinline__ void wgrad_range(const GemmKP& p, const int* cum, int z, int& kb0, int& nkb) {
+  int total = p.total_rb, per = p.kb_per_split;
+  if (p.ragged) {
+    total = cum[p.sched_n - 1];
+    per = (total + p.Z - 1) / p.Z;
+  }
+  kb0 = z * per;
+  const int rem = total - kb0;
+  nkb = rem < per ? rem : per;
+  if (nkb < 0) nkb = 0;
+}
+
+// compact reduction-block index g -> (batch zb, first row r0 of the 64-row block)
+struct RbCursor {
+  int zb, lb, nb;  // batch, local block, blocks of this batch
+};
+__device__ __forceinline__ RbCursor rb_seek(const GemmKP& p, const int* cum, int g) {
+  RbCursor c;
+  if (!p.ragged) {
+    c.zb = g / p.rb_per_batch;
+    c.lb = g - c.zb * p.rb_per_batch;
+    c.nb = p.rb_per_batch;
+  } else {
+    c.zb = ragged_find(cum, p.sched_n, g);
+    const int before = c.zb ? cum[c.zb - 1] : 0;
+    c.lb = g - before;
+    c.nb = cum[c.zb] - before;
+  }
+  return c;
+}
+__device__ __forceinline__ void rb_next(const GemmKP& p, const int* cum, RbCursor& c) {
+  if (++c.lb < c.nb) return;
+  c.lb = 0;
+  ++c.zb;
+  if (p.ragged) {
+    while (c.zb < p.sched_n && cum[c.zb] == cum[c.zb - 1]) ++c.zb;  // skip fully padded batches
+    c.nb = c.zb < p.sched_n ? cum[c.zb] - cum[c.zb - 1] : 1;
+  }
+}
 
 struct TileCoord {
   int z, tm, tn, nkb, kb0;
 };
 
-__device__ __forceinline__ TileCoord decode_tile(const GemmKP& p, int tile) {
+__device__ __forceinline__ TileCoord decode_tile(const GemmKP& p, const int* cum, int tile) {
   TileCoord t;
   t.tn = tile % p.tiles_n;
   int r = tile / p.tiles_n;
-  t.tm = r % p.tiles_m;
-  t.z = r / p.tiles_m;  // NORMAL: batch index; WGRAD: split index
   if (p.mode == FS2_GEMM_NORMAL) {
+    if (p.ragged) {  // r-th row tile that holds at least one valid row
+      t.z = ragged_find(cum, p.sched_n, r);
+      t.tm = r - (t.z ? cum[t.z - 1] : 0);
+    } else {
+      t.tm = r % p.tiles_m;
+      t.z = r / p.tiles_m;
+    }
     t.nkb = p.num_kb;
     t.kb0 = 0;
   } else {
-    t.kb0 = t.z * p.kb_per_split;
-    int rem = p.total_rb - t.kb0;
-    t.nkb = rem < p.kb_per_split ? rem : p.kb_per_split;
-    if (t.nkb < 0) t.nkb = 0;
+    t.tm = r % p.tiles_m;
+    t.z = r / p.tiles_m;  // split index
+    wgrad_range(p, cum, t.z, t.kb0, t.nkb);
   }
   return t;
 }
@@ -72,7 +167,7 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmKP& p, int tile) {
 template <bool F32OUT, bool ATOMIC = false>
 __device__ __forceinline__ void epilogue_chunk(const GemmKP& p, uint32_t taddr, uint8_t* stg, int lane,
                                                int m_w0, int n0, int nlimit, long long base_off,
-                                               const __nv_bfloat16* aux_base, bool tile_ok) {
+                                               const __nv_bfloat16* aux_base, bool tile_ok, bool row_ok = true) {
   constexpr int NC = F32OUT ? 32 : 64;  // accumulator columns per 128-byte output row segment
   float f[NC];
   {
@@ -150,6 +245,10 @@ __device__ __forceinline__ void epilogue_chunk(const GemmKP& p, uint32_t taddr, 
       }
       __syncwarp();
     }
+  }
+  if (!row_ok) {  // padded row (fs2_gemm::row_lens): the output is defined to be zero
+#pragma unroll
+    for (int j = 0; j < NC; ++j) f[j] = 0.f;
   }
   // own row -> staging
 #pragma unroll
@@ -238,6 +337,8 @@ __device__ __forceinline__ void epilogue_tile(const GemmKP& p, const TileCoord& 
   const uint32_t taddr = tmem_acc + (static_cast<uint32_t>(q * 32) << 16);
   const int m_w0 = t.tm * BM + q * 32;
   const bool ok = t.nkb > 0;
+  bool row_ok = true;
+  if (p.row_lens && p.mode == FS2_GEMM_NORMAL) row_ok = (m_w0 + lane) < p.row_lens[t.z / p.lens_zdiv];
   if (p.d_atomic) {  // split-K weight gradients: coalesced 16-byte vector reductions
 #pragma unroll 1
     for (int c0 = chalf * (BN / 2); c0 < (chalf + 1) * (BN / 2); c0 += 32) {
@@ -248,14 +349,44 @@ __device__ __forceinline__ void epilogue_tile(const GemmKP& p, const TileCoord& 
 #pragma unroll 1
     for (int c0 = chalf * (BN / 2); c0 < (chalf + 1) * (BN / 2); c0 += 32) {
       if (ncol0 + c0 >= nlimit) break;
-      epilogue_chunk<true>(p, taddr + c0, stg, lane, m_w0, ncol0 + c0, nlimit, base_off, nullptr, ok);
+      epilogue_chunk<true>(p, taddr + c0, stg, lane, m_w0, ncol0 + c0, nlimit, base_off, nullptr, ok, row_ok);
     }
   } else {
     const __nv_bfloat16* aux_base = p.aux ? p.aux + (long long)t.z * p.aux_batch_stride : nullptr;
 #pragma unroll 1
     for (int c0 = chalf * (BN / 2); c0 < (chalf + 1) * (BN / 2); c0 += 64) {
       if (ncol0 + c0 >= nlimit) break;
-      epilogue_chunk<false>(p, taddr + c0, stg, lane, m_w0, ncol0 + c0, nlimit, base_off, aux_base, ok);
+      epilogue_chunk<false>(p, taddr + c0, stg, lane, m_w0, ncol0 + c0, nlimit, base_off, aux_base, ok, row_ok);
+    }
+  }
+}
+
+// Ragged NORMAL outputs: rows of D[z] past the last scheduled row tile are written as zero by the epilogue
+// warps (256 threads, thread index `et`) of all CTAs before their first tile's accumulator is ready.
+template <int BN>
+__device__ __forceinline__ void zero_fill_padded(const GemmKP& p, const int* cum, int et, int cta, int ncta) {
+  const int epv = p.d_f32 ? 4 : 8;
+  for (int item = cta; item < p.sched_n * p.tiles_n; item += ncta) {
+    const int z = item / p.tiles_n, tn = item - z * p.tiles_n;
+    const int row0 = (cum[z] - (z ? cum[z - 1] : 0)) * p.unit_rows;
+    if (row0 >= p.M) continue;
+    const int c0 = tn * BN, c1 = (c0 + BN < p.N) ? c0 + BN : p.N;
+    const int vpr = (c1 - c0 + epv - 1) / epv;
+    const long long base = (long long)(z / p.d_zdiv) * p.d_zdiv_stride + (long long)(z % p.d_zdiv) * p.d_zmod_stride;
+    const long long nvec = (long long)(p.M - row0) * vpr;
+    for (long long i = et; i < nvec; i += 256) {
+      const int r = (int)(i / vpr), v = (int)(i - (long long)r * vpr);
+      const int col = c0 + v * epv;
+      const long long off = base + (long long)(row0 + r) * p.ldd + col;
+      if (col + epv <= c1) {
+        if (p.d_f32) *reinterpret_cast<uint4*>(static_cast<float*>(p.d) + off) = make_uint4(0u, 0u, 0u, 0u);
+        else *reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.d) + off) = make_uint4(0u, 0u, 0u, 0u);
+      } else {
+        for (int e = 0; col + e < c1; ++e) {
+          if (p.d_f32) static_cast<float*>(p.d)[off + e] = 0.f;
+          else reinterpret_cast<uint16_t*>(p.d)[off + e] = 0;
+        }
+      }
     }
   }
 }

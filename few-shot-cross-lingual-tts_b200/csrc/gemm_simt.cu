@@ -78,6 +78,14 @@ __global__ void gemm_simt_normal(const SimtP sp) {
   const int dzd = g.d_zdiv > 0 ? g.d_zdiv : 1;
   const long long off = (long long)(z / dzd) * g.d_zdiv_stride + (long long)(z % dzd) * g.d_zmod_stride +
                         (long long)m * g.ldd + n;
+  if (g.row_lens) {  // padded rows are defined to be zero
+    const int lzd = g.lens_zdiv > 0 ? g.lens_zdiv : 1;
+    if (m >= g.row_lens[z / lzd]) {
+      if (g.d_f32) static_cast<float*>(g.d)[off] = 0.f;
+      else static_cast<__nv_bfloat16*>(g.d)[off] = __float2bfloat16(0.f);
+      return;
+    }
+  }
   epilogue_store(g, acc, z, m, n, off);
 }
 

@@ -31,7 +31,8 @@ struct SmemLayout {
   static constexpr int BAR_OFF = STAGING_OFF + STAGING_BYTES;
   static constexpr int NUM_BARS = 2 * STAGES + 4;
   static constexpr int TMEM_PTR_OFF = BAR_OFF + NUM_BARS * 8;
-  static constexpr int TOTAL = TMEM_PTR_OFF + 16;
+  static constexpr int CUM_OFF = TMEM_PTR_OFF + 16;  // ragged-schedule prefix table
+  static constexpr int TOTAL = CUM_OFF + kMaxRaggedZ * 4;
   static constexpr int DYN_BYTES = TOTAL + 1024;  // slack for manual 1024-B alignment
 };
 
@@ -49,6 +50,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };
   auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + 2 + s); };
   volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(sgen + L::TMEM_PTR_OFF);
+  const int* cum = reinterpret_cast<const int*>(sgen + L::CUM_OFF);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -73,19 +75,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tmem_alloc(sbase + L::TMEM_PTR_OFF, TMEM_COLS);
     tmem_relinquish();
   }
+  if (warp == 3 && p.ragged) build_ragged_table(p, reinterpret_cast<int*>(sgen + L::CUM_OFF), lane);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  const int total_tiles = sched_total(p, cum, p.total_tiles);
 
   if (warp == 0) {
     // ======================= TMA producer =======================
     if (lane == 0) {
       int s = 0;
       uint32_t ph = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        const TileCoord t = decode_tile(p, tile);
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const TileCoord t = decode_tile(p, cum, tile);
         const int m0 = t.tm * BM;
+        RbCursor rc{};
+        if (p.mode != FS2_GEMM_NORMAL && t.nkb > 0) rc = rb_seek(p, cum, t.kb0);
         for (int kb = 0; kb < t.nkb; ++kb) {
           mbar_wait(empty_bar(s), ph ^ 1u);
           mbar_arrive_expect_tx(full_bar(s), L::STAGE_BYTES);
@@ -115,9 +121,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             ib + tap * p.b_tap_kstride + n0 + h * 64, k0, zb);
             }
           } else {
-            const int g = t.kb0 + kb;
-            const int zb = g / p.rb_per_batch;
-            const int r0 = (g - zb * p.rb_per_batch) * BK;
+            const int zb = rc.zb;
+            const int r0 = rc.lb * BK;
+            rb_next(p, cum, rc);
             const int tap = t.tn / p.n_tiles_per_tap;
             const int c0 = (t.tn - tap * p.n_tiles_per_tap) * BN;
 #pragma unroll
@@ -144,8 +150,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const uint32_t a_kstep = p.a_mn ? 16u * 128u : 32u, b_kstep = p.b_mn ? 16u * 128u : 32u;
       int s = 0, as = 0;
       uint32_t ph = 0, aph = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        const TileCoord t = decode_tile(p, tile);
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const TileCoord t = decode_tile(p, cum, tile);
         mbar_wait(tempty_bar(as), aph ^ 1u);
         tc_fence_after();
         const uint32_t tacc = tmem_base + as * BN;
@@ -181,8 +187,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     int as = 0;
     uint32_t aph = 0;
     uint8_t* stg = sgen + L::STAGING_OFF + (warp - 4) * 4096;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-      const TileCoord t = decode_tile(p, tile);
+    if (p.ragged && p.mode == FS2_GEMM_NORMAL)
+      zero_fill_padded<BN>(p, cum, threadIdx.x - 128, blockIdx.x, gridDim.x);
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const TileCoord t = decode_tile(p, cum, tile);
       mbar_wait(tfull_bar(as), aph);
       tc_fence_after();
       epilogue_tile<BN>(p, t, tmem_base + as * BN, stg, q, chalf, lane);
@@ -333,6 +341,23 @@ int gemm_fill_params(const fs2_gemm& g, GemmKP& kp) {
     kp.n_per_tap = g.N;
   } else {
     return set_error("gemm: unknown mode");
+  }
+  if (g.row_lens) {
+    kp.row_lens = reinterpret_cast<const long long*>(g.row_lens);
+    kp.lens_zdiv = g.lens_zdiv > 0 ? g.lens_zdiv : 1;
+    if (g.mode == FS2_GEMM_NORMAL) {
+      if (g.d_atomic) return set_error("gemm: row_lens and atomic outputs do not combine in NORMAL mode");
+      kp.sched_n = kp.Z;
+      kp.unit_rows = BM;  // the pair kernel doubles it
+      kp.units_max = kp.tiles_m;
+      kp.row_extent = g.M;
+    } else {
+      kp.sched_n = g.a.batches;
+      kp.unit_rows = BK;
+      kp.units_max = kp.rb_per_batch;
+      kp.row_extent = g.a.rows;
+    }
+    kp.ragged = kp.sched_n <= kMaxRaggedZ ? 1 : 0;  // larger batches: dense schedule, rows still zeroed
   }
   if (g.d_atomic && !g.d_f32) return set_error("atomic accumulation needs an f32 output");
   if (g.d_seg_rows > 0 && !(g.mode == FS2_GEMM_WGRAD && kp.d_col_stride == 1 && g.d_atomic))

@@ -39,7 +39,8 @@ constexpr int STAGING_BYTES = 8 * 32 * 128;
 constexpr int BAR_OFF = STAGING_OFF + STAGING_BYTES;
 constexpr int NUM_BARS = 2 * STAGES + 4;
 constexpr int TMEM_PTR_OFF = BAR_OFF + NUM_BARS * 8;
-constexpr int DYN_BYTES = TMEM_PTR_OFF + 16 + 1024;
+constexpr int CUM_OFF = TMEM_PTR_OFF + 16;  // ragged-schedule prefix table
+constexpr int DYN_BYTES = CUM_OFF + kMaxRaggedZ * 4 + 1024;
 constexpr int kThreads2 = 384;
 }  // namespace g2
 
@@ -109,6 +110,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };
   auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * STAGES + 2 + s); };
   volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(sgen + TMEM_PTR_OFF);
+  const int* cum = reinterpret_cast<const int*>(sgen + CUM_OFF);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
@@ -136,6 +138,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     tmem_alloc_2sm(sbase + TMEM_PTR_OFF, TMEM_COLS);
     tmem_relinquish_2sm();
   }
+  if (warp == 3 && p.ragged) build_ragged_table(p, reinterpret_cast<int*>(sgen + CUM_OFF), lane);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -143,21 +146,27 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 
   // A "pair tile" covers the 128-row tiles tm = 2*pm and 2*pm+1; this CTA works on tm = 2*pm + rank.
   const int pair_tiles_m = (p.tiles_m + 1) >> 1;
-  const int total_pair_tiles = pair_tiles_m * p.tiles_n * p.Z;
+  const int total_pair_tiles = sched_total(p, cum, pair_tiles_m * p.tiles_n * p.Z);
   auto decode_pair = [&](int ptile) {
     TileCoord t;
     t.tn = ptile % p.tiles_n;
     const int r = ptile / p.tiles_n;
-    t.tm = 2 * (r % pair_tiles_m) + (int)rank;  // this CTA's 128-row tile of the pair tile
-    t.z = r / pair_tiles_m;                      // NORMAL: batch index; WGRAD: split index
     if (p.mode == FS2_GEMM_NORMAL) {
+      int pm;
+      if (p.ragged) {  // r-th 256-row pair tile that holds at least one valid row
+        t.z = ragged_find(cum, p.sched_n, r);
+        pm = r - (t.z ? cum[t.z - 1] : 0);
+      } else {
+        pm = r % pair_tiles_m;
+        t.z = r / pair_tiles_m;
+      }
+      t.tm = 2 * pm + (int)rank;  // this CTA's 128-row tile of the pair tile
       t.nkb = p.num_kb;
       t.kb0 = 0;
     } else {
-      t.kb0 = t.z * p.kb_per_split;
-      const int rem = p.total_rb - t.kb0;
-      t.nkb = rem < p.kb_per_split ? rem : p.kb_per_split;
-      if (t.nkb < 0) t.nkb = 0;
+      t.tm = 2 * (r % pair_tiles_m) + (int)rank;
+      t.z = r / pair_tiles_m;  // split index
+      wgrad_range(p, cum, t.z, t.kb0, t.nkb);
     }
     return t;
   };
@@ -171,6 +180,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       for (int ptile = pair; ptile < total_pair_tiles; ptile += num_pairs) {
         const TileCoord t = decode_pair(ptile);
         const int m0 = t.tm * BM;
+        RbCursor rc{};
+        if (p.mode != FS2_GEMM_NORMAL && t.nkb > 0) rc = rb_seek(p, cum, t.kb0);
         for (int kb = 0; kb < t.nkb; ++kb) {
           mbar_wait(empty_bar(s), ph ^ 1u);
           if (leader) mbar_arrive_expect_tx(full_bar(s), 2 * STAGE_BYTES);
@@ -201,9 +212,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                                 zb);
             }
           } else {
-            const int g = t.kb0 + kb;
-            const int zb = g / p.rb_per_batch;
-            const int r0 = (g - zb * p.rb_per_batch) * BK;
+            const int zb = rc.zb;
+            const int r0 = rc.lb * BK;
+            rb_next(p, cum, rc);
             const int tap = t.tn / p.n_tiles_per_tap;
             const int c0 = (t.tn - tap * p.n_tiles_per_tap) * BN + (int)rank * (BN / 2);
 #pragma unroll
@@ -265,6 +276,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     uint32_t aph = 0;
     uint8_t* stg = sgen + STAGING_OFF + (warp - 4) * 4096;
     const uint32_t leader_tempty0 = mapa_rank(tempty_bar(0), 0);
+    if (p.ragged && p.mode == FS2_GEMM_NORMAL)
+      zero_fill_padded<BN>(p, cum, threadIdx.x - 128, blockIdx.x, gridDim.x);
     for (int ptile = pair; ptile < total_pair_tiles; ptile += num_pairs) {
       const TileCoord t = decode_pair(ptile);
       mbar_wait(tfull_bar(as), aph);
@@ -307,6 +320,10 @@ int gemm_tc2_launch(const fs2_gemm& g, GemmKP& kp, cudaStream_t stream) {
                                  g.b.mn_major ? 64 : BN / 2))
     return rc;
   kp.n_tiles_per_tap = (g.N + BN - 1) / BN;
+  if (kp.row_lens && g.mode == FS2_GEMM_NORMAL) {  // schedule units are 256-row pair tiles
+    kp.unit_rows = 2 * BM;
+    kp.units_max = (kp.tiles_m + 1) / 2;
+  }
   const int taps = g.taps > 0 ? g.taps : 1;
   kp.tiles_n = (g.mode == FS2_GEMM_NORMAL) ? kp.n_tiles_per_tap : taps * kp.n_tiles_per_tap;
   const int pair_tiles = ((kp.tiles_m + 1) / 2) * kp.tiles_n * kp.Z;

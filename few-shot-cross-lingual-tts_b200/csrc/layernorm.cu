@@ -35,7 +35,14 @@ struct LnArgs {
   __nv_bfloat16* dres;
   float* dgamma;
   float* dbeta;
+  float* dbias;  // optional: column sums of dx (bias gradient of the GEMM that produced x)
 };
+
+__device__ __forceinline__ bool ln_row_masked(const LnArgs& a, long long row) {
+  if (!a.lens) return false;
+  const int b = row / a.T;
+  return row - (long long)b * a.T >= a.lens[b];
+}
 
 template <int NV>
 __global__ void __launch_bounds__(256) ln_fwd_kernel(const LnArgs a) {
@@ -49,7 +56,8 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const LnArgs a) {
   long long row = (long long)blockIdx.x * warps_per_block + (threadIdx.x >> 5);
   // software pipeline: the next row's 16-byte vectors are in flight while this row is reduced
   bf16x8 nx[NV], nr[NV];
-  if (row < a.rows) {
+  bool nmask = row < a.rows && ln_row_masked(a, row);  // padded rows are never read
+  if (row < a.rows && !nmask) {
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       nx[i] = ld8(a.x + row * C + i * 256 + lane * 8);
@@ -57,20 +65,30 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const LnArgs a) {
     }
   }
   for (; row < a.rows; row += stride) {
-    const int b = row / a.T, t = row - (long long)b * a.T;
-    const bool masked = a.lens && t >= a.lens[b];
+    const bool masked = nmask;
     bf16x8 cx[NV], cr[NV];
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       cx[i] = nx[i];
       cr[i] = nr[i];
     }
-    if (row + stride < a.rows) {
+    nmask = row + stride < a.rows && ln_row_masked(a, row + stride);
+    if (row + stride < a.rows && !nmask) {
 #pragma unroll
       for (int i = 0; i < NV; ++i) {
         nx[i] = ld8(a.x + (row + stride) * C + i * 256 + lane * 8);
         if (a.res) nr[i] = ld8(a.res + (row + stride) * C + i * 256 + lane * 8);
       }
+    }
+    if (masked) {  // transformer/Layers.py:25,28: the row is zero whatever the sub-layer produced
+      const bf16x8 z = {};
+#pragma unroll
+      for (int i = 0; i < NV; ++i) st8(a.y + row * C + i * 256 + lane * 8, z);
+      if (lane == 0) {
+        a.mean[row] = 0.f;
+        a.rstd[row] = 0.f;
+      }
+      continue;
     }
     float v[NV][8];
     float s = 0.f;
@@ -110,10 +128,7 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const LnArgs a) {
     for (int i = 0; i < NV; ++i) {
       const int col = i * 256 + lane * 8;
       float o[8];
-      if (masked) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = 0.f;
-      } else {
+      {
         const float4 g0 = *reinterpret_cast<const float4*>(a.gamma + col);
         const float4 g1 = *reinterpret_cast<const float4*>(a.gamma + col + 4);
         const float4 b0 = *reinterpret_cast<const float4*>(a.beta + col);
@@ -142,16 +157,17 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const LnArgs a) {
   const uint32_t thresh = dropout_thresh(a.p_drop);
   const float keep_scale = a.p_drop > 0.f ? 1.f / (1.f - a.p_drop) : 1.f;
   const uint64_t seed = mix_seed(a.seed_dev, a.seed);
-  float acc_g[NV][8], acc_b[NV][8];
+  float acc_g[NV][8], acc_b[NV][8], acc_x[NV][8];
 #pragma unroll
   for (int i = 0; i < NV; ++i)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc_g[i][j] = acc_b[i][j] = 0.f;
+    for (int j = 0; j < 8; ++j) acc_g[i][j] = acc_b[i][j] = acc_x[i][j] = 0.f;
 
   const long long stride = (long long)gridDim.x * warps_per_block;
   long long row = (long long)blockIdx.x * warps_per_block + warp;
   bf16x8 nx[NV], nd[NV], nr[NV];
-  if (row < a.rows) {
+  bool nmask = row < a.rows && ln_row_masked(a, row);  // padded rows are never read
+  if (row < a.rows && !nmask) {
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       nx[i] = ld8(a.x + row * C + i * 256 + lane * 8);
@@ -160,8 +176,7 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const LnArgs a) {
     }
   }
   for (; row < a.rows; row += stride) {
-    const int b = row / a.T, t = row - (long long)b * a.T;
-    const bool masked = a.lens && t >= a.lens[b];
+    const bool masked = nmask;
     bf16x8 cx[NV], cd[NV], cr[NV];
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
@@ -169,7 +184,8 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const LnArgs a) {
       cd[i] = nd[i];
       cr[i] = nr[i];
     }
-    if (row + stride < a.rows) {
+    nmask = row + stride < a.rows && ln_row_masked(a, row + stride);
+    if (row + stride < a.rows && !nmask) {
 #pragma unroll
       for (int i = 0; i < NV; ++i) {
         nx[i] = ld8(a.x + (row + stride) * C + i * 256 + lane * 8);
@@ -243,23 +259,25 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const LnArgs a) {
         dxo[j] = (a.drop_mode == 1 && thresh) ? ((keep[i] >> j) & 1u ? dpre[j] * keep_scale : 0.f)
                                               : dpre[j];
         if (!((relu_pos[i] >> j) & 1u)) dxo[j] = 0.f;
+        acc_x[i][j] += dxo[j];
       }
       st8(a.dx + row * C + col, pack8(dxo));
       if (a.dres) st8(a.dres + row * C + col, pack8(dpre));
     }
   }
   // block reduction of the affine-parameter gradients, then one atomic per column per block
-  for (int pass = 0; pass < 2; ++pass) {
+  for (int pass = 0; pass < (a.dbias ? 3 : 2); ++pass) {
 #pragma unroll
     for (int i = 0; i < NV; ++i)
 #pragma unroll
       for (int j = 0; j < 8; ++j)
-        red[warp][i * 256 + lane * 8 + j] = pass == 0 ? acc_g[i][j] : acc_b[i][j];
+        red[warp][i * 256 + lane * 8 + j] = pass == 0 ? acc_g[i][j] : (pass == 1 ? acc_b[i][j] : acc_x[i][j]);
     __syncthreads();
+    float* dst = pass == 0 ? a.dgamma : (pass == 1 ? a.dbeta : a.dbias);
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
       float s = 0.f;
       for (int w = 0; w < warps_per_block; ++w) s += red[w][c];
-      atomicAdd((pass == 0 ? a.dgamma : a.dbeta) + c, s);
+      atomicAdd(dst + c, s);
     }
     __syncthreads();
   }
@@ -322,7 +340,7 @@ int fs2_ln_fwd_bf16(const void* x, const void* res, const float* gamma, const fl
 int fs2_ln_bwd_bf16(const void* dy, const void* x, const void* res, const float* gamma,
                     const float* mean, const float* rstd, const int64_t* lens, int B, int T, int C,
                     float p_drop, int drop_mode, int relu_x, uint64_t seed, const uint64_t* seed_dev,
-                    void* dx, void* dres, float* dgamma, float* dbeta, void* stream) {
+                    void* dx, void* dres, float* dgamma, float* dbeta, float* dbias, void* stream) {
   fs2::LnArgs a{};
   a.dy = static_cast<const __nv_bfloat16*>(dy);
   a.x = static_cast<const __nv_bfloat16*>(x);
@@ -342,6 +360,7 @@ int fs2_ln_bwd_bf16(const void* dy, const void* x, const void* res, const float*
   a.dres = static_cast<__nv_bfloat16*>(dres);
   a.dgamma = dgamma;
   a.dbeta = dbeta;
+  a.dbias = dbias;
   return fs2::ln_dispatch<true>(a, C, static_cast<cudaStream_t>(stream));
 }
 }

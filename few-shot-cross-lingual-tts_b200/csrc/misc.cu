@@ -102,9 +102,16 @@ add_f32_bf16_kernel(const float* __restrict__ a, const __nv_bfloat16* __restrict
 // Each thread owns 8 consecutive channels (one 16-byte load per row), 4 independent rows in flight.
 __global__ void __launch_bounds__(256)
 colsum_kernel(const __nv_bfloat16* __restrict__ x, long long ld, int rows_per_group, int C,
-              int rows_per_block, float* __restrict__ out) {
+              int rows_per_block, float* __restrict__ out, const int64_t* __restrict__ lens,
+              int out_group_stride) {
   extern __shared__ float s_acc[];  // [C]
   const int g = blockIdx.y;
+  const long long x_group_stride = (long long)rows_per_group * ld;
+  if (lens) {  // rows at / after lens[g] are padding (zero by contract): not read
+    const long long l = lens[g];
+    if ((long long)blockIdx.x * rows_per_block >= l) return;
+    if (l < rows_per_group) rows_per_group = (int)l;
+  }
   const int vpr = C / 8, rs = 256 / vpr;
   for (int i = threadIdx.x; i < C; i += 256) s_acc[i] = 0.f;
   __syncthreads();
@@ -115,7 +122,7 @@ colsum_kernel(const __nv_bfloat16* __restrict__ x, long long ld, int rows_per_gr
     for (int j = 0; j < 8; ++j) acc[j] = 0.f;
     const int r0 = blockIdx.x * rows_per_block;
     const int r1 = min(r0 + rows_per_block, rows_per_group);
-    const __nv_bfloat16* base = x + (long long)g * rows_per_group * ld + v * 8;
+    const __nv_bfloat16* base = x + (long long)g * x_group_stride + v * 8;
     int r = r0 + ro;
     for (; r + 3 * rs < r1; r += 4 * rs) {
       bf16x8 t[4];
@@ -139,7 +146,7 @@ colsum_kernel(const __nv_bfloat16* __restrict__ x, long long ld, int rows_per_gr
     for (int j = 0; j < 8; ++j) atomicAdd(&s_acc[v * 8 + j], acc[j]);
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < C; i += 256) atomicAdd(out + (long long)g * C + i, s_acc[i]);
+  for (int i = threadIdx.x; i < C; i += 256) atomicAdd(out + (long long)g * out_group_stride + i, s_acc[i]);
 }
 
 // grad[co][ci][tap] += packed[co][tap][ci]
@@ -315,8 +322,8 @@ int fs2_add_rowvec_bf16(const void* x, const float* e, int B, int T, int C, void
 }
 
 // out f32 [groups][C] += column sums of x bf16 [groups*rows_per_group][ld]
-int fs2_colsum_bf16(const void* x, int64_t ld, int groups, int rows_per_group, int C, float* out,
-                    void* stream) {
+static int colsum_launch(const void* x, int64_t ld, int groups, int rows_per_group, int C, float* out,
+                         const int64_t* lens, int out_group_stride, void* stream) {
   if (groups <= 0 || rows_per_group <= 0) return 0;
   if ((ld % 8) || (C % 8) || C / 8 > 256 || (reinterpret_cast<uintptr_t>(x) & 15))
     return fs2::set_error("colsum: ld and C must be multiples of 8 (16-byte aligned rows), C <= 2048");
@@ -324,9 +331,19 @@ int fs2_colsum_bf16(const void* x, int64_t ld, int groups, int rows_per_group, i
   if (rpb < 64) rpb = 64;
   dim3 grid((rows_per_group + rpb - 1) / rpb, groups);
   fs2::colsum_kernel<<<grid, 256, C * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __nv_bfloat16*>(x), ld, rows_per_group, C, rpb, out);
+      static_cast<const __nv_bfloat16*>(x), ld, rows_per_group, C, rpb, out, lens, out_group_stride);
   fs2::count_launch();
   return fs2::check_launch("colsum_kernel");
+}
+
+int fs2_colsum_bf16(const void* x, int64_t ld, int groups, int rows_per_group, int C, float* out,
+                    void* stream) {
+  return colsum_launch(x, ld, groups, rows_per_group, C, out, nullptr, C, stream);
+}
+
+int fs2_colsum_ragged_bf16(const void* x, int64_t ld, int B, int T, int C, const int64_t* lens, float* out,
+                           void* stream) {
+  return colsum_launch(x, ld, B, T, C, out, lens, 0, stream);
 }
 
 int fs2_colsum3_bf16(const void* x, int64_t ld, int rows, int seg_cols, float* out0, float* out1, float* out2,

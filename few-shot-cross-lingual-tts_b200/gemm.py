@@ -44,8 +44,11 @@ def run(g, impl=None):
 
 def gemm(a, b, d, M, N, K, Z=1, taps=1, tap_shift0=0, b_tap_kstride=0, ldd=None, bias=None,
          epilogue=EPI_NONE, aux=None, ld_aux=0, aux_batch_stride=0, alpha=1.0, d_zdiv=1,
-         d_zdiv_stride=0, d_zmod_stride=0, impl=None):
-    """D[z] = epi(alpha * sum_tap A[z][m+shift+tap] . B[z][n][tap*kstride+k] + bias)."""
+         d_zdiv_stride=0, d_zmod_stride=0, impl=None, row_lens=None, lens_zdiv=1):
+    """D[z] = epi(alpha * sum_tap A[z][m+shift+tap] . B[z][n][tap*kstride+k] + bias).
+
+    row_lens (int64 [Z / lens_zdiv]): rows m >= row_lens of D[z] are written as zero and row tiles that
+    hold only such rows are skipped (padded frames of an utterance batch)."""
     g = Gemm()
     g.a, g.b = a, b
     g.mode = GEMM_NORMAL
@@ -66,12 +69,22 @@ def gemm(a, b, d, M, N, K, Z=1, taps=1, tap_shift0=0, b_tap_kstride=0, ldd=None,
         assert bias.dtype == torch.float32
     g.aux = aux.data_ptr() if aux is not None else None
     g.ld_aux, g.aux_batch_stride = int(ld_aux), int(aux_batch_stride)
+    _set_lens(g, row_lens, lens_zdiv)
     run(g, impl)
 
 
+def _set_lens(g, row_lens, lens_zdiv):
+    if row_lens is not None:
+        assert row_lens.dtype == torch.int64 and row_lens.is_cuda and row_lens.is_contiguous()
+        g.row_lens = row_lens.data_ptr()
+        g.lens_zdiv = int(lens_zdiv)
+
+
 def wgrad(a, b, d, M, N, taps=1, tap_shift0=0, ldd=None, d_col_stride=1, d_tap_stride=0, splits=1,
-          accumulate=True, impl=None, segments=None):
-    """D[m][tap][n] (+)= sum_{z,r} A[z][r][m] * B[z][r+shift+tap][n]; D is fp32."""
+          accumulate=True, impl=None, segments=None, row_lens=None, lens_zdiv=1):
+    """D[m][tap][n] (+)= sum_{z,r} A[z][r][m] * B[z][r+shift+tap][n]; D is fp32.
+
+    row_lens: promise that rows r >= row_lens[z] of A[z] are zero -> their 64-row blocks are skipped."""
     if segments is not None:  # (rows_per_segment, [tensor, ...]): row block i of D lives in tensors[i]
         d = segments[1][0]
     assert d.dtype == torch.float32
@@ -97,4 +110,5 @@ def wgrad(a, b, d, M, N, taps=1, tap_shift0=0, ldd=None, d_col_stride=1, d_tap_s
         for i, t in enumerate(segments[1]):
             assert t.dtype == torch.float32 and t.is_contiguous()
             g.d_seg[i] = t.data_ptr()
+    _set_lens(g, row_lens, lens_zdiv)
     run(g, impl)

@@ -133,65 +133,97 @@ def _splits(m_out, n_out, taps, red_blocks):
 # --------------------------------------------------------------------------------------------------
 # raw kernels wrappers (no autograd)
 # --------------------------------------------------------------------------------------------------
-def linear_fwd(x2d, w_bf, bias, out_dtype=BF16, relu=False):
+# Ragged batches.  `lens` (int64 [B], device) given to the wrappers below means: rows t >= lens[b] of every
+# [B, T, .] operand are padding that the sub-layer zeroes anyway (transformer/Layers.py:25,28) -- the GEMM
+# engine then skips the row tiles / reduction blocks that hold only such rows and writes zeros for them,
+# so padded frames cost (almost) nothing instead of ~40 % of a LibriTTS-shaped batch.
+def linear_fwd(x2d, w_bf, bias, out_dtype=BF16, relu=False, lens=None, T=None):
     M, K = x2d.shape
     N = w_bf.shape[0]
     y = torch.empty(M, N, dtype=out_dtype, device=x2d.device)
-    G.gemm(G.operand(x2d, K, M), G.operand(w_bf, K, N), y, M, N, K, bias=bias,
-           epilogue=G.EPI_RELU if relu else G.EPI_NONE)
+    epi = G.EPI_RELU if relu else G.EPI_NONE
+    if lens is None:
+        G.gemm(G.operand(x2d, K, M), G.operand(w_bf, K, N), y, M, N, K, bias=bias, epilogue=epi)
+    else:  # one row-tile sequence per utterance so that whole tiles of padded frames can be skipped
+        B = M // T
+        G.gemm(G.operand(x2d, K, T, B), G.operand(w_bf, K, N), y, T, N, K, Z=B, bias=bias, epilogue=epi,
+               d_zdiv=1, d_zdiv_stride=T * N, row_lens=lens)
     return y
 
 
-def linear_dgrad(dy2d, w_bf, epilogue=G.EPI_NONE, aux=None):
+def linear_dgrad(dy2d, w_bf, epilogue=G.EPI_NONE, aux=None, lens=None, T=None):
     """dx[M,K] = dy[M,N] @ W[N,K]  (W read as an MN-major B operand: no transposed copy)."""
     M, N = dy2d.shape
     K = w_bf.shape[1]
     dx = torch.empty(M, K, dtype=BF16, device=dy2d.device)
-    G.gemm(G.operand(dy2d, N, M), G.operand(w_bf, K, N, mn_major=True), dx, M, K, N,
-           epilogue=epilogue, aux=aux, ld_aux=K)
+    if lens is None:
+        G.gemm(G.operand(dy2d, N, M), G.operand(w_bf, K, N, mn_major=True), dx, M, K, N,
+               epilogue=epilogue, aux=aux, ld_aux=K)
+    else:
+        B = M // T
+        G.gemm(G.operand(dy2d, N, T, B), G.operand(w_bf, K, N, mn_major=True), dx, T, K, N, Z=B,
+               epilogue=epilogue, aux=aux, ld_aux=K, aux_batch_stride=T * K, d_zdiv=1, d_zdiv_stride=T * K,
+               row_lens=lens)
     return dx
 
 
-def linear_wgrad(dy2d, x2d, dw, row0=0, rows=None):
+def _wgrad_operands(dy2d, x2d, lens, T, row0=0):
+    M, N = dy2d.shape
+    K = x2d.shape[1]
+    if lens is None:
+        return (G.operand(dy2d, N, M, mn_major=True, inner_base=row0), G.operand(x2d, K, M, mn_major=True))
+    B = M // T
+    return (G.operand(dy2d, N, T, B, mn_major=True, inner_base=row0), G.operand(x2d, K, T, B, mn_major=True))
+
+
+def linear_wgrad(dy2d, x2d, dw, row0=0, rows=None, lens=None, T=None):
     """dw[rows, K] += dy[:, row0:row0+rows]^T @ x"""
     M, N = dy2d.shape
     K = x2d.shape[1]
     rows = N if rows is None else rows
-    a = G.operand(dy2d, N, M, mn_major=True, inner_base=row0)
-    b = G.operand(x2d, K, M, mn_major=True)
-    G.wgrad(a, b, dw, rows, K, splits=_splits(rows, K, 1, (M + 63) // 64))
+    a, b = _wgrad_operands(dy2d, x2d, lens, T, row0)
+    G.wgrad(a, b, dw, rows, K, splits=_splits(rows, K, 1, (M + 63) // 64), row_lens=lens)
 
 
-def qkv_param_grads(dqkv, x2d, gbuf, HD):
+def qkv_param_grads(dqkv, x2d, gbuf, HD, lens=None, T=None):
     """Weight / bias gradients of the fused Q|K|V projection in ONE weight-gradient GEMM and one column
     sum pass; row block i of the [3*HD, D] result lands directly in the i-th parameter's gradient."""
     M, C3 = dqkv.shape
     D = x2d.shape[1]
-    G.wgrad(G.operand(dqkv, C3, M, mn_major=True), G.operand(x2d, D, M, mn_major=True), None, C3, D,
-            splits=_splits(C3, D, 1, (M + 63) // 64), segments=(HD, [gbuf[0][0], gbuf[2][0], gbuf[4][0]]))
-    _ck(_L().fs2_colsum3_bf16(_p(dqkv), C3, M, HD, _p(gbuf[1][0]), _p(gbuf[3][0]), _p(gbuf[5][0]), _st()),
-        "colsum3")
+    a, b = _wgrad_operands(dqkv, x2d, lens, T)
+    G.wgrad(a, b, None, C3, D, splits=_splits(C3, D, 1, (M + 63) // 64),
+            segments=(HD, [gbuf[0][0], gbuf[2][0], gbuf[4][0]]), row_lens=lens)
+    if lens is None:
+        _ck(_L().fs2_colsum3_bf16(_p(dqkv), C3, M, HD, _p(gbuf[1][0]), _p(gbuf[3][0]), _p(gbuf[5][0]), _st()),
+            "colsum3")
+    else:
+        for i in range(3):
+            colsum(dqkv, gbuf[2 * i + 1][0], col0=i * HD, cols=HD, lens=lens, T=T)
 
 
-def colsum(x2d, out, col0=0, cols=None):
-    """out[cols] += column sums of x2d[:, col0:col0+cols] (bias gradients)."""
+def colsum(x2d, out, col0=0, cols=None, lens=None, T=None):
+    """out[cols] += column sums of x2d[:, col0:col0+cols] (bias gradients); with `lens`, rows of padded
+    frames (zero by construction) are not read."""
     M, N = x2d.shape
     cols = N if cols is None else cols
     ptr = x2d.data_ptr() + 2 * col0
-    _ck(_L().fs2_colsum_bf16(ptr, N, 1, M, cols, _p(out), _st()), "colsum")
+    if lens is None:
+        _ck(_L().fs2_colsum_bf16(ptr, N, 1, M, cols, _p(out), _st()), "colsum")
+    else:
+        _ck(_L().fs2_colsum_ragged_bf16(ptr, N, M // T, T, cols, _p(lens), _p(out), _st()), "colsum_ragged")
 
 
-def conv_fwd(x, wp, bias, relu=False):
+def conv_fwd(x, wp, bias, relu=False, lens=None):
     B, T, Ci = x.shape
     Co, k, cpad = wp.shape
     y = torch.empty(B, T, Co, dtype=BF16, device=x.device)
     G.gemm(G.operand(x, Ci, T, B), G.operand(wp, k * cpad, Co), y, T, Co, Ci, Z=B, taps=k,
            tap_shift0=-((k - 1) // 2), b_tap_kstride=cpad, bias=bias,
-           epilogue=G.EPI_RELU if relu else G.EPI_NONE, d_zdiv=1, d_zdiv_stride=T * Co)
+           epilogue=G.EPI_RELU if relu else G.EPI_NONE, d_zdiv=1, d_zdiv_stride=T * Co, row_lens=lens)
     return y
 
 
-def conv_dgrad(dy, wp, Ci, epilogue=G.EPI_NONE, aux=None):
+def conv_dgrad(dy, wp, Ci, epilogue=G.EPI_NONE, aux=None, lens=None):
     """Input gradient of the channels-last Conv1d: the same implicit GEMM with flipped taps, reading the
     forward-packed weights [Co][k][Cpad] as an MN-major operand (negative tap stride)."""
     B, T, Co = dy.shape
@@ -200,11 +232,11 @@ def conv_dgrad(dy, wp, Ci, epilogue=G.EPI_NONE, aux=None):
     b = G.operand(wp, k * cpad, Co, mn_major=True, inner_base=(k - 1) * cpad)
     G.gemm(G.operand(dy, Co, T, B), b, dx, T, Ci, Co, Z=B, taps=k, tap_shift0=-((k - 1) // 2),
            b_tap_kstride=-cpad, epilogue=epilogue, aux=aux, ld_aux=Ci, aux_batch_stride=T * Ci,
-           d_zdiv=1, d_zdiv_stride=T * Ci)
+           d_zdiv=1, d_zdiv_stride=T * Ci, row_lens=lens)
     return dx
 
 
-def conv_wgrad(dy, x, dw):
+def conv_wgrad(dy, x, dw, lens=None):
     """dw[Co, Ci, k] (reference Conv1d.weight layout, fp32) += correlation of dy with x.
 
     k == 1 is a plain unit-stride weight gradient.  For k > 1 the split-K partial sums are reduced with
@@ -218,15 +250,15 @@ def conv_wgrad(dy, x, dw):
     b = G.operand(x, Ci, T, B, mn_major=True)
     splits = _splits(Co, Ci, k, B * ((T + 63) // 64))
     if k == 1:
-        G.wgrad(a, b, dw, Co, Ci, splits=splits)
+        G.wgrad(a, b, dw, Co, Ci, splits=splits, row_lens=lens)
         return
     if Ci % 4:
         G.wgrad(a, b, dw, Co, Ci, taps=k, tap_shift0=-((k - 1) // 2), ldd=Ci * k, d_col_stride=k, d_tap_stride=1,
-                splits=splits)
+                splits=splits, row_lens=lens)
         return
     scratch = torch.zeros(Co, k, Ci, dtype=F32, device=dy.device)
     G.wgrad(a, b, scratch, Co, Ci, taps=k, tap_shift0=-((k - 1) // 2), ldd=Ci * k, d_col_stride=1,
-            d_tap_stride=Ci, splits=splits)
+            d_tap_stride=Ci, splits=splits, row_lens=lens)
     _ck(_L().fs2_unpack_add_conv_grad(_p(scratch), Co, Ci, k, _p(dw), _st()), "unpack_add_conv_grad")
 
 
@@ -241,14 +273,16 @@ def ln_fwd(x, res, gamma, beta, lens, p, mode, salt):
     return y, mean, rstd
 
 
-def ln_bwd(dy, x, res, gamma, mean, rstd, lens, p, mode, salt, dgamma, dbeta, want_dres, relu_x=False):
+def ln_bwd(dy, x, res, gamma, mean, rstd, lens, p, mode, salt, dgamma, dbeta, want_dres, relu_x=False,
+           dbias=None):
+    """dbias (fp32 [C], accumulated): column sums of dx = bias gradient of the GEMM / conv that produced x."""
     B, T, C = x.shape
     dx = torch.empty_like(x)
     dres = torch.empty_like(x) if want_dres and p > 0 and mode == 1 else None
     seed_dev = _Rng.tensor(x.device) if p > 0 else None
     _ck(_L().fs2_ln_bwd_bf16(_p(dy), _p(x), _p(res), _p(gamma), _p(mean), _p(rstd), _p(lens), B, T, C, p,
                              mode, 1 if relu_x else 0, salt, _p(seed_dev), _p(dx), _p(dres), _p(dgamma),
-                             _p(dbeta), _st()), "ln_bwd")
+                             _p(dbeta), _p(dbias), _st()), "ln_bwd")
     if want_dres and dres is None:
         dres = dx  # without pre-LN dropout the two gradients are the same tensor
     return dx, dres
@@ -338,16 +372,18 @@ class MHASublayer(torch.autograd.Function):
             cast_bf16(w, wqkv[i * HD:(i + 1) * HD])
         bqkv = torch.cat([bq.detach(), bk.detach(), bv.detach()])
         x2 = x.view(B * T, D)
-        qkv = linear_fwd(x2, wqkv, bqkv)  # [B*T, 3*HD], head h of Q = cols [h*dk, (h+1)*dk)
+        fused = fused_attention_enabled(dk)
+        # padded frames: skipped by the GEMMs when the sub-layer zeroes them anyway (fused path only)
+        rl = lens if (zero_pad and fused) else None
+        qkv = linear_fwd(x2, wqkv, bqkv, lens=rl, T=T)  # [B*T, 3*HD], head h of Q = cols [h*dk, (h+1)*dk)
         Tp = _roundup(T, 128)
         Z = B * H
         C3 = 3 * HD
-        fused = fused_attention_enabled(dk)
         if fused:
             attn3, lse2 = attn_fwd(qkv.view(B, T, C3), lens, H, dk)
             attn = attn3.view(B * T, HD)
             wo_bf = cast_bf16(wo)
-            o = linear_fwd(attn, wo_bf, bo.detach())
+            o = linear_fwd(attn, wo_bf, bo.detach(), lens=rl, T=T)
             salt = _Rng.next_salt()
             y, mean, rstd = ln_fwd(o.view(B, T, D), x, gamma.detach(), beta.detach(),
                                    lens if zero_pad else None, p_drop, 1, salt)
@@ -386,19 +422,20 @@ class MHASublayer(torch.autograd.Function):
         dev = x.device
         dy = _contig(dy)
         gbuf = [grad_target(p) for p in (wq, bq, wk, bk, wv, bv, wo, bo, gamma, beta)]
+        rl = lens if (zero_pad and fused) else None
+        # the output-projection bias gradient (column sums of `do`) comes out of the LayerNorm backward
         do, dres = ln_bwd(dy, o.view(B, T, D), x, gamma_t, mean, rstd, lens if zero_pad else None, p_drop, 1,
-                          salt, gbuf[8][0], gbuf[9][0], want_dres=True)
+                          salt, gbuf[8][0], gbuf[9][0], want_dres=True, dbias=gbuf[7][0])
         do2 = do.view(M, D)
         # output projection
-        dattn = linear_dgrad(do2, wo_bf)
-        linear_wgrad(do2, attn, gbuf[6][0])
-        colsum(do2, gbuf[7][0])
+        dattn = linear_dgrad(do2, wo_bf, lens=rl, T=T)
+        linear_wgrad(do2, attn, gbuf[6][0], lens=rl, T=T)
         if fused:  # `P` slot of the saved tensors holds lse2; S / P / dS never touch HBM
             dqkv = attn_bwd(qkv.view(B, T, C3), attn.view(B, T, HD), dattn.view(B, T, HD), P, lens, H,
                             dk).view(M, C3)
             x2 = x.view(M, D)
-            dx = linear_dgrad(dqkv, wqkv, epilogue=G.EPI_ADD_AUX, aux=dres.view(M, D))
-            qkv_param_grads(dqkv, x2, gbuf, HD)
+            dx = linear_dgrad(dqkv, wqkv, epilogue=G.EPI_ADD_AUX, aux=dres.view(M, D), lens=rl, T=T)
+            qkv_param_grads(dqkv, x2, gbuf, HD, lens=rl, T=T)
             grads_done((wq, bq, wk, bk, wv, bv, wo, bo, gamma, beta))
             return (dx.view(B, T, D), None) + tuple(g[1] for g in gbuf) + (None, None, None)
         # attention core: dP = dO V^T ; dS = softmax'(P, dP) ; dQ = dS K ; dK = dS^T Q ; dV = P^T dO
@@ -441,8 +478,9 @@ class FFNSublayer(torch.autograd.Function):
         B, T, D = x.shape
         x = x.contiguous()
         w1p, w2p = pack_conv(w1), pack_conv(w2)
-        h = conv_fwd(x, w1p, b1.detach(), relu=True)
-        f = conv_fwd(h, w2p, b2.detach())
+        rl = lens if zero_pad else None  # padded frames are zeroed below: skip their GEMM tiles
+        h = conv_fwd(x, w1p, b1.detach(), relu=True, lens=rl)
+        f = conv_fwd(h, w2p, b2.detach(), lens=rl)
         salt = _Rng.next_salt()
         y, mean, rstd = ln_fwd(f, x, gamma.detach(), beta.detach(), lens if zero_pad else None, p_drop, 1,
                                salt)
@@ -460,14 +498,14 @@ class FFNSublayer(torch.autograd.Function):
         Dh = h.shape[2]
         dy = _contig(dy)
         gbuf = [grad_target(p) for p in (w1, b1, w2, b2, gamma, beta)]
-        df, dres = ln_bwd(dy, f, x, gamma_t, mean, rstd, lens if zero_pad else None, p_drop, 1, salt,
-                          gbuf[4][0], gbuf[5][0], want_dres=True)
-        dh = conv_dgrad(df, w2p, Dh, epilogue=G.EPI_RELU_BWD, aux=h)
-        conv_wgrad(df, h, gbuf[2][0])
-        colsum(df.view(B * T, D), gbuf[3][0])
-        dx = conv_dgrad(dh, w1p, D, epilogue=G.EPI_ADD_AUX, aux=dres)
-        conv_wgrad(dh, x, gbuf[0][0])
-        colsum(dh.view(B * T, Dh), gbuf[1][0])
+        rl = lens if zero_pad else None
+        df, dres = ln_bwd(dy, f, x, gamma_t, mean, rstd, rl, p_drop, 1, salt,
+                          gbuf[4][0], gbuf[5][0], want_dres=True, dbias=gbuf[3][0])  # dbias: w_2.bias gradient
+        dh = conv_dgrad(df, w2p, Dh, epilogue=G.EPI_RELU_BWD, aux=h, lens=rl)
+        conv_wgrad(df, h, gbuf[2][0], lens=rl)
+        dx = conv_dgrad(dh, w1p, D, epilogue=G.EPI_ADD_AUX, aux=dres, lens=rl)
+        conv_wgrad(dh, x, gbuf[0][0], lens=rl)
+        colsum(dh.view(B * T, Dh), gbuf[1][0], lens=rl, T=T)
         grads_done((w1, b1, w2, b2, gamma, beta))
         return (dx, None) + tuple(g[1] for g in gbuf) + (None, None)
 
@@ -512,16 +550,15 @@ class VariancePredictorFn(torch.autograd.Function):
         dn2 = torch.empty_like(n2)
         _ck(_L().fs2_rowdot_bwd(_p(dout), _p(n2), _p(lw2), _p(lens if use_mask else None), B, T, F_, _p(dn2),
                                 _p(gbuf[8][0]), _p(gbuf[9][0]), _st()), "rowdot_bwd")
+        # the conv bias gradients (column sums of da2 / da1) come out of the LayerNorm backward kernels
         da2, _ = ln_bwd(dn2, a2, None, g2t, m2, r2, None, p_drop, 2, s2, gbuf[6][0], gbuf[7][0],
-                        want_dres=False, relu_x=True)
+                        want_dres=False, relu_x=True, dbias=gbuf[5][0])
         dn1 = conv_dgrad(da2, c2p, n1.shape[2])
         conv_wgrad(da2, n1, gbuf[4][0])
-        colsum(da2.view(B * T, -1), gbuf[5][0])
         da1, _ = ln_bwd(dn1, a1, None, g1t, m1, r1, None, p_drop, 2, s1, gbuf[2][0], gbuf[3][0],
-                        want_dres=False, relu_x=True)
+                        want_dres=False, relu_x=True, dbias=gbuf[1][0])
         dx = conv_dgrad(da1, c1p, D)
         conv_wgrad(da1, x, gbuf[0][0])
-        colsum(da1.view(B * T, -1), gbuf[1][0])
         grads_done((c1w, c1b, g1, be1, c2w, c2b, g2, be2, lw, lb))
         return (dx, None) + tuple(g[1] for g in gbuf) + (None, None)
 

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define FS2_ABI_VERSION 1
+#define FS2_ABI_VERSION 2
 
 int fs2_version(void);
 const char* fs2_last_error(void);
@@ -95,6 +95,15 @@ typedef struct fs2_gemm {
   int32_t d_seg_rows;
   int32_t d_seg_pad;
   void* d_seg[4];
+  /* optional ragged rows (key/frame padding: transformer/Layers.py:25,28 zero those rows anyway, so their
+     GEMM work is skipped instead of computed and thrown away).  row_lens: int64 [.] valid-row counts;
+     NORMAL: rows m >= row_lens[z / lens_zdiv] of D[z] are written as ZERO and output tiles made only of
+             such rows skip their TMA loads and MMAs (compact tile schedule built on the device);
+     WGRAD:  the caller PROMISES that rows r >= row_lens[zb / lens_zdiv] of A_zb are zero; 64-row reduction
+             blocks made only of such rows are skipped (split-K ranges are cut over the remaining blocks). */
+  const int64_t* row_lens;
+  int32_t lens_zdiv;
+  int32_t lens_pad;
 } fs2_gemm;
 
 /* impl: 0 = tcgen05 (product path), 1 = plain CUDA-core kernel (debug cross-check only). */
@@ -109,7 +118,9 @@ int fs2_gemm_bf16(const fs2_gemm* g, int impl, void* stream);
 /*   lens: int64 [B] or NULL (rows t >= lens[b] are zeroed); drop_mode 1: LN(drop(x)+res),      */
 /*   2: drop(LN(x+res)); the mask is regenerated in the backward (Philox4x32-10) from         */
 /*   seed_dev[0] (device step counter, may be NULL) mixed with the call-site salt `seed`.      */
-/*   dgamma/dbeta: f32 [C], accumulated with atomics (zero them first).                        */
+/*   dgamma/dbeta: f32 [C], accumulated with atomics (zero them first); dbias (optional, f32    */
+/*   [C]): column sums of dx, i.e. the bias gradient of the GEMM / conv that produced x.        */
+/*   Rows t >= lens[b] are never read: y / dx / dres are zero there.                            */
 /* ------------------------------------------------------------------------------------------ */
 int fs2_ln_fwd_bf16(const void* x, const void* res, const float* gamma, const float* beta,
                     const int64_t* lens, int B, int T, int C, float p_drop, int drop_mode,
@@ -118,7 +129,7 @@ int fs2_ln_fwd_bf16(const void* x, const void* res, const float* gamma, const fl
 int fs2_ln_bwd_bf16(const void* dy, const void* x, const void* res, const float* gamma,
                     const float* mean, const float* rstd, const int64_t* lens, int B, int T, int C,
                     float p_drop, int drop_mode, int relu_x, uint64_t seed, const uint64_t* seed_dev,
-                    void* dx, void* dres, float* dgamma, float* dbeta, void* stream);
+                    void* dx, void* dres, float* dgamma, float* dbeta, float* dbias, void* stream);
 
 /* ------------------------------------------------------------------------------------------ */
 /* Key-padding-masked softmax (transformer/Modules.py:17-22), z = b*H + h                      */
@@ -182,6 +193,10 @@ int fs2_add_rowvec_bf16(const void* x, const float* e, int B, int T, int C, void
 int fs2_add_f32_bf16(const float* a, const void* b, int64_t n, float* out, void* stream);
 int fs2_colsum_bf16(const void* x, int64_t ld, int groups, int rows_per_group, int C, float* out,
                     void* stream);
+/* out[c] += sum_b sum_{t < lens[b]} x[b][t][c]: bias gradients of ragged batches (rows at / after lens[b]
+   are padding whose gradient is zero by construction, transformer/Layers.py:25,28; they are not read) */
+int fs2_colsum_ragged_bf16(const void* x, int64_t ld, int B, int T, int C, const int64_t* lens, float* out,
+                           void* stream);
 int fs2_colsum_f32(const float* x, int64_t ld, int rows, int C, float* out, void* stream);
 /* column sums of x[:, 0:3*seg_cols] split into three outputs (fused Q|K|V bias gradients) */
 int fs2_colsum3_bf16(const void* x, int64_t ld, int rows, int seg_cols, float* out0, float* out1, float* out2,

@@ -20,7 +20,7 @@ def test_library_exports_every_declared_symbol():
     for name in protos:
         assert hasattr(lib, name), "missing export: %s" % name
     lib.fs2_version.restype = ctypes.c_int
-    assert lib.fs2_version() == 1
+    assert lib.fs2_version() == 2
     lib.fs2_launch_count.restype = ctypes.c_int64
     assert lib.fs2_launch_count() == 0  # nothing launched without a GPU
 

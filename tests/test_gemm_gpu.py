@@ -193,3 +193,103 @@ def test_ops_conv_wgrad_reference_layout(B, T, Cin, Cout, k):
     dw = torch.ones(Cout, Cin, k, device="cuda")
     ops.conv_wgrad(dy, x, dw)
     assert rel_err(dw, w.grad + 1.0) < 2e-3
+
+
+# --------------------------------------------------------------------------------------------------
+# ragged rows (fs2_gemm::row_lens): padded frames are skipped, their output rows are zero
+# --------------------------------------------------------------------------------------------------
+def _lens(vals):
+    return torch.tensor(vals, device="cuda", dtype=torch.int64)
+
+
+RAGGED_LENS = [[200, 1, 129, 0, 128, 77], [0, 0, 0], [300, 300], [5]]
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+@pytest.mark.parametrize("lens", RAGGED_LENS)
+@pytest.mark.parametrize("T,N,K,f32", [(300, 768, 256, False), (300, 256, 1024, False), (257, 80, 256, True),
+                                       (300, 1024, 256, False)])
+def test_ragged_linear(impl, lens, T, N, K, f32):
+    """Batched per-utterance linear layer: valid rows equal the dense result, padded rows are exactly 0."""
+    B = len(lens)
+    torch.manual_seed(T + N + K + B)
+    x, w = rnd(B, T, K), rnd(N, K, scale=K ** -0.5)
+    bias = torch.randn(N, device="cuda")
+    aux = None if f32 else rnd(B, T, N)
+    y = torch.full((B, T, N), float("nan"), device="cuda", dtype=torch.float32 if f32 else torch.bfloat16)
+    G.gemm(G.operand(x, K, T, B), G.operand(w, K, N), y, T, N, K, Z=B, bias=bias, d_zdiv=1, d_zdiv_stride=T * N,
+           aux=aux, ld_aux=N, aux_batch_stride=T * N, epilogue=G.EPI_NONE if f32 else G.EPI_ADD_AUX,
+           row_lens=_lens(lens), impl=impl)
+    ref = x.float() @ w.float().t() + bias
+    if aux is not None:
+        ref = ref + aux.float()
+    valid = torch.arange(T, device="cuda")[None, :] < _lens(lens).clamp(max=T)[:, None]
+    ref = ref * valid[..., None]
+    assert torch.isfinite(y.float()).all()
+    assert (y[~valid] == 0).all()
+    if valid.any():
+        assert rel_err(y, ref) < (2e-3 if f32 else 1e-2), rel_err(y, ref)
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+@pytest.mark.parametrize("lens", [[200, 1, 129, 0, 128, 77], [0, 0], [260, 255, 256, 257]])
+@pytest.mark.parametrize("Cin,Cout,k", [(256, 1024, 9), (1024, 256, 1), (256, 256, 3)])
+def test_ragged_conv(impl, lens, Cin, Cout, k):
+    """Implicit-GEMM Conv1d with row_lens: same values as the dense conv on valid rows (the halo may read
+    padded input rows, which the caller keeps at zero), zeros on padded rows."""
+    B, T = len(lens), 260
+    torch.manual_seed(Cin + k + B)
+    ln = _lens(lens).clamp(max=T)
+    valid = torch.arange(T, device="cuda")[None, :] < ln[:, None]
+    x = rnd(B, T, Cin) * valid[..., None]
+    w = (torch.randn(Cout, Cin, k, device="cuda") * (Cin * k) ** -0.5).to(torch.bfloat16)
+    bias = torch.randn(Cout, device="cuda")
+    wp = w.permute(0, 2, 1).contiguous()
+    y = torch.full((B, T, Cout), float("nan"), device="cuda", dtype=torch.bfloat16)
+    G.gemm(G.operand(x, Cin, T, B), G.operand(wp, k * Cin, Cout), y, T, Cout, Cin, Z=B, taps=k,
+           tap_shift0=-((k - 1) // 2), b_tap_kstride=Cin, bias=bias, epilogue=G.EPI_RELU, d_zdiv=1,
+           d_zdiv_stride=T * Cout, row_lens=_lens(lens), impl=impl)
+    ref = torch.nn.functional.conv1d(x.float().transpose(1, 2), w.float(), bias,
+                                     padding=(k - 1) // 2).transpose(1, 2).relu() * valid[..., None]
+    assert (y[~valid] == 0).all()
+    if valid.any():
+        assert rel_err(y, ref) < 1e-2, rel_err(y, ref)
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+@pytest.mark.parametrize("lens", [[200, 1, 129, 0, 128, 77], [0, 0], [300, 64, 65]])
+@pytest.mark.parametrize("N,K,k,splits", [(768, 256, 1, 1), (768, 256, 1, 4), (256, 1024, 9, 3), (80, 256, 1, 2)])
+def test_ragged_wgrad(impl, lens, N, K, k, splits):
+    """Weight gradient with row_lens: reduction blocks of padded frames are skipped (dY is zero there)."""
+    B, T = len(lens), 300
+    torch.manual_seed(N + K + k + B)
+    ln = _lens(lens).clamp(max=T)
+    valid = torch.arange(T, device="cuda")[None, :] < ln[:, None]
+    dy = rnd(B, T, N) * valid[..., None]
+    x = rnd(B, T, K)  # padded rows of x are arbitrary (finite): they only ever meet zero rows of dY
+    if k > 1:
+        x = x * valid[..., None]
+    dw = torch.ones(N, k, K, device="cuda")
+    G.wgrad(G.operand(dy, N, T, B, mn_major=True), G.operand(x, K, T, B, mn_major=True), dw, N, K, taps=k,
+            tap_shift0=-((k - 1) // 2), ldd=K * k, d_col_stride=1, d_tap_stride=K, splits=splits,
+            row_lens=_lens(lens), impl=impl)
+    xf = x.float().requires_grad_(False)
+    w = torch.zeros(N, K, k, device="cuda", requires_grad=True)
+    yy = torch.nn.functional.conv1d(xf.transpose(1, 2), w, None, padding=(k - 1) // 2).transpose(1, 2)
+    yy.backward(dy.float())
+    ref = w.grad.permute(0, 2, 1) + 1.0
+    assert rel_err(dw, ref) < 2e-3, rel_err(dw, ref)
+
+
+def test_ragged_many_batches_falls_back_to_dense_schedule():
+    """More utterances than the on-chip schedule table holds: every tile is computed, rows still zeroed."""
+    B, T, N, K = 300, 40, 256, 256
+    torch.manual_seed(3)
+    lens = torch.randint(0, T + 1, (B,), device="cuda", dtype=torch.int64)
+    x, w = rnd(B, T, K), rnd(N, K, scale=K ** -0.5)
+    y = torch.full((B, T, N), float("nan"), device="cuda", dtype=torch.bfloat16)
+    G.gemm(G.operand(x, K, T, B), G.operand(w, K, N), y, T, N, K, Z=B, d_zdiv=1, d_zdiv_stride=T * N,
+           row_lens=lens)
+    valid = torch.arange(T, device="cuda")[None, :] < lens[:, None]
+    ref = (x.float() @ w.float().t()) * valid[..., None]
+    assert (y[~valid] == 0).all() and rel_err(y, ref) < 1e-2

@@ -114,8 +114,12 @@ def test_layernorm_fwd_bwd(with_res, with_lens):
     res = torch.randn(B, T, C, device="cuda").to(BF16) if with_res else None
     g, b = torch.randn(C, device="cuda"), torch.randn(C, device="cuda")
     lens = torch.tensor([37, 5, 20], device="cuda") if with_lens else None
-    y, mean, rstd = ops.ln_fwd(x, res, g, b, lens, 0.0, 1, 0)
     pre = (x.float() + (res.float() if with_res else 0)).requires_grad_()
+    if with_lens:  # padded rows are never read: poison them
+        pad = torch.arange(T, device="cuda")[None, :] >= lens[:, None]
+        x = x.masked_fill(pad[..., None], float("nan"))
+        res = res.masked_fill(pad[..., None], float("nan"))
+    y, mean, rstd = ops.ln_fwd(x, res, g, b, lens, 0.0, 1, 0)
     gr, br = g.clone().requires_grad_(), b.clone().requires_grad_()
     ref = F.layer_norm(pre, (C,), gr, br)
     if with_lens:
@@ -125,9 +129,15 @@ def test_layernorm_fwd_bwd(with_res, with_lens):
     dy = torch.randn(B, T, C, device="cuda").to(BF16)
     ref.backward(dy.float())
     dg, db = torch.zeros(C, device="cuda"), torch.zeros(C, device="cuda")
-    dx, dres = ops.ln_bwd(dy, x, res, g, mean, rstd, lens, 0.0, 1, 0, dg, db, want_dres=True)
+    dbias = torch.ones(C, device="cuda")
+    if with_lens:
+        dy = dy.masked_fill(pad[..., None], float("nan"))
+    dx, dres = ops.ln_bwd(dy, x, res, g, mean, rstd, lens, 0.0, 1, 0, dg, db, want_dres=True, dbias=dbias)
+    assert torch.isfinite(dx.float()).all() and torch.isfinite(y.float()).all()
     assert rel_err(dx, pre.grad) < 5e-3
     assert rel_err(dg, gr.grad) < 2e-3 and rel_err(db, br.grad) < 2e-3
+    # dbias: column sums of dx accumulated on top of the existing contents
+    assert rel_err(dbias, dx.float().sum((0, 1)) + 1.0) < 2e-3
 
 
 @pytest.mark.parametrize("mode", [1, 2])
@@ -300,3 +310,52 @@ def test_fft_block_matches_oracle_and_zeroes_padding():
     assert out.dtype == torch.float32 and attn is None
     assert rel_err(out, ref) < 1.5e-2
     assert out[1, 12:].abs().sum() == 0
+
+
+def test_fft_block_ragged_long_batch_forward_and_gradients():
+    """Utterances much shorter than the padded length: whole GEMM / attention tiles of padded frames are
+    skipped.  Outputs, input gradient and every parameter gradient must still match the fp32 oracle."""
+    torch.manual_seed(11)
+    L = sub("transformer.Layers")
+    blk = L.FFTBlock(256, 2, 128, 128, 1024, [9, 1], dropout=0.0).cuda().train()
+    T = 300
+    lens = torch.tensor([300, 5, 140, 129], device="cuda")
+    B = lens.numel()
+    mask = torch.arange(T, device="cuda")[None, :] >= lens[:, None]
+    x = torch.randn(B, T, 256, device="cuda").masked_fill(mask[..., None], 0.0)
+    w = torch.randn(B, T, 256, device="cuda")
+    sd = {"layer_stack.0." + k: v.detach().clone().requires_grad_() for k, v in blk.state_dict().items()}
+    xr = x.clone().requires_grad_()
+    ref = fs2_oracle.fft_stack(sd, "", xr, mask, 1, 2)
+    (ref * w).sum().backward()
+    xc = x.clone().requires_grad_()
+    out, _ = blk(xc, mask=mask, slf_attn_mask=mask[:, None, :].expand(-1, T, -1))
+    (out * w).sum().backward()
+    assert torch.isfinite(out).all() and out[mask].abs().sum() == 0
+    assert rel_err(out, ref) < 1.5e-2
+    assert torch.isfinite(xc.grad).all() and xc.grad[mask].abs().sum() == 0
+    assert rel_err(xc.grad, xr.grad) < 5e-2 and cosine(xc.grad, xr.grad) > 0.995
+    for name, p in blk.named_parameters():
+        if name == "slf_attn.w_ks.bias":  # softmax is invariant to a key bias: the true gradient is 0
+            assert p.grad.abs().max() < 2e-2 * blk.slf_attn.w_qs.bias.grad.abs().max()
+            continue
+        g_ref = sd["layer_stack.0." + name].grad
+        assert torch.isfinite(p.grad).all(), name
+        assert cosine(p.grad, g_ref) > 0.995, (name, cosine(p.grad, g_ref))
+        assert abs(p.grad.norm().item() / g_ref.norm().item() - 1) < 5e-2, name
+
+
+def test_colsum_ragged_skips_padded_rows():
+    torch.manual_seed(12)
+    B, T, C = 5, 130, 1024
+    lens = torch.tensor([130, 0, 64, 65, 1], device="cuda")
+    pad = torch.arange(T, device="cuda")[None, :] >= lens[:, None]
+    x = torch.randn(B, T, C, device="cuda").to(BF16)
+    ref = x.float().masked_fill(pad[..., None], 0).sum((0, 1)) + 1.0
+    x = x.masked_fill(pad[..., None], float("nan"))  # never read
+    out = torch.ones(C, device="cuda")
+    ops.colsum(x.view(B * T, C), out, lens=lens, T=T)
+    assert rel_err(out, ref) < 1e-5
+    out3 = torch.ones(256, device="cuda")
+    ops.colsum(x.view(B * T, C), out3, col0=512, cols=256, lens=lens, T=T)
+    assert rel_err(out3, ref[512:768]) < 1e-5

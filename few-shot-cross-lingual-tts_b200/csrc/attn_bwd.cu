@@ -41,12 +41,13 @@ struct AttnBwdP {
 // D = rowsum(dO o O) per (b, head, q); one warp per (b, q) row, both heads
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-attn_bwd_prep_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ d_o, int B, int T,
-                     int H, float scale, float* __restrict__ dsum) {
+attn_bwd_prep_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ d_o,
+                     const int64_t* __restrict__ lens, int B, int T, int H, float scale, float* __restrict__ dsum) {
   const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= (long long)B * T) return;
   const int lane = threadIdx.x & 31;
   const int b = row / T, t = row - (long long)b * T;
+  if (t >= lens[b]) return;  // padded query: its D is never read (and dO may be unwritten there)
   const int HD = H * ab::DK;
   for (int h = 0; h < H; ++h) {
     float s = 0.f;
@@ -281,7 +282,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmKV,   // qkv, box 64 x
         const int qq = i * 64 + (tid & 63);
         float val;
         if (tid < 64) val = qq < p.T ? __ldg(lse2 + qq) : INFINITY;  // +inf => P = 0 (padded queries too)
-        else val = qq < p.T ? __ldg(dsum + qq) : 0.f;
+        else val = qq < len ? __ldg(dsum + qq) : 0.f;  // D of padded queries is not computed
         s_stat[s * 128 + tid] = val;
       }
       softmax_bar_sync_bwd();
@@ -546,8 +547,8 @@ int fs2_attn_bwd_bf16(const void* qkv, const void* o, const void* d_o, const flo
   const int C3 = 3 * H * dk, HD = H * dk;
   const long long rows = (long long)B * T;
   attn_bwd_prep_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, s>>>(static_cast<const __nv_bfloat16*>(o),
-                                                                 static_cast<const __nv_bfloat16*>(d_o), B, T, H,
-                                                                 1.f / sqrtf((float)dk), dsum);
+                                                                 static_cast<const __nv_bfloat16*>(d_o), lens, B, T,
+                                                                 H, 1.f / sqrtf((float)dk), dsum);
   count_launch();
   if (int rc = check_launch("attn_bwd_prep_kernel")) return rc;
   CUtensorMap tm128, tm64, tmdo128, tmdo64;

@@ -46,6 +46,7 @@ struct GemmKP {
   int unit_rows;   // rows per schedule unit: NORMAL BM (1-CTA) / 2*BM (CTA pair); WGRAD BK
   int units_max;   // units per entry when nothing is padded
   int row_extent;  // rows per entry (NORMAL: M, WGRAD: a.rows)
+  int tail_zero;   // NORMAL: rows zeroed behind the last scheduled tile (0 = all, < 0 = none)
 };
 
 constexpr int kMaxRaggedZ = 256;  // prefix table lives in the ~1.9 KiB of shared memory left by the smem ring
@@ -365,17 +366,20 @@ __device__ __forceinline__ void epilogue_tile(const GemmKP& p, const TileCoord& 
 // warps (256 threads, thread index `et`) of all CTAs before their first tile's accumulator is ready.
 template <int BN>
 __device__ __forceinline__ void zero_fill_padded(const GemmKP& p, const int* cum, int et, int cta, int ncta) {
+  if (p.tail_zero < 0) return;
   const int epv = p.d_f32 ? 4 : 8;
   for (int item = cta; item < p.sched_n * p.tiles_n; item += ncta) {
     const int z = item / p.tiles_n, tn = item - z * p.tiles_n;
     const int row0 = (cum[z] - (z ? cum[z - 1] : 0)) * p.unit_rows;
-    if (row0 >= p.M) continue;
+    int row1 = p.M;
+    if (p.tail_zero > 0 && row0 + p.tail_zero < row1) row1 = row0 + p.tail_zero;
+    if (row0 >= row1) continue;
     const int c0 = tn * BN, c1 = (c0 + BN < p.N) ? c0 + BN : p.N;
     const int vpr = (c1 - c0 + epv - 1) / epv;
     const long long base = (long long)(z / p.d_zdiv) * p.d_zdiv_stride + (long long)(z % p.d_zdiv) * p.d_zmod_stride;
-    const long long nvec = (long long)(p.M - row0) * vpr;
-    for (long long i = et; i < nvec; i += 256) {
-      const int r = (int)(i / vpr), v = (int)(i - (long long)r * vpr);
+    const int nvec = (row1 - row0) * vpr;  // < 2^31: one tile column of one utterance
+    for (int i = et; i < nvec; i += 256) {
+      const int r = i / vpr, v = i - r * vpr;
       const int col = c0 + v * epv;
       const long long off = base + (long long)(row0 + r) * p.ldd + col;
       if (col + epv <= c1) {

@@ -345,6 +345,7 @@ int gemm_fill_params(const fs2_gemm& g, GemmKP& kp) {
   if (g.row_lens) {
     kp.row_lens = reinterpret_cast<const long long*>(g.row_lens);
     kp.lens_zdiv = g.lens_zdiv > 0 ? g.lens_zdiv : 1;
+    kp.tail_zero = g.tail_zero_rows;
     if (g.mode == FS2_GEMM_NORMAL) {
       if (g.d_atomic) return set_error("gemm: row_lens and atomic outputs do not combine in NORMAL mode");
       kp.sched_n = kp.Z;

@@ -327,8 +327,8 @@ static int colsum_launch(const void* x, int64_t ld, int groups, int rows_per_gro
   if (groups <= 0 || rows_per_group <= 0) return 0;
   if ((ld % 8) || (C % 8) || C / 8 > 256 || (reinterpret_cast<uintptr_t>(x) & 15))
     return fs2::set_error("colsum: ld and C must be multiples of 8 (16-byte aligned rows), C <= 2048");
-  int rpb = (rows_per_group * groups + 148 * 4 - 1) / (148 * 4);
-  if (rpb < 64) rpb = 64;
+  int rpb = (rows_per_group * groups + 148 * 8 - 1) / (148 * 8);
+  if (rpb < 32) rpb = 32;
   dim3 grid((rows_per_group + rpb - 1) / rpb, groups);
   fs2::colsum_kernel<<<grid, 256, C * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __nv_bfloat16*>(x), ld, rows_per_group, C, rpb, out, lens, out_group_stride);

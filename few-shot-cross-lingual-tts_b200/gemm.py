@@ -44,11 +44,12 @@ def run(g, impl=None):
 
 def gemm(a, b, d, M, N, K, Z=1, taps=1, tap_shift0=0, b_tap_kstride=0, ldd=None, bias=None,
          epilogue=EPI_NONE, aux=None, ld_aux=0, aux_batch_stride=0, alpha=1.0, d_zdiv=1,
-         d_zdiv_stride=0, d_zmod_stride=0, impl=None, row_lens=None, lens_zdiv=1):
+         d_zdiv_stride=0, d_zmod_stride=0, impl=None, row_lens=None, lens_zdiv=1, tail_rows=0):
     """D[z] = epi(alpha * sum_tap A[z][m+shift+tap] . B[z][n][tap*kstride+k] + bias).
 
     row_lens (int64 [Z / lens_zdiv]): rows m >= row_lens of D[z] are written as zero and row tiles that
-    hold only such rows are skipped (padded frames of an utterance batch)."""
+    hold only such rows are skipped (padded frames of an utterance batch).  tail_rows: rows zeroed behind the
+    last scheduled row tile (0 = all: every element of D is defined; n > 0: an n-row halo; < 0: none)."""
     g = Gemm()
     g.a, g.b = a, b
     g.mode = GEMM_NORMAL
@@ -70,6 +71,7 @@ def gemm(a, b, d, M, N, K, Z=1, taps=1, tap_shift0=0, b_tap_kstride=0, ldd=None,
     g.aux = aux.data_ptr() if aux is not None else None
     g.ld_aux, g.aux_batch_stride = int(ld_aux), int(aux_batch_stride)
     _set_lens(g, row_lens, lens_zdiv)
+    g.tail_zero_rows = int(tail_rows)
     run(g, impl)
 
 

@@ -137,7 +137,11 @@ def _splits(m_out, n_out, taps, red_blocks):
 # [B, T, .] operand are padding that the sub-layer zeroes anyway (transformer/Layers.py:25,28) -- the GEMM
 # engine then skips the row tiles / reduction blocks that hold only such rows and writes zeros for them,
 # so padded frames cost (almost) nothing instead of ~40 % of a LibriTTS-shaped batch.
-def linear_fwd(x2d, w_bf, bias, out_dtype=BF16, relu=False, lens=None, T=None):
+# `tail`: how many rows behind the last scheduled tile are zeroed (fs2_gemm::tail_zero_rows).  Buffers that
+# stay inside a sub-layer and whose consumers skip padded rows themselves use NO_TAIL; tensors handed back
+# to autograd (dx) keep the default 0 = every element defined.
+NO_TAIL = -1
+def linear_fwd(x2d, w_bf, bias, out_dtype=BF16, relu=False, lens=None, T=None, tail=0):
     M, K = x2d.shape
     N = w_bf.shape[0]
     y = torch.empty(M, N, dtype=out_dtype, device=x2d.device)
@@ -147,11 +151,11 @@ def linear_fwd(x2d, w_bf, bias, out_dtype=BF16, relu=False, lens=None, T=None):
     else:  # one row-tile sequence per utterance so that whole tiles of padded frames can be skipped
         B = M // T
         G.gemm(G.operand(x2d, K, T, B), G.operand(w_bf, K, N), y, T, N, K, Z=B, bias=bias, epilogue=epi,
-               d_zdiv=1, d_zdiv_stride=T * N, row_lens=lens)
+               d_zdiv=1, d_zdiv_stride=T * N, row_lens=lens, tail_rows=tail)
     return y
 
 
-def linear_dgrad(dy2d, w_bf, epilogue=G.EPI_NONE, aux=None, lens=None, T=None):
+def linear_dgrad(dy2d, w_bf, epilogue=G.EPI_NONE, aux=None, lens=None, T=None, tail=0):
     """dx[M,K] = dy[M,N] @ W[N,K]  (W read as an MN-major B operand: no transposed copy)."""
     M, N = dy2d.shape
     K = w_bf.shape[1]
@@ -163,7 +167,7 @@ def linear_dgrad(dy2d, w_bf, epilogue=G.EPI_NONE, aux=None, lens=None, T=None):
         B = M // T
         G.gemm(G.operand(dy2d, N, T, B), G.operand(w_bf, K, N, mn_major=True), dx, T, K, N, Z=B,
                epilogue=epilogue, aux=aux, ld_aux=K, aux_batch_stride=T * K, d_zdiv=1, d_zdiv_stride=T * K,
-               row_lens=lens)
+               row_lens=lens, tail_rows=tail)
     return dx
 
 
@@ -213,17 +217,18 @@ def colsum(x2d, out, col0=0, cols=None, lens=None, T=None):
         _ck(_L().fs2_colsum_ragged_bf16(ptr, N, M // T, T, cols, _p(lens), _p(out), _st()), "colsum_ragged")
 
 
-def conv_fwd(x, wp, bias, relu=False, lens=None):
+def conv_fwd(x, wp, bias, relu=False, lens=None, tail=0):
     B, T, Ci = x.shape
     Co, k, cpad = wp.shape
     y = torch.empty(B, T, Co, dtype=BF16, device=x.device)
     G.gemm(G.operand(x, Ci, T, B), G.operand(wp, k * cpad, Co), y, T, Co, Ci, Z=B, taps=k,
            tap_shift0=-((k - 1) // 2), b_tap_kstride=cpad, bias=bias,
-           epilogue=G.EPI_RELU if relu else G.EPI_NONE, d_zdiv=1, d_zdiv_stride=T * Co, row_lens=lens)
+           epilogue=G.EPI_RELU if relu else G.EPI_NONE, d_zdiv=1, d_zdiv_stride=T * Co, row_lens=lens,
+           tail_rows=tail)
     return y
 
 
-def conv_dgrad(dy, wp, Ci, epilogue=G.EPI_NONE, aux=None, lens=None):
+def conv_dgrad(dy, wp, Ci, epilogue=G.EPI_NONE, aux=None, lens=None, tail=0):
     """Input gradient of the channels-last Conv1d: the same implicit GEMM with flipped taps, reading the
     forward-packed weights [Co][k][Cpad] as an MN-major operand (negative tap stride)."""
     B, T, Co = dy.shape
@@ -232,7 +237,7 @@ def conv_dgrad(dy, wp, Ci, epilogue=G.EPI_NONE, aux=None, lens=None):
     b = G.operand(wp, k * cpad, Co, mn_major=True, inner_base=(k - 1) * cpad)
     G.gemm(G.operand(dy, Co, T, B), b, dx, T, Ci, Co, Z=B, taps=k, tap_shift0=-((k - 1) // 2),
            b_tap_kstride=-cpad, epilogue=epilogue, aux=aux, ld_aux=Ci, aux_batch_stride=T * Ci,
-           d_zdiv=1, d_zdiv_stride=T * Ci, row_lens=lens)
+           d_zdiv=1, d_zdiv_stride=T * Ci, row_lens=lens, tail_rows=tail)
     return dx
 
 
@@ -375,7 +380,9 @@ class MHASublayer(torch.autograd.Function):
         fused = fused_attention_enabled(dk)
         # padded frames: skipped by the GEMMs when the sub-layer zeroes them anyway (fused path only)
         rl = lens if (zero_pad and fused) else None
-        qkv = linear_fwd(x2, wqkv, bqkv, lens=rl, T=T)  # [B*T, 3*HD], head h of Q = cols [h*dk, (h+1)*dk)
+        # [B*T, 3*HD], head h of Q = cols [h*dk, (h+1)*dk); the attention kernels never read a padded key /
+        # query tile, the LayerNorm never reads a padded row of `o`
+        qkv = linear_fwd(x2, wqkv, bqkv, lens=rl, T=T, tail=NO_TAIL)
         Tp = _roundup(T, 128)
         Z = B * H
         C3 = 3 * HD
@@ -383,7 +390,7 @@ class MHASublayer(torch.autograd.Function):
             attn3, lse2 = attn_fwd(qkv.view(B, T, C3), lens, H, dk)
             attn = attn3.view(B * T, HD)
             wo_bf = cast_bf16(wo)
-            o = linear_fwd(attn, wo_bf, bo.detach(), lens=rl, T=T)
+            o = linear_fwd(attn, wo_bf, bo.detach(), lens=rl, T=T, tail=NO_TAIL)
             salt = _Rng.next_salt()
             y, mean, rstd = ln_fwd(o.view(B, T, D), x, gamma.detach(), beta.detach(),
                                    lens if zero_pad else None, p_drop, 1, salt)
@@ -428,7 +435,7 @@ class MHASublayer(torch.autograd.Function):
                           salt, gbuf[8][0], gbuf[9][0], want_dres=True, dbias=gbuf[7][0])
         do2 = do.view(M, D)
         # output projection
-        dattn = linear_dgrad(do2, wo_bf, lens=rl, T=T)
+        dattn = linear_dgrad(do2, wo_bf, lens=rl, T=T, tail=NO_TAIL)
         linear_wgrad(do2, attn, gbuf[6][0], lens=rl, T=T)
         if fused:  # `P` slot of the saved tensors holds lse2; S / P / dS never touch HBM
             dqkv = attn_bwd(qkv.view(B, T, C3), attn.view(B, T, HD), dattn.view(B, T, HD), P, lens, H,
@@ -479,8 +486,9 @@ class FFNSublayer(torch.autograd.Function):
         x = x.contiguous()
         w1p, w2p = pack_conv(w1), pack_conv(w2)
         rl = lens if zero_pad else None  # padded frames are zeroed below: skip their GEMM tiles
-        h = conv_fwd(x, w1p, b1.detach(), relu=True, lens=rl)
-        f = conv_fwd(h, w2p, b2.detach(), lens=rl)
+        # h feeds w_2 (halo (k2-1)//2 rows), f feeds the LayerNorm (skips padded rows)
+        h = conv_fwd(x, w1p, b1.detach(), relu=True, lens=rl, tail=(w2p.shape[1] - 1) // 2 or NO_TAIL)
+        f = conv_fwd(h, w2p, b2.detach(), lens=rl, tail=NO_TAIL)
         salt = _Rng.next_salt()
         y, mean, rstd = ln_fwd(f, x, gamma.detach(), beta.detach(), lens if zero_pad else None, p_drop, 1,
                                salt)
@@ -501,7 +509,9 @@ class FFNSublayer(torch.autograd.Function):
         rl = lens if zero_pad else None
         df, dres = ln_bwd(dy, f, x, gamma_t, mean, rstd, rl, p_drop, 1, salt,
                           gbuf[4][0], gbuf[5][0], want_dres=True, dbias=gbuf[3][0])  # dbias: w_2.bias gradient
-        dh = conv_dgrad(df, w2p, Dh, epilogue=G.EPI_RELU_BWD, aux=h, lens=rl)
+        # dh feeds the input gradient of w_1, which reads a (k1-1)//2-row halo behind the last valid frame
+        dh = conv_dgrad(df, w2p, Dh, epilogue=G.EPI_RELU_BWD, aux=h, lens=rl,
+                        tail=(w1p.shape[1] - 1) // 2 or NO_TAIL)
         conv_wgrad(df, h, gbuf[2][0], lens=rl)
         dx = conv_dgrad(dh, w1p, D, epilogue=G.EPI_ADD_AUX, aux=dres, lens=rl)
         conv_wgrad(dh, x, gbuf[0][0], lens=rl)
@@ -816,7 +826,9 @@ class PostNetFn(torch.autograd.Function):
             gbb.add_(dstats[0])  # dbeta / dgamma come back as [2][C]; tiny adds
             gbw.add_(dstats[1])
             conv_wgrad(dy, x, gcw)
-            colsum(dy.view(M, Co), gcb)
+            # conv.bias: its gradient is sum_rows(dy), and the backward of a train-mode BatchNorm removes the
+            # per-channel batch mean of its output gradient -- the sum is identically zero (the reference's
+            # autograd produces rounding noise of ~1e-8 here).  Nothing to accumulate into `gcb`.
             d, d_is_f32 = conv_dgrad(dy, wp, x.shape[2]), 0
             grads[7 * i:7 * i + 4] = [rcw, rcb, rbw, rbb]
             grads_done((cw, cb, bw, bb))

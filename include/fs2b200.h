@@ -103,7 +103,12 @@ typedef struct fs2_gemm {
              blocks made only of such rows are skipped (split-K ranges are cut over the remaining blocks). */
   const int64_t* row_lens;
   int32_t lens_zdiv;
-  int32_t lens_pad;
+  /* NORMAL + row_lens: what happens to the rows of D[z] behind the last scheduled row tile (scheduling unit:
+     128 rows, or 256 when the 2-CTA kernel runs).  0: all of them are written as zero (every element of D is
+     defined); n > 0: only the first n are zeroed (enough for a consumer that reads an n-row halo, e.g. the
+     input-gradient of a Conv1d with kernel 2n+1), the rest of D is left untouched; n < 0: none is written
+     (consumers that skip padded rows themselves: LayerNorm, attention, row_lens GEMMs with k = 1). */
+  int32_t tail_zero_rows;
 } fs2_gemm;
 
 /* impl: 0 = tcgen05 (product path), 1 = plain CUDA-core kernel (debug cross-check only). */

@@ -293,3 +293,27 @@ def test_ragged_many_batches_falls_back_to_dense_schedule():
     valid = torch.arange(T, device="cuda")[None, :] < lens[:, None]
     ref = (x.float() @ w.float().t()) * valid[..., None]
     assert (y[~valid] == 0).all() and rel_err(y, ref) < 1e-2
+
+
+@pytest.mark.parametrize("tail", [-1, 4, 0])
+@pytest.mark.parametrize("T,N", [(700, 1024), (200, 256)])  # T >= 256: 2-CTA kernel (256-row units); else 128
+def test_ragged_tail_rows(tail, T, N):
+    """fs2_gemm::tail_zero_rows: rows behind the last scheduled row tile are zeroed completely (0), for an
+    n-row halo only (n > 0) or not at all (< 0); rows inside scheduled tiles are always defined."""
+    lens = [T, 1, 130, 0, 300][:5]
+    B, K = len(lens), 256
+    torch.manual_seed(tail + T)
+    x, w = rnd(B, T, K), rnd(N, K, scale=K ** -0.5)
+    y = torch.full((B, T, N), float("nan"), device="cuda", dtype=torch.bfloat16)
+    G.gemm(G.operand(x, K, T, B), G.operand(w, K, N), y, T, N, K, Z=B, d_zdiv=1, d_zdiv_stride=T * N,
+           row_lens=_lens(lens), tail_rows=tail)
+    ref = x.float() @ w.float().t()
+    unit = 256 if T >= 256 else 128
+    for b, ln in enumerate(lens):
+        ln = min(ln, T)
+        covered = min(-(-ln // unit) * unit, T)
+        assert rel_err(y[b, :ln], ref[b, :ln]) < 1e-2 if ln else True
+        assert (y[b, ln:covered] == 0).all()
+        z_end = T if tail == 0 else min(T, covered + max(tail, 0))
+        assert (y[b, covered:z_end] == 0).all()
+        assert torch.isnan(y[b, z_end:].float()).all()  # untouched

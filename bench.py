@@ -178,7 +178,8 @@ def flops_fwd_ragged(src_lens, mel_lens, Ts, Tm):
 
 
 def dominant_kernel_roofline(B, Tm, bf16_peak):
-    """gemm_tc_kernel<256,4> on its largest instance: the decoder's k=9 Conv1d (256 -> 1024) forward."""
+    """The step's dominant kernel on its largest instance: the decoder's k=9 Conv1d (256 -> 1024) forward,
+    dense (all 64 x 1000 rows), i.e. conv_tc2_kernel (2-CTA tiles + activation-halo reuse)."""
     import torch
 
     from fs2b200 import sub
@@ -193,6 +194,7 @@ def dominant_kernel_roofline(B, Tm, bf16_peak):
     ts = []
     for _ in range(10):
         flush.zero_()
+        torch.cuda._sleep(400000)  # the GPU spins while the host enqueues e0 / kernel / e1 (no launch gap timed)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         ops.conv_fwd(x, wp, bias, relu=True)
@@ -210,7 +212,7 @@ def dominant_kernel_roofline(B, Tm, bf16_peak):
         except Exception:
             pass
     return {"bound": "tensor", "achieved": ach, "peak": bf16_peak, "unit": "TFLOP/s", "frac": ach / bf16_peak,
-            "traffic": traffic, "kernel": "gemm_tc_kernel<256,4> decoder Conv1d k=9 256->1024 fwd (M=%d)" % (B * Tm),
+            "traffic": traffic, "kernel": "conv_tc2_kernel decoder Conv1d k=9 256->1024 fwd, dense (M=%d)" % (B * Tm),
             "avg_launch_ms": ms, "flops_per_launch": fl}
 
 

@@ -58,13 +58,21 @@ __global__ void __launch_bounds__(256) bn_stats_kernel(const BnArgs a) {
     for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.f;
     const long long r0 = (long long)blockIdx.x * a.rows_per_block;
     const long long r1 = min(r0 + a.rows_per_block, a.M);
-    for (long long r = r0 + ro; r < r1; r += rs) {
-      float f[8];
-      load_vec8(a.y + r * a.C + v * 8, f);
+    for (long long r = r0 + ro; r < r1; r += 4 * rs) {  // 4 independent 16-byte loads in flight per thread
+      bf16x8 t[4];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        s[j] += f[j];
-        q[j] += f[j] * f[j];
+      for (int u = 0; u < 4; ++u)
+        if (r + u * rs < r1) t[u] = ld8(a.y + (r + u * rs) * a.C + v * 8);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (r + u * rs >= r1) break;
+        float f[8];
+        unpack8(t[u], f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          s[j] += f[j];
+          q[j] += f[j] * f[j];
+        }
       }
     }
 #pragma unroll

@@ -380,6 +380,7 @@ int gemm_fill_params(const fs2_gemm& g, GemmKP& kp) {
 }
 
 int gemm_tc2_launch(const fs2_gemm& g, GemmKP& kp, cudaStream_t stream);  // gemm_tc2.cu (2-CTA tiles)
+int conv_tc2_launch(const fs2_gemm& g, GemmKP& kp, cudaStream_t stream);  // conv_tc2.cu (2-CTA + halo reuse)
 
 int gemm_tc_launch(const fs2_gemm& g, cudaStream_t stream) {
   GemmKP kp;
@@ -390,6 +391,10 @@ int gemm_tc_launch(const fs2_gemm& g, cudaStream_t stream) {
   const int pad256 = ((n + 255) / 256) * 256, pad128 = ((n + 127) / 128) * 128;
   const bool use128 = (n <= 128) || (pad128 * 100 < pad256 * 92);
   if (use128) return launch_tc<128, 6>(g, kp, stream);
+  // Conv1d (taps > 1, K-major activations): one activation tile with halo serves every tap, 2-CTA tiles
+  static const bool no_halo = getenv("FS2_CONV_NO_HALO") != nullptr;
+  if (!no_halo && g.mode == FS2_GEMM_NORMAL && g.taps > 1 && g.taps <= 16 && !g.a.mn_major && g.M > 128)
+    return conv_tc2_launch(g, kp, stream);
   // 256-row x 256-column tiles on CTA pairs (cta_group::2) when every pair has two real row tiles:
   // halves the shared-memory traffic per FLOP, which is what limits the 1-CTA 128x256 tile.
   static const bool no_2cta = getenv("FS2_GEMM_NO_2CTA") != nullptr;

@@ -84,33 +84,60 @@ lr_gather_kernel(const uint4* __restrict__ x, const int32_t* __restrict__ idx, i
 }
 
 // bf16 gather fused with "+ speaker row + sinusoid row" (decoder input of the fused forward).
+// One warp owns ONE frame index t for a group of kLrGroup utterances: the fp32 sinusoid row of t is read
+// once into registers and reused for every utterance of the group (it is 2x the bytes of the bf16 output
+// row), and four gathered rows are in flight per lane.
+constexpr int kLrGroup = 16;
 __global__ void __launch_bounds__(256)
 lr_gather_fused_kernel(const __nv_bfloat16* __restrict__ x, const int32_t* __restrict__ idx,
                        const float* __restrict__ spk, const float* __restrict__ pe, int B, int Ts,
                        int max_len, int out_len, int C, __nv_bfloat16* __restrict__ out) {
-  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (row >= (long long)B * out_len) return;
+  const int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (t >= out_len) return;
   const int lane = threadIdx.x & 31;
-  const int b = row / out_len, t = row - (long long)b * out_len;
-  const int i = idx[(long long)b * max_len + t];
+  const int b0 = blockIdx.y * kLrGroup;
+  const int b1 = min(b0 + kLrGroup, B);
   for (int c = lane * 8; c < C; c += 256) {
-    float f[8];
-    if (i >= 0) {
-      unpack8(ld8(x + ((long long)b * Ts + i) * C + c), f);
-    } else {
+    float p8[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) f[j] = 0.f;
-    }
-    if (spk) {
-      // the reference adds in two rounded steps (x + spk, then + pe), each in fp32
-#pragma unroll
-      for (int j = 0; j < 8; ++j) f[j] += spk[(long long)b * C + c + j];
-    }
+    for (int j = 0; j < 8; ++j) p8[j] = 0.f;
     if (pe) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) f[j] += pe[(long long)t * C + c + j];
+      const float4 p0 = *reinterpret_cast<const float4*>(pe + (long long)t * C + c);
+      const float4 p1 = *reinterpret_cast<const float4*>(pe + (long long)t * C + c + 4);
+      p8[0] = p0.x; p8[1] = p0.y; p8[2] = p0.z; p8[3] = p0.w; p8[4] = p1.x; p8[5] = p1.y; p8[6] = p1.z; p8[7] = p1.w;
     }
-    st8(out + row * C + c, pack8(f));
+    for (int bb = b0; bb < b1; bb += 4) {
+      int i[4];
+      bf16x8 xv[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) i[u] = bb + u < b1 ? idx[(long long)(bb + u) * max_len + t] : -1;
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (i[u] >= 0) xv[u] = ld8(x + ((long long)(bb + u) * Ts + i[u]) * C + c);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int b = bb + u;
+        if (b >= b1) break;
+        float f[8];
+        if (i[u] >= 0) {
+          unpack8(xv[u], f);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) f[j] = 0.f;
+        }
+        if (spk) {
+          // the reference adds in two rounded steps (x + spk, then + pe), each in fp32
+          const float4 s0 = *reinterpret_cast<const float4*>(spk + (long long)b * C + c);
+          const float4 s1 = *reinterpret_cast<const float4*>(spk + (long long)b * C + c + 4);
+          f[0] += s0.x; f[1] += s0.y; f[2] += s0.z; f[3] += s0.w; f[4] += s1.x; f[5] += s1.y; f[6] += s1.z; f[7] += s1.w;
+        }
+        if (pe) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) f[j] += p8[j];
+        }
+        st8(out + ((long long)b * out_len + t) * C + c, pack8(f));
+      }
+    }
   }
 }
 
@@ -197,8 +224,10 @@ int fs2_lr_gather_fused_bf16(const void* x, const int32_t* idx, const float* spk
   if (C % 8) return fs2::set_error("lr_gather_fused: C must be a multiple of 8");
   const long long rows = (long long)B * out_len;
   if (rows <= 0) return 0;
-  fs2::lr_gather_fused_kernel<<<(unsigned)((rows + 7) / 8), 256, 0,
-                                static_cast<cudaStream_t>(stream)>>>(
+  if ((reinterpret_cast<uintptr_t>(spk) & 15) || (reinterpret_cast<uintptr_t>(pe) & 15) || (C % 4))
+    return fs2::set_error("lr_gather_fused: spk / pe rows must be 16-byte aligned");
+  const dim3 grid((unsigned)((out_len + 7) / 8), (unsigned)((B + fs2::kLrGroup - 1) / fs2::kLrGroup));
+  fs2::lr_gather_fused_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __nv_bfloat16*>(x), idx, spk, pe, B, Ts, max_len, out_len, C,
       static_cast<__nv_bfloat16*>(out));
   fs2::count_launch();

@@ -18,6 +18,7 @@ def timeit(fn, iters=20):
     ts = []
     for _ in range(iters):
         flush.zero_()
+        torch.cuda._sleep(400000)  # no launch gap inside the timed window
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         fn()

@@ -110,24 +110,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const uint32_t tmem_base = *tmem_ptr_smem;
 
   const int pair_tiles_m = (p.tiles_m + 1) >> 1;
-  const int total_pair_tiles = sched_total(p, cum, pair_tiles_m * p.tiles_n * p.Z);
-  auto decode_pair = [&](int ptile) {
-    TileCoord t;
-    t.tn = ptile % p.tiles_n;
-    const int r = ptile / p.tiles_n;
-    int pm;
-    if (p.ragged) {
-      t.z = ragged_find(cum, p.sched_n, r);
-      pm = r - (t.z ? cum[t.z - 1] : 0);
-    } else {
-      pm = r % pair_tiles_m;
-      t.z = r / pair_tiles_m;
-    }
-    t.tm = 2 * pm + (int)rank;
-    t.nkb = p.num_kb;
-    t.kb0 = 0;
-    return t;
-  };
+  const int total_pair_tiles = pair_sched_total(p, cum, pair_tiles_m * p.tiles_n * p.Z);
+  auto decode_pair = [&](int ptile) { return decode_pair_normal(p, cum, ptile, (int)rank, pair_tiles_m); };
 
   if (warp == 0) {
     // ======================= TMA producer (both CTAs) =======================
@@ -274,7 +258,9 @@ int conv_tc2_launch(const fs2_gemm& g, GemmKP& kp, cudaStream_t stream) {
     return rc;
   kp.n_tiles_per_tap = (g.N + BN - 1) / BN;
   kp.tiles_n = kp.n_tiles_per_tap;
-  if (kp.row_lens) {  // schedule units are 256-row pair tiles
+  if (kp.pair_any) {
+    // units stay single 128-row tiles; pairs are formed across utterances
+  } else if (kp.row_lens) {  // schedule units are 256-row pair tiles
     kp.unit_rows = 2 * BM;
     kp.units_max = (kp.tiles_m + 1) / 2;
   }

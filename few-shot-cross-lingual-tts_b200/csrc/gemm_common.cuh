@@ -47,6 +47,8 @@ struct GemmKP {
   int units_max;   // units per entry when nothing is padded
   int row_extent;  // rows per entry (NORMAL: M, WGRAD: a.rows)
   int tail_zero;   // NORMAL: rows zeroed behind the last scheduled tile (0 = all, < 0 = none)
+  int pair_any;    // 2-CTA kernels, ragged NORMAL, shared (un-batched) B: the two CTAs of a pair take ANY two
+                   // consecutive 128-row tiles of the compact list, also from different utterances
 };
 
 constexpr int kMaxRaggedZ = 256;  // prefix table lives in the ~1.9 KiB of shared memory left by the smem ring
@@ -134,7 +136,43 @@ __device__ __forceinline__ void rb_next(const GemmKP& p, const int* cum, RbCurso
 
 struct TileCoord {
   int z, tm, tn, nkb, kb0;
+  int valid = 1;  // 0: filler half of an odd pair -- operands are loaded and multiplied, nothing is stored
 };
+
+// Tile of CTA `rank` of pair tile `ptile` in the 2-CTA kernels (NORMAL mode).
+__device__ __forceinline__ TileCoord decode_pair_normal(const GemmKP& p, const int* cum, int ptile, int rank,
+                                                        int pair_tiles_m) {
+  TileCoord t;
+  t.tn = ptile % p.tiles_n;
+  const int r = ptile / p.tiles_n;
+  if (p.pair_any) {  // compact list of 128-row tiles, two consecutive entries per pair
+    const int total = cum[p.sched_n - 1];
+    int idx = 2 * r + rank;
+    if (idx >= total) {
+      idx = 2 * r;
+      t.valid = 0;
+    }
+    t.z = ragged_find(cum, p.sched_n, idx);
+    t.tm = idx - (t.z ? cum[t.z - 1] : 0);
+  } else {
+    int pm;
+    if (p.ragged) {  // r-th 256-row pair tile that holds at least one valid row
+      t.z = ragged_find(cum, p.sched_n, r);
+      pm = r - (t.z ? cum[t.z - 1] : 0);
+    } else {
+      pm = r % pair_tiles_m;
+      t.z = r / pair_tiles_m;
+    }
+    t.tm = 2 * pm + rank;  // this CTA's 128-row tile of the pair tile
+  }
+  t.nkb = p.num_kb;
+  t.kb0 = 0;
+  return t;
+}
+__device__ __forceinline__ int pair_sched_total(const GemmKP& p, const int* cum, int dense) {
+  if (p.mode == FS2_GEMM_NORMAL && p.pair_any) return ((cum[p.sched_n - 1] + 1) >> 1) * p.tiles_n;
+  return sched_total(p, cum, dense);
+}
 
 __device__ __forceinline__ TileCoord decode_tile(const GemmKP& p, const int* cum, int tile) {
   TileCoord t;
@@ -337,7 +375,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmKP& p, const TileCoord& 
   }
   const uint32_t taddr = tmem_acc + (static_cast<uint32_t>(q * 32) << 16);
   const int m_w0 = t.tm * BM + q * 32;
-  const bool ok = t.nkb > 0;
+  const bool ok = t.nkb > 0 && t.valid;
   bool row_ok = true;
   if (p.row_lens && p.mode == FS2_GEMM_NORMAL) row_ok = (m_w0 + lane) < p.row_lens[t.z / p.lens_zdiv];
   if (p.d_atomic) {  // split-K weight gradients: coalesced 16-byte vector reductions

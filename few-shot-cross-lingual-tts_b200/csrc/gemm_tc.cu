@@ -359,6 +359,10 @@ int gemm_fill_params(const fs2_gemm& g, GemmKP& kp) {
       kp.row_extent = g.a.rows;
     }
     kp.ragged = kp.sched_n <= kMaxRaggedZ ? 1 : 0;  // larger batches: dense schedule, rows still zeroed
+    // 2-CTA kernels may team up row tiles of different utterances when both see the same B operand
+    static const bool no_pair_any = getenv("FS2_NO_PAIR_ANY") != nullptr;  // A/B switch (tools/)
+    kp.pair_any = (!no_pair_any && kp.ragged && g.mode == FS2_GEMM_NORMAL && g.b.batches <= 1 &&
+                   g.b.zmod_stride == 0) ? 1 : 0;
   }
   if (g.d_atomic && !g.d_f32) return set_error("atomic accumulation needs an f32 output");
   if (g.d_seg_rows > 0 && !(g.mode == FS2_GEMM_WGRAD && kp.d_col_stride == 1 && g.d_atomic))
@@ -393,7 +397,11 @@ int gemm_tc_launch(const fs2_gemm& g, cudaStream_t stream) {
   if (use128) return launch_tc<128, 6>(g, kp, stream);
   // Conv1d (taps > 1, K-major activations): one activation tile with halo serves every tap, 2-CTA tiles
   static const bool no_halo = getenv("FS2_CONV_NO_HALO") != nullptr;
-  if (!no_halo && g.mode == FS2_GEMM_NORMAL && g.taps > 1 && g.taps <= 16 && !g.a.mn_major && g.M > 128)
+  // (with a ragged schedule and shared weights the pair kernels team up ANY two row tiles, so even
+  //  utterances of a single 128-row tile fill both CTAs)
+  const bool pair_any = kp.pair_any != 0;
+  if (!no_halo && g.mode == FS2_GEMM_NORMAL && g.taps > 1 && g.taps <= 16 && !g.a.mn_major &&
+      (g.M > 128 || pair_any))
     return conv_tc2_launch(g, kp, stream);
   // 256-row x 256-column tiles on CTA pairs (cta_group::2) when every pair has two real row tiles:
   // halves the shared-memory traffic per FLOP, which is what limits the 1-CTA 128x256 tile.
@@ -401,7 +409,8 @@ int gemm_tc_launch(const fs2_gemm& g, cudaStream_t stream) {
   // measured (tools/bench_gemm.py, B200): +14 % on the k=9 weight gradient, +7 % on K=1024 GEMMs, +2 % on
   // 8192^3, but -5 % on the implicit-GEMM conv forward -> taps > 1 stay on the 1-CTA kernel.
   const int taps_ = g.taps > 0 ? g.taps : 1;
-  if (!no_2cta && g.M >= 256 && (g.mode == FS2_GEMM_WGRAD || taps_ == 1)) return gemm_tc2_launch(g, kp, stream);
+  if (!no_2cta && (g.M >= 256 || pair_any) && (g.mode == FS2_GEMM_WGRAD || taps_ == 1))
+    return gemm_tc2_launch(g, kp, stream);
   return launch_tc<256, 4>(g, kp, stream);
 }
 

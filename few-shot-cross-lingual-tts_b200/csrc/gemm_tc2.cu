@@ -94,28 +94,15 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 
   // A "pair tile" covers the 128-row tiles tm = 2*pm and 2*pm+1; this CTA works on tm = 2*pm + rank.
   const int pair_tiles_m = (p.tiles_m + 1) >> 1;
-  const int total_pair_tiles = sched_total(p, cum, pair_tiles_m * p.tiles_n * p.Z);
+  const int total_pair_tiles = pair_sched_total(p, cum, pair_tiles_m * p.tiles_n * p.Z);
   auto decode_pair = [&](int ptile) {
+    if (p.mode == FS2_GEMM_NORMAL) return decode_pair_normal(p, cum, ptile, (int)rank, pair_tiles_m);
     TileCoord t;
     t.tn = ptile % p.tiles_n;
     const int r = ptile / p.tiles_n;
-    if (p.mode == FS2_GEMM_NORMAL) {
-      int pm;
-      if (p.ragged) {  // r-th 256-row pair tile that holds at least one valid row
-        t.z = ragged_find(cum, p.sched_n, r);
-        pm = r - (t.z ? cum[t.z - 1] : 0);
-      } else {
-        pm = r % pair_tiles_m;
-        t.z = r / pair_tiles_m;
-      }
-      t.tm = 2 * pm + (int)rank;  // this CTA's 128-row tile of the pair tile
-      t.nkb = p.num_kb;
-      t.kb0 = 0;
-    } else {
-      t.tm = 2 * (r % pair_tiles_m) + (int)rank;
-      t.z = r / pair_tiles_m;  // split index
-      wgrad_range(p, cum, t.z, t.kb0, t.nkb);
-    }
+    t.tm = 2 * (r % pair_tiles_m) + (int)rank;
+    t.z = r / pair_tiles_m;  // split index
+    wgrad_range(p, cum, t.z, t.kb0, t.nkb);
     return t;
   };
 
@@ -268,7 +255,9 @@ int gemm_tc2_launch(const fs2_gemm& g, GemmKP& kp, cudaStream_t stream) {
                                  g.b.mn_major ? 64 : BN / 2))
     return rc;
   kp.n_tiles_per_tap = (g.N + BN - 1) / BN;
-  if (kp.row_lens && g.mode == FS2_GEMM_NORMAL) {  // schedule units are 256-row pair tiles
+  if (kp.pair_any) {
+    // units stay single 128-row tiles; pairs are formed across utterances
+  } else if (kp.row_lens && g.mode == FS2_GEMM_NORMAL) {  // schedule units are 256-row pair tiles
     kp.unit_rows = 2 * BM;
     kp.units_max = (kp.tiles_m + 1) / 2;
   }

@@ -1,2 +1,3 @@
 from .dp import GradBuckets
+from .optim import FusedAdam
 from .step import TrainStep

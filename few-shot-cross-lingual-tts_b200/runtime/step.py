@@ -16,8 +16,11 @@ _TENSOR_SLOTS = (2, 3, 4, 6, 7, 9, 10, 11, 12)
 
 
 class TrainStep:
-    def __init__(self, model, loss_fn, example_batch, use_graph=True, buckets=None, device=None):
+    def __init__(self, model, loss_fn, example_batch, use_graph=True, buckets=None, device=None, optimizer=None):
+        """optimizer: optional runtime.FusedAdam built on `buckets`; its clip + Adam + LR-schedule launches then
+        become part of the captured step."""
         self.model, self.loss_fn = model, loss_fn
+        self.optimizer = optimizer
         self.device = device or next(model.parameters()).device
         self.buckets = buckets or GradBuckets(model.parameters(), device=self.device)
         ops.set_grad_listener(self.buckets.notify)
@@ -45,6 +48,8 @@ class TrainStep:
         losses = self.loss_fn(tuple(b[:12]), out)
         losses[0].backward()
         self.buckets.finish()
+        if self.optimizer is not None:
+            self.optimizer.step()
         self.losses.copy_(torch.stack([l.detach() for l in losses]))
         self.buckets.reduce_scalars(self.losses)
         ops.advance_rng()

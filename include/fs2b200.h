@@ -244,6 +244,23 @@ int fs2_bn_bwd(const void* dout, int dout_is_f32, const void* y, const float* st
                const float* beta, int64_t M, int C, int act_tanh, float p_drop, uint64_t seed,
                const uint64_t* seed_dev, float* dstats, void* dy, void* stream);
 
+/* ------------------------------------------------------------------------------------------ */
+/* Fused gradient clipping + Adam + LR schedule on flat fp32 buffers:       */
+/*   clip  : pytorch_lightning gradient_clip_val (main.py:104-110) = clip_grad_norm_(max_norm, 2) */
+/*   Adam  : torch.optim.Adam(betas, eps, weight_decay)        (lightning/optimizer.py:5-16)      */
+/*   sched : LambdaLR sqrt_schedule (1) / const_schedule (2)   (lightning/scheduler.py:21-62)     */
+/* p, g, m, v: f32 [n] device (16-byte aligned, n % 4 == 0); gnorm_sq: f32 [1] device, sum of g^2 */
+/* (fs2_sumsq_f32 accumulates into it; zero it first); step: int64 [1] device = optimizer steps    */
+/* already taken.  anneal_steps is a HOST array of n_anneal <= 8 ints (copied into the launch).    */
+/* fs2_optim_advance: step += 1, *gnorm_out = sqrt(*gnorm_sq) (optional), *gnorm_sq = 0.           */
+/* ------------------------------------------------------------------------------------------ */
+int fs2_sumsq_f32(const float* g, int64_t n, float* out, void* stream);
+int fs2_adam_step_f32(float* p, const float* g, float* m, float* v, int64_t n, const float* gnorm_sq,
+                      const int64_t* step, float lr0, float beta1, float beta2, float eps, float weight_decay,
+                      float max_norm, int sched_type, int warmup, const int32_t* anneal_steps, int n_anneal,
+                      float anneal_rate, void* stream);
+int fs2_optim_advance(int64_t* step, float* gnorm_sq, float* gnorm_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,5 +1,5 @@
 """Micro-benchmark of the HBM-bound kernels on the C2 shapes (B=64, Ts=200, Tm=1000): CUDA events on the
-launching stream, L2 flushed before every launch, median of 9.  Prints achieved GB/s on the ALGORITHMIC
+launching stream, L2 flushed (512 MiB read sweep) before every launch, median of 9.  Prints achieved GB/s on the ALGORITHMIC
 bytes of each kernel against the measured copy bandwidth of MEASURED_PEAKS.json.
 
   python tools/bench_membound.py [--json profiles/membound_rNN.json]
@@ -27,7 +27,8 @@ def timeit(fn, iters=9):
     torch.cuda.synchronize()
     ts = []
     for _ in range(iters):
-        flush.zero_()
+        flush.sum()  # read-only sweep of 512 MiB: L2 ends up full of CLEAN lines (a write flush would make the
+        #              timed kernel pay for evicting ~126 MB of dirty lines, which is not its own traffic)
         torch.cuda._sleep(400000)  # keep the GPU busy while the host enqueues e0 / kernel / e1: no launch gap is timed
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -40,7 +41,7 @@ def timeit(fn, iters=9):
 
 
 def main():
-    timeit.flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    timeit.flush = torch.zeros(128 << 20, dtype=torch.float32, device="cuda")
     peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
     rows = []
 
@@ -49,6 +50,15 @@ def main():
         rows.append({"kernel": name, "us": round(us, 2), "algorithmic_MB": round(nbytes / 1e6, 2),
                      "GBps": round(gbs, 1), "frac_of_peak": round(gbs / peak, 3)})
         print("%-58s %8.1f us %8.1f MB %8.0f GB/s  %4.1f %%" % (name, us, nbytes / 1e6, gbs, 100 * gbs / peak))
+
+    # size-matched yardstick: a plain device copy moving the same ~100 MB / ~330 MB as the kernels below (the
+    # MEASURED_PEAKS figure is a 4 GiB copy; launch ramp and tail are a visible share of a 20-50 us kernel)
+    for mb in (98, 328):
+        src = torch.empty(mb * 500_000 // 2, dtype=torch.bfloat16, device="cuda")
+        dst = torch.empty_like(src)
+        us = timeit(lambda: dst.copy_(src))
+        rec("yardstick: torch copy_ moving %d MB in total" % mb, us, 2 * src.numel() * 2)
+    del src, dst
 
     B, T, C = 64, 1000, 256
     batch = synth.make_batch(**synth.CONFIGS["C2"])
@@ -141,7 +151,7 @@ def main():
     if "--json" in sys.argv:
         path = sys.argv[sys.argv.index("--json") + 1]
         json.dump({"peak_hbm_GBps": peak, "shapes": "C2: B=64, Ts=200, Tm=1000, valid mel frames %d" % valid,
-                   "method": "CUDA events, 256 MiB L2 flush before every launch, median of 9", "kernels": rows},
+                   "method": "CUDA events, 512 MiB read-sweep L2 flush before every launch, median of 9", "kernels": rows},
                   open(path, "w"), indent=1)
 
 

@@ -42,6 +42,51 @@ def _roundup(x, m):
 
 
 # --------------------------------------------------------------------------------------------------
+# side stream for weight gradients
+# --------------------------------------------------------------------------------------------------
+# In a backward pass the weight / bias gradients are leaves: nothing downstream waits for them, while the
+# input-gradient chain is serial.  They are issued on a second stream so that their CTAs fill the SMs the
+# input-gradient kernels leave idle (partial last waves of the persistent tile loops, kernel tails).  Every
+# backward Function joins the side stream before it returns (`join_side`), so tensors are never freed while the
+# side stream still reads them and `grads_done` only announces finished gradients.  Stream forks / joins are
+# captured as parallel branches of the step's CUDA graph.  FS2_OVERLAP=0 issues everything on one stream.
+import os as _os
+
+OVERLAP = _os.environ.get("FS2_OVERLAP", "1") != "0"
+_side_streams = {}
+
+
+class fork_side:
+    """`with fork_side():` -- run the enclosed launches on the side stream, after everything issued so far."""
+
+    def __enter__(self):
+        if not OVERLAP:
+            return self
+        cur = torch.cuda.current_stream()
+        dev = cur.device
+        side = _side_streams.get(dev)
+        if side is None:
+            side = _side_streams[dev] = torch.cuda.Stream(dev)
+        side.wait_stream(cur)
+        self._ctx = torch.cuda.stream(side)
+        self._ctx.__enter__()
+        return self
+
+    def __exit__(self, *exc):
+        if OVERLAP:
+            self._ctx.__exit__(*exc)
+        return False
+
+
+def join_side():
+    if OVERLAP:
+        cur = torch.cuda.current_stream()
+        side = _side_streams.get(cur.device)
+        if side is not None:
+            cur.wait_stream(side)
+
+
+# --------------------------------------------------------------------------------------------------
 # dropout RNG state: a device-resident step counter (CUDA-graph friendly) + per-call-site salts
 # --------------------------------------------------------------------------------------------------
 class _Rng:
@@ -435,14 +480,17 @@ class MHASublayer(torch.autograd.Function):
                           salt, gbuf[8][0], gbuf[9][0], want_dres=True, dbias=gbuf[7][0])
         do2 = do.view(M, D)
         # output projection
+        with fork_side():
+            linear_wgrad(do2, attn, gbuf[6][0], lens=rl, T=T)
         dattn = linear_dgrad(do2, wo_bf, lens=rl, T=T, tail=NO_TAIL)
-        linear_wgrad(do2, attn, gbuf[6][0], lens=rl, T=T)
         if fused:  # `P` slot of the saved tensors holds lse2; S / P / dS never touch HBM
             dqkv = attn_bwd(qkv.view(B, T, C3), attn.view(B, T, HD), dattn.view(B, T, HD), P, lens, H,
                             dk).view(M, C3)
             x2 = x.view(M, D)
+            with fork_side():
+                qkv_param_grads(dqkv, x2, gbuf, HD, lens=rl, T=T)
             dx = linear_dgrad(dqkv, wqkv, epilogue=G.EPI_ADD_AUX, aux=dres.view(M, D), lens=rl, T=T)
-            qkv_param_grads(dqkv, x2, gbuf, HD, lens=rl, T=T)
+            join_side()
             grads_done((wq, bq, wk, bk, wv, bv, wo, bo, gamma, beta))
             return (dx.view(B, T, D), None) + tuple(g[1] for g in gbuf) + (None, None, None)
         # attention core: dP = dO V^T ; dS = softmax'(P, dP) ; dQ = dS K ; dK = dS^T Q ; dV = P^T dO
@@ -469,6 +517,7 @@ class MHASublayer(torch.autograd.Function):
         x2 = x.view(M, D)
         dx = linear_dgrad(dqkv, wqkv, epilogue=G.EPI_ADD_AUX, aux=dres.view(M, D))
         qkv_param_grads(dqkv, x2, gbuf, HD)
+        join_side()
         grads_done((wq, bq, wk, bk, wv, bv, wo, bo, gamma, beta))
         return (dx.view(B, T, D), None) + tuple(g[1] for g in gbuf) + (None, None, None)
 
@@ -510,12 +559,15 @@ class FFNSublayer(torch.autograd.Function):
         df, dres = ln_bwd(dy, f, x, gamma_t, mean, rstd, rl, p_drop, 1, salt,
                           gbuf[4][0], gbuf[5][0], want_dres=True, dbias=gbuf[3][0])  # dbias: w_2.bias gradient
         # dh feeds the input gradient of w_1, which reads a (k1-1)//2-row halo behind the last valid frame
+        with fork_side():
+            conv_wgrad(df, h, gbuf[2][0], lens=rl)
         dh = conv_dgrad(df, w2p, Dh, epilogue=G.EPI_RELU_BWD, aux=h, lens=rl,
                         tail=(w1p.shape[1] - 1) // 2 or NO_TAIL)
-        conv_wgrad(df, h, gbuf[2][0], lens=rl)
+        with fork_side():
+            conv_wgrad(dh, x, gbuf[0][0], lens=rl)
+            colsum(dh.view(B * T, Dh), gbuf[1][0], lens=rl, T=T)
         dx = conv_dgrad(dh, w1p, D, epilogue=G.EPI_ADD_AUX, aux=dres, lens=rl)
-        conv_wgrad(dh, x, gbuf[0][0], lens=rl)
-        colsum(dh.view(B * T, Dh), gbuf[1][0], lens=rl, T=T)
+        join_side()
         grads_done((w1, b1, w2, b2, gamma, beta))
         return (dx, None) + tuple(g[1] for g in gbuf) + (None, None)
 
@@ -563,12 +615,15 @@ class VariancePredictorFn(torch.autograd.Function):
         # the conv bias gradients (column sums of da2 / da1) come out of the LayerNorm backward kernels
         da2, _ = ln_bwd(dn2, a2, None, g2t, m2, r2, None, p_drop, 2, s2, gbuf[6][0], gbuf[7][0],
                         want_dres=False, relu_x=True, dbias=gbuf[5][0])
+        with fork_side():
+            conv_wgrad(da2, n1, gbuf[4][0])
         dn1 = conv_dgrad(da2, c2p, n1.shape[2])
-        conv_wgrad(da2, n1, gbuf[4][0])
         da1, _ = ln_bwd(dn1, a1, None, g1t, m1, r1, None, p_drop, 2, s1, gbuf[2][0], gbuf[3][0],
                         want_dres=False, relu_x=True, dbias=gbuf[1][0])
+        with fork_side():
+            conv_wgrad(da1, x, gbuf[0][0])
         dx = conv_dgrad(da1, c1p, D)
-        conv_wgrad(da1, x, gbuf[0][0])
+        join_side()
         grads_done((c1w, c1b, g1, be1, c2w, c2b, g2, be2, lw, lb))
         return (dx, None) + tuple(g[1] for g in gbuf) + (None, None)
 
@@ -825,12 +880,14 @@ class PostNetFn(torch.autograd.Function):
             (gcw, rcw), (gcb, rcb), (gbw, rbw), (gbb, rbb) = (grad_target(t) for t in (cw, cb, bw, bb))
             gbb.add_(dstats[0])  # dbeta / dgamma come back as [2][C]; tiny adds
             gbw.add_(dstats[1])
-            conv_wgrad(dy, x, gcw)
+            with fork_side():
+                conv_wgrad(dy, x, gcw)
             # conv.bias: its gradient is sum_rows(dy), and the backward of a train-mode BatchNorm removes the
             # per-channel batch mean of its output gradient -- the sum is identically zero (the reference's
             # autograd produces rounding noise of ~1e-8 here).  Nothing to accumulate into `gcb`.
             d, d_is_f32 = conv_dgrad(dy, wp, x.shape[2]), 0
             grads[7 * i:7 * i + 4] = [rcw, rcb, rbw, rbb]
+            join_side()
             grads_done((cw, cb, bw, bb))
         dmel = torch.empty(B, T, n_mel, dtype=F32, device=dev)
         _ck(_L().fs2_add_f32_bf16(_p(dout), _p(d), dout.numel(), _p(dmel), _st()), "add_f32_bf16")

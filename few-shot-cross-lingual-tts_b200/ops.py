@@ -120,7 +120,106 @@ def advance_rng():
 # --------------------------------------------------------------------------------------------------
 # weight preparation and gradient buffers
 # --------------------------------------------------------------------------------------------------
+# --------------------------------------------------------------------------------------------------
+# per-step weight cache: all bf16 operand copies refreshed by ONE launch (csrc/weight_prep.cu)
+# --------------------------------------------------------------------------------------------------
+_wcache = None
+
+
+def set_weight_cache(cache):
+    """runtime.TrainStep installs a WeightCache that it refreshes at the start of every step; the operators
+    below then pick the cached bf16 copies instead of casting / packing per call."""
+    global _wcache
+    _wcache = cache
+
+
+def _cached(kind, param):
+    if _wcache is None:
+        return None
+    return _wcache.lookup(kind, param)
+
+
+class WeightCache:
+    """bf16 copies of every GEMM operand weight of `model` (+ the gathered Q|K|V biases) in persistent buffers,
+    refreshed from the fp32 master parameters by one multi-tensor kernel."""
+
+    def __init__(self, model):
+        import ctypes
+
+        from .transformer.SubLayers import MultiHeadAttention
+
+        self.map = {}
+        ents = []  # (src param, dst tensor, rows, ci, k, cpad, kind)
+        dev = next(model.parameters()).device
+
+        def add_pack(w, dst_rows=None, dst=None, row_off=0):
+            w3 = w if w.dim() == 3 else w.unsqueeze(-1)
+            Co, Ci, k = w3.shape
+            cpad = _roundup(Ci, 64) if w.dim() == 3 else Ci
+            if Ci * k > 4096 or (w.dim() == 2 and Ci % 8):
+                return None
+            if dst is None:
+                dst = torch.zeros((Co, k, cpad) if w.dim() == 3 else (Co, Ci), dtype=BF16, device=dev)
+            view = dst[row_off:row_off + Co]
+            ents.append((w, view, Co, Ci, k, cpad, 0))
+            return dst
+
+        in_mha = set()
+        for m in model.modules():
+            if isinstance(m, MultiHeadAttention):
+                HD, D = m.w_qs.weight.shape
+                if m.w_ks.weight.shape != (HD, D) or m.w_vs.weight.shape != (HD, D) or D % 8:
+                    continue
+                wqkv = torch.zeros(3 * HD, D, dtype=BF16, device=dev)
+                bqkv = torch.zeros(3 * HD, dtype=F32, device=dev)
+                for i, lin in enumerate((m.w_qs, m.w_ks, m.w_vs)):
+                    add_pack(lin.weight, dst=wqkv, row_off=i * HD)
+                    ents.append((lin.bias, bqkv[i * HD:(i + 1) * HD], 1, HD, 1, HD, 1))
+                    in_mha.add(id(lin))
+                self.map[("qkv", id(m.w_qs.weight))] = wqkv
+                self.map[("bqkv", id(m.w_qs.bias))] = bqkv
+        for m in model.modules():
+            if isinstance(m, torch.nn.Conv1d):
+                d = add_pack(m.weight)
+                if d is not None:
+                    self.map[("conv", id(m.weight))] = d
+            elif isinstance(m, torch.nn.Linear) and id(m) not in in_mha and m.weight.shape[0] > 1:
+                d = add_pack(m.weight)
+                if d is not None:
+                    self.map[("lin", id(m.weight))] = d
+        # device table (fs2_prep_entry): ptr, ptr, 6 x int32
+        self._keep = ents
+        rec = []
+        row0 = 0
+        for (w, dst, rows, ci, k, cpad, kind) in ents:
+            rec.append((w.data_ptr(), dst.data_ptr(), rows, ci, k, cpad, kind, row0))
+            row0 += rows
+        self.total_rows = row0
+        self.n = len(rec)
+        import struct
+
+        blob = b"".join(struct.pack("<QQiiiiii", *r) for r in rec)
+        self.table = torch.frombuffer(bytearray(blob), dtype=torch.uint8).to(dev)
+        self._src_ptrs = [w.data_ptr() for (w, *_rest) in ents]
+
+    def lookup(self, kind, param):
+        return self.map.get((kind, id(param)))
+
+    def refresh(self):
+        """One launch: every cached copy := current fp32 parameter values (stream-ordered)."""
+        if not torch.cuda.is_current_stream_capturing():
+            for (w, *_r), ptr in zip(self._keep, self._src_ptrs):
+                if w.data_ptr() != ptr:
+                    raise RuntimeError("WeightCache: a parameter was re-allocated after the cache was built "
+                                       "(build FusedAdam / move the model BEFORE TrainStep)")
+        _ck(_L().fs2_weight_prep(self.table.data_ptr(), self.n, self.total_rows, _st()), "weight_prep")
+
+
 def cast_bf16(w, out=None):
+    if out is None:
+        c = _cached("lin", w)
+        if c is not None:
+            return c
     w = w.detach()
     assert w.dtype == F32 and w.is_contiguous()
     if out is None:
@@ -137,6 +236,9 @@ def cast_f32(x):
 
 def pack_conv(w):
     """Conv1d.weight [Co, Ci, k] fp32 -> [Co, k, Cpad] bf16 (Cpad = Ci rounded up to 64, zero filled)."""
+    c = _cached("conv", w)
+    if c is not None:
+        return c
     w = w.detach()
     Co, Ci, k = w.shape
     cpad = _roundup(Ci, 64)
@@ -417,10 +519,12 @@ class MHASublayer(torch.autograd.Function):
         assert dk % 64 == 0 and wq.shape[0] == wk.shape[0] == wv.shape[0] and D % 8 == 0
         HD = H * dk
         dev = x.device
-        wqkv = torch.empty(3 * HD, D, dtype=BF16, device=dev)
-        for i, w in enumerate((wq, wk, wv)):
-            cast_bf16(w, wqkv[i * HD:(i + 1) * HD])
-        bqkv = torch.cat([bq.detach(), bk.detach(), bv.detach()])
+        wqkv, bqkv = _cached("qkv", wq), _cached("bqkv", bq)
+        if wqkv is None or bqkv is None:
+            wqkv = torch.empty(3 * HD, D, dtype=BF16, device=dev)
+            for i, w in enumerate((wq, wk, wv)):
+                cast_bf16(w, wqkv[i * HD:(i + 1) * HD])
+            bqkv = torch.cat([bq.detach(), bk.detach(), bv.detach()])
         x2 = x.view(B * T, D)
         fused = fused_attention_enabled(dk)
         # padded frames: skipped by the GEMMs when the sub-layer zeroes them anyway (fused path only)

@@ -24,6 +24,8 @@ class TrainStep:
         self.device = device or next(model.parameters()).device
         self.buckets = buckets or GradBuckets(model.parameters(), device=self.device)
         ops.set_grad_listener(self.buckets.notify)
+        # all bf16 operand copies of the weights are refreshed by one launch at the start of every step
+        self.wcache = ops.WeightCache(model)
         self.static = list(example_batch)
         self.host = {}
         for i in _TENSOR_SLOTS:
@@ -43,10 +45,15 @@ class TrainStep:
     # ---------------------------------------------------------------------------------------------
     def _body(self):
         b = self.static
-        self.buckets.zero()
-        out = self.model(b[2], b[3], *b[4:12], lang_args=b[12])
-        losses = self.loss_fn(tuple(b[:12]), out)
-        losses[0].backward()
+        self.wcache.refresh()
+        ops.set_weight_cache(self.wcache)  # valid for this step only: the copies were just refreshed
+        try:
+            self.buckets.zero()
+            out = self.model(b[2], b[3], *b[4:12], lang_args=b[12])
+            losses = self.loss_fn(tuple(b[:12]), out)
+            losses[0].backward()
+        finally:
+            ops.set_weight_cache(None)
         self.buckets.finish()
         if self.optimizer is not None:
             self.optimizer.step()

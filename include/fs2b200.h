@@ -245,6 +245,20 @@ int fs2_bn_bwd(const void* dout, int dout_is_f32, const void* y, const float* st
                const uint64_t* seed_dev, float* dstats, void* dy, void* stream);
 
 /* ------------------------------------------------------------------------------------------ */
+/* Multi-tensor weight refresh: every bf16 operand copy of the fp32 master weights in ONE launch */
+/* (nn.Linear: cast; nn.Conv1d [Co][Ci][k] -> packed [Co][k][Cpad], as fs2_pack_conv_weight;     */
+/* kind 1: plain f32 copy, used to gather the Q|K|V biases).  `table` is a DEVICE array.          */
+/* ------------------------------------------------------------------------------------------ */
+typedef struct fs2_prep_entry {
+  const float* src;  /* f32 [rows][ci][k] */
+  void* dst;         /* kind 0: bf16 [rows][k][cpad]; kind 1: f32 [rows][ci*k] */
+  int32_t rows, ci, k, cpad;
+  int32_t kind;
+  int32_t row0;      /* sum of `rows` of the entries before this one */
+} fs2_prep_entry;
+int fs2_weight_prep(const void* table, int n_entries, int total_rows, void* stream);
+
+/* ------------------------------------------------------------------------------------------ */
 /* Fused gradient clipping + Adam + LR schedule on flat fp32 buffers:       */
 /*   clip  : pytorch_lightning gradient_clip_val (main.py:104-110) = clip_grad_norm_(max_norm, 2) */
 /*   Adam  : torch.optim.Adam(betas, eps, weight_decay)        (lightning/optimizer.py:5-16)      */

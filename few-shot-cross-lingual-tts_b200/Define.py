@@ -14,6 +14,11 @@ import torch
 
 DEBUG = False
 NOLID = False
+# SSL upstream of the few-shot systems (Define.py:28-48): feature width, number of layers, selected layer
+UPSTREAM = "hubert_large_ll60k"
+UPSTREAM_DIM = 1024
+UPSTREAM_LAYER = 25
+LAYER_IDX = None
 DEVICE = torch.device("cuda" if torch.cuda.is_available() else "cpu")
 ALLSTATS = {
     "global": [56.88630676269531, 953.1358032226562, 186.0852184530204, 46.16604905177577,

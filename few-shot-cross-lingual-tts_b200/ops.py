@@ -911,6 +911,41 @@ class LinearF32Out(torch.autograd.Function):
         return dx.view(B, T, D), rw, rb
 
 
+class LinearFn(torch.autograd.Function):
+    """nn.Linear on channels-last activations with a bf16 result -- the `embedding` of the ADA encoder
+    (lightning/model/ada_encoder.py:18,22-23) and any other stand-alone projection on the path."""
+
+    @staticmethod
+    def forward(ctx, x, w, b):
+        B, T, K = x.shape
+        x = x.contiguous()
+        assert x.dtype == BF16 and K % 8 == 0, "Linear input: bf16 with a multiple of 8 features"
+        w_bf = cast_bf16(w)
+        y = linear_fwd(x.view(B * T, K), w_bf, None if b is None else b.detach())
+        ctx.save_for_backward(x, w_bf)
+        ctx.params = (w, b)
+        return y.view(B, T, -1)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w_bf = ctx.saved_tensors
+        w, b = ctx.params
+        B, T, K = x.shape
+        N = w.shape[0]
+        dy2 = _contig(dy).view(B * T, N)
+        gw, rw = grad_target(w)
+        with fork_side():
+            linear_wgrad(dy2, x.view(B * T, K), gw)
+            rb = None
+            if b is not None:
+                gb, rb = grad_target(b)
+                colsum(dy2, gb)
+        dx = linear_dgrad(dy2, w_bf).view(B, T, K) if ctx.needs_input_grad[0] else None
+        join_side()
+        grads_done((w,) if b is None else (w, b))
+        return dx, rw, rb
+
+
 class PostNetFn(torch.autograd.Function):
     """postnet(mel) + mel: 5 x [Conv1d k5 -> BatchNorm1d -> tanh (not last) -> dropout 0.5]
     -- transformer/Layers.py:67-137, fastspeech2m.py:145.  Batch statistics include padded frames."""
@@ -996,6 +1031,81 @@ class PostNetFn(torch.autograd.Function):
         dmel = torch.empty(B, T, n_mel, dtype=F32, device=dev)
         _ck(_L().fs2_add_f32_bf16(_p(dout), _p(d), dout.numel(), _p(dmel), _st()), "add_f32_bf16")
         return (dmel, None, None, None) + tuple(grads)
+
+
+# --------------------------------------------------------------------------------------------------
+# few-shot phoneme-embedding front-end
+# --------------------------------------------------------------------------------------------------
+class CodebookAttnFn(torch.autograd.Function):
+    """SoftMultiAttCodebook2.forward (lightning/systems/language/embeddings.py:109-142): layer-weighted sum of the
+    SSL features -> q_linear -> H-head attention over the codebook.  ref: fp32 [rows, n_layer, D] (or [rows, D] with
+    w_raw None), never differentiated (the upstream is frozen).  Returns fp32 [rows, E]."""
+
+    @staticmethod
+    def forward(ctx, ref, w_raw, wq, bq, att_banks, emb_banks, n_head, temperature):
+        ref = ref.contiguous().to(F32)
+        rows = ref.shape[0]
+        n_layer = ref.shape[1] if ref.dim() == 3 else 1
+        D = ref.shape[-1]
+        C, E = att_banks.shape
+        assert D % 8 == 0 and wq.shape == (E, D)
+        dev = ref.device
+        x = torch.empty(rows, D, dtype=BF16, device=dev)
+        _ck(_L().fs2_layer_weighted_sum_bf16(_p(ref), _p(None if w_raw is None else w_raw.detach().reshape(-1).contiguous()),
+                                             rows, n_layer, D, _p(x), _st()), "layer_weighted_sum")
+        wq_bf = cast_bf16(wq)
+        q = linear_fwd(x, wq_bf, bq.detach(), out_dtype=F32)
+        out = torch.empty(rows, E, dtype=F32, device=dev)
+        p = torch.empty(rows, n_head, C, dtype=F32, device=dev)
+        att, emb = att_banks.detach().contiguous(), emb_banks.detach().contiguous()
+        _ck(_L().fs2_codebook_attn_fwd_f32(_p(q), _p(att), _p(emb), rows, C, E, n_head, 1.0 / temperature, _p(out),
+                                           _p(p), _st()), "codebook_attn_fwd")
+        ctx.save_for_backward(x, q, p, att, emb)
+        ctx.params = (wq, bq, att_banks, emb_banks)
+        ctx.cfg = (n_head, temperature)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, q, p, att, emb = ctx.saved_tensors
+        wq, bq, att_banks, emb_banks = ctx.params
+        n_head, temperature = ctx.cfg
+        rows, E = q.shape
+        C = att.shape[0]
+        dout = _contig(dout.to(F32))
+        (gw, rw), (gb, rb), (ga, ra), (ge, re_) = (grad_target(t) for t in (wq, bq, att_banks, emb_banks))
+        dq = torch.empty_like(q)
+        _ck(_L().fs2_codebook_attn_bwd_f32(_p(dout), _p(q), _p(att), _p(emb), _p(p), rows, C, E, n_head,
+                                           1.0 / temperature, _p(dq), _p(ga), _p(ge), _st()), "codebook_attn_bwd")
+        dq_bf = torch.empty(rows, E, dtype=BF16, device=q.device)
+        _ck(_L().fs2_cast_f32_bf16(_p(dq), dq.numel(), _p(dq_bf), _st()), "cast(dq)")
+        linear_wgrad(dq_bf, x, gw)
+        _ck(_L().fs2_colsum_f32(_p(dq), E, rows, E, _p(gb), _st()), "colsum_f32(dq)")
+        grads_done((wq, bq, att_banks, emb_banks))
+        return None, None, rw, rb, ra, re_, None, None
+
+
+def phoneme_class_mean(representations, avg_frames, n_symbols, phonemes, two_stage=True):
+    """PhonemeQueryExtractor(mode="average") (lightning/model/reduction.py:42-110) on the device: returns fp32
+    [n_symbols, *dims].  representations: list of [T_i, *dims] CUDA tensors; avg_frames / phonemes: lists of int lists."""
+    dims = tuple(representations[0].shape[1:])
+    D = 1
+    for d in dims:
+        D *= d
+    dev = representations[0].device
+    table = torch.zeros(n_symbols, D, dtype=F32, device=dev)
+    count = torch.zeros(n_symbols, dtype=F32, device=dev)
+    for rep, d_list, ph in zip(representations, avg_frames, phonemes):
+        L = min(len(d_list), len(ph))
+        if L == 0:
+            continue
+        x = rep.detach().to(F32).contiguous().view(rep.shape[0], D)
+        dur = torch.as_tensor([int(v) for v in d_list[:L]], dtype=torch.int64).to(dev, non_blocking=True)
+        cls = torch.as_tensor([int(v) for v in ph[:L]], dtype=torch.int64).to(dev, non_blocking=True)
+        _ck(_L().fs2_segment_class_accum_f32(_p(x), _p(dur), _p(cls), L, x.shape[0], D, n_symbols,
+                                             1 if two_stage else 0, _p(table), _p(count), _st()), "segment_class_accum")
+    _ck(_L().fs2_class_mean_finalize_f32(_p(table), _p(count), n_symbols, D, _st()), "class_mean_finalize")
+    return table.view((n_symbols,) + dims)
 
 
 # --------------------------------------------------------------------------------------------------

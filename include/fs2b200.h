@@ -245,6 +245,28 @@ int fs2_bn_bwd(const void* dout, int dout_is_f32, const void* y, const float* st
                const uint64_t* seed_dev, float* dstats, void* dy, void* stream);
 
 /* ------------------------------------------------------------------------------------------ */
+/* Phoneme-embedding front-end of the few-shot systems                      */
+/*  - PhonemeQueryExtractor "average" (lightning/model/reduction.py:42-110): per utterance,       */
+/*    table_sum[cls[i]] += mean (two_stage) or sum of the frames of segment i; x: f32 [T][D],     */
+/*    dur / cls: int64 [L] device; count[c] += 1 (two_stage) or #frames; then finalize = sum/count */
+/*  - SoftMultiAttCodebook2 (lightning/systems/language/embeddings.py:77-142): layer-weighted sum */
+/*    (softmax(w_raw) over n_layer, NaN -> 0; w_raw NULL = plain cast of [rows][1][D]), then       */
+/*    multi-head attention of q [rows][E] over att_banks / emb_banks [C][E] with H heads           */
+/*    (transformer/Modules.py:28-47); p: f32 [rows][H][C] saved for the backward; d_att / d_emb    */
+/*    are accumulated with atomics (zero them first).                                             */
+/* ------------------------------------------------------------------------------------------ */
+int fs2_segment_class_accum_f32(const float* x, const int64_t* dur, const int64_t* cls, int L, int64_t T, int64_t D,
+                                int n_classes, int two_stage, float* table_sum, float* count, void* stream);
+int fs2_class_mean_finalize_f32(float* table, const float* count, int n_classes, int64_t D, void* stream);
+int fs2_layer_weighted_sum_bf16(const float* ref, const float* w_raw, int64_t rows, int n_layer, int D, void* out,
+                                void* stream);
+int fs2_codebook_attn_fwd_f32(const float* q, const float* att_banks, const float* emb_banks, int rows, int C, int E,
+                              int H, float inv_temp, float* out, float* p, void* stream);
+int fs2_codebook_attn_bwd_f32(const float* dout, const float* q, const float* att_banks, const float* emb_banks,
+                              const float* p, int rows, int C, int E, int H, float inv_temp, float* dq, float* d_att,
+                              float* d_emb, void* stream);
+
+/* ------------------------------------------------------------------------------------------ */
 /* Multi-tensor weight refresh: every bf16 operand copy of the fp32 master weights in ONE launch */
 /* (nn.Linear: cast; nn.Conv1d [Co][Ci][k] -> packed [Co][k][Cpad], as fs2_pack_conv_weight;     */
 /* kind 1: plain f32 copy, used to gather the Q|K|V biases).  `table` is a DEVICE array.          */

@@ -166,3 +166,35 @@ def test_inference_path_predicted_durations_and_eval_batchnorm():
     assert torch.isfinite(mel).all() and torch.isfinite(post).all()
     # padded phonemes predict nothing
     assert (p_pred * src_masks).abs().sum() == 0 and (log_d * src_masks).abs().sum() == 0
+
+
+def test_ada_encoder_matches_reference_composition():
+    """ADAEncoder (lightning/model/ada_encoder.py:11-25): Linear(80 -> 256) on mel frames + Encoder2, forward and
+    gradients against fp32 torch / oracle FFT blocks; state_dict keys as in the reference."""
+    ADA = sub("lightning.model.ada_encoder").ADAEncoder
+    cfg = synth.model_cfg(encoder_layer=2)
+    torch.manual_seed(4)
+    ada = disable_dropout(ADA(80, cfg).cuda().train())
+    keys = set(ada.state_dict().keys())
+    assert {"embedding.weight", "embedding.bias", "encoder.position_enc",
+            "encoder.layer_stack.1.pos_ffn.w_1.weight"} <= keys
+    B, T = 3, 150
+    lens = torch.tensor([150, 64, 129], device="cuda")
+    mel = torch.randn(B, T, 80, device="cuda")
+    w = torch.randn(B, T, 256, device="cuda")
+    out = ada(mel, lens)
+    assert out.dtype == torch.float32 and out.shape == (B, T, 256)
+    (out * w).sum().backward()
+    # fp32 reference
+    sd = {k: v.detach().clone().requires_grad_(v.is_floating_point() and "position_enc" not in k)
+          for k, v in ada.state_dict().items()}
+    mask = torch.arange(T, device="cuda")[None, :] >= lens[:, None]
+    x = torch.nn.functional.linear(mel, sd["embedding.weight"], sd["embedding.bias"]) + \
+        sd["encoder.position_enc"][:, :T]
+    enc_sd = {k[len("encoder."):]: v for k, v in sd.items() if k.startswith("encoder.")}
+    ref = fs2_oracle.fft_stack(enc_sd, "", x, mask, 2, cfg["transformer"]["encoder_head"])
+    (ref * w).sum().backward()
+    assert rel_err(out, ref) <= 3e-2 and out[mask].abs().sum() == 0
+    for k in ("embedding.weight", "embedding.bias", "encoder.layer_stack.0.pos_ffn.w_1.weight"):
+        g, r = dict(ada.named_parameters())[k].grad, sd[k].grad
+        assert cosine(g, r) >= 0.99 and abs(float(g.norm() / r.norm()) - 1) < 5e-2, (k, cosine(g, r))

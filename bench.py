@@ -8,8 +8,9 @@ Workload (BASELINE.json configs[1], SURVEY.md 8d "C2"): LibriTTS-shaped multi-sp
 utterances PER GPU (weak scaling), src_len ~ U{20..200}, durations ~ U{1..11}, mel clipped to 1000
 frames, bf16 operands / fp32 accumulation, dropout ON, train-mode BatchNorm, synthetic data and
 seeded random-init weights.  `value` times graph replays with inputs resident in HBM; `e2e` times the
-public TrainStep.step_e2e() call (pinned-host -> device copy of the batch, step, device -> host read
-of the six losses).  One JSON line on stdout (rank 0).
+public TrainStep calls a training loop makes every step: run() on the batch prefetched during the previous
+step, prefetch_batch() of the next one (pinned host -> device on a copy stream, overlapping the step), and
+read_losses() (device -> host read of the six losses, synchronising).  One JSON line on stdout (rank 0).
 """
 import argparse
 import json
@@ -339,10 +340,13 @@ def run_ours(args):
     dbg("timed loop done %.2f ms" % dev_ms)
 
     def e2e_iter(i):
-        load(i)
+        # public API, one training step: run on the batch prefetched during the previous step, start the
+        # pinned-host -> device copy of the next batch (overlaps this step), read this step's six losses back
         step.run()
+        step.prefetch_batch(pinned=variants[(i + 1) % 3])
         step.read_losses()
 
+    step.prefetch_batch(pinned=variants[0])
     for i in range(2):
         e2e_iter(i)
     e2e_ms, e2e_wall = timed(e2e_iter, args.steps)

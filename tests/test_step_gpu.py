@@ -66,3 +66,27 @@ def test_train_step_with_fused_adam_learns_and_counts_steps():
     assert not torch.equal(model.mel_linear.weight.detach(), w0)
     assert last < 0.9 * first, (first, last)  # same batch every step: the loss must go down
     assert float(opt.grad_norm) > 0
+
+
+def test_prefetched_batches_are_the_ones_that_run():
+    """prefetch_batch() stages the NEXT batch on a copy stream; run() must consume exactly that batch."""
+    rt = sub("runtime")
+    b1 = synth.make_batch(B=4, src_len=(10, 40), dur=synth.uniform_dur(1, 8), seed=31)
+    model, loss_fn, _ = _build()
+    step = rt.TrainStep(model, loss_fn, b1, use_graph=True)
+    ref1 = step.step_e2e(b1).clone()
+    # same padded shape, different contents: permute the utterances and perturb the mel targets
+    perm = torch.tensor([2, 0, 3, 1])
+    b2 = list(b1)
+    for i in (2, 3, 4, 6, 7, 9, 10, 11, 12):
+        b2[i] = b1[i][perm].clone()
+    b2[6] = b2[6] + 0.5
+    ref2 = step.step_e2e(tuple(b2)).clone()
+    assert abs(float(ref2[1]) - float(ref1[1])) > 1e-3  # the mel loss moved
+    step.prefetch_batch(b1)
+    step.run()
+    got1 = step.read_losses().clone()
+    step.prefetch_batch(tuple(b2))
+    step.run()
+    got2 = step.read_losses().clone()
+    assert torch.allclose(got1, ref1, rtol=1e-4) and torch.allclose(got2, ref2, rtol=1e-4)

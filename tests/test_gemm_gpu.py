@@ -317,3 +317,37 @@ def test_ragged_tail_rows(tail, T, N):
         z_end = T if tail == 0 else min(T, covered + max(tail, 0))
         assert (y[b, covered:z_end] == 0).all()
         assert torch.isnan(y[b, z_end:].float()).all()  # untouched
+
+
+@pytest.mark.parametrize("case", ["ragged_conv", "ragged_linear", "dense_conv", "wgrad"])
+def test_outputs_stay_inside_their_buffer(case):
+    """Guard bands around the output: no kernel of the engine may write a byte outside D (compute-sanitizer is not
+    available on the test pool, so the bounds are checked with sentinels)."""
+    torch.manual_seed(17)
+    B, T, Cin, Cout, k = 5, 333, 256, 512, 5
+    lens = _lens([333, 0, 130, 257, 64])
+    x = rnd(B, T, Cin)
+    guard = 4096
+    if case == "wgrad":
+        dy = rnd(B, T, Cout)
+        buf = torch.full((guard + Cout * k * Cin + guard,), 7.0, device="cuda")
+        dw = buf[guard:guard + Cout * k * Cin].view(Cout, k, Cin)
+        dw.zero_()
+        G.wgrad(G.operand(dy, Cout, T, B, mn_major=True), G.operand(x, Cin, T, B, mn_major=True), dw, Cout, Cin,
+                taps=k, tap_shift0=-2, ldd=Cin * k, d_col_stride=1, d_tap_stride=Cin, splits=3, row_lens=lens)
+        assert torch.isfinite(dw).all()
+    else:
+        n = B * T * Cout
+        buf = torch.full((guard + n + guard,), 7.0, device="cuda", dtype=torch.bfloat16)
+        y = buf[guard:guard + n].view(B, T, Cout)
+        if case == "ragged_linear":
+            w = rnd(Cout, Cin)
+            G.gemm(G.operand(x, Cin, T, B), G.operand(w, Cin, Cout), y, T, Cout, Cin, Z=B, d_zdiv=1,
+                   d_zdiv_stride=T * Cout, row_lens=lens, tail_rows=3)
+        else:
+            wp = rnd(Cout, k * Cin)
+            G.gemm(G.operand(x, Cin, T, B), G.operand(wp, k * Cin, Cout), y, T, Cout, Cin, Z=B, taps=k, tap_shift0=-2,
+                   b_tap_kstride=Cin, d_zdiv=1, d_zdiv_stride=T * Cout,
+                   row_lens=lens if case == "ragged_conv" else None)
+    torch.cuda.synchronize()
+    assert (buf[:guard] == 7.0).all() and (buf[-guard:] == 7.0).all()

@@ -398,3 +398,47 @@ int fs2_rowdot_bwd(const float* dout, const void* x, const float* w, const int64
   return fs2::check_launch("rowdot_bwd_kernel");
 }
 }
+
+// ------------------------------------------------------------------------------------------------
+// Device-side collate: dst[b][t][:] = t < len_b ? src[offsets[b] + t][:] : 0 for ragged rows
+// concatenated in `src` -- the pad_1D / pad_2D of the reference's host collate (lightning/utils/tool.py:134-165,
+// lightning/collates/utils.py:8-85) done after ONE host -> device copy of the un-padded bytes.
+// ------------------------------------------------------------------------------------------------
+namespace fs2 {
+template <typename V>
+__global__ void __launch_bounds__(256)
+pad_ragged_kernel(const V* __restrict__ src, const long long* __restrict__ offsets, int B, int max_len, int vec_per_row,
+                  V* __restrict__ dst) {
+  const long long n = (long long)B * max_len * vec_per_row;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int v = i % vec_per_row;
+    const long long row = i / vec_per_row;
+    const int t = row % max_len;
+    const int b = row / max_len;
+    const long long o0 = offsets[b], len = offsets[b + 1] - o0;
+    V val = V();
+    if (t < len) val = src[(o0 + t) * vec_per_row + v];
+    dst[i] = val;
+  }
+}
+}  // namespace fs2
+
+extern "C" int fs2_pad_ragged(const void* src, const int64_t* offsets, int B, int max_len, int row_bytes, void* dst,
+                              void* stream) {
+  if (B <= 0 || max_len <= 0) return 0;
+  if (row_bytes <= 0 || row_bytes % 4) return fs2::set_error("pad_ragged: row bytes must be a positive multiple of 4");
+  const bool v16 = row_bytes % 16 == 0 && !(reinterpret_cast<uintptr_t>(src) & 15) && !(reinterpret_cast<uintptr_t>(dst) & 15);
+  const long long n = (long long)B * max_len * (row_bytes / (v16 ? 16 : 4));
+  const unsigned grid = fs2::grid_for(n, 256);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (v16)
+    fs2::pad_ragged_kernel<uint4><<<grid, 256, 0, s>>>(static_cast<const uint4*>(src),
+                                                       reinterpret_cast<const long long*>(offsets), B, max_len,
+                                                       row_bytes / 16, static_cast<uint4*>(dst));
+  else
+    fs2::pad_ragged_kernel<uint32_t><<<grid, 256, 0, s>>>(static_cast<const uint32_t*>(src),
+                                                          reinterpret_cast<const long long*>(offsets), B, max_len,
+                                                          row_bytes / 4, static_cast<uint32_t*>(dst));
+  fs2::count_launch();
+  return fs2::check_launch("pad_ragged_kernel");
+}

@@ -267,6 +267,15 @@ int fs2_codebook_attn_bwd_f32(const float* dout, const float* q, const float* at
                               float* d_emb, void* stream);
 
 /* ------------------------------------------------------------------------------------------ */
+/* Device-side collate: zero-padding of ragged rows -- pad_1D / pad_2D of    */
+/* lightning/utils/tool.py:134-165 as used by lightning/collates/utils.py:8-85.                   */
+/* src: rows of all B items back to back ([sum len_b][row_bytes]); offsets: int64 [B+1] (device);  */
+/* dst: [B][max_len][row_bytes]; row_bytes % 4 == 0.                                               */
+/* ------------------------------------------------------------------------------------------ */
+int fs2_pad_ragged(const void* src, const int64_t* offsets, int B, int max_len, int row_bytes, void* dst,
+                   void* stream);
+
+/* ------------------------------------------------------------------------------------------ */
 /* Multi-tensor weight refresh: every bf16 operand copy of the fp32 master weights in ONE launch */
 /* (nn.Linear: cast; nn.Conv1d [Co][Ci][k] -> packed [Co][k][Cpad], as fs2_pack_conv_weight;     */
 /* kind 1: plain f32 copy, used to gather the Q|K|V biases).  `table` is a DEVICE array.          */

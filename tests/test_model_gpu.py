@@ -91,6 +91,10 @@ def test_against_reference_golden(case):
 
 @pytest.mark.parametrize("name,over,bkw", [
     ("mid", dict(), dict(B=4, src_len=(30, 60), dur=synth.uniform_dur(1, 8), seed=31)),
+    # very different utterance lengths in one batch: whole 128-row tiles of padded frames are skipped by the
+    # ragged schedule in every FFT-block GEMM / conv / attention kernel, in the encoder and in the decoder
+    ("ragged_wide", dict(encoder_layer=2, decoder_layer=3), dict(B=6, src_len=(8, 150), dur=synth.uniform_dur(2, 7),
+                                                                  seed=41)),
     ("C4_long_skewed", dict(max_seq_len=1500, multi_speaker=True),
      dict(B=2, src_len=(220, 220), fixed_src_len=220, dur=synth.skewed_dur, seed=4, n_speaker=7)),
 ])

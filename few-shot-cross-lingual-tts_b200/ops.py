@@ -161,7 +161,13 @@ class WeightCache:
             if dst is None:
                 dst = torch.zeros((Co, k, cpad) if w.dim() == 3 else (Co, Ci), dtype=BF16, device=dev)
             view = dst[row_off:row_off + Co]
-            ents.append((w, view, Co, Ci, k, cpad, 0))
+            if w.dim() == 3 and k > 1 and w.stride() == (k * Ci, 1, Ci):
+                # parameter re-homed by FusedAdam in the [Co][k][Ci] order of its gradient: already "packed",
+                # only the per-tap channel padding and the cast remain (rows = Co * k)
+                ents.append((w, view, Co * k, Ci, 1, cpad, 0))
+            else:
+                assert w.is_contiguous(), "WeightCache: unexpected parameter strides"
+                ents.append((w, view, Co, Ci, k, cpad, 0))
             return dst
 
         in_mha = set()
@@ -239,7 +245,7 @@ def pack_conv(w):
     c = _cached("conv", w)
     if c is not None:
         return c
-    w = w.detach()
+    w = w.detach().contiguous()
     Co, Ci, k = w.shape
     cpad = _roundup(Ci, 64)
     out = torch.empty(Co, k, cpad, dtype=BF16, device=w.device)
@@ -391,9 +397,9 @@ def conv_wgrad(dy, x, dw, lens=None):
     """dw[Co, Ci, k] (reference Conv1d.weight layout, fp32) += correlation of dy with x.
 
     k == 1 is a plain unit-stride weight gradient.  For k > 1 the split-K partial sums are reduced with
-    coalesced 16-byte vector atomics into a [Co][k][Ci] scratch (the GEMM's natural N order) and then
-    folded into the reference layout by one small kernel -- strided scalar atomics straight into
-    [Co][Ci][k] cost more than the extra 2 x 9 MB of traffic."""
+    coalesced 16-byte vector atomics in the GEMM's natural [Co][k][Ci] order: directly into the gradient
+    bucket when it keeps that order (TrainStep / GradBuckets), else into a scratch that one small kernel
+    folds into a contiguous reference-layout gradient (eager autograd)."""
     B, T, Co = dy.shape
     Ci = x.shape[2]
     k = dw.shape[2]
@@ -403,10 +409,13 @@ def conv_wgrad(dy, x, dw, lens=None):
     if k == 1:
         G.wgrad(a, b, dw, Co, Ci, splits=splits, row_lens=lens)
         return
-    if Ci % 4:
-        G.wgrad(a, b, dw, Co, Ci, taps=k, tap_shift0=-((k - 1) // 2), ldd=Ci * k, d_col_stride=k, d_tap_stride=1,
-                splits=splits, row_lens=lens)
+    if dw.stride() == (k * Ci, 1, Ci):
+        # the flat gradient bucket keeps Conv1d weight gradients in [Co][k][Ci] order (runtime/dp.py): `dw` is the
+        # permuted view of it -> accumulate straight into the underlying buffer, no scratch, no re-layout kernel
+        G.wgrad(a, b, dw.permute(0, 2, 1), Co, Ci, taps=k, tap_shift0=-((k - 1) // 2), ldd=Ci * k, d_col_stride=1,
+                d_tap_stride=Ci, splits=splits, row_lens=lens)
         return
+    assert dw.is_contiguous() and Ci % 4 == 0
     scratch = torch.zeros(Co, k, Ci, dtype=F32, device=dy.device)
     G.wgrad(a, b, scratch, Co, Ci, taps=k, tap_shift0=-((k - 1) // 2), ldd=Ci * k, d_col_stride=1,
             d_tap_stride=Ci, splits=splits, row_lens=lens)

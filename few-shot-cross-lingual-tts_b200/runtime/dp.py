@@ -29,7 +29,14 @@ class GradBuckets:
         off, bstart, bcount = 0, 0, 0
         for p in order:
             n = p.numel()
-            view = self.flat[off:off + n].view(p.shape)
+            if p.dim() == 3 and p.shape[2] > 1 and p.shape[1] % 4 == 0 and device.type == "cuda":
+                # Conv1d weight [Co, Ci, k]: the gradient lives in the weight-gradient GEMM's natural order
+                # [Co][k][Ci] (unit-stride vector atomics, no scratch + re-layout pass); `main_grad` / `.grad`
+                # are the permuted view with the parameter's logical shape, so optimizers see matching elements
+                Co, Ci, k = p.shape
+                view = self.flat[off:off + n].view(Co, k, Ci).permute(0, 2, 1)
+            else:
+                view = self.flat[off:off + n].view(p.shape)
             p.main_grad = view
             p.grad = view  # autograd-produced gradients (embeddings) accumulate in place as well
             self._bucket_of[id(p)] = len(self.buckets)

@@ -47,7 +47,13 @@ class FusedAdam:
         for p in buckets.params:
             off = p.main_grad.data_ptr() - g.data_ptr()
             assert off % 4 == 0
-            view = self.flat_param[off // 4: off // 4 + p.numel()].view(p.shape)
+            flat = self.flat_param[off // 4: off // 4 + p.numel()]
+            if p.main_grad.is_contiguous():
+                view = flat.view(p.shape)
+            else:  # Conv1d weight whose gradient is kept in [Co][k][Ci] order: same element order for the value
+                Co, Ci, k = p.shape
+                assert p.main_grad.stride() == (k * Ci, 1, Ci)
+                view = flat.view(Co, k, Ci).permute(0, 2, 1)
             view.copy_(p.data)
             p.data = view
         self.exp_avg = torch.zeros_like(g)

@@ -90,3 +90,37 @@ def test_prefetched_batches_are_the_ones_that_run():
     step.run()
     got2 = step.read_losses().clone()
     assert torch.allclose(got1, ref1, rtol=1e-4) and torch.allclose(got2, ref2, rtol=1e-4)
+
+
+def test_fused_adam_first_step_moves_every_weight_against_its_gradient():
+    """Conv1d weight gradients live in [Co][k][Ci] order inside the flat bucket and FusedAdam re-homes the weights
+    in the same order.  First Adam step: delta = -lr * g / (|g| + eps) = -lr * sign(g) element by element, so a layout
+    mismatch between value and gradient would show up as ~50 % sign agreement."""
+    rt = sub("runtime")
+    batch = synth.make_batch(B=4, src_len=(10, 40), dur=synth.uniform_dur(1, 8), seed=23)
+    model_e, loss_fn, _ = _build(seed=2)
+    b = cuda_batch(batch)
+    out = model_e(b[2], b[3], *b[4:12], lang_args=b[12])
+    loss_fn(b[:-1], out)[0].backward()
+    model, loss_fn2, _ = _build(seed=2)
+    before = {k: p.detach().clone() for k, p in model.named_parameters()}
+    buckets = rt.GradBuckets(model.parameters(), device=torch.device("cuda"))
+    lr = 1e-3
+    opt = rt.FusedAdam(buckets, lr=lr, betas=(0.9, 0.98), eps=1e-12, weight_decay=0.0, max_grad_norm=0.0,
+                       scheduler_type="none")
+    step = rt.TrainStep(model, loss_fn2, batch, use_graph=False, buckets=buckets, optimizer=opt)
+    step.run()
+    torch.cuda.synchronize()
+    assert int(opt.step_dev) == 1
+    grads_e = dict((k, p.grad) for k, p in model_e.named_parameters())
+    for k in ("decoder.layer_stack.0.pos_ffn.w_1.weight", "postnet.convolutions.1.0.conv.weight",
+              "variance_adaptor.duration_predictor.conv_layer.conv1d_1.conv.weight", "mel_linear.weight"):
+        p = dict(model.named_parameters())[k]
+        delta = p.detach() - before[k]
+        g = grads_e[k]
+        big = g.abs() > 0.05 * g.abs().mean()  # elements whose sign is not rounding noise
+        agree = ((delta < 0) == (g > 0))[big].float().mean().item()
+        assert agree > 0.97, (k, agree)
+        assert torch.allclose(delta.abs()[big], torch.full_like(delta[big], lr), rtol=2e-2), k
+    # state_dict still has the reference's shapes, whatever the storage order
+    assert model.state_dict()["decoder.layer_stack.0.pos_ffn.w_1.weight"].shape == (1024, 256, 9)

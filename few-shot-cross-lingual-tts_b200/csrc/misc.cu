@@ -103,9 +103,13 @@ add_f32_bf16_kernel(const float* __restrict__ a, const __nv_bfloat16* __restrict
 __global__ void __launch_bounds__(256)
 colsum_kernel(const __nv_bfloat16* __restrict__ x, long long ld, int rows_per_group, int C,
               int rows_per_block, float* __restrict__ out, const int64_t* __restrict__ lens,
-              int out_group_stride) {
+              int out_group_stride, int seg_stride, float* __restrict__ out_b) {
   extern __shared__ float s_acc[];  // [C]
   const int g = blockIdx.y;
+  if (blockIdx.z) {  // second column segment of the same rows (e.g. the V block next to the Q block of dQKV)
+    x += (long long)blockIdx.z * seg_stride;
+    out = out_b;
+  }
   const long long x_group_stride = (long long)rows_per_group * ld;
   if (lens) {  // rows at / after lens[g] are padding (zero by contract): not read
     const long long l = lens[g];
@@ -323,15 +327,17 @@ int fs2_add_rowvec_bf16(const void* x, const float* e, int B, int T, int C, void
 
 // out f32 [groups][C] += column sums of x bf16 [groups*rows_per_group][ld]
 static int colsum_launch(const void* x, int64_t ld, int groups, int rows_per_group, int C, float* out,
-                         const int64_t* lens, int out_group_stride, void* stream) {
+                         const int64_t* lens, int out_group_stride, void* stream, int seg_stride = 0,
+                         float* out_b = nullptr) {
   if (groups <= 0 || rows_per_group <= 0) return 0;
   if ((ld % 8) || (C % 8) || C / 8 > 256 || (reinterpret_cast<uintptr_t>(x) & 15))
     return fs2::set_error("colsum: ld and C must be multiples of 8 (16-byte aligned rows), C <= 2048");
   int rpb = (rows_per_group * groups + 148 * 8 - 1) / (148 * 8);
   if (rpb < 32) rpb = 32;
-  dim3 grid((rows_per_group + rpb - 1) / rpb, groups);
+  dim3 grid((rows_per_group + rpb - 1) / rpb, groups, out_b ? 2 : 1);
   fs2::colsum_kernel<<<grid, 256, C * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __nv_bfloat16*>(x), ld, rows_per_group, C, rpb, out, lens, out_group_stride);
+      static_cast<const __nv_bfloat16*>(x), ld, rows_per_group, C, rpb, out, lens, out_group_stride, seg_stride,
+      out_b);
   fs2::count_launch();
   return fs2::check_launch("colsum_kernel");
 }
@@ -344,6 +350,12 @@ int fs2_colsum_bf16(const void* x, int64_t ld, int groups, int rows_per_group, i
 int fs2_colsum_ragged_bf16(const void* x, int64_t ld, int B, int T, int C, const int64_t* lens, float* out,
                            void* stream) {
   return colsum_launch(x, ld, B, T, C, out, lens, 0, stream);
+}
+
+int fs2_colsum_ragged2_bf16(const void* x, int64_t ld, int B, int T, int C, const int64_t* lens, int seg_stride,
+                            float* out0, float* out1, void* stream) {
+  if ((seg_stride % 8) || !out1) return fs2::set_error("colsum_ragged2: segment stride must be a multiple of 8 columns");
+  return colsum_launch(x, ld, B, T, C, out0, lens, 0, stream, seg_stride, out1);
 }
 
 int fs2_colsum3_bf16(const void* x, int64_t ld, int rows, int seg_cols, float* out0, float* out1, float* out2,

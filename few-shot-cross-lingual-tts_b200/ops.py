@@ -353,8 +353,12 @@ def qkv_param_grads(dqkv, x2d, gbuf, HD, lens=None, T=None):
     # bias gradients = column sums of dQ and dV.  The K bias gets none: adding a constant to every key shifts all
     # scores of a query row by the same amount, which softmax ignores -- its gradient is identically zero (the
     # reference's autograd produces rounding noise of ~1e-8 there), so the dK column sum is not computed.
-    for i in (0, 2):
-        colsum(dqkv, gbuf[2 * i + 1][0], col0=i * HD, cols=HD, lens=lens, T=T)
+    if lens is not None and HD % 8 == 0:  # Q and V column blocks of the same rows: one launch
+        _ck(_L().fs2_colsum_ragged2_bf16(_p(dqkv), C3, M // T, T, HD, _p(lens), 2 * HD, _p(gbuf[1][0]),
+                                         _p(gbuf[5][0]), _st()), "colsum_ragged2")
+    else:
+        for i in (0, 2):
+            colsum(dqkv, gbuf[2 * i + 1][0], col0=i * HD, cols=HD, lens=lens, T=T)
 
 
 def colsum(x2d, out, col0=0, cols=None, lens=None, T=None):

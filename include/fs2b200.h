@@ -202,6 +202,10 @@ int fs2_colsum_bf16(const void* x, int64_t ld, int groups, int rows_per_group, i
    are padding whose gradient is zero by construction, transformer/Layers.py:25,28; they are not read) */
 int fs2_colsum_ragged_bf16(const void* x, int64_t ld, int B, int T, int C, const int64_t* lens, float* out,
                            void* stream);
+/* two column segments of the same rows in one launch: out0 += colsum(x[:, 0:C]), out1 += colsum(x[:, seg_stride:
+   seg_stride + C]) -- the Q and V bias gradients from the fused dQ|dK|dV buffer */
+int fs2_colsum_ragged2_bf16(const void* x, int64_t ld, int B, int T, int C, const int64_t* lens, int seg_stride,
+                            float* out0, float* out1, void* stream);
 int fs2_colsum_f32(const float* x, int64_t ld, int rows, int C, float* out, void* stream);
 /* column sums of x[:, 0:3*seg_cols] split into three outputs (fused Q|K|V bias gradients) */
 int fs2_colsum3_bf16(const void* x, int64_t ld, int rows, int seg_cols, float* out0, float* out1, float* out2,

@@ -78,12 +78,41 @@ class fork_side:
         return False
 
 
-def join_side():
+# Deferred joins (runtime.TrainStep sets DEFER_JOIN around its backward pass): a Function then does NOT wait for
+# its weight-gradient kernels before returning -- it only parks the tensors those kernels read in `_keepalive` (the
+# autograd engine would otherwise free them, and the allocator could hand their memory to the main stream while the
+# side stream still reads it).  The serial input-gradient chain so never stalls on a weight gradient;
+# `final_join()` after the whole backward pass makes the main stream wait once and releases the tensors.
+DEFER_JOIN = False
+_keepalive = []
+
+
+def join_side(*side_inputs):
+    """Order the current stream after the side stream -- or, with DEFER_JOIN, keep `side_inputs` alive instead."""
+    if not OVERLAP:
+        return
+    if DEFER_JOIN:
+        _keepalive.extend(side_inputs)
+        return
+    cur = torch.cuda.current_stream()
+    side = _side_streams.get(cur.device)
+    if side is not None:
+        cur.wait_stream(side)
+
+
+def final_join():
     if OVERLAP:
         cur = torch.cuda.current_stream()
         side = _side_streams.get(cur.device)
         if side is not None:
             cur.wait_stream(side)
+    _keepalive.clear()
+
+
+def side_stream_of(device):
+    """The side stream of `device`, or None when nothing was ever forked (used by runtime/dp.py: a gradient
+    bucket may only go on the wire after the side stream has produced its weight gradients)."""
+    return _side_streams.get(device) if OVERLAP else None
 
 
 # --------------------------------------------------------------------------------------------------
@@ -606,7 +635,7 @@ class MHASublayer(torch.autograd.Function):
             with fork_side():
                 qkv_param_grads(dqkv, x2, gbuf, HD, lens=rl, T=T)
             dx = linear_dgrad(dqkv, wqkv, epilogue=G.EPI_ADD_AUX, aux=dres.view(M, D), lens=rl, T=T)
-            join_side()
+            join_side(do, attn, dqkv, x, lens)
             grads_done((wq, bq, wk, bk, wv, bv, wo, bo, gamma, beta))
             return (dx.view(B, T, D), None) + tuple(g[1] for g in gbuf) + (None, None, None)
         # attention core: dP = dO V^T ; dS = softmax'(P, dP) ; dQ = dS K ; dK = dS^T Q ; dV = P^T dO
@@ -633,7 +662,7 @@ class MHASublayer(torch.autograd.Function):
         x2 = x.view(M, D)
         dx = linear_dgrad(dqkv, wqkv, epilogue=G.EPI_ADD_AUX, aux=dres.view(M, D))
         qkv_param_grads(dqkv, x2, gbuf, HD)
-        join_side()
+        join_side(do, attn, dqkv, x, lens)
         grads_done((wq, bq, wk, bk, wv, bv, wo, bo, gamma, beta))
         return (dx.view(B, T, D), None) + tuple(g[1] for g in gbuf) + (None, None, None)
 
@@ -683,7 +712,7 @@ class FFNSublayer(torch.autograd.Function):
             conv_wgrad(dh, x, gbuf[0][0], lens=rl)
             colsum(dh.view(B * T, Dh), gbuf[1][0], lens=rl, T=T)
         dx = conv_dgrad(dh, w1p, D, epilogue=G.EPI_ADD_AUX, aux=dres, lens=rl)
-        join_side()
+        join_side(df, h, dh, x, lens)
         grads_done((w1, b1, w2, b2, gamma, beta))
         return (dx, None) + tuple(g[1] for g in gbuf) + (None, None)
 
@@ -739,7 +768,7 @@ class VariancePredictorFn(torch.autograd.Function):
         with fork_side():
             conv_wgrad(da1, x, gbuf[0][0])
         dx = conv_dgrad(da1, c1p, D)
-        join_side()
+        join_side(da2, n1, da1, x)
         grads_done((c1w, c1b, g1, be1, c2w, c2b, g2, be2, lw, lb))
         return (dx, None) + tuple(g[1] for g in gbuf) + (None, None)
 
@@ -953,7 +982,7 @@ class LinearFn(torch.autograd.Function):
                 gb, rb = grad_target(b)
                 colsum(dy2, gb)
         dx = linear_dgrad(dy2, w_bf).view(B, T, K) if ctx.needs_input_grad[0] else None
-        join_side()
+        join_side(dy2, x)
         grads_done((w,) if b is None else (w, b))
         return dx, rw, rb
 
@@ -1038,7 +1067,7 @@ class PostNetFn(torch.autograd.Function):
             # autograd produces rounding noise of ~1e-8 here).  Nothing to accumulate into `gcb`.
             d, d_is_f32 = conv_dgrad(dy, wp, x.shape[2]), 0
             grads[7 * i:7 * i + 4] = [rcw, rcb, rbw, rbb]
-            join_side()
+            join_side(dy, x)
             grads_done((cw, cb, bw, bb))
         dmel = torch.empty(B, T, n_mel, dtype=F32, device=dev)
         _ck(_L().fs2_add_f32_bf16(_p(dout), _p(d), dout.numel(), _p(dmel), _st()), "add_f32_bf16")

@@ -70,7 +70,12 @@ class GradBuckets:
 
     def _launch(self, b):
         if self.comm_stream is not None:
-            self.comm_stream.wait_stream(torch.cuda.current_stream())
+            cur = torch.cuda.current_stream()
+            self.comm_stream.wait_stream(cur)
+            from .. import ops  # weight gradients are produced on the side stream (ops.fork_side)
+            side = ops.side_stream_of(cur.device)
+            if side is not None:
+                self.comm_stream.wait_stream(side)
             with torch.cuda.stream(self.comm_stream):
                 self._all_reduce(b)
         else:

@@ -11,6 +11,8 @@ import torch
 from .. import ops
 from .dp import GradBuckets
 
+_DEFER = __import__("os").environ.get("FS2_NO_DEFER") is None  # A/B switch for tools
+
 # batch tuple slots that are device tensors (lightning/collates/utils.py:70-85)
 _TENSOR_SLOTS = (2, 3, 4, 6, 7, 9, 10, 11, 12)
 
@@ -58,7 +60,12 @@ class TrainStep:
             self.buckets.zero()
             out = self.model(b[2], b[3], *b[4:12], lang_args=b[12])
             losses = self.loss_fn(tuple(b[:12]), out)
-            losses[0].backward()
+            ops.DEFER_JOIN = _DEFER  # weight gradients run free on the side stream until the end of the backward
+            try:
+                losses[0].backward()
+            finally:
+                ops.DEFER_JOIN = False
+                ops.final_join()
         finally:
             ops.set_weight_cache(None)
         self.buckets.finish()

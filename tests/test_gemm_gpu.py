@@ -232,8 +232,8 @@ def test_ragged_linear(impl, lens, T, N, K, f32):
 
 
 @pytest.mark.parametrize("impl", IMPLS)
-@pytest.mark.parametrize("lens", [[200, 1, 129, 0, 128, 77], [0, 0], [260, 255, 256, 257]])
-@pytest.mark.parametrize("Cin,Cout,k", [(256, 1024, 9), (1024, 256, 1), (256, 256, 3)])
+@pytest.mark.parametrize("lens", [[200, 1, 129, 0, 128, 77], [0, 0], [260, 255, 256, 257], [129, 1, 1], [7]])
+@pytest.mark.parametrize("Cin,Cout,k", [(256, 1024, 9), (1024, 256, 1), (256, 256, 3), (80, 512, 5)])
 def test_ragged_conv(impl, lens, Cin, Cout, k):
     """Implicit-GEMM Conv1d with row_lens: same values as the dense conv on valid rows (the halo may read
     padded input rows, which the caller keeps at zero), zeros on padded rows."""
@@ -244,10 +244,12 @@ def test_ragged_conv(impl, lens, Cin, Cout, k):
     x = rnd(B, T, Cin) * valid[..., None]
     w = (torch.randn(Cout, Cin, k, device="cuda") * (Cin * k) ** -0.5).to(torch.bfloat16)
     bias = torch.randn(Cout, device="cuda")
-    wp = w.permute(0, 2, 1).contiguous()
+    cpad = ((Cin + 63) // 64) * 64  # packed weights [Co][k][Cpad] (zero-padded channels), as ops.pack_conv
+    wp = torch.zeros(Cout, k, cpad, device="cuda", dtype=torch.bfloat16)
+    wp[:, :, :Cin] = w.permute(0, 2, 1)
     y = torch.full((B, T, Cout), float("nan"), device="cuda", dtype=torch.bfloat16)
-    G.gemm(G.operand(x, Cin, T, B), G.operand(wp, k * Cin, Cout), y, T, Cout, Cin, Z=B, taps=k,
-           tap_shift0=-((k - 1) // 2), b_tap_kstride=Cin, bias=bias, epilogue=G.EPI_RELU, d_zdiv=1,
+    G.gemm(G.operand(x, Cin, T, B), G.operand(wp, k * cpad, Cout), y, T, Cout, Cin, Z=B, taps=k,
+           tap_shift0=-((k - 1) // 2), b_tap_kstride=cpad, bias=bias, epilogue=G.EPI_RELU, d_zdiv=1,
            d_zdiv_stride=T * Cout, row_lens=_lens(lens), impl=impl)
     ref = torch.nn.functional.conv1d(x.float().transpose(1, 2), w.float(), bias,
                                      padding=(k - 1) // 2).transpose(1, 2).relu() * valid[..., None]

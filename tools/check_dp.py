@@ -9,7 +9,7 @@ import torch.distributed as dist
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from fs2b200 import sub  # noqa: E402
-from oracle import synth  # noqa: E402
+synth = sub("synthetic")  # the package's own generators (oracle/ is for tests only)
 from tests.util_parity import disable_dropout  # noqa: E402
 
 

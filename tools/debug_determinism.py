@@ -3,7 +3,7 @@ outputs / gradients are bit-identical, and how large is the spread of those that
 import os, sys, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from fs2b200 import sub
-from oracle import synth
+synth = sub("synthetic")  # the package's own generators (oracle/ is for tests only)
 from tests.util_parity import cuda_batch, disable_dropout, rel_err
 M = sub("lightning.model"); ops = sub("ops")
 def build():

@@ -10,7 +10,7 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from fs2b200 import sub  # noqa: E402
-from oracle import synth  # noqa: E402
+synth = sub("synthetic")  # the package's own generators (oracle/ is for tests only)
 from tests.util_parity import cuda_batch, disable_dropout  # noqa: E402
 
 print("import %.1fs" % (time.time() - t0)); t0 = time.time()

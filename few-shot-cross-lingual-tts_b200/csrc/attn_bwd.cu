@@ -43,6 +43,7 @@ struct AttnBwdP {
 __global__ void __launch_bounds__(256)
 attn_bwd_prep_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ d_o,
                      const int64_t* __restrict__ lens, int B, int T, int H, float scale, float* __restrict__ dsum) {
+  pdl_sync();
   const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= (long long)B * T) return;
   const int lane = threadIdx.x & 31;
@@ -149,6 +150,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmKV,   // qkv, box 64 x
                     const __grid_constant__ CUtensorMap tmQ,    // qkv, box 64 x 64 rows
                     const __grid_constant__ CUtensorMap tmDO,   // dO,  box 64 x 64 rows
                     const __grid_constant__ AttnBwdP p) {
+  pdl_sync();
   using namespace dkv;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -358,6 +360,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ128,  // qkv, box 64 x
                    const __grid_constant__ CUtensorMap tmKV64,  // qkv, box 64 x 64 rows
                    const __grid_constant__ CUtensorMap tmDO128, // dO,  box 64 x 128 rows
                    const __grid_constant__ AttnBwdP p) {
+  pdl_sync();
   using namespace dq;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -546,7 +549,7 @@ int fs2_attn_bwd_bf16(const void* qkv, const void* o, const void* d_o, const flo
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int C3 = 3 * H * dk, HD = H * dk;
   const long long rows = (long long)B * T;
-  attn_bwd_prep_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, s>>>(static_cast<const __nv_bfloat16*>(o),
+  FS2_LAUNCH((attn_bwd_prep_kernel), (unsigned)((rows + 7) / 8), 256, 0, s, static_cast<const __nv_bfloat16*>(o),
                                                                  static_cast<const __nv_bfloat16*>(d_o), lens, B, T,
                                                                  H, 1.f / sqrtf((float)dk), dsum);
   count_launch();
@@ -565,10 +568,10 @@ int fs2_attn_bwd_bf16(const void* qkv, const void* o, const void* d_o, const flo
   p.n_outer = (T + 127) / 128;
   p.n_inner = (T + 63) / 64;
   const unsigned grid = (unsigned)(p.n_outer * B * H);
-  attn_bwd_dkv_kernel<<<grid, 320, dkv::SMEM_BYTES, s>>>(tm128, tm64, tmdo64, p);
+  FS2_LAUNCH((attn_bwd_dkv_kernel), grid, 320, dkv::SMEM_BYTES, s, tm128, tm64, tmdo64, p);
   count_launch();
   if (int rc = check_launch("attn_bwd_dkv_kernel")) return rc;
-  attn_bwd_dq_kernel<<<grid, 320, dq::SMEM_BYTES, s>>>(tm128, tm64, tmdo128, p);
+  FS2_LAUNCH((attn_bwd_dq_kernel), grid, 320, dq::SMEM_BYTES, s, tm128, tm64, tmdo128, p);
   count_launch();
   return check_launch("attn_bwd_dq_kernel");
 }

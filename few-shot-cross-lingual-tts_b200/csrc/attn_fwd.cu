@@ -61,6 +61,7 @@ __device__ __forceinline__ void softmax_bar_sync() { asm volatile("bar.sync 1, 2
 __global__ void __launch_bounds__(320, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constant__ CUtensorMap tmV,
                 const __grid_constant__ AttnFwdP p) {
+  pdl_sync();
   using namespace af;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -329,7 +330,7 @@ int fs2_attn_fwd_bf16(const void* qkv, const int64_t* lens, int B, int T, int H,
   p.scale_log2 = 1.4426950408889634f / sqrtf((float)dk);
   p.out = static_cast<__nv_bfloat16*>(out);
   p.lse2 = lse2;
-  attn_fwd_kernel<<<p.nq * B * H, 320, af::SMEM_BYTES, static_cast<cudaStream_t>(stream)>>>(tmQK, tmV, p);
+  FS2_LAUNCH((attn_fwd_kernel), p.nq * B * H, 320, af::SMEM_BYTES, static_cast<cudaStream_t>(stream), tmQK, tmV, p);
   count_launch();
   return check_launch("attn_fwd_kernel");
 }

@@ -47,6 +47,7 @@ __device__ __forceinline__ float fast_tanh(float x) {
 }
 
 __global__ void __launch_bounds__(256) bn_stats_kernel(const BnArgs a) {
+  pdl_sync();
   extern __shared__ float sh[];  // [2][C]
   const int vpr = a.C / 8, rs = 256 / vpr;
   for (int i = threadIdx.x; i < 2 * a.C; i += 256) sh[i] = 0.f;
@@ -88,6 +89,7 @@ __global__ void __launch_bounds__(256) bn_stats_kernel(const BnArgs a) {
 // Thread = one 8-channel column vector (fixed for the whole kernel) x a strided set of rows, so the
 // per-channel affine parameters live in registers; 64 consecutive threads cover one 1 KiB row (C=512).
 __global__ void __launch_bounds__(256) bn_apply_kernel(const BnArgs a) {
+  pdl_sync();
   const int vpr = a.C / 8, rs = 256 / vpr;
   const int v = threadIdx.x % vpr, ro = threadIdx.x / vpr;
   if (ro >= rs) return;
@@ -136,6 +138,7 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const BnArgs a) {
 }
 
 __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const BnArgs a) {
+  pdl_sync();
   extern __shared__ float s_acc[];  // [2][C]: sum g, sum g*yhat
   const int vpr = a.C / 8, rs = 256 / vpr;
   for (int i = threadIdx.x; i < 2 * a.C; i += 256) s_acc[i] = 0.f;
@@ -197,6 +200,7 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const BnArgs a) {
 }
 
 __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BnArgs a) {
+  pdl_sync();
   const int vpr = a.C / 8, rs = 256 / vpr;
   const int v = threadIdx.x % vpr, ro = threadIdx.x / vpr;
   if (ro >= rs) return;
@@ -247,6 +251,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BnArgs a) {
 
 __global__ void bn_running_kernel(const float* __restrict__ fstats, long long M, int C, float momentum,
                                   float* running_mean, float* running_var, int64_t* num_batches) {
+  pdl_sync();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c == 0 && num_batches) *num_batches += 1;
   if (c >= C) return;
@@ -286,7 +291,7 @@ int fs2_bn_stats_bf16(const void* y, int64_t M, int C, float* stats, void* strea
   a.M = M; a.C = C; a.stats = stats;
   a.rows_per_block = fs2::rows_per_block_for(M);
   const unsigned grid = (unsigned)((M + a.rows_per_block - 1) / a.rows_per_block);
-  fs2::bn_stats_kernel<<<grid, 256, 2 * C * sizeof(float), static_cast<cudaStream_t>(stream)>>>(a);
+  FS2_LAUNCH((fs2::bn_stats_kernel), grid, 256, 2 * C * sizeof(float), static_cast<cudaStream_t>(stream), a);
   fs2::count_launch();
   return fs2::check_launch("bn_stats_kernel");
 }
@@ -304,8 +309,7 @@ int fs2_bn_apply_fwd(const void* y, const float* stats, const float* gamma, cons
   a.act_tanh = act_tanh; a.p_drop = p_drop; a.seed = seed; a.seed_dev = seed_dev;
   a.out_bf16 = static_cast<__nv_bfloat16*>(out_bf16); a.out_f32 = out_f32; a.res_f32 = res_f32;
   a.rows_per_block = fs2::rows_per_block_for(M);
-  fs2::bn_apply_kernel<<<(unsigned)((M + a.rows_per_block - 1) / a.rows_per_block), 256, 0,
-                         static_cast<cudaStream_t>(stream)>>>(a);
+  FS2_LAUNCH((fs2::bn_apply_kernel), (unsigned)((M + a.rows_per_block - 1) / a.rows_per_block), 256, 0, static_cast<cudaStream_t>(stream), a);
   fs2::count_launch();
   return fs2::check_launch("bn_apply_kernel");
 }
@@ -313,7 +317,7 @@ int fs2_bn_apply_fwd(const void* y, const float* stats, const float* gamma, cons
 int fs2_bn_update_running(const float* stats, int64_t M, int C, float momentum, float* running_mean,
                           float* running_var, int64_t* num_batches_tracked, void* stream) {
   if (int rc = fs2::bn_check(M, C)) return rc;
-  fs2::bn_running_kernel<<<(C + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+  FS2_LAUNCH((fs2::bn_running_kernel), (C + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream), 
       stats, M, C, momentum, running_mean, running_var, num_batches_tracked);
   fs2::count_launch();
   return fs2::check_launch("bn_running_kernel");
@@ -334,10 +338,10 @@ int fs2_bn_bwd(const void* dout, int dout_is_f32, const void* y, const float* st
   a.rows_per_block = fs2::rows_per_block_for(M);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const unsigned grid = (unsigned)((M + a.rows_per_block - 1) / a.rows_per_block);
-  fs2::bn_bwd_reduce_kernel<<<grid, 256, 2 * C * sizeof(float), s>>>(a);
+  FS2_LAUNCH((fs2::bn_bwd_reduce_kernel), grid, 256, 2 * C * sizeof(float), s, a);
   fs2::count_launch();
   if (int rc = fs2::check_launch("bn_bwd_reduce_kernel")) return rc;
-  fs2::bn_bwd_apply_kernel<<<grid, 256, 0, s>>>(a);
+  FS2_LAUNCH((fs2::bn_bwd_apply_kernel), grid, 256, 0, s, a);
   fs2::count_launch();
   return fs2::check_launch("bn_bwd_apply_kernel");
 }

@@ -16,6 +16,7 @@ __global__ void __launch_bounds__(256)
 segment_class_accum_kernel(const float* __restrict__ x, const long long* __restrict__ dur, const long long* __restrict__ cls,
                            int L, long long T, long long D, int n_classes, int two_stage, float* __restrict__ table_sum,
                            float* __restrict__ count) {
+  pdl_sync();
   const int i = blockIdx.x;
   __shared__ long long s_t0;
   if (threadIdx.x == 0) {  // exclusive prefix of the (clamped) durations before segment i
@@ -50,6 +51,7 @@ segment_class_accum_kernel(const float* __restrict__ x, const long long* __restr
 
 __global__ void __launch_bounds__(256)
 class_mean_finalize_kernel(float* __restrict__ table, const float* __restrict__ count, long long n, long long D) {
+  pdl_sync();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const float c = count[i / D];
     table[i] = c > 0.f ? table[i] / c : 0.f;
@@ -60,6 +62,7 @@ class_mean_finalize_kernel(float* __restrict__ table, const float* __restrict__ 
 __global__ void __launch_bounds__(256)
 layer_weighted_sum_kernel(const float* __restrict__ ref, const float* __restrict__ w_raw, long long rows, int n_layer,
                           int D, __nv_bfloat16* __restrict__ out) {
+  pdl_sync();
   __shared__ float s_w[64];
   if (threadIdx.x < 64) {
     float w = 1.f;
@@ -93,6 +96,7 @@ layer_weighted_sum_kernel(const float* __restrict__ ref, const float* __restrict
 __global__ void __launch_bounds__(256)
 codebook_attn_fwd_kernel(const float* __restrict__ q, const float* __restrict__ att, const float* __restrict__ emb,
                          int C, int E, int H, float inv_temp, float* __restrict__ out, float* __restrict__ p_out) {
+  pdl_sync();
   extern __shared__ float sm[];  // [H][C] probabilities
   const int r = blockIdx.x, h = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (h >= H) return;
@@ -135,6 +139,7 @@ __global__ void __launch_bounds__(256)
 codebook_attn_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ q, const float* __restrict__ att,
                          const float* __restrict__ emb, const float* __restrict__ p_in, int C, int E, int H,
                          float inv_temp, float* __restrict__ dq, float* __restrict__ d_att, float* __restrict__ d_emb) {
+  pdl_sync();
   extern __shared__ float sm[];  // [H][C] dS
   const int r = blockIdx.x, h = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (h >= H) return;
@@ -178,7 +183,7 @@ int fs2_segment_class_accum_f32(const float* x, const int64_t* dur, const int64_
   if (D % 4 || (reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(table_sum) & 15))
     return fs2::set_error("segment_class_accum: D must be a multiple of 4, buffers 16-byte aligned");
   dim3 grid(L, (unsigned)((D + 1023) / 1024));
-  fs2::segment_class_accum_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  FS2_LAUNCH((fs2::segment_class_accum_kernel), grid, 256, 0, static_cast<cudaStream_t>(stream), 
       x, reinterpret_cast<const long long*>(dur), reinterpret_cast<const long long*>(cls), L, T, D, n_classes,
       two_stage, table_sum, count);
   fs2::count_launch();
@@ -190,7 +195,7 @@ int fs2_class_mean_finalize_f32(float* table, const float* count, int n_classes,
   if (n <= 0) return 0;
   long long g = (n + 255) / 256;
   if (g > 148 * 8) g = 148 * 8;
-  fs2::class_mean_finalize_kernel<<<(unsigned)g, 256, 0, static_cast<cudaStream_t>(stream)>>>(table, count, n, D);
+  FS2_LAUNCH((fs2::class_mean_finalize_kernel), (unsigned)g, 256, 0, static_cast<cudaStream_t>(stream), table, count, n, D);
   fs2::count_launch();
   return fs2::check_launch("class_mean_finalize_kernel");
 }
@@ -202,7 +207,7 @@ int fs2_layer_weighted_sum_bf16(const float* ref, const float* w_raw, int64_t ro
   const long long n = rows * D;
   long long g = (n + 255) / 256;
   if (g > 148 * 8) g = 148 * 8;
-  fs2::layer_weighted_sum_kernel<<<(unsigned)g, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  FS2_LAUNCH((fs2::layer_weighted_sum_kernel), (unsigned)g, 256, 0, static_cast<cudaStream_t>(stream), 
       ref, w_raw, rows, n_layer, D, static_cast<__nv_bfloat16*>(out));
   fs2::count_launch();
   return fs2::check_launch("layer_weighted_sum_kernel");
@@ -212,7 +217,7 @@ int fs2_codebook_attn_fwd_f32(const float* q, const float* att_banks, const floa
                               int H, float inv_temp, float* out, float* p, void* stream) {
   if (rows <= 0) return 0;
   if (H < 1 || H > 8 || E % H || C < 1 || C > 1024) return fs2::set_error("codebook_attn: H <= 8, C <= 1024, E % H == 0");
-  fs2::codebook_attn_fwd_kernel<<<rows, 256, (size_t)H * C * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
+  FS2_LAUNCH((fs2::codebook_attn_fwd_kernel), rows, 256, (size_t)H * C * sizeof(float), static_cast<cudaStream_t>(stream), 
       q, att_banks, emb_banks, C, E, H, inv_temp, out, p);
   fs2::count_launch();
   return fs2::check_launch("codebook_attn_fwd_kernel");
@@ -223,7 +228,7 @@ int fs2_codebook_attn_bwd_f32(const float* dout, const float* q, const float* at
                               float* d_emb, void* stream) {
   if (rows <= 0) return 0;
   if (H < 1 || H > 8 || E % H || C < 1 || C > 1024) return fs2::set_error("codebook_attn: H <= 8, C <= 1024, E % H == 0");
-  fs2::codebook_attn_bwd_kernel<<<rows, 256, (size_t)H * C * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
+  FS2_LAUNCH((fs2::codebook_attn_bwd_kernel), rows, 256, (size_t)H * C * sizeof(float), static_cast<cudaStream_t>(stream), 
       dout, q, att_banks, emb_banks, p, C, E, H, inv_temp, dq, d_att, d_emb);
   fs2::count_launch();
   return fs2::check_launch("codebook_attn_bwd_kernel");

@@ -2,6 +2,7 @@
 
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 namespace fs2 {
@@ -25,6 +26,10 @@ int check_launch(const char* kernel_name) {
   return 0;
 }
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+bool pdl_enabled() {
+  static const bool on = std::getenv("FS2_NO_PDL") == nullptr;
+  return on;
+}
 }  // namespace fs2
 
 extern "C" {

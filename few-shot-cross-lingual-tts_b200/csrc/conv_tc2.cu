@@ -58,6 +58,7 @@ constexpr int kThreadsC2 = 384;
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(c2::kThreadsC2, 1)
 conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const __grid_constant__ GemmKP p, const int taps) {
+  pdl_trigger();
   using namespace c2;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -103,6 +104,7 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     tmem_alloc_2sm(sbase + TMEM_PTR_OFF, TMEM_COLS);
     tmem_relinquish_2sm();
   }
+  pdl_wait();  // everything above is independent of the previous kernel's output
   if (warp == 3 && p.ragged) build_ragged_table(p, reinterpret_cast<int*>(sgen + CUM_OFF), lane);
   tc_fence_before();
   __syncthreads();
@@ -274,7 +276,7 @@ int conv_tc2_launch(const fs2_gemm& g, GemmKP& kp, cudaStream_t stream) {
   }
   const int max_pairs = c2_num_sms / 2;
   const int pairs = pair_tiles < max_pairs ? pair_tiles : max_pairs;
-  conv_tc2_kernel<<<2 * pairs, kThreadsC2, DYN_BYTES, stream>>>(tmA, tmB, kp, taps);
+  FS2_LAUNCH((conv_tc2_kernel), 2 * pairs, kThreadsC2, DYN_BYTES, stream, tmA, tmB, kp, taps);
   count_launch();
   return check_launch("conv_tc2_kernel");
 }

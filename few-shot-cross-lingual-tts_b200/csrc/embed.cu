@@ -20,6 +20,7 @@ bucket_embed_add_kernel(const __nv_bfloat16* __restrict__ x, const TgtT* __restr
                         const float* __restrict__ bins, int nb, const float* __restrict__ table,
                         long long rows, int C, __nv_bfloat16* __restrict__ y,
                         int32_t* __restrict__ idx_out) {
+  pdl_sync();
   extern __shared__ float s_bins[];
   for (int i = threadIdx.x; i < nb; i += blockDim.x) s_bins[i] = bins[i];
   __syncthreads();
@@ -48,6 +49,7 @@ bucket_embed_add_kernel(const __nv_bfloat16* __restrict__ x, const TgtT* __restr
 __global__ void __launch_bounds__(256)
 embedding_fwd_kernel(const int64_t* __restrict__ ids, const float* __restrict__ table, long long rows,
                      int C, int n_rows_table, int pad_idx, __nv_bfloat16* __restrict__ y) {
+  pdl_sync();
   const int lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -72,6 +74,7 @@ __global__ void __launch_bounds__(256)
 embedding_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const IdxT* __restrict__ ids,
                      long long rows, int C, int n_rows_table, int pad_idx,
                      float* __restrict__ dtable) {
+  pdl_sync();
   const int lane = threadIdx.x & 31;
   const long long w = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const long long r0 = w * kEmbRowsPerWarp;
@@ -121,11 +124,11 @@ int fs2_bucket_embed_add_bf16(const void* x, const void* target, int target_is_f
   const unsigned grid = (unsigned)((rows + 7) / 8);
   const size_t smem = (size_t)n_bins_minus_1 * sizeof(float);
   if (target_is_f64)
-    fs2::bucket_embed_add_kernel<double><<<grid, 256, smem, s>>>(
+    FS2_LAUNCH((fs2::bucket_embed_add_kernel<double>), grid, 256, smem, s, 
         static_cast<const __nv_bfloat16*>(x), static_cast<const double*>(target), bins,
         n_bins_minus_1, table, rows, C, static_cast<__nv_bfloat16*>(y), idx_out);
   else
-    fs2::bucket_embed_add_kernel<float><<<grid, 256, smem, s>>>(
+    FS2_LAUNCH((fs2::bucket_embed_add_kernel<float>), grid, 256, smem, s, 
         static_cast<const __nv_bfloat16*>(x), static_cast<const float*>(target), bins, n_bins_minus_1,
         table, rows, C, static_cast<__nv_bfloat16*>(y), idx_out);
   fs2::count_launch();
@@ -136,7 +139,7 @@ int fs2_embedding_fwd_bf16(const int64_t* ids, const float* table, int64_t rows,
                            int n_rows_table, int pad_idx, void* y, void* stream) {
   if (C % 8) return fs2::set_error("embedding_fwd: C must be a multiple of 8");
   if (rows <= 0) return 0;
-  fs2::embedding_fwd_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  FS2_LAUNCH((fs2::embedding_fwd_kernel), (unsigned)((rows + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream), 
       ids, table, rows, C, n_rows_table, pad_idx, static_cast<__nv_bfloat16*>(y));
   fs2::count_launch();
   return fs2::check_launch("embedding_fwd_kernel");
@@ -150,11 +153,11 @@ int fs2_embedding_bwd_f32(const void* dy, const void* ids, int ids_is_i64, int64
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const unsigned grid = (unsigned)((rows + 8 * fs2::kEmbRowsPerWarp - 1) / (8 * fs2::kEmbRowsPerWarp));
   if (ids_is_i64)
-    fs2::embedding_bwd_kernel<int64_t><<<grid, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(dy),
+    FS2_LAUNCH((fs2::embedding_bwd_kernel<int64_t>), grid, 256, 0, s, static_cast<const __nv_bfloat16*>(dy),
                                                             static_cast<const int64_t*>(ids), rows, C,
                                                             n_rows_table, pad_idx, dtable);
   else
-    fs2::embedding_bwd_kernel<int32_t><<<grid, 256, 0, s>>>(static_cast<const __nv_bfloat16*>(dy),
+    FS2_LAUNCH((fs2::embedding_bwd_kernel<int32_t>), grid, 256, 0, s, static_cast<const __nv_bfloat16*>(dy),
                                                             static_cast<const int32_t*>(ids), rows, C,
                                                             n_rows_table, pad_idx, dtable);
   fs2::count_launch();

@@ -47,6 +47,7 @@ __device__ __forceinline__ void epilogue_store(const fs2_gemm& g, float acc, int
 }
 
 __global__ void gemm_simt_normal(const SimtP sp) {
+  pdl_sync();
   const fs2_gemm& g = sp.g;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int Z = g.Z > 0 ? g.Z : 1;
@@ -90,6 +91,7 @@ __global__ void gemm_simt_normal(const SimtP sp) {
 }
 
 __global__ void gemm_simt_wgrad(const SimtP sp) {
+  pdl_sync();
   const fs2_gemm& g = sp.g;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int taps = g.taps > 0 ? g.taps : 1;
@@ -117,11 +119,11 @@ int gemm_simt_launch(const fs2_gemm& g, cudaStream_t stream) {
   if (g.mode == FS2_GEMM_NORMAL) {
     total = (long long)(g.Z > 0 ? g.Z : 1) * g.M * g.N;
     if (total == 0) return 0;
-    gemm_simt_normal<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(sp);
+    FS2_LAUNCH((gemm_simt_normal), (unsigned)((total + 255) / 256), 256, 0, stream, sp);
   } else {
     total = (long long)g.M * g.N * taps;
     if (total == 0) return 0;
-    gemm_simt_wgrad<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(sp);
+    FS2_LAUNCH((gemm_simt_wgrad), (unsigned)((total + 255) / 256), 256, 0, stream, sp);
   }
   count_launch();
   return check_launch("gemm_simt");

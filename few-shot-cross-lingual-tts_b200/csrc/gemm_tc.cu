@@ -40,6 +40,7 @@ template <int BN, int STAGES>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ GemmKP p) {
+  pdl_trigger();
   using L = SmemLayout<BN, STAGES>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -75,6 +76,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tmem_alloc(sbase + L::TMEM_PTR_OFF, TMEM_COLS);
     tmem_relinquish();
   }
+  pdl_wait();  // everything above is independent of the previous kernel's output
   if (warp == 3 && p.ragged) build_ragged_table(p, reinterpret_cast<int*>(sgen + L::CUM_OFF), lane);
   tc_fence_before();
   __syncthreads();
@@ -279,7 +281,7 @@ static int launch_tc(const fs2_gemm& g, GemmKP& kp, cudaStream_t stream) {
     cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
   }
   const int grid = kp.total_tiles < g_num_sms ? kp.total_tiles : g_num_sms;
-  gemm_tc_kernel<BN, STAGES><<<grid, kThreads, L::DYN_BYTES, stream>>>(tmA, tmB, kp);
+  FS2_LAUNCH((gemm_tc_kernel<BN, STAGES>), grid, kThreads, L::DYN_BYTES, stream, tmA, tmB, kp);
   count_launch();
   return check_launch("gemm_tc_kernel");
 }

@@ -48,6 +48,7 @@ constexpr int kThreads2 = 384;
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(g2::kThreads2, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const __grid_constant__ GemmKP p) {
+  pdl_trigger();
   using namespace g2;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -86,6 +87,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     tmem_alloc_2sm(sbase + TMEM_PTR_OFF, TMEM_COLS);
     tmem_relinquish_2sm();
   }
+  pdl_wait();  // everything above is independent of the previous kernel's output
   if (warp == 3 && p.ragged) build_ragged_table(p, reinterpret_cast<int*>(sgen + CUM_OFF), lane);
   tc_fence_before();
   __syncthreads();
@@ -273,7 +275,7 @@ int gemm_tc2_launch(const fs2_gemm& g, GemmKP& kp, cudaStream_t stream) {
   }
   const int max_pairs = g2_num_sms / 2;
   const int pairs = pair_tiles < max_pairs ? pair_tiles : max_pairs;
-  gemm_tc2_kernel<<<2 * pairs, kThreads2, DYN_BYTES, stream>>>(tmA, tmB, kp);
+  FS2_LAUNCH((gemm_tc2_kernel), 2 * pairs, kThreads2, DYN_BYTES, stream, tmA, tmB, kp);
   count_launch();
   return check_launch("gemm_tc2_kernel");
 }

@@ -46,6 +46,7 @@ __device__ __forceinline__ bool ln_row_masked(const LnArgs& a, long long row) {
 
 template <int NV>
 __global__ void __launch_bounds__(256) ln_fwd_kernel(const LnArgs a) {
+  pdl_sync();
   constexpr int C = NV * 256;
   const int lane = threadIdx.x & 31;
   const int warps_per_block = blockDim.x >> 5;
@@ -150,6 +151,7 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const LnArgs a) {
 
 template <int NV>
 __global__ void __launch_bounds__(256) ln_bwd_kernel(const LnArgs a) {
+  pdl_sync();
   constexpr int C = NV * 256;
   __shared__ float red[8][C];  // per-warp partials, reused for dgamma then dbeta
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -296,13 +298,13 @@ static int ln_dispatch(const LnArgs& a, int C, cudaStream_t s) {
   const int grid = BWD ? ln_grid(a.rows, 148 * 4) : ln_grid(a.rows, 148 * 8);
   switch (C) {
     case 256:
-      if (BWD) ln_bwd_kernel<1><<<grid, 256, 0, s>>>(a); else ln_fwd_kernel<1><<<grid, 256, 0, s>>>(a);
+      if (BWD) FS2_LAUNCH((ln_bwd_kernel<1>), grid, 256, 0, s, a); else FS2_LAUNCH((ln_fwd_kernel<1>), grid, 256, 0, s, a);
       break;
     case 512:
-      if (BWD) ln_bwd_kernel<2><<<grid, 256, 0, s>>>(a); else ln_fwd_kernel<2><<<grid, 256, 0, s>>>(a);
+      if (BWD) FS2_LAUNCH((ln_bwd_kernel<2>), grid, 256, 0, s, a); else FS2_LAUNCH((ln_fwd_kernel<2>), grid, 256, 0, s, a);
       break;
     case 1024:
-      if (BWD) ln_bwd_kernel<4><<<grid, 256, 0, s>>>(a); else ln_fwd_kernel<4><<<grid, 256, 0, s>>>(a);
+      if (BWD) FS2_LAUNCH((ln_bwd_kernel<4>), grid, 256, 0, s, a); else FS2_LAUNCH((ln_fwd_kernel<4>), grid, 256, 0, s, a);
       break;
     default:
       return set_error("layernorm: C must be 256, 512 or 1024");

@@ -21,6 +21,7 @@ template <typename DurT>
 __global__ void __launch_bounds__(256)
 lr_index_kernel(const DurT* __restrict__ dur, int Ts, int max_len, int64_t* __restrict__ cum,
                 int32_t* __restrict__ idx, int64_t* __restrict__ mel_len) {
+  pdl_sync();
   extern __shared__ long long s_cum[];  // Ts entries
   __shared__ long long s_warp[8];
   __shared__ long long s_carry;
@@ -73,6 +74,7 @@ lr_index_kernel(const DurT* __restrict__ dur, int Ts, int max_len, int64_t* __re
 __global__ void __launch_bounds__(256)
 lr_gather_kernel(const uint4* __restrict__ x, const int32_t* __restrict__ idx, int B, int Ts,
                  int max_len, int out_len, int vec_per_row, uint4* __restrict__ out) {
+  pdl_sync();
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= (long long)B * out_len) return;
   const int lane = threadIdx.x & 31;
@@ -92,6 +94,7 @@ __global__ void __launch_bounds__(256)
 lr_gather_fused_kernel(const __nv_bfloat16* __restrict__ x, const int32_t* __restrict__ idx,
                        const float* __restrict__ spk, const float* __restrict__ pe, int B, int Ts,
                        int max_len, int out_len, int C, __nv_bfloat16* __restrict__ out) {
+  pdl_sync();
   const int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (t >= out_len) return;
   const int lane = threadIdx.x & 31;
@@ -145,6 +148,7 @@ lr_gather_fused_kernel(const __nv_bfloat16* __restrict__ x, const int32_t* __res
 __global__ void __launch_bounds__(256)
 lr_bwd_kernel(const __nv_bfloat16* __restrict__ dout, const int64_t* __restrict__ cum, int B, int Ts,
               int n_rows, int C, __nv_bfloat16* __restrict__ dx) {
+  pdl_sync();
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= (long long)B * Ts) return;
   const int lane = threadIdx.x & 31;
@@ -168,6 +172,7 @@ lr_bwd_kernel(const __nv_bfloat16* __restrict__ dout, const int64_t* __restrict_
 __global__ void __launch_bounds__(256)
 lr_bwd_f32_kernel(const float* __restrict__ dout, const int64_t* __restrict__ cum, int B, int Ts,
                   int n_rows, int C, float* __restrict__ dx) {
+  pdl_sync();
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= (long long)B * Ts) return;
   const int lane = threadIdx.x & 31;
@@ -195,10 +200,10 @@ int fs2_lr_index(const void* dur, int dur_is_f32, int B, int Ts, int max_len, in
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const size_t smem = (size_t)(Ts > 0 ? Ts : 1) * sizeof(long long);
   if (dur_is_f32)
-    fs2::lr_index_kernel<float><<<B, 256, smem, s>>>(static_cast<const float*>(dur), Ts, max_len, cum,
+    FS2_LAUNCH((fs2::lr_index_kernel<float>), B, 256, smem, s, static_cast<const float*>(dur), Ts, max_len, cum,
                                                      idx, mel_len);
   else
-    fs2::lr_index_kernel<int64_t><<<B, 256, smem, s>>>(static_cast<const int64_t*>(dur), Ts, max_len,
+    FS2_LAUNCH((fs2::lr_index_kernel<int64_t>), B, 256, smem, s, static_cast<const int64_t*>(dur), Ts, max_len,
                                                        cum, idx, mel_len);
   fs2::count_launch();
   return fs2::check_launch("lr_index_kernel");
@@ -211,7 +216,7 @@ int fs2_lr_gather(const void* x, const int32_t* idx, int B, int Ts, int max_len,
   if (row_bytes % 16) return fs2::set_error("lr_gather: row bytes must be a multiple of 16");
   const long long rows = (long long)B * out_len;
   if (rows <= 0) return 0;
-  fs2::lr_gather_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  FS2_LAUNCH((fs2::lr_gather_kernel), (unsigned)((rows + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream), 
       static_cast<const uint4*>(x), idx, B, Ts, max_len, out_len, row_bytes / 16,
       static_cast<uint4*>(out));
   fs2::count_launch();
@@ -227,7 +232,7 @@ int fs2_lr_gather_fused_bf16(const void* x, const int32_t* idx, const float* spk
   if ((reinterpret_cast<uintptr_t>(spk) & 15) || (reinterpret_cast<uintptr_t>(pe) & 15) || (C % 4))
     return fs2::set_error("lr_gather_fused: spk / pe rows must be 16-byte aligned");
   const dim3 grid((unsigned)((out_len + 7) / 8), (unsigned)((B + fs2::kLrGroup - 1) / fs2::kLrGroup));
-  fs2::lr_gather_fused_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  FS2_LAUNCH((fs2::lr_gather_fused_kernel), grid, 256, 0, static_cast<cudaStream_t>(stream), 
       static_cast<const __nv_bfloat16*>(x), idx, spk, pe, B, Ts, max_len, out_len, C,
       static_cast<__nv_bfloat16*>(out));
   fs2::count_launch();
@@ -240,7 +245,7 @@ int fs2_lr_bwd_bf16(const void* dout, const int64_t* cum, int B, int Ts, int n_r
   if (C % 8) return fs2::set_error("lr_bwd: C must be a multiple of 8");
   const long long rows = (long long)B * Ts;
   if (rows <= 0) return 0;
-  fs2::lr_bwd_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  FS2_LAUNCH((fs2::lr_bwd_kernel), (unsigned)((rows + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream), 
       static_cast<const __nv_bfloat16*>(dout), cum, B, Ts, n_rows, C, static_cast<__nv_bfloat16*>(dx));
   fs2::count_launch();
   return fs2::check_launch("lr_bwd_kernel");
@@ -250,7 +255,7 @@ int fs2_lr_bwd_f32(const float* dout, const int64_t* cum, int B, int Ts, int n_r
                    void* stream) {
   const long long rows = (long long)B * Ts;
   if (rows <= 0) return 0;
-  fs2::lr_bwd_f32_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  FS2_LAUNCH((fs2::lr_bwd_f32_kernel), (unsigned)((rows + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream), 
       dout, cum, B, Ts, n_rows, C, dx);
   fs2::count_launch();
   return fs2::check_launch("lr_bwd_f32_kernel");

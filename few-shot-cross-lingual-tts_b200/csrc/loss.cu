@@ -62,6 +62,7 @@ __device__ __forceinline__ float energy_target(const LossArgs& a, long long i) {
 }
 
 __global__ void __launch_bounds__(kLossThreads) loss_partial_kernel(const LossArgs a) {
+  pdl_sync();
   __shared__ float sh[8];
   float s[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
   const int nmel_blocks = a.B * a.mel_blocks_per_b;
@@ -107,6 +108,7 @@ __global__ void __launch_bounds__(kLossThreads) loss_partial_kernel(const LossAr
 }
 
 __global__ void __launch_bounds__(kLossThreads) loss_final_kernel(const LossArgs a) {
+  pdl_sync();
   __shared__ float sh[8];
   float s[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
   for (int i = threadIdx.x; i < a.n_blocks; i += kLossThreads)
@@ -139,6 +141,7 @@ __global__ void __launch_bounds__(kLossThreads) loss_final_kernel(const LossArgs
 __device__ __forceinline__ float sgn(float v) { return v > 0.f ? 1.f : (v < 0.f ? -1.f : 0.f); }
 
 __global__ void __launch_bounds__(kLossThreads) loss_bwd_kernel(const LossArgs a) {
+  pdl_sync();
   const float g0 = a.gout[0];
   const float n_mel = a.out[6], n_src = a.out[7];
   const int nmel_blocks = a.B * a.mel_blocks_per_b;
@@ -222,10 +225,10 @@ int fs2_loss_fwd(const float* mel_pred, const float* post_pred, const float* mel
   a.partials = partials; a.out = out8;
   if (int rc = fs2::fill_grid(a)) return rc;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  fs2::loss_partial_kernel<<<a.n_blocks, fs2::kLossThreads, 0, s>>>(a);
+  FS2_LAUNCH((fs2::loss_partial_kernel), a.n_blocks, fs2::kLossThreads, 0, s, a);
   fs2::count_launch();
   if (int rc = fs2::check_launch("loss_partial_kernel")) return rc;
-  fs2::loss_final_kernel<<<1, fs2::kLossThreads, 0, s>>>(a);
+  FS2_LAUNCH((fs2::loss_final_kernel), 1, fs2::kLossThreads, 0, s, a);
   fs2::count_launch();
   return fs2::check_launch("loss_final_kernel");
 }
@@ -245,7 +248,7 @@ int fs2_loss_bwd(const float* gout6, const float* out8, const float* mel_pred, c
   a.B = B; a.Ts = Ts; a.Tm = Tm; a.Tm_tgt = Tm_tgt; a.n_mel = n_mel;
   a.d_mel = d_mel; a.d_post = d_post; a.d_p = d_p; a.d_e = d_e; a.d_d = d_d;
   if (int rc = fs2::fill_grid(a)) return rc;
-  fs2::loss_bwd_kernel<<<a.n_blocks, fs2::kLossThreads, 0, static_cast<cudaStream_t>(stream)>>>(a);
+  FS2_LAUNCH((fs2::loss_bwd_kernel), a.n_blocks, fs2::kLossThreads, 0, static_cast<cudaStream_t>(stream), a);
   fs2::count_launch();
   return fs2::check_launch("loss_bwd_kernel");
 }

@@ -10,6 +10,7 @@ template <typename InT>
 __global__ void __launch_bounds__(256)
 posenc_add_kernel(const InT* __restrict__ x, const float* __restrict__ pe, long long n_vec, int T, int C,
                   long long x_batch_stride, __nv_bfloat16* __restrict__ y) {
+  pdl_sync();
   const int vec_per_row = C / 8;
   for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < n_vec;
        v += (long long)gridDim.x * blockDim.x) {
@@ -36,6 +37,7 @@ posenc_add_kernel(const InT* __restrict__ x, const float* __restrict__ pe, long 
 
 __global__ void __launch_bounds__(256)
 cast_f32_bf16_kernel(const float* __restrict__ x, long long n, __nv_bfloat16* __restrict__ y) {
+  pdl_sync();
   for (long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n;
        i += (long long)gridDim.x * blockDim.x * 4) {
     if (i + 3 < n) {
@@ -51,6 +53,7 @@ cast_f32_bf16_kernel(const float* __restrict__ x, long long n, __nv_bfloat16* __
 
 __global__ void __launch_bounds__(256)
 cast_bf16_f32_kernel(const __nv_bfloat16* __restrict__ x, long long n, float* __restrict__ y) {
+  pdl_sync();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (long long)gridDim.x * blockDim.x)
     y[i] = __bfloat162float(x[i]);
@@ -60,6 +63,7 @@ cast_bf16_f32_kernel(const __nv_bfloat16* __restrict__ x, long long n, float* __
 __global__ void __launch_bounds__(256)
 pack_conv_weight_kernel(const float* __restrict__ w, int Co, int Ci, int k, int Cpad,
                         __nv_bfloat16* __restrict__ wp) {
+  pdl_sync();
   const long long n = (long long)Co * k * Cpad;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (long long)gridDim.x * blockDim.x) {
@@ -74,6 +78,7 @@ pack_conv_weight_kernel(const float* __restrict__ w, int Co, int Ci, int k, int 
 __global__ void __launch_bounds__(256)
 add_rowvec_kernel(const __nv_bfloat16* x, const float* __restrict__ e, long long n_vec, int T, int C,
                   __nv_bfloat16* y) {
+  pdl_sync();
   const int vec_per_row = C / 8;
   for (long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x; v < n_vec;
        v += (long long)gridDim.x * blockDim.x) {
@@ -92,6 +97,7 @@ add_rowvec_kernel(const __nv_bfloat16* x, const float* __restrict__ e, long long
 __global__ void __launch_bounds__(256)
 add_f32_bf16_kernel(const float* __restrict__ a, const __nv_bfloat16* __restrict__ b, long long n,
                     float* __restrict__ out) {
+  pdl_sync();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (long long)gridDim.x * blockDim.x)
     out[i] = a[i] + __bfloat162float(b[i]);
@@ -104,6 +110,7 @@ __global__ void __launch_bounds__(256)
 colsum_kernel(const __nv_bfloat16* __restrict__ x, long long ld, int rows_per_group, int C,
               int rows_per_block, float* __restrict__ out, const int64_t* __restrict__ lens,
               int out_group_stride, int seg_stride, float* __restrict__ out_b) {
+  pdl_sync();
   extern __shared__ float s_acc[];  // [C]
   const int g = blockIdx.y;
   if (blockIdx.z) {  // second column segment of the same rows (e.g. the V block next to the Q block of dQKV)
@@ -156,6 +163,7 @@ colsum_kernel(const __nv_bfloat16* __restrict__ x, long long ld, int rows_per_gr
 // grad[co][ci][tap] += packed[co][tap][ci]
 __global__ void __launch_bounds__(256)
 unpack_add_conv_grad_kernel(const float* __restrict__ packed, int Co, int Ci, int k, float* __restrict__ grad) {
+  pdl_sync();
   const long long n = (long long)Co * Ci * k;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (long long)gridDim.x * blockDim.x) {
@@ -170,6 +178,7 @@ unpack_add_conv_grad_kernel(const float* __restrict__ packed, int Co, int Ci, in
 __global__ void __launch_bounds__(256)
 colsum_f32_kernel(const float* __restrict__ x, long long ld, int rows, int C, int rows_per_block,
                   float* __restrict__ out) {
+  pdl_sync();
   const int r0 = blockIdx.x * rows_per_block;
   const int r1 = min(r0 + rows_per_block, rows);
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
@@ -184,6 +193,7 @@ __global__ void __launch_bounds__(256)
 rowdot_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w,
                   const float* __restrict__ bias, const int64_t* __restrict__ lens, long long rows, int T,
                   int C, float* __restrict__ out) {
+  pdl_sync();
   const int lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -206,6 +216,7 @@ __global__ void __launch_bounds__(256)
 rowdot_bwd_kernel(const float* __restrict__ dout, const __nv_bfloat16* __restrict__ x,
                   const float* __restrict__ w, const int64_t* __restrict__ lens, long long rows, int T,
                   int C, __nv_bfloat16* __restrict__ dx, float* __restrict__ dw, float* __restrict__ db) {
+  pdl_sync();
   __shared__ float red[8][1024];
   __shared__ float red_b[8];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -269,10 +280,10 @@ int fs2_posenc_add(const void* x, int x_is_f32, int64_t x_batch_stride, const fl
   if (n_vec <= 0) return 0;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (x_is_f32)
-    fs2::posenc_add_kernel<float><<<fs2::grid_for(n_vec, 256), 256, 0, s>>>(
+    FS2_LAUNCH((fs2::posenc_add_kernel<float>), fs2::grid_for(n_vec, 256), 256, 0, s, 
         static_cast<const float*>(x), pe, n_vec, T, C, x_batch_stride, static_cast<__nv_bfloat16*>(y));
   else
-    fs2::posenc_add_kernel<__nv_bfloat16><<<fs2::grid_for(n_vec, 256), 256, 0, s>>>(
+    FS2_LAUNCH((fs2::posenc_add_kernel<__nv_bfloat16>), fs2::grid_for(n_vec, 256), 256, 0, s, 
         static_cast<const __nv_bfloat16*>(x), pe, n_vec, T, C, x_batch_stride,
         static_cast<__nv_bfloat16*>(y));
   fs2::count_launch();
@@ -283,7 +294,7 @@ int fs2_cast_f32_bf16(const float* x, int64_t n, void* y, void* stream) {
   if (n <= 0) return 0;
   if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(y) & 7))
     return fs2::set_error("cast_f32_bf16: misaligned pointers");
-  fs2::cast_f32_bf16_kernel<<<fs2::grid_for(n, 1024), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  FS2_LAUNCH((fs2::cast_f32_bf16_kernel), fs2::grid_for(n, 1024), 256, 0, static_cast<cudaStream_t>(stream), 
       x, n, static_cast<__nv_bfloat16*>(y));
   fs2::count_launch();
   return fs2::check_launch("cast_f32_bf16_kernel");
@@ -291,7 +302,7 @@ int fs2_cast_f32_bf16(const float* x, int64_t n, void* y, void* stream) {
 
 int fs2_cast_bf16_f32(const void* x, int64_t n, float* y, void* stream) {
   if (n <= 0) return 0;
-  fs2::cast_bf16_f32_kernel<<<fs2::grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  FS2_LAUNCH((fs2::cast_bf16_f32_kernel), fs2::grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream), 
       static_cast<const __nv_bfloat16*>(x), n, y);
   fs2::count_launch();
   return fs2::check_launch("cast_bf16_f32_kernel");
@@ -301,7 +312,7 @@ int fs2_pack_conv_weight(const float* w, int Co, int Ci, int k, int Cpad, void* 
   const long long n = (long long)Co * k * Cpad;
   if (n <= 0) return 0;
   if (Cpad < Ci) return fs2::set_error("pack_conv_weight: Cpad < Ci");
-  fs2::pack_conv_weight_kernel<<<fs2::grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  FS2_LAUNCH((fs2::pack_conv_weight_kernel), fs2::grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream), 
       w, Co, Ci, k, Cpad, static_cast<__nv_bfloat16*>(wp));
   fs2::count_launch();
   return fs2::check_launch("pack_conv_weight_kernel");
@@ -309,7 +320,7 @@ int fs2_pack_conv_weight(const float* w, int Co, int Ci, int k, int Cpad, void* 
 
 int fs2_add_f32_bf16(const float* a, const void* b, int64_t n, float* out, void* stream) {
   if (n <= 0) return 0;
-  fs2::add_f32_bf16_kernel<<<fs2::grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  FS2_LAUNCH((fs2::add_f32_bf16_kernel), fs2::grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream), 
       a, static_cast<const __nv_bfloat16*>(b), n, out);
   fs2::count_launch();
   return fs2::check_launch("add_f32_bf16_kernel");
@@ -319,7 +330,7 @@ int fs2_add_rowvec_bf16(const void* x, const float* e, int B, int T, int C, void
   if (C % 8) return fs2::set_error("add_rowvec: C must be a multiple of 8");
   const long long n_vec = (long long)B * T * (C / 8);
   if (n_vec <= 0) return 0;
-  fs2::add_rowvec_kernel<<<fs2::grid_for(n_vec, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  FS2_LAUNCH((fs2::add_rowvec_kernel), fs2::grid_for(n_vec, 256), 256, 0, static_cast<cudaStream_t>(stream), 
       static_cast<const __nv_bfloat16*>(x), e, n_vec, T, C, static_cast<__nv_bfloat16*>(y));
   fs2::count_launch();
   return fs2::check_launch("add_rowvec_kernel");
@@ -335,7 +346,7 @@ static int colsum_launch(const void* x, int64_t ld, int groups, int rows_per_gro
   int rpb = (rows_per_group * groups + 148 * 8 - 1) / (148 * 8);
   if (rpb < 32) rpb = 32;
   dim3 grid((rows_per_group + rpb - 1) / rpb, groups, out_b ? 2 : 1);
-  fs2::colsum_kernel<<<grid, 256, C * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
+  FS2_LAUNCH((fs2::colsum_kernel), grid, 256, C * sizeof(float), static_cast<cudaStream_t>(stream), 
       static_cast<const __nv_bfloat16*>(x), ld, rows_per_group, C, rpb, out, lens, out_group_stride, seg_stride,
       out_b);
   fs2::count_launch();
@@ -371,7 +382,7 @@ int fs2_colsum3_bf16(const void* x, int64_t ld, int rows, int seg_cols, float* o
 int fs2_unpack_add_conv_grad(const float* packed, int Co, int Ci, int k, float* grad, void* stream) {
   const long long n = (long long)Co * Ci * k;
   if (n <= 0) return 0;
-  fs2::unpack_add_conv_grad_kernel<<<fs2::grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  FS2_LAUNCH((fs2::unpack_add_conv_grad_kernel), fs2::grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream), 
       packed, Co, Ci, k, grad);
   fs2::count_launch();
   return fs2::check_launch("unpack_add_conv_grad_kernel");
@@ -380,7 +391,7 @@ int fs2_unpack_add_conv_grad(const float* packed, int Co, int Ci, int k, float* 
 int fs2_colsum_f32(const float* x, int64_t ld, int rows, int C, float* out, void* stream) {
   if (rows <= 0) return 0;
   const int rpb = 64;
-  fs2::colsum_f32_kernel<<<(rows + rpb - 1) / rpb, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+  FS2_LAUNCH((fs2::colsum_f32_kernel), (rows + rpb - 1) / rpb, 128, 0, static_cast<cudaStream_t>(stream), 
       x, ld, rows, C, rpb, out);
   fs2::count_launch();
   return fs2::check_launch("colsum_f32_kernel");
@@ -391,7 +402,7 @@ int fs2_rowdot_fwd(const void* x, const float* w, const float* bias, const int64
   if (C % 8 || C > 1024) return fs2::set_error("rowdot: C must be a multiple of 8, <= 1024");
   const long long rows = (long long)B * T;
   if (rows <= 0) return 0;
-  fs2::rowdot_fwd_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  FS2_LAUNCH((fs2::rowdot_fwd_kernel), (unsigned)((rows + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream), 
       static_cast<const __nv_bfloat16*>(x), w, bias, lens, rows, T, C, out);
   fs2::count_launch();
   return fs2::check_launch("rowdot_fwd_kernel");
@@ -402,8 +413,7 @@ int fs2_rowdot_bwd(const float* dout, const void* x, const float* w, const int64
   if (C % 256 || C > 1024) return fs2::set_error("rowdot_bwd: C must be 256/512/768/1024");
   const long long rows = (long long)B * T;
   if (rows <= 0) return 0;
-  fs2::rowdot_bwd_kernel<<<fs2::grid_for(rows, 32, 148 * 2), 256, 0,
-                           static_cast<cudaStream_t>(stream)>>>(
+  FS2_LAUNCH((fs2::rowdot_bwd_kernel), fs2::grid_for(rows, 32, 148 * 2), 256, 0, static_cast<cudaStream_t>(stream), 
       dout, static_cast<const __nv_bfloat16*>(x), w, lens, rows, T, C, static_cast<__nv_bfloat16*>(dx),
       dw, db);
   fs2::count_launch();
@@ -421,6 +431,7 @@ template <typename V>
 __global__ void __launch_bounds__(256)
 pad_ragged_kernel(const V* __restrict__ src, const long long* __restrict__ offsets, int B, int max_len, int vec_per_row,
                   V* __restrict__ dst) {
+  pdl_sync();
   const long long n = (long long)B * max_len * vec_per_row;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const int v = i % vec_per_row;
@@ -444,11 +455,11 @@ extern "C" int fs2_pad_ragged(const void* src, const int64_t* offsets, int B, in
   const unsigned grid = fs2::grid_for(n, 256);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (v16)
-    fs2::pad_ragged_kernel<uint4><<<grid, 256, 0, s>>>(static_cast<const uint4*>(src),
+    FS2_LAUNCH((fs2::pad_ragged_kernel<uint4>), grid, 256, 0, s, static_cast<const uint4*>(src),
                                                        reinterpret_cast<const long long*>(offsets), B, max_len,
                                                        row_bytes / 16, static_cast<uint4*>(dst));
   else
-    fs2::pad_ragged_kernel<uint32_t><<<grid, 256, 0, s>>>(static_cast<const uint32_t*>(src),
+    FS2_LAUNCH((fs2::pad_ragged_kernel<uint32_t>), grid, 256, 0, s, static_cast<const uint32_t*>(src),
                                                           reinterpret_cast<const long long*>(offsets), B, max_len,
                                                           row_bytes / 4, static_cast<uint32_t*>(dst));
   fs2::count_launch();

@@ -31,6 +31,7 @@ struct AdamArgs {
 };
 
 __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g, long long n, float* __restrict__ out) {
+  pdl_sync();
   __shared__ float red[8];
   float s = 0.f;
   const long long n4 = n >> 2;
@@ -69,6 +70,7 @@ __device__ __forceinline__ float lr_factor(const AdamArgs& a, long long step) {
 }
 
 __global__ void __launch_bounds__(256) adam_step_kernel(const AdamArgs a) {
+  pdl_sync();
   const long long step = *a.step;  // steps already taken; this is step number step + 1
   // clip_grad_norm_: coef = max_norm / (total_norm + 1e-6), clamped to 1
   float clip = 1.f;
@@ -108,6 +110,7 @@ __global__ void __launch_bounds__(256) adam_step_kernel(const AdamArgs a) {
 }
 
 __global__ void optim_advance_kernel(long long* step, float* gnorm_sq, float* gnorm_out) {
+  pdl_sync();
   if (threadIdx.x == 0 && blockIdx.x == 0) {
     *step += 1;
     if (gnorm_out) *gnorm_out = sqrtf(*gnorm_sq);  // for logging: the un-clipped global gradient norm
@@ -122,7 +125,7 @@ extern "C" {
 int fs2_sumsq_f32(const float* g, int64_t n, float* out, void* stream) {
   if (n <= 0) return 0;
   if (reinterpret_cast<uintptr_t>(g) & 15) return fs2::set_error("sumsq: buffer must be 16-byte aligned");
-  fs2::sumsq_kernel<<<148 * 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(g, n, out);
+  FS2_LAUNCH((fs2::sumsq_kernel), 148 * 8, 256, 0, static_cast<cudaStream_t>(stream), g, n, out);
   fs2::count_launch();
   return fs2::check_launch("sumsq_kernel");
 }
@@ -145,13 +148,13 @@ int fs2_adam_step_f32(float* p, const float* g, float* m, float* v, int64_t n, c
   a.lr0 = lr0; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.weight_decay = weight_decay; a.max_norm = max_norm;
   a.sched_type = sched_type; a.warmup = warmup; a.n_anneal = n_anneal; a.anneal_rate = anneal_rate;
   for (int i = 0; i < n_anneal; ++i) a.anneal_steps[i] = anneal_steps[i];
-  fs2::adam_step_kernel<<<148 * 8, 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
+  FS2_LAUNCH((fs2::adam_step_kernel), 148 * 8, 256, 0, static_cast<cudaStream_t>(stream), a);
   fs2::count_launch();
   return fs2::check_launch("adam_step_kernel");
 }
 
 int fs2_optim_advance(int64_t* step, float* gnorm_sq, float* gnorm_out, void* stream) {
-  fs2::optim_advance_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(reinterpret_cast<long long*>(step),
+  FS2_LAUNCH((fs2::optim_advance_kernel), 1, 32, 0, static_cast<cudaStream_t>(stream), reinterpret_cast<long long*>(step),
                                                                             gnorm_sq, gnorm_out);
   fs2::count_launch();
   return fs2::check_launch("optim_advance_kernel");

@@ -17,6 +17,7 @@ constexpr int kMaxVec = 16;  // 16 float4 per lane = 2048 columns
 __global__ void __launch_bounds__(256)
 softmax_fwd_kernel(const float* __restrict__ S, const int64_t* __restrict__ lens, int H, int T, int Tp,
                    long long rows, __nv_bfloat16* __restrict__ P) {
+  pdl_sync();
   const int lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -73,6 +74,7 @@ __global__ void __launch_bounds__(256)
 softmax_bwd_kernel(const __nv_bfloat16* __restrict__ P, const float* __restrict__ dP,
                    const int64_t* __restrict__ lens, int H, int T, int Tp, long long rows, float alpha,
                    __nv_bfloat16* __restrict__ dS) {
+  pdl_sync();
   const int lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -129,7 +131,7 @@ int fs2_softmax_fwd(const float* S, const int64_t* lens, int Z, int H, int T, in
   if (Tp % 128 || Tp > 128 * fs2::kMaxVec || Tp < T) return fs2::set_error("softmax: bad Tp");
   const long long rows = (long long)Z * T;
   if (rows == 0) return 0;
-  fs2::softmax_fwd_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  FS2_LAUNCH((fs2::softmax_fwd_kernel), (unsigned)((rows + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream), 
       S, lens, H, T, Tp, rows, static_cast<__nv_bfloat16*>(P));
   fs2::count_launch();
   return fs2::check_launch("softmax_fwd_kernel");
@@ -140,7 +142,7 @@ int fs2_softmax_bwd(const void* P, const float* dP, const int64_t* lens, int Z, 
   if (Tp % 128 || Tp > 128 * fs2::kMaxVec || Tp < T) return fs2::set_error("softmax: bad Tp");
   const long long rows = (long long)Z * T;
   if (rows == 0) return 0;
-  fs2::softmax_bwd_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  FS2_LAUNCH((fs2::softmax_bwd_kernel), (unsigned)((rows + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream), 
       static_cast<const __nv_bfloat16*>(P), dP, lens, H, T, Tp, rows, alpha,
       static_cast<__nv_bfloat16*>(dS));
   fs2::count_launch();

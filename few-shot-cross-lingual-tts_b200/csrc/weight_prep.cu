@@ -23,6 +23,7 @@ constexpr int kPrepMaxRow = 4096;  // floats of one source row (Ci * k) held in 
 
 __global__ void __launch_bounds__(256) weight_prep_kernel(const PrepEntry* __restrict__ tab, int n_entries,
                                                           int total_rows) {
+  pdl_sync();
   __shared__ float srow[kPrepMaxRow];
   for (int grow = blockIdx.x; grow < total_rows; grow += gridDim.x) {
     int lo = 0, hi = n_entries - 1;  // last entry with row0 <= grow
@@ -66,7 +67,7 @@ int fs2_weight_prep(const void* table, int n_entries, int total_rows, void* stre
   if (n_entries <= 0 || total_rows <= 0) return 0;
   static_assert(sizeof(fs2::PrepEntry) == sizeof(fs2_prep_entry), "fs2_prep_entry layout");
   int grid = total_rows < 148 * 16 ? total_rows : 148 * 16;
-  fs2::weight_prep_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  FS2_LAUNCH((fs2::weight_prep_kernel), grid, 256, 0, static_cast<cudaStream_t>(stream), 
       static_cast<const fs2::PrepEntry*>(table), n_entries, total_rows);
   fs2::count_launch();
   return fs2::check_launch("weight_prep_kernel");

@@ -133,7 +133,7 @@ def run_reference(args):
     torch.set_num_threads(cores)
     cfg = synth.model_cfg(multi_speaker=True)
     batch = synth.make_batch(**synth.CONFIGS[args.config])
-    step, frames, sample = cpu_reference_step_fn(cfg, batch, n_utt=8)
+    step, frames, sample = cpu_reference_step_fn(cfg, batch, n_utt=16)
     for _ in range(max(args.warmup, 1)):
         step()
     t0 = time.time()
@@ -395,15 +395,15 @@ def run_ours(args):
         if world == 1 and not args.no_cpu_baseline:
             try:
                 torch.set_num_threads(os.cpu_count() or 1)
-                cstep, cframes, sample = cpu_reference_step_fn(cfg, base, n_utt=8)
+                cstep, cframes, sample = cpu_reference_step_fn(cfg, base, n_utt=16)
                 cstep()
                 t0 = time.time()
-                n = 2
+                n = 4
                 for _ in range(n):
                     cstep()
                 dt = time.time() - t0
                 line["cpu_baseline"] = {"value": cframes * n / dt, "unit": UNIT, "cores": os.cpu_count(),
-                                        "kind": "port", "sample": sample + ", 1 warm-up + 2 timed steps"}
+                                        "kind": "port", "sample": sample + ", 1 warm-up + 4 timed steps"}
             except Exception as e:  # the baseline must never take the GPU number down with it
                 line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
                                         "sample": "failed: %r" % (e,)}

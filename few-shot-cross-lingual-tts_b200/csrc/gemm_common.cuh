@@ -47,6 +47,7 @@ struct GemmKP {
   int units_max;   // units per entry when nothing is padded
   int row_extent;  // rows per entry (NORMAL: M, WGRAD: a.rows)
   int tail_zero;   // NORMAL: rows zeroed behind the last scheduled tile (0 = all, < 0 = none)
+  unsigned long long* relu_mask;  // optional 1-bit ReLU mask [Z*M][N/64] (written by EPI_RELU, read by EPI_RELU_BWD)
   int pair_any;    // 2-CTA kernels, ragged NORMAL, shared (un-batched) B: the two CTAs of a pair take ANY two
                    // consecutive 128-row tiles of the compact list, also from different utterances
 };
@@ -206,7 +207,8 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmKP& p, const int* cum
 template <bool F32OUT, bool ATOMIC = false>
 __device__ __forceinline__ void epilogue_chunk(const GemmKP& p, uint32_t taddr, uint8_t* stg, int lane,
                                                int m_w0, int n0, int nlimit, long long base_off,
-                                               const __nv_bfloat16* aux_base, bool tile_ok, bool row_ok = true) {
+                                               const __nv_bfloat16* aux_base, bool tile_ok, bool row_ok = true,
+                                               unsigned long long* mask_row = nullptr) {
   constexpr int NC = F32OUT ? 32 : 64;  // accumulator columns per 128-byte output row segment
   float f[NC];
   {
@@ -252,6 +254,26 @@ __device__ __forceinline__ void epilogue_chunk(const GemmKP& p, uint32_t taddr, 
     for (int j = 0; j < NC; ++j) f[j] = fmaxf(f[j], 0.f);
   }
   if constexpr (!F32OUT) {
+    if (mask_row) {  // 1-bit ReLU mask of this thread's row, word n0 / 64 (this thread owns the whole 64-column chunk)
+      unsigned long long* mw = mask_row + (n0 >> 6);
+      if (p.epilogue == FS2_EPI_RELU) {
+        unsigned int lo = 0, hi = 0;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          lo |= (f[j] > 0.f ? 1u : 0u) << j;
+          hi |= (f[32 + j] > 0.f ? 1u : 0u) << j;
+        }
+        if (tile_ok) *mw = (static_cast<unsigned long long>(hi) << 32) | lo;
+      } else if (p.epilogue == FS2_EPI_RELU_BWD) {
+        const unsigned long long m = tile_ok ? *mw : 0ull;
+        const unsigned int lo = static_cast<unsigned int>(m), hi = static_cast<unsigned int>(m >> 32);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          f[j] = (lo >> j) & 1u ? f[j] : 0.f;
+          f[32 + j] = (hi >> j) & 1u ? f[32 + j] : 0.f;
+        }
+      }
+    }
     if (aux_base) {  // bf16 aux tile, 64 columns = 128 B per row
 #pragma unroll
       for (int it = 0; it < 8; ++it) {
@@ -392,10 +414,18 @@ __device__ __forceinline__ void epilogue_tile(const GemmKP& p, const TileCoord& 
     }
   } else {
     const __nv_bfloat16* aux_base = p.aux ? p.aux + (long long)t.z * p.aux_batch_stride : nullptr;
+    unsigned long long* mask_row = nullptr;
+    bool ok_row = ok;
+    if (p.relu_mask) {  // this thread's row of the 1-bit mask (rows outside the output are neither read nor written)
+      const int gm = m_w0 + lane;
+      mask_row = p.relu_mask + ((long long)t.z * p.M + (gm < p.M ? gm : 0)) * (p.N >> 6);
+      ok_row = ok && gm < p.M;
+    }
 #pragma unroll 1
     for (int c0 = chalf * (BN / 2); c0 < (chalf + 1) * (BN / 2); c0 += 64) {
       if (ncol0 + c0 >= nlimit) break;
-      epilogue_chunk<false>(p, taddr + c0, stg, lane, m_w0, ncol0 + c0, nlimit, base_off, aux_base, ok, row_ok);
+      epilogue_chunk<false>(p, taddr + c0, stg, lane, m_w0, ncol0 + c0, nlimit, base_off, aux_base, ok, row_ok,
+                            mask_row ? (ok_row ? mask_row : nullptr) : nullptr);
     }
   }
 }

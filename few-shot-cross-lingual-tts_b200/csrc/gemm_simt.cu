@@ -26,6 +26,14 @@ __device__ __forceinline__ void epilogue_store(const fs2_gemm& g, float acc, int
   acc *= g.alpha;
   if (g.bias) acc += g.bias[ncol];
   if (g.epilogue == FS2_EPI_RELU) acc = fmaxf(acc, 0.f);
+  if (g.relu_mask) {  // 1-bit mask [Z*M][N/64]; the cross-check ORs its bit in (the caller zeroes the mask first)
+    unsigned long long* w = static_cast<unsigned long long*>(g.relu_mask) + ((long long)z * g.M + m) * (g.N >> 6) + (ncol >> 6);
+    if (g.epilogue == FS2_EPI_RELU) {
+      if (acc > 0.f) atomicOr(w, 1ull << (ncol & 63));
+    } else if (g.epilogue == FS2_EPI_RELU_BWD) {
+      acc = ((*w >> (ncol & 63)) & 1ull) ? acc : 0.f;
+    }
+  } else
   if (g.epilogue == FS2_EPI_RELU_BWD || g.epilogue == FS2_EPI_ADD_AUX) {
     const float a = ld_bf16(g.aux, (long long)z * g.aux_batch_stride + (long long)m * g.ld_aux + ncol);
     acc = g.epilogue == FS2_EPI_RELU_BWD ? (a > 0.f ? acc : 0.f) : acc + a;

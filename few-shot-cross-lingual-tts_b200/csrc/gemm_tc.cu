@@ -379,8 +379,15 @@ int gemm_fill_params(const fs2_gemm& g, GemmKP& kp) {
   if (g.aux && (g.d_f32 || (g.N & 7))) return set_error("gemm: aux epilogues need a bf16 output and N % 8 == 0");
   if (g.aux && ((reinterpret_cast<uintptr_t>(g.aux) & 15) || (g.ld_aux & 7) || (g.aux_batch_stride & 7)))
     return set_error("gemm: aux rows must be 16-byte aligned");
-  if ((g.epilogue == FS2_EPI_RELU_BWD || g.epilogue == FS2_EPI_ADD_AUX) && !g.aux)
-    return set_error("epilogue needs aux");
+  if (g.epilogue == FS2_EPI_ADD_AUX && !g.aux) return set_error("epilogue needs aux");
+  if (g.epilogue == FS2_EPI_RELU_BWD && !g.aux && !g.relu_mask) return set_error("ReLU backward needs aux or relu_mask");
+  if (g.relu_mask) {
+    if (g.mode != FS2_GEMM_NORMAL || g.d_f32 || (g.N & 63) || (reinterpret_cast<uintptr_t>(g.relu_mask) & 7))
+      return set_error("gemm: relu_mask needs NORMAL mode, a bf16 output and N % 64 == 0");
+    if (g.epilogue == FS2_EPI_RELU_BWD && g.aux) return set_error("gemm: pass either aux or relu_mask to the ReLU backward");
+    if (g.epilogue != FS2_EPI_RELU && g.epilogue != FS2_EPI_RELU_BWD) return set_error("gemm: relu_mask without a ReLU epilogue");
+    kp.relu_mask = static_cast<unsigned long long*>(g.relu_mask);
+  }
   if (kp.d_col_stride != 1) return set_error("gemm: outputs must have unit column stride (d_col_stride = 1)");
   return 0;
 }

@@ -44,7 +44,7 @@ def run(g, impl=None):
 
 def gemm(a, b, d, M, N, K, Z=1, taps=1, tap_shift0=0, b_tap_kstride=0, ldd=None, bias=None,
          epilogue=EPI_NONE, aux=None, ld_aux=0, aux_batch_stride=0, alpha=1.0, d_zdiv=1,
-         d_zdiv_stride=0, d_zmod_stride=0, impl=None, row_lens=None, lens_zdiv=1, tail_rows=0):
+         d_zdiv_stride=0, d_zmod_stride=0, impl=None, row_lens=None, lens_zdiv=1, tail_rows=0, relu_mask=None):
     """D[z] = epi(alpha * sum_tap A[z][m+shift+tap] . B[z][n][tap*kstride+k] + bias).
 
     row_lens (int64 [Z / lens_zdiv]): rows m >= row_lens of D[z] are written as zero and row tiles that
@@ -72,6 +72,9 @@ def gemm(a, b, d, M, N, K, Z=1, taps=1, tap_shift0=0, b_tap_kstride=0, ldd=None,
     g.ld_aux, g.aux_batch_stride = int(ld_aux), int(aux_batch_stride)
     _set_lens(g, row_lens, lens_zdiv)
     g.tail_zero_rows = int(tail_rows)
+    if relu_mask is not None:  # int64 [Z*M, N/64]: written by EPI_RELU, read by EPI_RELU_BWD instead of `aux`
+        assert relu_mask.dtype == torch.int64 and relu_mask.is_contiguous() and relu_mask.numel() == Z * M * (N // 64)
+        g.relu_mask = relu_mask.data_ptr()
     run(g, impl)
 
 

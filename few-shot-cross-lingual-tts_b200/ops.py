@@ -402,18 +402,19 @@ def colsum(x2d, out, col0=0, cols=None, lens=None, T=None):
         _ck(_L().fs2_colsum_ragged_bf16(ptr, N, M // T, T, cols, _p(lens), _p(out), _st()), "colsum_ragged")
 
 
-def conv_fwd(x, wp, bias, relu=False, lens=None, tail=0):
+def conv_fwd(x, wp, bias, relu=False, lens=None, tail=0, relu_mask=None):
+    """relu_mask (int64 [B*T, Co/64], written): 1-bit mask of the positive outputs for the backward."""
     B, T, Ci = x.shape
     Co, k, cpad = wp.shape
     y = torch.empty(B, T, Co, dtype=BF16, device=x.device)
     G.gemm(G.operand(x, Ci, T, B), G.operand(wp, k * cpad, Co), y, T, Co, Ci, Z=B, taps=k,
            tap_shift0=-((k - 1) // 2), b_tap_kstride=cpad, bias=bias,
            epilogue=G.EPI_RELU if relu else G.EPI_NONE, d_zdiv=1, d_zdiv_stride=T * Co, row_lens=lens,
-           tail_rows=tail)
+           tail_rows=tail, relu_mask=relu_mask)
     return y
 
 
-def conv_dgrad(dy, wp, Ci, epilogue=G.EPI_NONE, aux=None, lens=None, tail=0):
+def conv_dgrad(dy, wp, Ci, epilogue=G.EPI_NONE, aux=None, lens=None, tail=0, relu_mask=None):
     """Input gradient of the channels-last Conv1d: the same implicit GEMM with flipped taps, reading the
     forward-packed weights [Co][k][Cpad] as an MN-major operand (negative tap stride)."""
     B, T, Co = dy.shape
@@ -422,7 +423,7 @@ def conv_dgrad(dy, wp, Ci, epilogue=G.EPI_NONE, aux=None, lens=None, tail=0):
     b = G.operand(wp, k * cpad, Co, mn_major=True, inner_base=(k - 1) * cpad)
     G.gemm(G.operand(dy, Co, T, B), b, dx, T, Ci, Co, Z=B, taps=k, tap_shift0=-((k - 1) // 2),
            b_tap_kstride=-cpad, epilogue=epilogue, aux=aux, ld_aux=Ci, aux_batch_stride=T * Ci,
-           d_zdiv=1, d_zdiv_stride=T * Ci, row_lens=lens, tail_rows=tail)
+           d_zdiv=1, d_zdiv_stride=T * Ci, row_lens=lens, tail_rows=tail, relu_mask=relu_mask)
     return dx
 
 
@@ -681,12 +682,18 @@ class FFNSublayer(torch.autograd.Function):
         w1p, w2p = pack_conv(w1), pack_conv(w2)
         rl = lens if zero_pad else None  # padded frames are zeroed below: skip their GEMM tiles
         # h feeds w_2 (halo (k2-1)//2 rows), f feeds the LayerNorm (skips padded rows)
-        h = conv_fwd(x, w1p, b1.detach(), relu=True, lens=rl, tail=(w2p.shape[1] - 1) // 2 or NO_TAIL)
+        # 1-bit ReLU mask of h for the backward (the ReLU-backward epilogue then reads 1/16 of the bytes of h)
+        Dh_ = w1p.shape[0]
+        use_mask = Dh_ % 64 == 0 and _os.environ.get("FS2_NO_RELU_MASK") is None
+        hmask = torch.empty(B * T, Dh_ // 64, dtype=torch.int64, device=x.device) if use_mask else None
+        h = conv_fwd(x, w1p, b1.detach(), relu=True, lens=rl, tail=(w2p.shape[1] - 1) // 2 or NO_TAIL,
+                     relu_mask=hmask)
         f = conv_fwd(h, w2p, b2.detach(), lens=rl, tail=NO_TAIL)
         salt = _Rng.next_salt()
         y, mean, rstd = ln_fwd(f, x, gamma.detach(), beta.detach(), lens if zero_pad else None, p_drop, 1,
                                salt)
         ctx.save_for_backward(x, lens, h, f, mean, rstd, w1p, w2p, gamma)
+        ctx.hmask = hmask
         ctx.params = (w1, b1, w2, b2, gamma, beta)
         ctx.cfg = (p_drop, zero_pad, salt)
         return y
@@ -706,8 +713,9 @@ class FFNSublayer(torch.autograd.Function):
         # dh feeds the input gradient of w_1, which reads a (k1-1)//2-row halo behind the last valid frame
         with fork_side():
             conv_wgrad(df, h, gbuf[2][0], lens=rl)
-        dh = conv_dgrad(df, w2p, Dh, epilogue=G.EPI_RELU_BWD, aux=h, lens=rl,
-                        tail=(w1p.shape[1] - 1) // 2 or NO_TAIL)
+        hmask = ctx.hmask
+        dh = conv_dgrad(df, w2p, Dh, epilogue=G.EPI_RELU_BWD, aux=None if hmask is not None else h, lens=rl,
+                        tail=(w1p.shape[1] - 1) // 2 or NO_TAIL, relu_mask=hmask)
         with fork_side():
             conv_wgrad(dh, x, gbuf[0][0], lens=rl)
             colsum(dh.view(B * T, Dh), gbuf[1][0], lens=rl, T=T)

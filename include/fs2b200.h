@@ -109,6 +109,11 @@ typedef struct fs2_gemm {
      input-gradient of a Conv1d with kernel 2n+1), the rest of D is left untouched; n < 0: none is written
      (consumers that skip padded rows themselves: LayerNorm, attention, row_lens GEMMs with k = 1). */
   int32_t tail_zero_rows;
+  /* optional 1-bit ReLU mask (NORMAL mode, bf16 D, N % 64 == 0): uint64 [Z*M rows][N/64], bit j of word w of a row =
+     column 64*w + j.  FS2_EPI_RELU writes it (output > 0); FS2_EPI_RELU_BWD reads it INSTEAD of the bf16 `aux`
+     tensor -- the backward of Conv1d -> ReLU -> Conv1d (transformer/SubLayers.py:87-89) then re-reads 1/16 of the
+     bytes of the hidden activation.  NULL = off. */
+  void* relu_mask;
 } fs2_gemm;
 
 /* impl: 0 = tcgen05 (product path), 1 = plain CUDA-core kernel (debug cross-check only). */

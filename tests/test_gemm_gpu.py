@@ -353,3 +353,34 @@ def test_outputs_stay_inside_their_buffer(case):
                    row_lens=lens if case == "ragged_conv" else None)
     torch.cuda.synchronize()
     assert (buf[:guard] == 7.0).all() and (buf[-guard:] == 7.0).all()
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+@pytest.mark.parametrize("lens", [None, [300, 1, 129, 0, 128]])
+def test_relu_bitmask_forward_and_backward(impl, lens):
+    """fs2_gemm::relu_mask: the ReLU forward writes a 1-bit mask of its positive outputs, the ReLU-backward
+    epilogue of a later GEMM reads it instead of the bf16 activation (same result as the `aux` path)."""
+    torch.manual_seed(29)
+    B, T, K, N = 5, 300, 256, 1024
+    x, w = rnd(B, T, K), rnd(N, K, scale=K ** -0.5)
+    bias = torch.randn(N, device="cuda") * 0.1
+    rl = None if lens is None else _lens(lens)
+    h = torch.zeros(B, T, N, device="cuda", dtype=torch.bfloat16)
+    mask = torch.zeros(B * T, N // 64, device="cuda", dtype=torch.int64)
+    G.gemm(G.operand(x, K, T, B), G.operand(w, K, N), h, T, N, K, Z=B, bias=bias, epilogue=G.EPI_RELU, d_zdiv=1,
+           d_zdiv_stride=T * N, row_lens=rl, relu_mask=mask, impl=impl)
+    valid = torch.ones(B, T, dtype=torch.bool, device="cuda") if lens is None else \
+        torch.arange(T, device="cuda")[None, :] < rl[:, None]
+    bits = ((mask.view(B, T, N // 64, 1) >> torch.arange(64, device="cuda")) & 1).bool().view(B, T, N)
+    assert torch.equal(bits[valid], (h > 0)[valid])
+    # backward of the ReLU through a second GEMM: dh = (dy @ W2) * (h > 0), once with the mask, once with aux = h
+    dy, w2 = rnd(B, T, 256), rnd(256, N, scale=256 ** -0.5)  # W2 [256, N] read as an MN-major B operand
+    outs = []
+    for kw in (dict(relu_mask=mask), dict(aux=h, ld_aux=N, aux_batch_stride=T * N)):
+        dh = torch.full((B, T, N), float("nan"), device="cuda", dtype=torch.bfloat16)
+        G.gemm(G.operand(dy, 256, T, B), G.operand(w2, N, 256, mn_major=True), dh, T, N, 256, Z=B,
+               epilogue=G.EPI_RELU_BWD, d_zdiv=1, d_zdiv_stride=T * N, row_lens=rl, impl=impl, **kw)
+        outs.append(dh)
+    assert torch.equal(outs[0][valid], outs[1][valid])
+    ref = (dy.float() @ w2.float()) * (h > 0)
+    assert rel_err(outs[0][valid], ref[valid]) < 1e-2

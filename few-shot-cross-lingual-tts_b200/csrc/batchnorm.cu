@@ -19,7 +19,8 @@ struct BnArgs {
   const __nv_bfloat16* y;  // conv output [M][C]
   long long M;
   int C;
-  float* stats;        // [2][C]: sum, sumsq (forward)   |  backward: [2][C] dbeta, dgamma
+  float* stats;        // backward apply: [2][C] dbeta, dgamma (finalized)
+  float* part;         // per-block partial sums [grid][2][C] (statistics / backward reduction)
   const float* fstats; // forward stats (read-only in apply / backward)
   const float* gamma;
   const float* beta;
@@ -46,17 +47,40 @@ __device__ __forceinline__ float fast_tanh(float x) {
   return y;
 }
 
+// Deterministic column reductions (used by the statistics and by the backward reduction): every thread owns
+// one 8-channel column vector and a fixed strided set of rows; the `rs` row groups of a block are combined in
+// row-group order through shared memory and the block writes ONE partial vector [2][C] to part[blockIdx.x];
+// bn_finalize_kernel then adds the partials in block order.  No atomics anywhere: two runs give the same bits
+// (the fp32 atomics this replaces made BatchNorm statistics -- and with them every downstream activation --
+// differ from run to run).
+__device__ __forceinline__ void block_partial_store(float* sh, const float (&s)[8], const float (&q)[8], int v, int ro,
+                                                    int rs, int C, float* part_row) {
+  // sh: [rs][2][C]
+  if (ro < rs) {
+    float* d = sh + (size_t)ro * 2 * C + v * 8;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      d[j] = s[j];
+      d[C + j] = q[j];
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * C; i += 256) {
+    float acc = 0.f;
+    for (int g = 0; g < rs; ++g) acc += sh[(size_t)g * 2 * C + i];
+    part_row[i] = acc;
+  }
+}
+
 __global__ void __launch_bounds__(256) bn_stats_kernel(const BnArgs a) {
   pdl_sync();
-  extern __shared__ float sh[];  // [2][C]
+  extern __shared__ float sh[];  // [rs][2][C]
   const int vpr = a.C / 8, rs = 256 / vpr;
-  for (int i = threadIdx.x; i < 2 * a.C; i += 256) sh[i] = 0.f;
-  __syncthreads();
   const int v = threadIdx.x % vpr, ro = threadIdx.x / vpr;
-  if (ro < rs) {
-    float s[8], q[8];
+  float s[8], q[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.f;
+  for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.f;
+  if (ro < rs) {
     const long long r0 = (long long)blockIdx.x * a.rows_per_block;
     const long long r1 = min(r0 + a.rows_per_block, a.M);
     for (long long r = r0 + ro; r < r1; r += 4 * rs) {  // 4 independent 16-byte loads in flight per thread
@@ -76,14 +100,65 @@ __global__ void __launch_bounds__(256) bn_stats_kernel(const BnArgs a) {
         }
       }
     }
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      atomicAdd(&sh[v * 8 + j], s[j]);
-      atomicAdd(&sh[a.C + v * 8 + j], q[j]);
-    }
   }
+  block_partial_store(sh, s, q, v, ro, rs, a.C, a.part + (size_t)blockIdx.x * 2 * a.C);
+}
+
+// Fixed-order sum of the per-block partials: block = 32 columns (lane = column, coalesced 128-byte reads), warp w
+// adds partials w, w + 8, ... and the 8 warps are combined in warp order.  Optionally (forward) updates the running
+// statistics, (backward) accumulates dbeta / dgamma into the parameter gradients.
+struct BnFinalArgs {
+  const float* part;
+  int nparts, C;
+  float* out;  // [2][C]
+  long long M;
+  float momentum;
+  float* running_mean;
+  float* running_var;
+  int64_t* num_batches;
+  float* acc0;  // += out[0][c]   (dbeta)
+  float* acc1;  // += out[1][c]   (dgamma)
+};
+__global__ void __launch_bounds__(256) bn_finalize_kernel(const BnFinalArgs a) {
+  pdl_sync();
+  __shared__ float sh[8][32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int col = blockIdx.x * 32 + lane;  // column of the [2C] vector
+  float acc = 0.f;
+  if (col < 2 * a.C)
+    for (int p = w; p < a.nparts; p += 8) acc += a.part[(size_t)p * 2 * a.C + col];
+  sh[w][lane] = acc;
   __syncthreads();
-  for (int i = threadIdx.x; i < 2 * a.C; i += 256) atomicAdd(a.stats + i, sh[i]);
+  if (w == 0 && col < 2 * a.C) {
+    float t = 0.f;
+#pragma unroll
+    for (int g = 0; g < 8; ++g) t += sh[g][lane];
+    a.out[col] = t;
+    if (a.acc0 && col < a.C) a.acc0[col] += t;
+    if (a.acc1 && col >= a.C) a.acc1[col - a.C] += t;
+  }
+  if (a.running_mean) {
+    // running statistics need the sum AND the sum of squares of a channel; the block that owns sum column c adds
+    // the partial square sums of c itself, in the same fixed order as the block that owns column C + c
+    float accq = 0.f;
+    if (col < a.C)
+      for (int p = w; p < a.nparts; p += 8) accq += a.part[(size_t)p * 2 * a.C + a.C + col];
+    __syncthreads();
+    sh[w][lane] = accq;
+    __syncthreads();
+    if (w == 0 && col < a.C) {
+      float q = 0.f;
+#pragma unroll
+      for (int g = 0; g < 8; ++g) q += sh[g][lane];
+      const float invM = 1.f / (float)a.M;
+      const float m = a.out[col] * invM;  // written by this thread above
+      const float var = fmaxf(q * invM - m * m, 0.f);
+      const float unbiased = a.M > 1 ? var * ((float)a.M / (float)(a.M - 1)) : var;
+      a.running_mean[col] = (1.f - a.momentum) * a.running_mean[col] + a.momentum * m;
+      a.running_var[col] = (1.f - a.momentum) * a.running_var[col] + a.momentum * unbiased;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0 && a.num_batches) *a.num_batches += 1;
+  }
 }
 
 // Thread = one 8-channel column vector (fixed for the whole kernel) x a strided set of rows, so the
@@ -139,11 +214,12 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const BnArgs a) {
 
 __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const BnArgs a) {
   pdl_sync();
-  extern __shared__ float s_acc[];  // [2][C]: sum g, sum g*yhat
+  extern __shared__ float s_acc[];  // [rs][2][C]: sum g, sum g*yhat per row group
   const int vpr = a.C / 8, rs = 256 / vpr;
-  for (int i = threadIdx.x; i < 2 * a.C; i += 256) s_acc[i] = 0.f;
-  __syncthreads();
   const int v = threadIdx.x % vpr, ro = threadIdx.x / vpr;
+  float sb[8], sg[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) sb[j] = sg[j] = 0.f;
   if (ro < rs) {
     const int c = v * 8;
     const float invM = 1.f / (float)a.M;
@@ -160,9 +236,6 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const BnArgs a) {
     const uint32_t thresh = dropout_thresh(a.p_drop);
     const float keep_scale = a.p_drop > 0.f ? 1.f / (1.f - a.p_drop) : 1.f;
     const uint64_t seed = mix_seed(a.seed_dev, a.seed);
-    float sb[8], sg[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) sb[j] = sg[j] = 0.f;
     const long long r0 = (long long)blockIdx.x * a.rows_per_block;
     const long long r1 = min(r0 + a.rows_per_block, a.M);
     for (long long r = r0 + ro; r < r1; r += rs) {
@@ -189,14 +262,8 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const BnArgs a) {
         sg[j] += gg * yh;
       }
     }
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      atomicAdd(&s_acc[c + j], sb[j]);
-      atomicAdd(&s_acc[a.C + c + j], sg[j]);
-    }
   }
-  __syncthreads();
-  for (int i = threadIdx.x; i < 2 * a.C; i += 256) atomicAdd(a.stats + i, s_acc[i]);
+  block_partial_store(s_acc, sb, sg, v, ro, rs, a.C, a.part + (size_t)blockIdx.x * 2 * a.C);
 }
 
 __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BnArgs a) {
@@ -249,20 +316,6 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BnArgs a) {
   }
 }
 
-__global__ void bn_running_kernel(const float* __restrict__ fstats, long long M, int C, float momentum,
-                                  float* running_mean, float* running_var, int64_t* num_batches) {
-  pdl_sync();
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c == 0 && num_batches) *num_batches += 1;
-  if (c >= C) return;
-  const float invM = 1.f / (float)M;
-  const float m = fstats[c] * invM;
-  const float var = fmaxf(fstats[C + c] * invM - m * m, 0.f);
-  const float unbiased = M > 1 ? var * ((float)M / (float)(M - 1)) : var;
-  running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * m;
-  running_var[c] = (1.f - momentum) * running_var[c] + momentum * unbiased;
-}
-
 static int bn_check(long long M, int C) {
   if (C % 8 || C > 2048 || C / 8 > 256) return set_error("batchnorm: C must be a multiple of 8, <= 2048");
   if (M <= 0) return set_error("batchnorm: empty batch");
@@ -283,17 +336,41 @@ static unsigned ew_grid(long long n_vec) {
 
 extern "C" {
 
-// stats f32 [2][C] must be zero on entry (sum, sum of squares are accumulated with atomics).
-int fs2_bn_stats_bf16(const void* y, int64_t M, int C, float* stats, void* stream) {
+// floats of workspace the statistics / backward reductions need for [M][C] (per-block partial sums)
+int64_t fs2_bn_workspace_floats(int64_t M, int C) {
+  if (M <= 0 || C <= 0) return 0;
+  const int rpb = fs2::rows_per_block_for(M);
+  return ((M + rpb - 1) / rpb) * 2 * C;
+}
+
+static int bn_finalize(const float* part, int nparts, int C, float* out, int64_t M, float momentum, float* rm,
+                       float* rv, int64_t* nb, float* acc0, float* acc1, cudaStream_t s) {
+  fs2::BnFinalArgs f{};
+  f.part = part; f.nparts = nparts; f.C = C; f.out = out; f.M = M; f.momentum = momentum;
+  f.running_mean = rm; f.running_var = rv; f.num_batches = nb; f.acc0 = acc0; f.acc1 = acc1;
+  FS2_LAUNCH((fs2::bn_finalize_kernel), (2 * C + 31) / 32, 256, 0, s, f);
+  fs2::count_launch();
+  return fs2::check_launch("bn_finalize_kernel");
+}
+
+// stats f32 [2][C] := column sums and sums of squares of y (written, not accumulated; fixed summation order ->
+// bit-reproducible).  ws: fs2_bn_workspace_floats(M, C) floats of scratch.  running_mean / running_var /
+// num_batches_tracked (optional): the nn.BatchNorm1d running-statistics update (momentum, unbiased variance).
+int fs2_bn_stats_bf16(const void* y, int64_t M, int C, float* ws, float* stats, float momentum, float* running_mean,
+                      float* running_var, int64_t* num_batches_tracked, void* stream) {
   if (int rc = fs2::bn_check(M, C)) return rc;
   fs2::BnArgs a{};
   a.y = static_cast<const __nv_bfloat16*>(y);
-  a.M = M; a.C = C; a.stats = stats;
+  a.M = M; a.C = C; a.part = ws;
   a.rows_per_block = fs2::rows_per_block_for(M);
   const unsigned grid = (unsigned)((M + a.rows_per_block - 1) / a.rows_per_block);
-  FS2_LAUNCH((fs2::bn_stats_kernel), grid, 256, 2 * C * sizeof(float), static_cast<cudaStream_t>(stream), a);
+  const int rs = 256 / (C / 8);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  FS2_LAUNCH((fs2::bn_stats_kernel), grid, 256, (size_t)rs * 2 * C * sizeof(float), s, a);
   fs2::count_launch();
-  return fs2::check_launch("bn_stats_kernel");
+  if (int rc = fs2::check_launch("bn_stats_kernel")) return rc;
+  return bn_finalize(ws, (int)grid, C, stats, M, momentum, running_mean, running_var, num_batches_tracked, nullptr,
+                     nullptr, s);
 }
 
 // out = dropout(act(bn(y)));  exactly one of out_bf16 / out_f32 is non-NULL; res_f32 (optional) is
@@ -314,33 +391,29 @@ int fs2_bn_apply_fwd(const void* y, const float* stats, const float* gamma, cons
   return fs2::check_launch("bn_apply_kernel");
 }
 
-int fs2_bn_update_running(const float* stats, int64_t M, int C, float momentum, float* running_mean,
-                          float* running_var, int64_t* num_batches_tracked, void* stream) {
-  if (int rc = fs2::bn_check(M, C)) return rc;
-  FS2_LAUNCH((fs2::bn_running_kernel), (C + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream), 
-      stats, M, C, momentum, running_mean, running_var, num_batches_tracked);
-  fs2::count_launch();
-  return fs2::check_launch("bn_running_kernel");
-}
-
-// dstats f32 [2][C] must be zero on entry; on exit dstats[0][c] = dbeta, dstats[1][c] = dgamma.
+// dstats f32 [2][C] (written): dstats[0][c] = dbeta, dstats[1][c] = dgamma, summed in a fixed order; dbeta_acc /
+// dgamma_acc (optional, f32 [C]) additionally accumulate them (the parameter gradients).  ws as above.
 // dout is bf16 [M][C] (dout_is_f32 = 0) or f32.
 int fs2_bn_bwd(const void* dout, int dout_is_f32, const void* y, const float* stats, const float* gamma,
                const float* beta, int64_t M, int C, int act_tanh, float p_drop, uint64_t seed,
-               const uint64_t* seed_dev, float* dstats, void* dy, void* stream) {
+               const uint64_t* seed_dev, float* ws, float* dstats, float* dbeta_acc, float* dgamma_acc, void* dy,
+               void* stream) {
   if (int rc = fs2::bn_check(M, C)) return rc;
   fs2::BnArgs a{};
   a.y = static_cast<const __nv_bfloat16*>(y);
   a.M = M; a.C = C; a.fstats = stats; a.gamma = gamma; a.beta = beta;
   a.act_tanh = act_tanh; a.p_drop = p_drop; a.seed = seed; a.seed_dev = seed_dev;
-  a.dout = dout; a.dout_is_f32 = dout_is_f32; a.stats = dstats;
+  a.dout = dout; a.dout_is_f32 = dout_is_f32; a.stats = dstats; a.part = ws;
   a.dy = static_cast<__nv_bfloat16*>(dy);
   a.rows_per_block = fs2::rows_per_block_for(M);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const unsigned grid = (unsigned)((M + a.rows_per_block - 1) / a.rows_per_block);
-  FS2_LAUNCH((fs2::bn_bwd_reduce_kernel), grid, 256, 2 * C * sizeof(float), s, a);
+  const int rs = 256 / (C / 8);
+  FS2_LAUNCH((fs2::bn_bwd_reduce_kernel), grid, 256, (size_t)rs * 2 * C * sizeof(float), s, a);
   fs2::count_launch();
   if (int rc = fs2::check_launch("bn_bwd_reduce_kernel")) return rc;
+  if (int rc = bn_finalize(ws, (int)grid, C, dstats, M, 0.f, nullptr, nullptr, nullptr, dbeta_acc, dgamma_acc, s))
+    return rc;
   FS2_LAUNCH((fs2::bn_bwd_apply_kernel), grid, 256, 0, s, a);
   fs2::count_launch();
   return fs2::check_launch("bn_bwd_apply_kernel");

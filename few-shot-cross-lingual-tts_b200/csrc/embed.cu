@@ -111,9 +111,130 @@ embedding_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const IdxT* __restric
   }
 }
 
+// ---- lookup in the CONCATENATION of several tables without materialising it -----------------------------------
+// MultilingualEmbedding.forward (lightning/systems/language/embeddings.py:25-31) does torch.cat(all tables) on every
+// call and F.embedding(padding_idx) on the result; here the per-language tables stay where they are and a row id is
+// resolved against the cumulative row counts (<= kMaxTables tables, passed by value in the kernel parameters).
+constexpr int kMaxTables = 32;
+struct EmbTables {
+  const float* ptr[kMaxTables];  // forward: table values; backward: table gradients
+  int row0[kMaxTables + 1];      // first concatenated row of table k; row0[n] = total rows
+  int n;
+};
+__device__ __forceinline__ int find_table(const EmbTables& t, long long id) {
+  int k = 0;
+  while (k + 1 < t.n && id >= t.row0[k + 1]) ++k;
+  return k;
+}
+
+__global__ void __launch_bounds__(256)
+embedding_multi_fwd_kernel(const int64_t* __restrict__ ids, const __grid_constant__ EmbTables tabs, long long rows,
+                           int C, int pad_idx, __nv_bfloat16* __restrict__ y) {
+  pdl_sync();
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  long long id = ids[row];
+  if (id < 0 || id >= tabs.row0[tabs.n]) id = pad_idx >= 0 ? pad_idx : 0;
+  const int k = find_table(tabs, id);
+  const float* e = tabs.ptr[k] + (id - tabs.row0[k]) * C;
+  for (int c = lane * 8; c < C; c += 256) {
+    const float4 e0 = *reinterpret_cast<const float4*>(e + c);
+    const float4 e1 = *reinterpret_cast<const float4*>(e + c + 4);
+    const float f[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
+    st8(y + row * C + c, pack8(f));
+  }
+}
+
+__global__ void __launch_bounds__(256)
+embedding_multi_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const int64_t* __restrict__ ids,
+                           const __grid_constant__ EmbTables tabs, long long rows, int C, int pad_idx) {
+  pdl_sync();
+  const int lane = threadIdx.x & 31;
+  const long long w = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long long r0 = w * kEmbRowsPerWarp;
+  if (r0 >= rows) return;
+  const long long r1 = min(r0 + (long long)kEmbRowsPerWarp, rows);
+  for (int c = lane * 8; c < C; c += 256) {
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    long long cur = -1;
+    auto flush = [&]() {
+      if (cur < 0) return;
+      const int k = find_table(tabs, cur);
+      float* d = const_cast<float*>(tabs.ptr[k]) + (cur - tabs.row0[k]) * C + c;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) atomicAdd(d + j, acc[j]);
+    };
+    for (long long r = r0; r < r1; ++r) {
+      long long id = ids[r];
+      if (id < 0 || id >= tabs.row0[tabs.n] || id == pad_idx) id = -1;  // padding_idx row gets no gradient
+      if (id != cur) {
+        flush();
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+        cur = id;
+      }
+      if (id >= 0) {
+        float f[8];
+        unpack8(ld8(dy + r * C + c), f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] += f[j];
+      }
+    }
+    flush();
+  }
+}
+
+static int fill_tables(EmbTables& t, const void* const* tables, const int32_t* table_rows, int n_tables) {
+  if (n_tables < 1 || n_tables > kMaxTables) return set_error("embedding_multi: 1..32 tables");
+  t.n = n_tables;
+  int r = 0;
+  for (int k = 0; k < n_tables; ++k) {
+    if (!tables[k] || table_rows[k] <= 0) return set_error("embedding_multi: empty table");
+    t.ptr[k] = static_cast<const float*>(tables[k]);
+    t.row0[k] = r;
+    r += table_rows[k];
+  }
+  t.row0[n_tables] = r;
+  return 0;
+}
+
 }  // namespace fs2
 
 extern "C" {
+
+// tables / table_rows: HOST arrays (n_tables device pointers to f32 [rows_k][C] tables, and their row counts); ids
+// index the concatenation of the tables in array order.  pad_idx: concatenated row that gets no gradient
+// (F.embedding padding_idx), -1 = none.
+int fs2_embedding_multi_fwd_bf16(const int64_t* ids, const void* const* tables, const int32_t* table_rows,
+                                 int n_tables, int64_t rows, int C, int pad_idx, void* y, void* stream) {
+  if (C % 8) return fs2::set_error("embedding_multi_fwd: C must be a multiple of 8");
+  if (rows <= 0) return 0;
+  fs2::EmbTables t;
+  if (int rc = fs2::fill_tables(t, tables, table_rows, n_tables)) return rc;
+  FS2_LAUNCH((fs2::embedding_multi_fwd_kernel), (unsigned)((rows + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream),
+             ids, t, rows, C, pad_idx, static_cast<__nv_bfloat16*>(y));
+  fs2::count_launch();
+  return fs2::check_launch("embedding_multi_fwd_kernel");
+}
+
+// dtables: HOST array of device pointers to the f32 [rows_k][C] table GRADIENTS (accumulated with atomics).
+int fs2_embedding_multi_bwd_f32(const void* dy, const int64_t* ids, const void* const* dtables,
+                                const int32_t* table_rows, int n_tables, int64_t rows, int C, int pad_idx,
+                                void* stream) {
+  if (C % 8) return fs2::set_error("embedding_multi_bwd: C must be a multiple of 8");
+  if (rows <= 0) return 0;
+  fs2::EmbTables t;
+  if (int rc = fs2::fill_tables(t, dtables, table_rows, n_tables)) return rc;
+  const unsigned grid = (unsigned)((rows + 8 * fs2::kEmbRowsPerWarp - 1) / (8 * fs2::kEmbRowsPerWarp));
+  FS2_LAUNCH((fs2::embedding_multi_bwd_kernel), grid, 256, 0, static_cast<cudaStream_t>(stream),
+             static_cast<const __nv_bfloat16*>(dy), ids, t, rows, C, pad_idx);
+  fs2::count_launch();
+  return fs2::check_launch("embedding_multi_bwd_kernel");
+}
+
 
 int fs2_bucket_embed_add_bf16(const void* x, const void* target, int target_is_f64, const float* bins,
                               int n_bins_minus_1, const float* table, int64_t rows, int C, void* y,

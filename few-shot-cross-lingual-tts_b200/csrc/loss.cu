@@ -30,9 +30,12 @@ struct LossArgs {
   const int64_t* src_lens;
   const int64_t* mel_lens;
   int B, Ts, Tm, Tm_tgt, n_mel;
+  int p_T, p_ld, e_T, e_ld;   // pitch / energy: prediction row length, target row stride
+  const int64_t* p_lens;      // src_lens (phoneme level) or mel_lens (frame level)
+  const int64_t* e_lens;
   int mel_blocks_per_b, n_blocks;
   float* partials;  // [n_blocks][5]
-  float* out;       // [8] total, mel, post, pitch, energy, duration, N_mel, N_src
+  float* out;       // [10] total, mel, post, pitch, energy, duration, N_mel, N_pitch, N_energy, N_duration
   // backward
   const float* gout;  // [6] d(loss)/d(out[0..5])
   float* d_mel;
@@ -60,6 +63,15 @@ __device__ __forceinline__ float energy_target(const LossArgs& a, long long i) {
   return a.e_tgt_is_f64 ? static_cast<float>(static_cast<const double*>(a.e_tgt)[i])
                         : static_cast<const float*>(a.e_tgt)[i];
 }
+// number of valid positions of a [B][T] feature
+__device__ __forceinline__ double count_valid(const int64_t* lens, int B, int T) {
+  double n = 0;
+  for (int b = 0; b < B; ++b) {
+    const long long l = min((long long)lens[b], (long long)T);
+    n += (double)(l > 0 ? l : 0);
+  }
+  return n;
+}
 
 __global__ void __launch_bounds__(kLossThreads) loss_partial_kernel(const LossArgs a) {
   pdl_sync();
@@ -86,16 +98,26 @@ __global__ void __launch_bounds__(kLossThreads) loss_partial_kernel(const LossAr
     }
   } else {
     const int blk = blockIdx.x - nmel_blocks;
-    const long long n = (long long)a.B * a.Ts;
-    for (long long i = (long long)blk * kLossThreads + threadIdx.x; i < n;
-         i += (long long)(a.n_blocks - nmel_blocks) * kLossThreads) {
+    const long long stride = (long long)(a.n_blocks - nmel_blocks) * kLossThreads;
+    const long long i0 = (long long)blk * kLossThreads + threadIdx.x;
+    for (long long i = i0; i < (long long)a.B * a.p_T; i += stride) {
+      const int b = i / a.p_T, t = i - (long long)b * a.p_T;
+      if (t < a.p_lens[b]) {
+        const float dp = a.p_pred[i] - a.p_tgt[(long long)b * a.p_ld + t];
+        s[2] += dp * dp;
+      }
+    }
+    for (long long i = i0; i < (long long)a.B * a.e_T; i += stride) {
+      const int b = i / a.e_T, t = i - (long long)b * a.e_T;
+      if (t < a.e_lens[b]) {
+        const float de = a.e_pred[i] - energy_target(a, (long long)b * a.e_ld + t);
+        s[3] += de * de;
+      }
+    }
+    for (long long i = i0; i < (long long)a.B * a.Ts; i += stride) {
       const int b = i / a.Ts, t = i - (long long)b * a.Ts;
       if (t < a.src_lens[b]) {
-        const float dp = a.p_pred[i] - a.p_tgt[i];
-        const float de = a.e_pred[i] - energy_target(a, i);
         const float dd = a.d_pred[i] - logf(static_cast<float>(a.d_tgt[i]) + 1.f);
-        s[2] += dp * dp;
-        s[3] += de * de;
         s[4] += dd * dd;
       }
     }
@@ -118,15 +140,11 @@ __global__ void __launch_bounds__(kLossThreads) loss_final_kernel(const LossArgs
 #pragma unroll
   for (int k = 0; k < 5; ++k) r[k] = block_sum(s[k], sh);
   if (threadIdx.x == 0) {
-    double n_mel = 0, n_src = 0;
-    for (int b = 0; b < a.B; ++b) {
-      long long lm = min((long long)a.mel_lens[b], (long long)a.Tm);
-      long long ls = min((long long)a.src_lens[b], (long long)a.Ts);
-      n_mel += (double)(lm > 0 ? lm : 0) * a.n_mel;
-      n_src += (double)(ls > 0 ? ls : 0);
-    }
+    const double n_mel = count_valid(a.mel_lens, a.B, a.Tm) * a.n_mel;
+    const double n_p = count_valid(a.p_lens, a.B, a.p_T), n_e = count_valid(a.e_lens, a.B, a.e_T);
+    const double n_d = count_valid(a.src_lens, a.B, a.Ts);
     const float mel = r[0] / (float)n_mel, post = r[1] / (float)n_mel;
-    const float pitch = r[2] / (float)n_src, energy = r[3] / (float)n_src, dur = r[4] / (float)n_src;
+    const float pitch = r[2] / (float)n_p, energy = r[3] / (float)n_e, dur = r[4] / (float)n_d;
     a.out[0] = mel + post + dur + pitch + energy;  // same association order as loss.py:77-79
     a.out[1] = mel;
     a.out[2] = post;
@@ -134,7 +152,9 @@ __global__ void __launch_bounds__(kLossThreads) loss_final_kernel(const LossArgs
     a.out[4] = energy;
     a.out[5] = dur;
     a.out[6] = (float)n_mel;
-    a.out[7] = (float)n_src;
+    a.out[7] = (float)n_p;
+    a.out[8] = (float)n_e;
+    a.out[9] = (float)n_d;
   }
 }
 
@@ -143,7 +163,7 @@ __device__ __forceinline__ float sgn(float v) { return v > 0.f ? 1.f : (v < 0.f 
 __global__ void __launch_bounds__(kLossThreads) loss_bwd_kernel(const LossArgs a) {
   pdl_sync();
   const float g0 = a.gout[0];
-  const float n_mel = a.out[6], n_src = a.out[7];
+  const float n_mel = a.out[6];
   const int nmel_blocks = a.B * a.mel_blocks_per_b;
   if ((int)blockIdx.x < nmel_blocks) {
     const float wm = (g0 + a.gout[1]) / n_mel, wp = (g0 + a.gout[2]) / n_mel;
@@ -171,17 +191,22 @@ __global__ void __launch_bounds__(kLossThreads) loss_bwd_kernel(const LossArgs a
       *reinterpret_cast<float4*>(a.d_post + base + i) = dp;
     }
   } else {
-    const float w_p = 2.f * (g0 + a.gout[3]) / n_src, w_e = 2.f * (g0 + a.gout[4]) / n_src,
-                w_d = 2.f * (g0 + a.gout[5]) / n_src;
+    const float w_p = 2.f * (g0 + a.gout[3]) / a.out[7], w_e = 2.f * (g0 + a.gout[4]) / a.out[8],
+                w_d = 2.f * (g0 + a.gout[5]) / a.out[9];
     const int blk = blockIdx.x - nmel_blocks;
-    const long long n = (long long)a.B * a.Ts;
-    for (long long i = (long long)blk * kLossThreads + threadIdx.x; i < n;
-         i += (long long)(a.n_blocks - nmel_blocks) * kLossThreads) {
+    const long long stride = (long long)(a.n_blocks - nmel_blocks) * kLossThreads;
+    const long long i0 = (long long)blk * kLossThreads + threadIdx.x;
+    for (long long i = i0; i < (long long)a.B * a.p_T; i += stride) {
+      const int b = i / a.p_T, t = i - (long long)b * a.p_T;
+      a.d_p[i] = t < a.p_lens[b] ? w_p * (a.p_pred[i] - a.p_tgt[(long long)b * a.p_ld + t]) : 0.f;
+    }
+    for (long long i = i0; i < (long long)a.B * a.e_T; i += stride) {
+      const int b = i / a.e_T, t = i - (long long)b * a.e_T;
+      a.d_e[i] = t < a.e_lens[b] ? w_e * (a.e_pred[i] - energy_target(a, (long long)b * a.e_ld + t)) : 0.f;
+    }
+    for (long long i = i0; i < (long long)a.B * a.Ts; i += stride) {
       const int b = i / a.Ts, t = i - (long long)b * a.Ts;
-      const bool ok = t < a.src_lens[b];
-      a.d_p[i] = ok ? w_p * (a.p_pred[i] - a.p_tgt[i]) : 0.f;
-      a.d_e[i] = ok ? w_e * (a.e_pred[i] - energy_target(a, i)) : 0.f;
-      a.d_d[i] = ok ? w_d * (a.d_pred[i] - logf(static_cast<float>(a.d_tgt[i]) + 1.f)) : 0.f;
+      a.d_d[i] = t < a.src_lens[b] ? w_d * (a.d_pred[i] - logf(static_cast<float>(a.d_tgt[i]) + 1.f)) : 0.f;
     }
   }
 }
@@ -189,9 +214,12 @@ __global__ void __launch_bounds__(kLossThreads) loss_bwd_kernel(const LossArgs a
 static int fill_grid(LossArgs& a) {
   if (a.n_mel % 4) return set_error("loss: n_mel must be a multiple of 4");
   if (a.Tm > a.Tm_tgt) return set_error("loss: mel target shorter than the prediction");
+  if (a.p_T > a.p_ld || a.e_T > a.e_ld) return set_error("loss: pitch / energy target shorter than the prediction");
   const long long per_b = (long long)a.Tm * a.n_mel;
   a.mel_blocks_per_b = (int)((per_b + kElemsPerBlock - 1) / kElemsPerBlock);
-  const long long nsrc = (long long)a.B * a.Ts;
+  long long nsrc = (long long)a.B * a.Ts;
+  if ((long long)a.B * a.p_T > nsrc) nsrc = (long long)a.B * a.p_T;
+  if ((long long)a.B * a.e_T > nsrc) nsrc = (long long)a.B * a.e_T;
   int src_blocks = (int)((nsrc + kLossThreads - 1) / kLossThreads);
   if (src_blocks > 64) src_blocks = 64;
   if (src_blocks < 1) src_blocks = 1;
@@ -203,26 +231,36 @@ static int fill_grid(LossArgs& a) {
 
 extern "C" {
 
-// Number of floats the caller must provide in `partials`.
-int64_t fs2_loss_workspace_floats(int B, int Ts, int Tm, int n_mel) {
+// Number of floats the caller must provide in `partials` (T_feat = the longest of Ts and the pitch / energy rows).
+int64_t fs2_loss_workspace_floats(int B, int T_feat, int Tm, int n_mel) {
   fs2::LossArgs a{};
-  a.B = B; a.Ts = Ts; a.Tm = Tm; a.Tm_tgt = Tm; a.n_mel = n_mel;
+  a.B = B; a.Ts = T_feat; a.Tm = Tm; a.Tm_tgt = Tm; a.n_mel = n_mel;
   if (fs2::fill_grid(a)) return -1;
   return (int64_t)a.n_blocks * 5;
 }
 
-int fs2_loss_fwd(const float* mel_pred, const float* post_pred, const float* mel_tgt,
-                 const float* p_pred, const float* p_tgt, const float* e_pred, const void* e_tgt,
-                 int e_tgt_is_f64, const float* d_pred, const int64_t* d_tgt, const int64_t* src_lens,
-                 const int64_t* mel_lens, int B, int Ts, int Tm, int Tm_tgt, int n_mel, float* partials,
-                 float* out8, void* stream) {
-  fs2::LossArgs a{};
+static void loss_common(fs2::LossArgs& a, const float* mel_pred, const float* post_pred, const float* mel_tgt,
+                        const float* p_pred, const float* p_tgt, int p_T, int p_ld, const int64_t* p_lens,
+                        const float* e_pred, const void* e_tgt, int e_tgt_is_f64, int e_T, int e_ld,
+                        const int64_t* e_lens, const float* d_pred, const int64_t* d_tgt, const int64_t* src_lens,
+                        const int64_t* mel_lens, int B, int Ts, int Tm, int Tm_tgt, int n_mel) {
   a.mel_pred = mel_pred; a.post_pred = post_pred; a.mel_tgt = mel_tgt;
   a.p_pred = p_pred; a.p_tgt = p_tgt; a.e_pred = e_pred; a.e_tgt = e_tgt;
   a.e_tgt_is_f64 = e_tgt_is_f64; a.d_pred = d_pred; a.d_tgt = d_tgt;
   a.src_lens = src_lens; a.mel_lens = mel_lens;
+  a.p_T = p_T; a.p_ld = p_ld; a.p_lens = p_lens; a.e_T = e_T; a.e_ld = e_ld; a.e_lens = e_lens;
   a.B = B; a.Ts = Ts; a.Tm = Tm; a.Tm_tgt = Tm_tgt; a.n_mel = n_mel;
-  a.partials = partials; a.out = out8;
+}
+
+int fs2_loss_fwd(const float* mel_pred, const float* post_pred, const float* mel_tgt, const float* p_pred,
+                 const float* p_tgt, int p_T, int p_ld, const int64_t* p_lens, const float* e_pred, const void* e_tgt,
+                 int e_tgt_is_f64, int e_T, int e_ld, const int64_t* e_lens, const float* d_pred,
+                 const int64_t* d_tgt, const int64_t* src_lens, const int64_t* mel_lens, int B, int Ts, int Tm,
+                 int Tm_tgt, int n_mel, float* partials, float* out10, void* stream) {
+  fs2::LossArgs a{};
+  loss_common(a, mel_pred, post_pred, mel_tgt, p_pred, p_tgt, p_T, p_ld, p_lens, e_pred, e_tgt, e_tgt_is_f64, e_T, e_ld,
+              e_lens, d_pred, d_tgt, src_lens, mel_lens, B, Ts, Tm, Tm_tgt, n_mel);
+  a.partials = partials; a.out = out10;
   if (int rc = fs2::fill_grid(a)) return rc;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   FS2_LAUNCH((fs2::loss_partial_kernel), a.n_blocks, fs2::kLossThreads, 0, s, a);
@@ -233,19 +271,16 @@ int fs2_loss_fwd(const float* mel_pred, const float* post_pred, const float* mel
   return fs2::check_launch("loss_final_kernel");
 }
 
-int fs2_loss_bwd(const float* gout6, const float* out8, const float* mel_pred, const float* post_pred,
-                 const float* mel_tgt, const float* p_pred, const float* p_tgt, const float* e_pred,
-                 const void* e_tgt, int e_tgt_is_f64, const float* d_pred, const int64_t* d_tgt,
-                 const int64_t* src_lens, const int64_t* mel_lens, int B, int Ts, int Tm, int Tm_tgt,
-                 int n_mel, float* d_mel, float* d_post, float* d_p, float* d_e, float* d_d,
-                 void* stream) {
+int fs2_loss_bwd(const float* gout6, const float* out10, const float* mel_pred, const float* post_pred,
+                 const float* mel_tgt, const float* p_pred, const float* p_tgt, int p_T, int p_ld,
+                 const int64_t* p_lens, const float* e_pred, const void* e_tgt, int e_tgt_is_f64, int e_T, int e_ld,
+                 const int64_t* e_lens, const float* d_pred, const int64_t* d_tgt, const int64_t* src_lens,
+                 const int64_t* mel_lens, int B, int Ts, int Tm, int Tm_tgt, int n_mel, float* d_mel, float* d_post,
+                 float* d_p, float* d_e, float* d_d, void* stream) {
   fs2::LossArgs a{};
-  a.gout = gout6; a.out = const_cast<float*>(out8);
-  a.mel_pred = mel_pred; a.post_pred = post_pred; a.mel_tgt = mel_tgt;
-  a.p_pred = p_pred; a.p_tgt = p_tgt; a.e_pred = e_pred; a.e_tgt = e_tgt;
-  a.e_tgt_is_f64 = e_tgt_is_f64; a.d_pred = d_pred; a.d_tgt = d_tgt;
-  a.src_lens = src_lens; a.mel_lens = mel_lens;
-  a.B = B; a.Ts = Ts; a.Tm = Tm; a.Tm_tgt = Tm_tgt; a.n_mel = n_mel;
+  loss_common(a, mel_pred, post_pred, mel_tgt, p_pred, p_tgt, p_T, p_ld, p_lens, e_pred, e_tgt, e_tgt_is_f64, e_T, e_ld,
+              e_lens, d_pred, d_tgt, src_lens, mel_lens, B, Ts, Tm, Tm_tgt, n_mel);
+  a.gout = gout6; a.out = const_cast<float*>(out10);
   a.d_mel = d_mel; a.d_post = d_post; a.d_p = d_p; a.d_e = d_e; a.d_d = d_d;
   if (int rc = fs2::fill_grid(a)) return rc;
   FS2_LAUNCH((fs2::loss_bwd_kernel), a.n_blocks, fs2::kLossThreads, 0, static_cast<cudaStream_t>(stream), a);

@@ -84,14 +84,17 @@ class FastSpeech2(nn.Module):
             x, src_masks, mel_masks, max_mel_len, p_targets, e_targets, d_targets, p_control, e_control,
             d_control, src_lens=src_lens, _fused=fused)
 
+        # decoder key mask / frame validity: the INPUT mel_lens when they are given (the reference builds mel_masks
+        # from them, fastspeech2m.py:70-74), the LengthRegulator's lengths otherwise (inference)
+        len_src = mel_lens if mel_lens is not None else mel_lens_out
         if fused is not None:
-            dec_lens = torch.clamp(mel_lens_out, max=t_dec)
+            dec_lens = torch.clamp(len_src, max=t_dec)
             x = self.decoder.forward_prepared(x, dec_lens)
             mel_masks = mel_masks[:, :t_dec] if mel_masks is not None else None
         else:
             if self.speaker_emb is not None:
                 x = ops.AddRowVec.apply(x, self._speaker_rows(speaker_args, B, average_spk_emb))
-            dec_lens = torch.clamp(mel_lens_out, max=x.shape[1])
+            dec_lens = torch.clamp(len_src, max=x.shape[1])
             x, mel_masks = self.decoder(x, mel_masks, lens=dec_lens)
             if x.dtype != torch.bfloat16:
                 x = x.to(torch.bfloat16)

@@ -1,7 +1,8 @@
-"""MultilingualEmbedding: per-language phoneme tables, looked up in the concatenation of all tables
-(reference: lightning/systems/language/embeddings.py:8-31).  The gather and its scatter-add backward
-are CUDA kernels (ops.EmbeddingFn); the concatenation keeps the per-language ParameterDict (and so the
-state_dict keys `tables.table-<id>`) of the reference."""
+"""MultilingualEmbedding: per-language phoneme tables, looked up in the (virtual) concatenation of all tables
+(reference: lightning/systems/language/embeddings.py:8-31).  The gather and its scatter-add backward are CUDA
+kernels (ops.MultiEmbeddingFn / ops.EmbeddingFn) that resolve an id against the cumulative row counts, so the
+concatenated table is never built; the per-language ParameterDict (state_dict keys `tables.table-<id>`) is the
+reference's."""
 from math import sqrt
 from typing import Optional
 
@@ -28,10 +29,10 @@ class MultilingualEmbedding(nn.Module):
     def forward(self, x, symbol_id: Optional[str] = None):
         """x: int64 ids [B, T] -> fp32 [B, T, dim] (bf16 internally; the model re-casts on entry)."""
         if symbol_id is None:
-            table = torch.cat([p for p in self.tables.values()], dim=0)
-        else:
-            table = self.tables[f"table-{symbol_id}"]
-        return ops.EmbeddingFn.apply(x, table, self.padding_idx)
+            # ids index the concatenation of all tables; the reference's per-call torch.cat is replaced by a lookup
+            # against the cumulative row counts inside the kernel (gradients go straight to each table)
+            return ops.MultiEmbeddingFn.apply(x, self.padding_idx, *self.tables.values())
+        return ops.EmbeddingFn.apply(x, self.tables[f"table-{symbol_id}"], self.padding_idx)
 
 
 class SoftMultiAttCodebook2(nn.Module):

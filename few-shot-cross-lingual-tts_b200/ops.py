@@ -817,7 +817,8 @@ class BucketEmbedAdd(torch.autograd.Function):
 
 
 class EmbeddingFn(torch.autograd.Function):
-    """F.embedding(ids, table, padding_idx) -> bf16 -- lightning/systems/language/embeddings.py:25-31."""
+    """F.embedding(ids, table, padding_idx) -> bf16 -- lightning/systems/language/embeddings.py:25-31,
+    transformer/Models.py:56-58 (`Encoder.src_word_emb`)."""
 
     @staticmethod
     def forward(ctx, ids, table, pad_idx):
@@ -828,18 +829,66 @@ class EmbeddingFn(torch.autograd.Function):
         _ck(_L().fs2_embedding_fwd_bf16(_p(ids), _p(tb), ids.numel(), C, table.shape[0],
                                         -1 if pad_idx is None else pad_idx, _p(y), _st()), "embedding_fwd")
         ctx.save_for_backward(ids)
-        ctx.meta = (table.shape, pad_idx)
+        ctx.table = table
+        ctx.pad_idx = pad_idx
         return y
 
     @staticmethod
     def backward(ctx, dy):
         (ids,) = ctx.saved_tensors
-        shape, pad_idx = ctx.meta
+        table, pad_idx = ctx.table, ctx.pad_idx
         dy = _contig(dy)
-        g = torch.zeros(shape, dtype=F32, device=dy.device)
-        _ck(_L().fs2_embedding_bwd_f32(_p(dy), _p(ids), 1, ids.numel(), shape[1], shape[0],
+        g, ret = grad_target(table)
+        if not g.is_contiguous():
+            raise RuntimeError("EmbeddingFn: table gradient must be contiguous")
+        _ck(_L().fs2_embedding_bwd_f32(_p(dy), _p(ids), 1, ids.numel(), table.shape[1], table.shape[0],
                                        -1 if pad_idx is None else pad_idx, _p(g), _st()), "embedding_bwd")
-        return None, g, None
+        grads_done((table,))
+        return None, ret, None
+
+
+class MultiEmbeddingFn(torch.autograd.Function):
+    """F.embedding(ids, torch.cat(tables), padding_idx) without the concatenation (embeddings.py:25-31: the reference
+    re-builds the concatenated table on every call): ids are resolved against the cumulative row counts inside the
+    kernels, gradients are scattered straight into each table's own gradient."""
+
+    @staticmethod
+    def forward(ctx, ids, pad_idx, *tables):
+        import ctypes
+
+        ids = ids.contiguous()
+        C = tables[0].shape[1]
+        n = len(tables)
+        dev = tables[0].device
+        for t in tables:
+            assert t.dtype == F32 and t.is_contiguous() and t.shape[1] == C and t.device == dev
+        y = torch.empty(ids.shape + (C,), dtype=BF16, device=dev)
+        ptrs = (ctypes.c_void_p * n)(*[t.data_ptr() for t in tables])
+        rows = (ctypes.c_int32 * n)(*[t.shape[0] for t in tables])
+        _ck(_L().fs2_embedding_multi_fwd_bf16(_p(ids), ctypes.cast(ptrs, ctypes.c_void_p),
+                                              ctypes.cast(rows, ctypes.c_void_p), n, ids.numel(), C,
+                                              -1 if pad_idx is None else pad_idx, _p(y), _st()), "embedding_multi_fwd")
+        ctx.save_for_backward(ids)
+        ctx.tables = tables
+        ctx.pad_idx = pad_idx
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        import ctypes
+
+        (ids,) = ctx.saved_tensors
+        tables, pad_idx = ctx.tables, ctx.pad_idx
+        dy = _contig(dy)
+        n = len(tables)
+        gbuf = [grad_target(t) for t in tables]
+        ptrs = (ctypes.c_void_p * n)(*[g[0].data_ptr() for g in gbuf])
+        rows = (ctypes.c_int32 * n)(*[t.shape[0] for t in tables])
+        _ck(_L().fs2_embedding_multi_bwd_f32(_p(dy), _p(ids), ctypes.cast(ptrs, ctypes.c_void_p),
+                                             ctypes.cast(rows, ctypes.c_void_p), n, ids.numel(), tables[0].shape[1],
+                                             -1 if pad_idx is None else pad_idx, _st()), "embedding_multi_bwd")
+        grads_done(tables)
+        return (None, None) + tuple(g[1] for g in gbuf)
 
 
 class AddRowVec(torch.autograd.Function):
@@ -1017,11 +1066,11 @@ class PostNetFn(torch.autograd.Function):
             wp = pack_conv(cw)
             y = conv_fwd(x, wp, cb.detach())
             Co = y.shape[2]
-            if training:
-                stats = torch.zeros(2, Co, dtype=F32, device=dev)
-                _ck(_L().fs2_bn_stats_bf16(_p(y), M, Co, _p(stats), _st()), "bn_stats")
-                _ck(_L().fs2_bn_update_running(_p(stats), M, Co, 0.1, _p(rm), _p(rv), _p(nb), _st()),
-                    "bn_update_running")
+            if training:  # fixed-order (bit-reproducible) column sums + running-statistics update
+                stats = torch.empty(2, Co, dtype=F32, device=dev)
+                ws = torch.empty(_L().fs2_bn_workspace_floats(M, Co), dtype=F32, device=dev)
+                _ck(_L().fs2_bn_stats_bf16(_p(y), M, Co, _p(ws), _p(stats), 0.1, _p(rm), _p(rv), _p(nb), _st()),
+                    "bn_stats")
             else:  # eval: express the running statistics as (sum, sum of squares)
                 stats = torch.stack([rm * M, (rv + rm * rm) * M]).to(F32).contiguous()
             salt = _Rng.next_salt()
@@ -1060,14 +1109,14 @@ class PostNetFn(torch.autograd.Function):
             x, y, stats, wp = saved[4 * i:4 * i + 4]
             cw, cb, bw, bb = ctx.params[i]
             Co = y.shape[2]
-            dstats = torch.zeros(2, Co, dtype=F32, device=dev)
+            dstats = torch.empty(2, Co, dtype=F32, device=dev)
+            ws = torch.empty(_L().fs2_bn_workspace_floats(M, Co), dtype=F32, device=dev)
             dy = torch.empty_like(y)
-            _ck(_L().fs2_bn_bwd(_p(d), d_is_f32, _p(y), _p(stats), _p(bw.detach()), _p(bb.detach()), M, Co,
-                                0 if i == n_layers - 1 else 1, p, salts[i], _p(seed_dev), _p(dstats), _p(dy),
-                                _st()), "bn_bwd")
             (gcw, rcw), (gcb, rcb), (gbw, rbw), (gbb, rbb) = (grad_target(t) for t in (cw, cb, bw, bb))
-            gbb.add_(dstats[0])  # dbeta / dgamma come back as [2][C]; tiny adds
-            gbw.add_(dstats[1])
+            # dbeta / dgamma are accumulated into the parameter gradients by the reduction's finalize kernel
+            _ck(_L().fs2_bn_bwd(_p(d), d_is_f32, _p(y), _p(stats), _p(bw.detach()), _p(bb.detach()), M, Co,
+                                0 if i == n_layers - 1 else 1, p, salts[i], _p(seed_dev), _p(ws), _p(dstats),
+                                _p(gbb), _p(gbw), _p(dy), _st()), "bn_bwd")
             with fork_side():
                 conv_wgrad(dy, x, gcw)
             # conv.bias: its gradient is sum_rows(dy), and the backward of a train-mode BatchNorm removes the
@@ -1161,12 +1210,15 @@ def phoneme_class_mean(representations, avg_frames, n_symbols, phonemes, two_sta
 # loss
 # --------------------------------------------------------------------------------------------------
 class FastSpeech2LossFn(torch.autograd.Function):
-    """lightning/model/loss.py:15-89 in two kernels forward, one backward."""
+    """lightning/model/loss.py:15-89 in two kernels forward, one backward.  `p_frame` / `e_frame`: the pitch /
+    energy feature is frame-level ([B, Tm] rows masked by the mel lengths, loss.py:50-52,57-59) instead of
+    phoneme-level ([B, Ts], source lengths)."""
 
     @staticmethod
-    def forward(ctx, mel, post, p_pred, e_pred, d_pred, mel_tgt, p_tgt, e_tgt, d_tgt, src_lens, mel_lens):
+    def forward(ctx, mel, post, p_pred, e_pred, d_pred, mel_tgt, p_tgt, e_tgt, d_tgt, src_lens, mel_lens,
+                p_frame=False, e_frame=False):
         B, Tm, n_mel = mel.shape
-        Ts = p_pred.shape[1]
+        Ts = d_pred.shape[1]
         dev = mel.device
         mel, post = mel.contiguous(), post.contiguous()
         p_pred, e_pred, d_pred = (t.contiguous().to(F32) for t in (p_pred, e_pred, d_pred))
@@ -1179,31 +1231,37 @@ class FastSpeech2LossFn(torch.autograd.Function):
         src_lens = src_lens.contiguous().to(torch.int64)
         mel_lens = mel_lens.contiguous().to(torch.int64)
         Tm_t = mel_tgt.shape[1]
-        nws = _L().fs2_loss_workspace_floats(B, Ts, Tm, n_mel)
+        p_T, e_T = p_pred.shape[1], e_pred.shape[1]
+        feat = (p_T, p_tgt.shape[1], mel_lens if p_frame else src_lens,
+                e_T, e_tgt.shape[1], mel_lens if e_frame else src_lens)
+        nws = _L().fs2_loss_workspace_floats(B, max(Ts, p_T, e_T), Tm, n_mel)
         if nws < 0:
             _ck(1, "loss_workspace")
         ws = torch.empty(nws, dtype=F32, device=dev)
-        out8 = torch.empty(8, dtype=F32, device=dev)
+        out10 = torch.empty(10, dtype=F32, device=dev)
         e64 = 1 if e_tgt.dtype == torch.float64 else 0
-        _ck(_L().fs2_loss_fwd(_p(mel), _p(post), _p(mel_tgt), _p(p_pred), _p(p_tgt), _p(e_pred), _p(e_tgt), e64,
-                              _p(d_pred), _p(d_tgt), _p(src_lens), _p(mel_lens), B, Ts, Tm, Tm_t, n_mel, _p(ws),
-                              _p(out8), _st()), "loss_fwd")
-        ctx.save_for_backward(out8, mel, post, mel_tgt, p_pred, p_tgt, e_pred, e_tgt, d_pred, d_tgt, src_lens,
+        _ck(_L().fs2_loss_fwd(_p(mel), _p(post), _p(mel_tgt), _p(p_pred), _p(p_tgt), feat[0], feat[1], _p(feat[2]),
+                              _p(e_pred), _p(e_tgt), e64, feat[3], feat[4], _p(feat[5]), _p(d_pred), _p(d_tgt),
+                              _p(src_lens), _p(mel_lens), B, Ts, Tm, Tm_t, n_mel, _p(ws), _p(out10), _st()),
+            "loss_fwd")
+        ctx.save_for_backward(out10, mel, post, mel_tgt, p_pred, p_tgt, e_pred, e_tgt, d_pred, d_tgt, src_lens,
                               mel_lens)
-        ctx.meta = (B, Ts, Tm, Tm_t, n_mel, e64)
-        return tuple(out8[i] for i in range(6))
+        ctx.meta = (B, Ts, Tm, Tm_t, n_mel, e64, p_frame, e_frame)
+        return tuple(out10[i] for i in range(6))
 
     @staticmethod
     def backward(ctx, *gouts):
-        (out8, mel, post, mel_tgt, p_pred, p_tgt, e_pred, e_tgt, d_pred, d_tgt, src_lens,
+        (out10, mel, post, mel_tgt, p_pred, p_tgt, e_pred, e_tgt, d_pred, d_tgt, src_lens,
          mel_lens) = ctx.saved_tensors
-        B, Ts, Tm, Tm_t, n_mel, e64 = ctx.meta
+        B, Ts, Tm, Tm_t, n_mel, e64, p_frame, e_frame = ctx.meta
         dev = mel.device
         g6 = torch.stack([torch.zeros((), dtype=F32, device=dev) if g is None else g.to(F32).reshape(())
                           for g in gouts])
         d_mel, d_post = torch.empty_like(mel), torch.empty_like(post)
         d_p, d_e, d_d = torch.empty_like(p_pred), torch.empty_like(e_pred), torch.empty_like(d_pred)
-        _ck(_L().fs2_loss_bwd(_p(g6), _p(out8), _p(mel), _p(post), _p(mel_tgt), _p(p_pred), _p(p_tgt), _p(e_pred),
-                              _p(e_tgt), e64, _p(d_pred), _p(d_tgt), _p(src_lens), _p(mel_lens), B, Ts, Tm, Tm_t,
+        _ck(_L().fs2_loss_bwd(_p(g6), _p(out10), _p(mel), _p(post), _p(mel_tgt), _p(p_pred), _p(p_tgt),
+                              p_pred.shape[1], p_tgt.shape[1], _p(mel_lens if p_frame else src_lens), _p(e_pred),
+                              _p(e_tgt), e64, e_pred.shape[1], e_tgt.shape[1], _p(mel_lens if e_frame else src_lens),
+                              _p(d_pred), _p(d_tgt), _p(src_lens), _p(mel_lens), B, Ts, Tm, Tm_t,
                               n_mel, _p(d_mel), _p(d_post), _p(d_p), _p(d_e), _p(d_d), _st()), "loss_bwd")
-        return d_mel, d_post, d_p, d_e, d_d, None, None, None, None, None, None
+        return d_mel, d_post, d_p, d_e, d_d, None, None, None, None, None, None, None, None

@@ -13,7 +13,8 @@ import torch.distributed as dist
 
 class GradBuckets:
     def __init__(self, params, bucket_bytes=32 << 20, process_group=None, device=None):
-        self.params = [p for p in params if p.requires_grad]
+        self.all_params = list(params)  # given order, frozen parameters included (torch.optim state indices)
+        self.params = [p for p in self.all_params if p.requires_grad]
         self.group = process_group
         self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
         device = device or self.params[0].device
@@ -25,7 +26,7 @@ class GradBuckets:
         self.flat = torch.zeros(total, dtype=torch.float32, device=device)
         self.buckets = []  # (start, end) element ranges of self.flat
         self._bucket_of = {}
-        self._pending0 = []
+        self._pending0 = []  # parameters per bucket (sizes only; membership is in self._members)
         off, bstart, bcount = 0, 0, 0
         for p in order:
             n = p.numel()
@@ -49,23 +50,38 @@ class GradBuckets:
         if off > bstart:
             self.buckets.append((bstart, off))
             self._pending0.append(bcount)
-        self._pending = list(self._pending0)
+        self._members = [set() for _ in self.buckets]  # parameter ids per bucket
+        for pid, b in self._bucket_of.items():
+            self._members[b].add(pid)
+        self._pending = [set(m) for m in self._members]
         self._launched = [False] * len(self.buckets)
+        self._late = set()  # buckets that received a gradient announcement after they went on the wire
         self.comm_stream = torch.cuda.Stream(device) if device.type == "cuda" else None
         self.overlap = True
+        # NCCL averages inside the collective (no separate divide pass over the 138 MB); gloo has no AVG
+        self._avg = False
+        if self.world > 1:
+            try:
+                self._avg = dist.get_backend(process_group) == "nccl"
+            except Exception:
+                self._avg = False
 
     # -- per-step protocol ---------------------------------------------------------------------------
     def zero(self):
         self.flat.zero_()
-        self._pending = list(self._pending0)
+        self._pending = [set(m) for m in self._members]
         self._launched = [False] * len(self.buckets)
+        self._late.clear()
 
     def _all_reduce(self, b):
         s, e = self.buckets[b]
         chunk = self.flat[s:e]
         if self.world > 1:
-            dist.all_reduce(chunk, op=dist.ReduceOp.SUM, group=self.group)
-            chunk.div_(self.world)
+            if self._avg:
+                dist.all_reduce(chunk, op=dist.ReduceOp.AVG, group=self.group)
+            else:
+                dist.all_reduce(chunk, op=dist.ReduceOp.SUM, group=self.group)
+                chunk.div_(self.world)
         self._launched[b] = True
 
     def _launch(self, b):
@@ -89,12 +105,22 @@ class GradBuckets:
             b = self._bucket_of.get(id(p))
             if b is None:
                 continue
-            self._pending[b] -= 1
-            if self._pending[b] == 0 and not self._launched[b]:
+            if self._launched[b]:
+                # a parameter whose backward Function runs more than once per step (module called twice, shared
+                # weights, few-shot inner loops) was announced again AFTER its bucket was reduced: the late
+                # contribution would be added on top of an already averaged bucket.  Refuse loudly.
+                self._late.add(b)
+                continue
+            self._pending[b].discard(id(p))  # once per distinct parameter, however often it is announced
+            if not self._pending[b]:
                 self._launch(b)
 
     def finish(self):
         """Reduce whatever has not been sent yet and join the side stream."""
+        if self._late:
+            raise RuntimeError("GradBuckets: gradients of bucket(s) %s were announced again after the bucket had been "
+                               "all-reduced (a module ran twice in one backward pass); set buckets.overlap = False "
+                               "for such steps so that every bucket is reduced in finish()" % sorted(self._late))
         if self.world > 1:
             for b in range(len(self.buckets)):
                 if not self._launched[b]:
@@ -105,6 +131,9 @@ class GradBuckets:
     def reduce_scalars(self, t):
         """Mean over ranks of a small tensor (the six logged losses: FastSpeech2.py:89 sync_dist=True)."""
         if self.world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
-            t.div_(self.world)
+            if self._avg:
+                dist.all_reduce(t, op=dist.ReduceOp.AVG, group=self.group)
+            else:
+                dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+                t.div_(self.world)
         return t

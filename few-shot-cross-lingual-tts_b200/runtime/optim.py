@@ -78,11 +78,58 @@ class FusedAdam:
         _cabi.check(L.fs2_optim_advance(self.step_dev.data_ptr(), self.gnorm_sq.data_ptr(),
                                         self.grad_norm.data_ptr(), st), "optim_advance")
 
-    # -- checkpointing (flat tensors; the parameter state itself is in the model's state_dict) ---------
+    # -- checkpointing: torch.optim.Adam's own state_dict format ------------------------------------------------
+    # (the reference's Lightning checkpoints store `optimizer_states` = [torch.optim.Adam.state_dict()] for
+    # Adam(model.parameters()), lightning/optimizer.py:5-16, main.py resume_from_checkpoint): per-parameter entries
+    # keyed by the parameter's index in the list the optimizer was built over, tensors in the parameter's LOGICAL
+    # shape -- independent of the flat bucket order / the [Co][k][Ci] storage of Conv1d weights used internally.
+    def _logical_view(self, buf, p):
+        off = (p.main_grad.data_ptr() - self.buckets.flat.data_ptr()) // 4
+        flat = buf[off: off + p.numel()]
+        if p.main_grad.is_contiguous():
+            return flat.view(p.shape)
+        Co, Ci, k = p.shape
+        return flat.view(Co, k, Ci).permute(0, 2, 1)
+
     def state_dict(self):
-        return {"step": self.step_dev.clone(), "exp_avg": self.exp_avg.clone(), "exp_avg_sq": self.exp_avg_sq.clone()}
+        index = {id(p): i for i, p in enumerate(self.buckets.all_params)}
+        step = self.step_dev.to(torch.float32).reshape(()).clone()
+        state = {}
+        if int(self.step_dev) > 0:  # torch.optim.Adam has no state before its first step
+            for p in self.buckets.params:
+                state[index[id(p)]] = {"step": step.clone(),
+                                       "exp_avg": self._logical_view(self.exp_avg, p).contiguous().clone(),
+                                       "exp_avg_sq": self._logical_view(self.exp_avg_sq, p).contiguous().clone()}
+        group = {"lr": self.lr0, "betas": (self.beta1, self.beta2), "eps": self.eps,
+                 "weight_decay": self.weight_decay, "amsgrad": False, "maximize": False,
+                 "params": list(range(len(self.buckets.all_params)))}
+        return {"state": state, "param_groups": [group]}
 
     def load_state_dict(self, sd):
-        self.step_dev.copy_(sd["step"])
-        self.exp_avg.copy_(sd["exp_avg"])
-        self.exp_avg_sq.copy_(sd["exp_avg_sq"])
+        """Accepts the format above, i.e. also the `optimizer_states[0]` of a reference checkpoint."""
+        if "state" not in sd or "param_groups" not in sd:
+            raise ValueError("FusedAdam.load_state_dict: expected a torch.optim.Adam-style state_dict "
+                             "({'state': {index: {step, exp_avg, exp_avg_sq}}, 'param_groups': [...]})")
+        n_all = len(self.buckets.all_params)
+        listed = sd["param_groups"][0]["params"]
+        if len(listed) != n_all:
+            raise ValueError("FusedAdam.load_state_dict: the checkpoint optimises %d parameters, this model has %d"
+                             % (len(listed), n_all))
+        index = {id(p): i for i, p in enumerate(self.buckets.all_params)}
+        self.exp_avg.zero_()
+        self.exp_avg_sq.zero_()
+        steps = set()
+        for p in self.buckets.params:
+            ent = sd["state"].get(listed[index[id(p)]])
+            if ent is None:
+                continue
+            for key, buf in (("exp_avg", self.exp_avg), ("exp_avg_sq", self.exp_avg_sq)):
+                t = ent[key]
+                if tuple(t.shape) != tuple(p.shape):
+                    raise ValueError("FusedAdam.load_state_dict: %s of parameter %d has shape %s, expected %s"
+                                     % (key, index[id(p)], tuple(t.shape), tuple(p.shape)))
+                self._logical_view(buf, p).copy_(t)
+            steps.add(int(ent["step"]))
+        if len(steps) > 1:
+            raise ValueError("FusedAdam.load_state_dict: parameters with different step counts %s" % sorted(steps))
+        self.step_dev.fill_(steps.pop() if steps else 0)

@@ -18,13 +18,34 @@ _TENSOR_SLOTS = (2, 3, 4, 6, 7, 9, 10, 11, 12)
 
 
 class TrainStep:
-    def __init__(self, model, loss_fn, example_batch, use_graph=True, buckets=None, device=None, optimizer=None):
+    def __init__(self, model, loss_fn, example_batch, use_graph=True, buckets=None, device=None, optimizer=None,
+                 embedding_model=None, model_kwargs=None):
         """optimizer: optional runtime.FusedAdam built on `buckets`; its clip + Adam + LR-schedule launches then
-        become part of the captured step."""
+        become part of the captured step.
+
+        embedding_model: optional phoneme-embedding module (MultilingualEmbedding, ...).  Batch slot 3 then holds
+        the int64 phoneme ids `[B, Ts]` and `emb_texts = embedding_model(batch[3])` is computed INSIDE the step, as
+        in the reference (lightning/systems/language/FastSpeech2.py:53-55); its parameters are part of the gradient
+        buckets, so they are all-reduced, clipped and updated together with the model's
+        (`nn.ModuleList([model, embedding_model])`, FastSpeech2.py:47-48).  Without it slot 3 holds already
+        embedded phonemes `[B, Ts, d]` and no gradient flows past them.  `buckets`, when passed, must have been
+        built over the parameters of both modules.
+
+        model_kwargs: extra keyword arguments of the model call (e.g. average_spk_emb=True for FSCL task steps)."""
         self.model, self.loss_fn = model, loss_fn
+        self.embedding_model = embedding_model
+        self.model_kwargs = dict(model_kwargs or {})
         self.optimizer = optimizer
         self.device = device or next(model.parameters()).device
-        self.buckets = buckets or GradBuckets(model.parameters(), device=self.device)
+        params = list(model.parameters())
+        if embedding_model is not None:
+            params += [p for p in embedding_model.parameters()]
+        self.buckets = buckets or GradBuckets(params, device=self.device)
+        if embedding_model is not None:
+            missing = [p for p in embedding_model.parameters() if p.requires_grad and
+                       getattr(p, "main_grad", None) is None]
+            if missing:
+                raise ValueError("TrainStep: `buckets` does not cover the embedding model's parameters")
         ops.set_grad_listener(self.buckets.notify)
         # all bf16 operand copies of the weights are refreshed by one launch at the start of every step
         self.wcache = ops.WeightCache(model)
@@ -58,7 +79,8 @@ class TrainStep:
         ops.set_weight_cache(self.wcache)  # valid for this step only: the copies were just refreshed
         try:
             self.buckets.zero()
-            out = self.model(b[2], b[3], *b[4:12], lang_args=b[12])
+            emb = b[3] if self.embedding_model is None else self.embedding_model(b[3])
+            out = self.model(b[2], emb, *b[4:12], lang_args=b[12], **self.model_kwargs)
             losses = self.loss_fn(tuple(b[:12]), out)
             ops.DEFER_JOIN = _DEFER  # weight gradients run free on the side stream until the end of the backward
             try:
@@ -83,16 +105,50 @@ class TrainStep:
         dbg = (lambda m: print("[step] " + m, file=sys.stderr, flush=True)) if os.environ.get("FS2_DEBUG") \
             else (lambda m: None)
         with torch.cuda.stream(s):
-            for i in range(2):  # warm-up outside capture (allocator, lazy inits, NCCL communicators)
+            # warm-up outside capture (allocator, lazy inits, NCCL communicators).  The warm-up bodies are REAL steps
+            # on the example batch (Adam updates, BatchNorm running statistics, dropout counter): everything they
+            # mutate is snapshotted and put back, so constructing a TrainStep leaves the training state untouched.
+            snap = self._snapshot()
+            for i in range(2):
                 self._body()
                 torch.cuda.synchronize()
                 dbg("warm-up body %d done" % i)
+            self._restore(snap)
+            del snap
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             self._body()
         dbg("captured")
+
+    def _mutable_state(self):
+        """Every tensor a step body writes besides the gradient buffers and the loss read-back."""
+        ts = []
+        mods = [self.model] + ([self.embedding_model] if self.embedding_model is not None else [])
+        for m in mods:
+            ts += [b for b in m.buffers()]
+            if self.optimizer is not None:
+                ts += [p.data for p in m.parameters()]
+        if self.optimizer is not None:
+            o = self.optimizer
+            ts += [o.flat_param, o.exp_avg, o.exp_avg_sq, o.step_dev, o.gnorm_sq, o.grad_norm]
+        ts.append(ops._Rng.tensor(self.device))  # dropout step counter (created on first use)
+        return ts
+
+    def _snapshot(self):
+        return [(t, t.clone()) for t in self._mutable_state()]
+
+    def _restore(self, snap):
+        for t, c in snap:
+            t.copy_(c)
+
+    def close(self):
+        """Drop the captured graph (and with it the captured NCCL kernels) -- call before
+        torch.distributed.destroy_process_group()."""
+        torch.cuda.synchronize(self.device)
+        self.graph = None
+        ops.set_grad_listener(None)
 
     # ---------------------------------------------------------------------------------------------
     def load_batch(self, batch=None):

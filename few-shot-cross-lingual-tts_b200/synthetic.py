@@ -131,6 +131,31 @@ CONFIGS = {
 }
 
 
+# model settings per BASELINE.json config (SURVEY.md 8d "Model config"): C1 single-speaker fastspeech2.yaml; C2
+# multi-speaker (247 LibriTTS speakers); C3-C5 multilingual-fastspeech2.yaml (multi_lingual, max_seq_len 1500)
+CONFIG_MODEL = {
+    "C1": dict(),
+    "C2": dict(multi_speaker=True),
+    "C2_8": dict(multi_speaker=True),
+    "C3": dict(multi_speaker=True, multi_lingual=True, max_seq_len=1500),
+    "C4": dict(multi_speaker=True, multi_lingual=True, max_seq_len=1500),
+    "C5": dict(multi_speaker=True, multi_lingual=True, max_seq_len=1500),
+}
+CONFIG_CALL = {"C3": dict(average_spk_emb=True)}  # FSCL task step (TransEmbOrig.py:93-126)
+N_SPEAKER = 247
+
+
+def build_config(name, M, device=None, weight_seed=0):
+    """(cfg, model, loss_fn, model_kwargs) of a BASELINE.json configuration; M = the lightning.model package."""
+    cfg = model_cfg(**CONFIG_MODEL[name])
+    spk = {"emb_type": "table", "speakers": list(range(N_SPEAKER))} if cfg.get("multi_speaker") else None
+    model = M.FastSpeech2(cfg, spk_config=spk) if spk else M.FastSpeech2(cfg)
+    model.load_state_dict(init_state_dict(model.state_dict(), weight_seed))
+    if device is not None:
+        model = model.to(device)
+    return cfg, model.train(), M.FastSpeech2Loss(cfg), dict(CONFIG_CALL.get(name, {}))
+
+
 def count_real_frames(batch, max_seq_len):
     """mel frames that reach the loss: sum_b min(mel_len_b, max_seq_len)."""
     return int(torch.clamp(batch[7], max=max_seq_len).sum())

@@ -187,6 +187,15 @@ int fs2_embedding_fwd_bf16(const int64_t* ids, const float* table, int64_t rows,
                            int n_rows_table, int pad_idx, void* y, void* stream);
 int fs2_embedding_bwd_f32(const void* dy, const void* ids, int ids_is_i64, int64_t rows, int C,
                           int n_rows_table, int pad_idx, float* dtable, void* stream);
+/* MultilingualEmbedding (lightning/systems/language/embeddings.py:25-31) without the per-call torch.cat: ids index the
+   concatenation of n_tables (<= 32) f32 tables; tables / dtables / table_rows are HOST arrays (device pointers, row
+   counts) that are copied into the kernel parameters. */
+int fs2_embedding_multi_fwd_bf16(const int64_t* ids, const void* const* tables, const int32_t* table_rows,
+                                 int n_tables, int64_t rows, int C, int pad_idx, void* y, void* stream);
+int fs2_embedding_multi_bwd_f32(const void* dy, const int64_t* ids, const void* const* dtables,
+                                const int32_t* table_rows, int n_tables, int64_t rows, int C, int pad_idx,
+                                void* stream);
+
 
 /* ------------------------------------------------------------------------------------------ */
 /* Small helpers: sinusoid add (transformer/Models.py:155-157,224-226), casts, Conv1d weight   */
@@ -223,35 +232,45 @@ int fs2_rowdot_bwd(const float* dout, const void* x, const float* w, const int64
                    int C, void* dx, float* dw, float* db, void* stream);
 
 /* ------------------------------------------------------------------------------------------ */
-/* FastSpeech2Loss (lightning/model/loss.py:15-89): out8 = total, mel, postnet, pitch, energy, */
-/* duration, N_mel, N_src.  partials: f32 workspace of fs2_loss_workspace_floats() elements.   */
+/* FastSpeech2Loss (lightning/model/loss.py:15-89): out10 = total, mel, postnet, pitch, energy, */
+/* duration, N_mel, N_pitch, N_energy, N_duration.  partials: f32 workspace of                  */
+/* fs2_loss_workspace_floats(B, max(Ts, p_T, e_T), Tm, n_mel) elements.  Pitch / energy are     */
+/* phoneme-level (p_T = Ts, p_lens = src_lens) or frame-level (p_T = Tm, p_lens = mel_lens),    */
+/* loss.py:47-60; p_ld / e_ld = row stride of the target (>= p_T / e_T).                        */
 /* ------------------------------------------------------------------------------------------ */
-int64_t fs2_loss_workspace_floats(int B, int Ts, int Tm, int n_mel);
-int fs2_loss_fwd(const float* mel_pred, const float* post_pred, const float* mel_tgt,
-                 const float* p_pred, const float* p_tgt, const float* e_pred, const void* e_tgt,
-                 int e_tgt_is_f64, const float* d_pred, const int64_t* d_tgt, const int64_t* src_lens,
-                 const int64_t* mel_lens, int B, int Ts, int Tm, int Tm_tgt, int n_mel, float* partials,
-                 float* out8, void* stream);
-int fs2_loss_bwd(const float* gout6, const float* out8, const float* mel_pred, const float* post_pred,
-                 const float* mel_tgt, const float* p_pred, const float* p_tgt, const float* e_pred,
-                 const void* e_tgt, int e_tgt_is_f64, const float* d_pred, const int64_t* d_tgt,
-                 const int64_t* src_lens, const int64_t* mel_lens, int B, int Ts, int Tm, int Tm_tgt,
-                 int n_mel, float* d_mel, float* d_post, float* d_p, float* d_e, float* d_d,
-                 void* stream);
+int64_t fs2_loss_workspace_floats(int B, int T_feat, int Tm, int n_mel);
+int fs2_loss_fwd(const float* mel_pred, const float* post_pred, const float* mel_tgt, const float* p_pred,
+                 const float* p_tgt, int p_T, int p_ld, const int64_t* p_lens, const float* e_pred, const void* e_tgt,
+                 int e_tgt_is_f64, int e_T, int e_ld, const int64_t* e_lens, const float* d_pred,
+                 const int64_t* d_tgt, const int64_t* src_lens, const int64_t* mel_lens, int B, int Ts, int Tm,
+                 int Tm_tgt, int n_mel, float* partials, float* out10, void* stream);
+int fs2_loss_bwd(const float* gout6, const float* out10, const float* mel_pred, const float* post_pred,
+                 const float* mel_tgt, const float* p_pred, const float* p_tgt, int p_T, int p_ld,
+                 const int64_t* p_lens, const float* e_pred, const void* e_tgt, int e_tgt_is_f64, int e_T, int e_ld,
+                 const int64_t* e_lens, const float* d_pred, const int64_t* d_tgt, const int64_t* src_lens,
+                 const int64_t* mel_lens, int B, int Ts, int Tm, int Tm_tgt, int n_mel, float* d_mel, float* d_post,
+                 float* d_p, float* d_e, float* d_d, void* stream);
 
 /* ------------------------------------------------------------------------------------------ */
 /* PostNet BatchNorm1d(train) + tanh + dropout (transformer/Layers.py:129-137,                 */
-/* fastspeech2m.py:145); y: bf16 [M][C] conv output; stats: f32 [2][C] (sum, sum of squares)   */
+/* fastspeech2m.py:145); y: bf16 [M][C] conv output; stats: f32 [2][C] (sum, sum of squares),   */
+/* WRITTEN by fs2_bn_stats_bf16 with a fixed summation order (bit-reproducible, no atomics);    */
+/* ws: f32 scratch of fs2_bn_workspace_floats(M, C) elements (per-block partial sums).          */
+/* fs2_bn_stats_bf16 also performs nn.BatchNorm1d's running-statistics update (momentum,        */
+/* unbiased variance, num_batches_tracked += 1) when running_mean is non-NULL.                  */
+/* fs2_bn_bwd: dstats f32 [2][C] written (dbeta, dgamma); dbeta_acc / dgamma_acc (optional,     */
+/* f32 [C]) accumulate them into the parameter gradients.                                       */
 /* ------------------------------------------------------------------------------------------ */
-int fs2_bn_stats_bf16(const void* y, int64_t M, int C, float* stats, void* stream);
+int64_t fs2_bn_workspace_floats(int64_t M, int C);
+int fs2_bn_stats_bf16(const void* y, int64_t M, int C, float* ws, float* stats, float momentum, float* running_mean,
+                      float* running_var, int64_t* num_batches_tracked, void* stream);
 int fs2_bn_apply_fwd(const void* y, const float* stats, const float* gamma, const float* beta, int64_t M,
                      int C, int act_tanh, float p_drop, uint64_t seed, const uint64_t* seed_dev,
                      void* out_bf16, float* out_f32, const float* res_f32, void* stream);
-int fs2_bn_update_running(const float* stats, int64_t M, int C, float momentum, float* running_mean,
-                          float* running_var, int64_t* num_batches_tracked, void* stream);
 int fs2_bn_bwd(const void* dout, int dout_is_f32, const void* y, const float* stats, const float* gamma,
                const float* beta, int64_t M, int C, int act_tanh, float p_drop, uint64_t seed,
-               const uint64_t* seed_dev, float* dstats, void* dy, void* stream);
+               const uint64_t* seed_dev, float* ws, float* dstats, float* dbeta_acc, float* dgamma_acc, void* dy,
+               void* stream);
 
 /* ------------------------------------------------------------------------------------------ */
 /* Phoneme-embedding front-end of the few-shot systems                      */

@@ -87,34 +87,59 @@ def variance_predictor(sd, pre, x, mask):
     return out.masked_fill(mask, 0.0) if mask is not None else out
 
 
-def postnet(sd, pre, x, n_layers=5, running=None):
-    """transformer/Layers.py:129-137; train-mode BatchNorm over all B*T positions (padding included)."""
+def postnet(sd, pre, x, n_layers=5, running=None, training=True):
+    """transformer/Layers.py:129-137; train-mode BatchNorm over all B*T positions (padding included), or -- with
+    training=False -- eval-mode BatchNorm on the running statistics stored in `sd` (F.dropout(..., self.training) is
+    the identity there)."""
     x = x.transpose(1, 2)
     for i in range(n_layers):
         c = "%sconvolutions.%d." % (pre, i)
         w = sd[c + "0.conv.weight"]
         x = F.conv1d(x, w, sd[c + "0.conv.bias"], padding=(w.shape[2] - 1) // 2)
         rm = rv = None
-        if running is not None:
+        if not training:
+            rm, rv = sd[c + "1.running_mean"], sd[c + "1.running_var"]
+        elif running is not None:
             rm, rv = running[c + "1.running_mean"], running[c + "1.running_var"]
-        x = F.batch_norm(x, rm, rv, sd[c + "1.weight"], sd[c + "1.bias"], training=True, momentum=0.1,
+        x = F.batch_norm(x, rm, rv, sd[c + "1.weight"], sd[c + "1.bias"], training=training, momentum=0.1,
                          eps=1e-5)
         if i < n_layers - 1:
             x = torch.tanh(x)
     return x.transpose(1, 2)
 
 
+def sinusoid_table(n_position, d_hid):
+    """transformer/Models.py:10-30 with padding_idx=None (the eval-mode long-sequence branch, :148-153, :211-218)."""
+    import numpy as np
+
+    pos = np.arange(n_position)[:, None].astype(np.float64)
+    hid = np.arange(d_hid)[None, :]
+    ang = pos / np.power(10000, 2 * (hid // 2) / d_hid)
+    ang[:, 0::2] = np.sin(ang[:, 0::2])
+    ang[:, 1::2] = np.cos(ang[:, 1::2])
+    return torch.FloatTensor(ang)
+
+
 def forward(sd, cfg, speaker_args, texts, src_lens, max_src_len, mels=None, mel_lens=None, max_mel_len=None,
             p_targets=None, e_targets=None, d_targets=None, lang_args=None, average_spk_emb=False,
-            running=None):
-    """lightning/model/fastspeech2m.py:48-163, training (teacher-forced) branch, train-mode semantics
-    (decoder truncation to max_seq_len, Models.py:220-228).  Returns the reference's 10-tuple."""
+            running=None, training=True, p_control=1.0, e_control=1.0, d_control=1.0, inject=None):
+    """lightning/model/fastspeech2m.py:48-163.  training=True: train-mode semantics (decoder truncation to
+    max_seq_len, Models.py:220-228, batch-statistics BatchNorm); training=False: eval mode (no truncation, sinusoid
+    table rebuilt for sequences longer than max_seq_len, running-statistics BatchNorm).  Without targets the
+    predictions drive the embeddings / durations (modules.py:84-91,133-139); `inject` = {"pitch", "energy",
+    "duration"} optionally replaces those predictions by externally supplied values (the parity tests feed the CUDA
+    path's own predictions so that bucket / rounding decisions are identical on both sides).  Pitch / energy are
+    phoneme- or frame-level per cfg (modules.py:117-128,141-150).  Returns the reference's 10-tuple."""
     t = cfg["transformer"]
+    inject = inject or {}
     max_src_len = int(max_src_len)
     src_masks = mask_from_lengths(src_lens, max_src_len)
     mel_masks = mask_from_lengths(mel_lens, int(max_mel_len)) if mel_lens is not None else None
     # Encoder2 (Models.py:139-166)
-    x = texts + sd["encoder.position_enc"][:, :max_src_len]
+    if not training and max_src_len > cfg["max_seq_len"]:
+        x = texts + sinusoid_table(max_src_len, t["encoder_hidden"])[None].to(texts.device)
+    else:
+        x = texts + sd["encoder.position_enc"][:, :max_src_len]
     x = fft_stack(sd, "encoder.", x, src_masks, t["encoder_layer"], t["encoder_head"])
     spk = None
     if "speaker_emb.model.weight" in sd:  # fastspeech2m.py:84-89 (table embedding)
@@ -124,37 +149,63 @@ def forward(sd, cfg, speaker_args, texts, src_lens, max_src_len, mels=None, mel_
         x = x + spk[:, None, :]
     if "language_emb.model.weight" in sd and lang_args is not None:  # :98-101
         x = x + sd["language_emb.model.weight"][lang_args][:, None, :]
-    # VarianceAdaptor (modules.py:104-160), phoneme-level features
+    # VarianceAdaptor (modules.py:104-160)
     va = "variance_adaptor."
+
+    def variance(name, x, target, mask, control):  # modules.py:82-102
+        pred = variance_predictor(sd, va + name + "_predictor.", x, mask)
+        if target is None:
+            pred = pred * control
+            target = inject.get(name, pred.detach())
+        emb = sd[va + name + "_embedding.weight"][torch.bucketize(target, sd[va + name + "_bins"])]
+        return pred, x + emb
+
     log_d = variance_predictor(sd, va + "duration_predictor.", x, src_masks)
-    p_pred = variance_predictor(sd, va + "pitch_predictor.", x, src_masks)
-    x = x + sd[va + "pitch_embedding.weight"][torch.bucketize(p_targets, sd[va + "pitch_bins"])]
-    e_pred = variance_predictor(sd, va + "energy_predictor.", x, src_masks)
-    x = x + sd[va + "energy_embedding.weight"][torch.bucketize(e_targets, sd[va + "energy_bins"])]
-    x, mel_len = length_regulate(x, d_targets, max_mel_len)
-    if spk is not None:  # :132-136 (max(mel_lens) == x.shape[1] for teacher-forced batches)
+    p_pred = e_pred = None
+    if cfg["pitch"]["feature"] == "phoneme_level":
+        p_pred, x = variance("pitch", x, p_targets, src_masks, p_control)
+    if cfg["energy"]["feature"] == "phoneme_level":
+        e_pred, x = variance("energy", x, e_targets, src_masks, e_control)
+    if d_targets is not None:
+        d_rounded = d_targets
+        x, mel_len = length_regulate(x, d_targets, max_mel_len)
+    else:
+        d_rounded = torch.clamp(torch.round(torch.exp(log_d.detach()) - 1) * d_control, min=0)
+        d_rounded = inject.get("duration", d_rounded)
+        x, mel_len = length_regulate(x, d_rounded, max_mel_len)
+        mel_masks = mask_from_lengths(mel_len, x.shape[1])
+    if cfg["pitch"]["feature"] == "frame_level":
+        p_pred, x = variance("pitch", x, p_targets, mel_masks, p_control)
+    if cfg["energy"]["feature"] == "frame_level":
+        e_pred, x = variance("energy", x, e_targets, mel_masks, e_control)
+    if spk is not None:  # :132-136 (max(mel_lens) == x.shape[1])
         x = x + spk[:, None, :]
-    # Decoder (Models.py:205-237), train mode: truncate to max_seq_len
-    T = min(x.shape[1], cfg["max_seq_len"])
-    x = x[:, :T] + sd["decoder.position_enc"][:, :T]
-    mel_masks = mel_masks[:, :T]
+    # Decoder (Models.py:205-237)
+    if not training and x.shape[1] > cfg["max_seq_len"]:
+        x = x + sinusoid_table(x.shape[1], t["decoder_hidden"])[None].to(x.device)
+    else:
+        T = min(x.shape[1], cfg["max_seq_len"])
+        x = x[:, :T] + sd["decoder.position_enc"][:, :T]
+        mel_masks = mel_masks[:, :T]
     x = fft_stack(sd, "decoder.", x, mel_masks, t["decoder_layer"], t["decoder_head"])
     mel = F.linear(x, sd["mel_linear.weight"], sd["mel_linear.bias"])
-    post = postnet(sd, "postnet.", mel, running=running) + mel
-    return (mel, post, p_pred, e_pred, log_d, d_targets, src_masks, mel_masks, src_lens, mel_len)
+    post = postnet(sd, "postnet.", mel, running=running, training=training) + mel
+    return (mel, post, p_pred, e_pred, log_d, d_rounded, src_masks, mel_masks, src_lens, mel_len)
 
 
-def loss(inputs, predictions):
-    """lightning/model/loss.py:15-89."""
+def loss(inputs, predictions, pitch_level="phoneme_level", energy_level="phoneme_level"):
+    """lightning/model/loss.py:15-89 (pitch / energy masked by the source or the mel mask, :47-60)."""
     mel_t, _, _, p_t, e_t, d_t = inputs[6:12]
     mel, post, p_pred, e_pred, log_d, _, src_masks, mel_masks, _, _ = predictions
     sm, mm = ~src_masks, ~mel_masks
     log_d_t = torch.log(d_t.float() + 1)
     mel_t = mel_t[:, : mm.shape[1], :]
     l1 = lambda a, b: (a.masked_select(mm[..., None]) - b.masked_select(mm[..., None])).abs().mean()
-    mse = lambda a, b: ((a.masked_select(sm) - b.masked_select(sm).float()) ** 2).mean()
+    mse = lambda a, b, m=sm: ((a.masked_select(m) - b.masked_select(m).float()) ** 2).mean()
     mel_loss, post_loss = l1(mel, mel_t), l1(post, mel_t)
-    pitch_loss, energy_loss, dur_loss = mse(p_pred, p_t), mse(e_pred, e_t), mse(log_d, log_d_t)
+    pitch_loss = mse(p_pred, p_t, sm if pitch_level == "phoneme_level" else mm)
+    energy_loss = mse(e_pred, e_t, sm if energy_level == "phoneme_level" else mm)
+    dur_loss = mse(log_d, log_d_t)
     total = mel_loss + post_loss + dur_loss + pitch_loss + energy_loss
     return total, mel_loss, post_loss, pitch_loss, energy_loss, dur_loss
 
@@ -167,9 +218,19 @@ def step(sd, cfg, batch, grad_keys=None):
     for v in params.values():
         v.requires_grad_(True)
     out = forward(sd, cfg, batch[2], batch[3], *batch[4:12], lang_args=batch[12])
-    losses = loss(batch[:12], out)
+    losses = loss(batch[:12], out, cfg["pitch"]["feature"], cfg["energy"]["feature"])
     keys = list(params) if grad_keys is None else list(grad_keys)
     grads = torch.autograd.grad(losses[0], [params[k] for k in keys], allow_unused=True)
     for v in params.values():
         v.requires_grad_(False)
     return out, losses, dict(zip(keys, grads))
+
+
+def ada_loss(mel_targets, predictions):
+    """FastSpeech2ADALoss, lightning/model/loss.py:104-140: L1(mel) + L1(postnet mel) over the valid mel elements."""
+    mel, post, mel_masks = predictions
+    mm = ~mel_masks
+    mel_t = mel_targets[:, : mm.shape[1], :]
+    l1 = lambda a: (a.masked_select(mm[..., None]) - mel_t.masked_select(mm[..., None])).abs().mean()
+    mel_loss, post_loss = l1(mel), l1(post)
+    return mel_loss + post_loss, mel_loss, post_loss

@@ -97,3 +97,24 @@ def test_bucket_views_alias_flat_buffer_in_reverse_order():
     covered = sorted(b.buckets)
     assert covered[0][0] == 0 and covered[-1][1] == b.flat.numel()
     assert all(covered[i][1] == covered[i + 1][0] for i in range(len(covered) - 1))
+
+
+def test_bucket_refuses_gradients_announced_after_the_reduce():
+    """A parameter announced again after its bucket went on the wire (module called twice per step) must not be
+    averaged silently with a partial gradient (notify() counted notifications, not parameters)."""
+    dp = sub("runtime.dp")
+    lin = torch.nn.Linear(8, 8)
+    b = dp.GradBuckets(lin.parameters(), device=torch.device("cpu"))
+    b.world = 2  # pretend: exercise the bookkeeping without a process group
+    launched = []
+    b._launch = lambda i: (launched.append(i), b._launched.__setitem__(i, True))
+    b.zero()
+    b.notify([lin.weight])
+    b.notify([lin.weight])  # same parameter twice: still waiting for the bias
+    assert launched == []
+    b.notify([lin.bias])
+    assert launched == [0]
+    b.notify([lin.weight])  # late contribution
+    b.world = 1
+    with pytest.raises(RuntimeError):
+        b.finish()

@@ -7,8 +7,8 @@ import torch
 import torch.nn.functional as F
 
 from fs2b200 import sub
-from oracle import fs2_oracle
-from tests.util_parity import cosine, load_golden, rel_err
+from oracle import fs2_oracle, synth
+from tests.util_parity import cosine, disable_dropout, load_golden, rel_err
 
 pytestmark = pytest.mark.gpu
 BF16 = torch.bfloat16
@@ -101,6 +101,78 @@ def test_embedding_backward_scatter_add():
                                                         w.float().view(-1, C))
     assert rel_err(table.grad, ref) < 1e-5
     assert torch.equal(x.grad, w)
+
+
+def test_embedding_fn_and_multilingual_embedding_match_f_embedding():
+    """ops.EmbeddingFn / ops.MultiEmbeddingFn against F.embedding(padding_idx) on the concatenated table
+    (lightning/systems/language/embeddings.py:25-31): forward bit-exact up to the bf16 output cast, gradients per
+    table equal to the slices of the concatenated table's gradient, no gradient for the padding row."""
+    import torch.nn.functional as F
+
+    EMB = sub("lightning.systems.language.embeddings")
+    torch.manual_seed(2)
+    id2symbols = {"en": ["s%d" % i for i in range(41)], "zh": ["s%d" % i for i in range(73)], "empty": [],
+                  "de": ["s%d" % i for i in range(18)]}
+    emb = EMB.MultilingualEmbedding(id2symbols, 256).cuda()
+    assert set(emb.state_dict().keys()) == {"tables.table-en", "tables.table-zh", "tables.table-de"}
+    n = 41 + 73 + 18
+    ids = torch.randint(0, n, (5, 37), device="cuda")
+    ids[:, 30:] = 0  # padded positions
+    ids[0, :4] = torch.tensor([0, 40, 41, n - 1])  # table boundaries
+    w = torch.randn(5, 37, 256, device="cuda")
+    out = emb(ids)
+    assert out.dtype == BF16 and out.shape == (5, 37, 256)
+    (out.float() * w).sum().backward()
+    cat = torch.cat([p.detach() for p in emb.tables.values()]).requires_grad_(True)
+    ref = F.embedding(ids, cat, padding_idx=0)
+    assert torch.equal(out.float(), ref.to(BF16).float())
+    (ref * w.to(BF16).float()).sum().backward()
+    r0 = 0
+    for p in emb.tables.values():
+        assert rel_err(p.grad, cat.grad[r0:r0 + p.shape[0]]) < 1e-5
+        r0 += p.shape[0]
+    assert float(emb.tables["table-en"].grad[0].abs().sum()) == 0.0  # padding_idx row
+    assert float(emb.tables["table-zh"].grad[0].abs().sum()) > 0.0   # row 41 of the concatenation is an ordinary row
+    # single-table path (symbol_id given)
+    for p in emb.tables.values():
+        p.grad = None
+    ids_zh = torch.randint(0, 73, (3, 11), device="cuda")
+    o2 = emb(ids_zh, "zh")
+    (o2.float() * w[:3, :11]).sum().backward()
+    t = emb.tables["table-zh"].detach().clone().requires_grad_(True)
+    r2 = F.embedding(ids_zh, t, padding_idx=0)
+    (r2 * w[:3, :11].to(BF16).float()).sum().backward()
+    assert torch.equal(o2.float(), r2.to(BF16).float()) and rel_err(emb.tables["table-zh"].grad, t.grad) < 1e-5
+    assert emb.tables["table-en"].grad is None
+
+
+def test_encoder_with_symbol_embedding_matches_oracle_stack():
+    """transformer.Models.Encoder (Models.py:33-100: nn.Embedding(len(symbols)+1, d, padding_idx=0) + Encoder2's
+    stack): forward and the embedding-table gradient against F.embedding + the oracle FFT stack."""
+    import torch.nn.functional as F
+
+    Models = sub("transformer.Models")
+    cfg = synth.model_cfg(encoder_layer=2)
+    torch.manual_seed(6)
+    enc = disable_dropout(Models.Encoder(cfg).cuda().train())
+    B, T = 3, 50
+    lens = torch.tensor([50, 17, 33], device="cuda")
+    n_vocab = enc.src_word_emb.weight.shape[0]
+    ids = torch.randint(1, n_vocab, (B, T), device="cuda")
+    mask = torch.arange(T, device="cuda")[None, :] >= lens[:, None]
+    ids = ids.masked_fill(mask, 0)
+    w = torch.randn(B, T, 256, device="cuda")
+    out = enc(ids, mask)
+    (out.float() * w).sum().backward()
+    sd = {k: v.detach().clone().requires_grad_(v.is_floating_point() and "position_enc" not in k)
+          for k, v in enc.state_dict().items()}
+    x = F.embedding(ids, sd["src_word_emb.weight"], padding_idx=0) + sd["position_enc"][:, :T]
+    ref = fs2_oracle.fft_stack(sd, "", x, mask, 2, cfg["transformer"]["encoder_head"])
+    (ref * w).sum().backward()
+    assert rel_err(out, ref) <= 3e-2 and float(out.float()[mask].abs().sum()) == 0.0
+    g, r = enc.src_word_emb.weight.grad, sd["src_word_emb.weight"].grad
+    assert float(g[0].abs().sum()) == 0.0
+    assert cosine(g, r) >= 0.999 and abs(float(g.norm() / r.norm()) - 1) < 5e-2, cosine(g, r)
 
 
 # ------------------------------------------------------------------------------------------------------

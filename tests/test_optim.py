@@ -105,3 +105,79 @@ def test_fused_adam_large_flat_buffer_vs_oracle_and_graph_capture():
     assert int(opt.step_dev) == 3
     for p, r in zip(model.ps, ref):
         assert torch.allclose(p.detach(), r, rtol=2e-5, atol=1e-7), (p.detach() - r).abs().max()
+
+
+@pytest.mark.gpu
+def test_fused_adam_state_dict_round_trips_through_torch_adam():
+    """FusedAdam.state_dict() is torch.optim.Adam's format (what the reference's Lightning checkpoints hold in
+    `optimizer_states`, lightning/optimizer.py:5-16): a torch Adam loads it and takes the same next step, and a
+    FusedAdam loads the torch optimizer's state back -- although the fused buffers keep Conv1d states in [Co][k][Ci]
+    order and the buckets in reverse registration order."""
+    rt = sub("runtime")
+    torch.manual_seed(3)
+
+    def make():
+        torch.manual_seed(5)
+        m = torch.nn.Sequential(torch.nn.Conv1d(8, 12, 5), torch.nn.Linear(7, 6), torch.nn.LayerNorm(6)).cuda()
+        m[1].bias.requires_grad_(False)  # a frozen parameter keeps its index in torch's param list
+        return m
+
+    hp = dict(lr=1e-3, betas=(0.9, 0.98), eps=1e-9, weight_decay=0.0)
+    m1, m2 = make(), make()
+    buckets = rt.GradBuckets(m1.parameters(), device=torch.device("cuda"))
+    fused = rt.FusedAdam(buckets, lr=hp["lr"], betas=hp["betas"], eps=hp["eps"], weight_decay=0.0, max_grad_norm=0.0,
+                         scheduler_type="none")
+    ref = torch.optim.Adam(m2.parameters(), **hp)
+    gs = [[torch.randn_like(p) for p in m1.parameters()] for _ in range(4)]
+
+    def step_fused(g):
+        buckets.zero()
+        for p, gi in zip(m1.parameters(), g):
+            if p.requires_grad:
+                p.main_grad.copy_(gi)
+        fused.step()
+
+    def step_ref(g):
+        for p, gi in zip(m2.parameters(), g):
+            p.grad = gi.clone() if p.requires_grad else None
+        ref.step()
+
+    for g in gs[:3]:
+        step_fused(g)
+        step_ref(g)
+    sd = fused.state_dict()
+    assert sorted(sd["state"].keys()) == [i for i, p in enumerate(m1.parameters()) if p.requires_grad]
+    assert sd["state"][0]["exp_avg"].shape == (12, 8, 5)
+    for i, ent in ref.state_dict()["state"].items():
+        assert torch.allclose(sd["state"][i]["exp_avg"], ent["exp_avg"], rtol=1e-5, atol=1e-8)
+        assert torch.allclose(sd["state"][i]["exp_avg_sq"], ent["exp_avg_sq"], rtol=1e-5, atol=1e-10)
+        assert float(sd["state"][i]["step"]) == float(ent["step"]) == 3.0
+    # torch Adam <- fused state, fused <- torch state: one more identical step on both
+    m3 = make()
+    with torch.no_grad():
+        for a, b in zip(m3.parameters(), m1.parameters()):
+            a.copy_(b)
+    ref3 = torch.optim.Adam(m3.parameters(), **hp)
+    ref3.load_state_dict(sd)
+    m4 = make()
+    b4 = rt.GradBuckets(m4.parameters(), device=torch.device("cuda"))
+    fused4 = rt.FusedAdam(b4, lr=hp["lr"], betas=hp["betas"], eps=hp["eps"], weight_decay=0.0, max_grad_norm=0.0,
+                          scheduler_type="none")
+    with torch.no_grad():
+        for a, b in zip(m4.parameters(), m2.parameters()):
+            a.copy_(b)
+    fused4.load_state_dict(ref.state_dict())
+    assert int(fused4.step_dev) == 3
+    for p, gi in zip(m3.parameters(), gs[3]):
+        p.grad = gi.clone() if p.requires_grad else None
+    ref3.step()
+    step_ref(gs[3])
+    b4.zero()
+    for p, gi in zip(m4.parameters(), gs[3]):
+        if p.requires_grad:
+            p.main_grad.copy_(gi)
+    fused4.step()
+    for a, b, c in zip(m2.parameters(), m3.parameters(), m4.parameters()):
+        assert torch.allclose(a, b, rtol=2e-5, atol=1e-7) and torch.allclose(a, c, rtol=2e-5, atol=1e-7)
+    with pytest.raises(ValueError):
+        fused4.load_state_dict({"step": 1})

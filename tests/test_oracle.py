@@ -65,3 +65,44 @@ def test_oracle_matches_reference_live():
     for a, b in zip(out[:5], o_out[:5]):
         assert torch.allclose(a, b, atol=1e-6)
     assert torch.allclose(torch.stack(list(losses)), torch.stack(list(o_losses)), atol=1e-6)
+
+
+# ---- round-2 fixtures (oracle/make_golden2.py, unmodified reference): eval-mode inference, frame-level features,
+# ---- FastSpeech2ADALoss --------------------------------------------------------------------------------------
+def _eval_sd(case):
+    sd = synth.init_state_dict(_template_state_dict(case["cfg"], None), 0)
+    sd.update({k: v.clone() for k, v in case["sd_overrides"].items()})
+    return sd
+
+
+@pytest.mark.parametrize("idx", [0, 1])
+def test_oracle_eval_inference_matches_golden(idx):
+    case = load_golden("model_eval.pt")[idx]
+    b, (pc, ec, dc) = case["batch"], case["controls"]
+    with torch.no_grad():
+        o = fs2_oracle.forward(_eval_sd(case), case["cfg"], b[2], b[3], b[4], b[5], training=False, p_control=pc,
+                               e_control=ec, d_control=dc)
+    ref = case["out"]
+    assert torch.equal(o[5], ref["d_rounded"]) and torch.equal(o[9], ref["mel_len"])
+    for n, t in zip(("mel", "post", "pitch", "energy", "log_d"), o[:5]):
+        assert torch.allclose(t, ref[n], atol=2e-5, rtol=1e-4), n
+    if case["name"] == "eval_long":  # longer than max_seq_len: no truncation in eval mode (Models.py:211-218)
+        assert o[0].shape[1] > case["cfg"]["max_seq_len"]
+
+
+def test_oracle_frame_level_features_match_golden():
+    fx = load_golden("model_frame_level.pt")
+    sd = synth.init_state_dict(_template_state_dict(fx["cfg"], None), fx["weight_seed"])
+    out, losses, grads = fs2_oracle.step(sd, fx["cfg"], fx["batch"])
+    for n, t in zip(("mel", "post", "pitch", "energy", "log_d"), out[:5]):
+        assert torch.allclose(t, fx["out"][n], atol=2e-5, rtol=1e-4), n
+    assert out[2].shape[1] == int(fx["batch"][8])  # predictions per mel frame
+    assert torch.allclose(torch.stack(losses), fx["losses"], atol=1e-5, rtol=1e-5)
+    for k, (norm, head) in fx["grad_digest"].items():
+        assert abs(float(grads[k].norm()) - norm) <= 1e-4 * max(norm, 1e-3), k
+
+
+def test_oracle_ada_loss_matches_golden():
+    for c in load_golden("ada_loss.pt"):
+        o = fs2_oracle.ada_loss(c["target"], (c["mel"], c["post"], c["masks"]))
+        assert torch.allclose(torch.stack(o), c["losses"], atol=1e-6)

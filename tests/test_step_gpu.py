@@ -58,11 +58,15 @@ def test_train_step_with_fused_adam_learns_and_counts_steps():
     opt = rt.FusedAdam(buckets, train_config=cfg)
     w0 = model.mel_linear.weight.detach().clone()
     step = rt.TrainStep(model, loss_fn, batch, use_graph=True, buckets=buckets, optimizer=opt)
-    n0 = int(opt.step_dev)  # warm-up bodies + capture do not replay, but the eager warm-up steps count
+    # constructing the step (two eager warm-up bodies + capture) must leave the training state untouched
+    assert int(opt.step_dev) == 0 and float(opt.exp_avg.abs().sum()) == 0.0
+    assert torch.equal(model.mel_linear.weight.detach(), w0)
+    assert int(model.postnet.convolutions[0][1].num_batches_tracked) == 0
     first = float(step.step_e2e(batch)[0])
     for _ in range(20):
         last = float(step.step_e2e(batch)[0])
-    assert int(opt.step_dev) == n0 + 21
+    assert int(opt.step_dev) == 21
+    assert int(model.postnet.convolutions[0][1].num_batches_tracked) == 21
     assert not torch.equal(model.mel_linear.weight.detach(), w0)
     assert last < 0.9 * first, (first, last)  # same batch every step: the loss must go down
     assert float(opt.grad_norm) > 0

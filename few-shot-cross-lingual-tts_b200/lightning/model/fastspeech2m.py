@@ -68,7 +68,11 @@ class FastSpeech2(nn.Module):
 
         # variance adaptor; the `+ speaker` after it, the decoder's truncation and `+ position_enc`
         # (fastspeech2m.py:132-141, Models.py:220-226) are folded into the LengthRegulator gather.
-        teacher = d_targets is not None and max_mel_len is not None
+        # (frame-level pitch / energy run their predictors on the LengthRegulator output, modules.py:141-150, so the
+        # adds cannot be folded into the gather there)
+        va = self.variance_adaptor
+        frame_level = "frame_level" in (va.pitch_feature_level, va.energy_feature_level)
+        teacher = d_targets is not None and max_mel_len is not None and not frame_level
         if teacher:
             T_lr = int(max_mel_len)
             t_dec = self.decoder.out_len(T_lr)

@@ -6,8 +6,9 @@ kernels, the reference is fp32 end to end):
   mel / postnet-mel outputs : norm-wise rel-err <= 3e-2
   predictor outputs         : norm-wise rel-err <= 3e-2
   six losses                : rel-err <= 1e-2
-  parameter gradients       : cosine >= 0.99 and norm ratio within 5 % for every tensor whose reference
-                              gradient norm is non-negligible (>= 1e-4 of the largest)
+  parameter gradients       : cosine >= 0.999 (0.99 on the variance predictors' first-layer tensors, see
+                              tests/util_parity.COS_EXCEPTIONS) and norm ratio within 5 % for every tensor whose
+                              reference gradient norm is non-negligible (>= 1e-4 of the largest)
   LengthRegulator lengths   : torch.equal
 """
 import pytest
@@ -15,7 +16,7 @@ import torch
 
 from fs2b200 import sub
 from oracle import fs2_oracle, synth
-from tests.util_parity import cosine, cuda_batch, disable_dropout, load_golden, rel_err
+from tests.util_parity import cos_floor, cosine, cuda_batch, disable_dropout, load_golden, rel_err
 
 pytestmark = pytest.mark.gpu
 
@@ -38,7 +39,9 @@ def run_step(model, loss_fn, batch):
     return out, losses
 
 
-def check_grads(model, ref_digest=None, ref_full=None, ref_grads=None, cos_min=0.99):
+def check_grads(model, ref_digest=None, ref_full=None, ref_grads=None, cos_min=None):
+    """cos_min=None: the per-tensor floor of tests/util_parity.cos_floor (0.999; 0.99 on the variance predictors'
+    ReLU-kink-sensitive tensors)."""
     worst = (1.0, None)
     gmax = max((n for n, _ in ref_digest.values()), default=0.0) if ref_digest else max(
         float(g.norm()) for g in ref_grads.values() if g is not None)
@@ -63,12 +66,12 @@ def check_grads(model, ref_digest=None, ref_full=None, ref_grads=None, cos_min=0
         if ref_grads is not None:
             c = cosine(p.grad, ref_grads[k])
             worst = min(worst, (c, k))
-            assert c >= cos_min, (k, c)
+            assert c >= (cos_floor(k) if cos_min is None else cos_min), (k, c)
     if ref_full:
         for k, g in ref_full.items():
             c = cosine(dict(model.named_parameters())[k].grad, g)
             worst = min(worst, (c, k))
-            assert c >= cos_min, (k, c)
+            assert c >= (cos_floor(k) if cos_min is None else cos_min), (k, c)
     return worst
 
 

@@ -23,9 +23,7 @@ from tests.util_parity import cosine, cuda_batch, disable_dropout, rel_err
 
 pytestmark = pytest.mark.gpu
 
-COS_MIN = 0.999
-# tensors allowed below COS_MIN, with the reason (filled from measurements)
-COS_EXCEPTIONS = {}
+from tests.util_parity import COS_MIN, cos_floor  # noqa: E402
 
 
 def _report(name, rows, extra):
@@ -84,6 +82,5 @@ def test_config_through_trainstep_graph_against_cpu_oracle(name):
     assert all(e <= 3e-2 for e in errs.values()), errs
     assert max(lerr) <= 1e-2, lerr
     for c, k, ratio, rn in rows:
-        floor = COS_EXCEPTIONS.get(k, (COS_MIN, ""))[0]
-        assert c >= floor, (name, k, c)
+        assert c >= cos_floor(k), (name, k, c)
         assert 0.95 < ratio < 1.05, (name, k, ratio)

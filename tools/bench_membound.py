@@ -84,22 +84,27 @@ def main():
     M, Cb = B * T, 512
     yb = torch.randn(M, Cb, device="cuda").to(BF16)
     stats = torch.zeros(2, Cb, device="cuda")
-    L.fs2_bn_stats_bf16(yb.data_ptr(), M, Cb, stats.data_ptr(), ops._st())
+    ws = torch.empty(L.fs2_bn_workspace_floats(M, Cb), device="cuda")
+
+    def bn_stats():
+        L.fs2_bn_stats_bf16(yb.data_ptr(), M, Cb, ws.data_ptr(), stats.data_ptr(), 0.1, None, None, None, ops._st())
+
+    bn_stats()
     gb, bb = torch.ones(Cb, device="cuda"), torch.zeros(Cb, device="cuda")
     ob = torch.empty_like(yb)
     seed = torch.zeros(1, dtype=torch.int64, device="cuda")
     dob = torch.randn(M, Cb, device="cuda").to(BF16)
     dst = torch.zeros(2, Cb, device="cuda")
     dyb = torch.empty_like(yb)
-    us = timeit(lambda: L.fs2_bn_stats_bf16(yb.data_ptr(), M, Cb, stats.data_ptr(), ops._st()))
-    rec("bn_stats [64000 x 512]", us, M * Cb * 2)
+    us = timeit(bn_stats)
+    rec("bn_stats [64000 x 512] (fixed-order partials + finalize)", us, M * Cb * 2)
     us = timeit(lambda: L.fs2_bn_apply_fwd(yb.data_ptr(), stats.data_ptr(), gb.data_ptr(), bb.data_ptr(), M, Cb, 1,
                                            0.5, 7, seed.data_ptr(), ob.data_ptr(), None, None, ops._st()))
     rec("bn_apply + tanh + dropout 0.5", us, 2 * M * Cb * 2)
     us = timeit(lambda: L.fs2_bn_bwd(dob.data_ptr(), 0, yb.data_ptr(), stats.data_ptr(), gb.data_ptr(),
-                                     bb.data_ptr(), M, Cb, 1, 0.5, 7, seed.data_ptr(), dst.data_ptr(),
-                                     dyb.data_ptr(), ops._st()))
-    rec("bn_bwd (reduce + apply, 2 kernels)", us, 5 * M * Cb * 2)
+                                     bb.data_ptr(), M, Cb, 1, 0.5, 7, seed.data_ptr(), ws.data_ptr(),
+                                     dst.data_ptr(), None, None, dyb.data_ptr(), ops._st()))
+    rec("bn_bwd (reduce + finalize + apply, 3 kernels)", us, 5 * M * Cb * 2)
 
     # bias-gradient column sums of the FFN hidden gradient [64000 x 1024]
     xx = torch.randn(B * T, 1024, device="cuda").to(BF16)

@@ -48,6 +48,7 @@ struct GemmKP {
   int row_extent;  // rows per entry (NORMAL: M, WGRAD: a.rows)
   int tail_zero;   // NORMAL: rows zeroed behind the last scheduled tile (0 = all, < 0 = none)
   unsigned long long* relu_mask;  // optional 1-bit ReLU mask [Z*M][N/64] (written by EPI_RELU, read by EPI_RELU_BWD)
+  int dbg;         // FS2_GEMM_DBG ablation bits (tools only): 1 no global stores, 2 no epilogue math, 4 no TMA, 8 no MMA
   int pair_any;    // 2-CTA kernels, ragged NORMAL, shared (un-batched) B: the two CTAs of a pair take ANY two
                    // consecutive 128-row tiles of the compact list, also from different utterances
 };
@@ -397,7 +398,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmKP& p, const TileCoord& 
   }
   const uint32_t taddr = tmem_acc + (static_cast<uint32_t>(q * 32) << 16);
   const int m_w0 = t.tm * BM + q * 32;
-  const bool ok = t.nkb > 0 && t.valid;
+  const bool ok = t.nkb > 0 && t.valid && !(p.dbg & 1);
   bool row_ok = true;
   if (p.row_lens && p.mode == FS2_GEMM_NORMAL) row_ok = (m_w0 + lane) < p.row_lens[t.z / p.lens_zdiv];
   if (p.d_atomic) {  // split-K weight gradients: coalesced 16-byte vector reductions

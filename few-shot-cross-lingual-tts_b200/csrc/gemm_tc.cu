@@ -288,6 +288,8 @@ static int launch_tc(const fs2_gemm& g, GemmKP& kp, cudaStream_t stream) {
 
 int gemm_fill_params(const fs2_gemm& g, GemmKP& kp) {
   kp = GemmKP{};
+  static const int dbg = getenv("FS2_GEMM_DBG") ? atoi(getenv("FS2_GEMM_DBG")) : 0;
+  kp.dbg = dbg;
   kp.mode = g.mode;
   kp.M = g.M;
   kp.N = g.N;

@@ -121,6 +121,14 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         if (p.mode != FS2_GEMM_NORMAL && t.nkb > 0) rc = rb_seek(p, cum, t.kb0);
         for (int kb = 0; kb < t.nkb; ++kb) {
           mbar_wait(empty_bar(s), ph ^ 1u);
+          if (p.dbg & 4) {  // ablation: no operand loads
+            if (leader) mbar_arrive(full_bar(s));
+            if (++s == STAGES) {
+              s = 0;
+              ph ^= 1u;
+            }
+            continue;
+          }
           if (leader) mbar_arrive_expect_tx(full_bar(s), 2 * STAGE_BYTES);
           const uint32_t lfull = leader_full0 + 8u * s;
           const uint32_t sa = sbase + s * STAGE_BYTES;
@@ -187,11 +195,13 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           tc_fence_after();
           const uint32_t sa = sbase + s * STAGE_BYTES;
           const uint32_t sb = sa + A_BYTES;
+          if (!(p.dbg & 8)) {
 #pragma unroll
-          for (int j = 0; j < BK / 16; ++j) {
-            const uint64_t ad = make_smem_desc(sa + j * a_kstep, a_lbo, 1024u);
-            const uint64_t bd = make_smem_desc(sb + j * b_kstep, b_lbo, 1024u);
-            umma_f16_2sm(tacc, ad, bd, idesc, (kb > 0 || j > 0) ? 1u : 0u);
+            for (int j = 0; j < BK / 16; ++j) {
+              const uint64_t ad = make_smem_desc(sa + j * a_kstep, a_lbo, 1024u);
+              const uint64_t bd = make_smem_desc(sb + j * b_kstep, b_lbo, 1024u);
+              umma_f16_2sm(tacc, ad, bd, idesc, (kb > 0 || j > 0) ? 1u : 0u);
+            }
           }
           umma_commit_2sm(empty_bar(s));
           if (++s == STAGES) {
@@ -219,7 +229,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const TileCoord t = decode_pair(ptile);
       mbar_wait(tfull_bar(as), aph);
       tc_fence_after();
-      epilogue_tile<BN>(p, t, tmem_base + as * BN, stg, q, chalf, lane);
+      if (!(p.dbg & 2)) epilogue_tile<BN>(p, t, tmem_base + as * BN, stg, q, chalf, lane);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_remote(leader_tempty0 + 8u * as);

@@ -23,7 +23,7 @@ from tests.util_parity import cosine, cuda_batch, disable_dropout, rel_err
 
 pytestmark = pytest.mark.gpu
 
-from tests.util_parity import COS_MIN, cos_floor  # noqa: E402
+from tests.util_parity import COS_MIN, cos_floor, ratio_tol  # noqa: E402
 
 
 def _report(name, rows, extra):
@@ -78,9 +78,10 @@ def test_config_through_trainstep_graph_against_cpu_oracle(name):
     print(name, "outputs rel-err", errs, "loss rel-err", max(lerr))
     for c, k, ratio, rn in rows[:8]:
         print("  cos %.5f  ratio %.4f  |g_ref| %.3e  %s" % (c, ratio, rn, k))
-    _report(name, rows, {"out_rel_err": errs, "loss_rel_err": lerr, "n_tensors": len(rows)})
+    _report(name, rows, {"out_rel_err": errs, "loss_rel_err": lerr, "n_tensors": len(rows),
+                         "ratio_outliers": [r for r in rows if not (0.97 < r[2] < 1.03)]})
     assert all(e <= 3e-2 for e in errs.values()), errs
     assert max(lerr) <= 1e-2, lerr
-    for c, k, ratio, rn in rows:
-        assert c >= cos_floor(k), (name, k, c)
-        assert 0.95 < ratio < 1.05, (name, k, ratio)
+    bad = [(k, round(c, 5), round(ratio, 4), rn) for c, k, ratio, rn in rows
+           if c < cos_floor(k) or abs(ratio - 1.0) >= ratio_tol(k)]
+    assert not bad, (name, bad)

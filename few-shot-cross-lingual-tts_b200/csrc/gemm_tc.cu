@@ -396,6 +396,8 @@ int gemm_fill_params(const fs2_gemm& g, GemmKP& kp) {
 
 int gemm_tc2_launch(const fs2_gemm& g, GemmKP& kp, cudaStream_t stream);  // gemm_tc2.cu (2-CTA tiles)
 int conv_tc2_launch(const fs2_gemm& g, GemmKP& kp, cudaStream_t stream);  // conv_tc2.cu (2-CTA + halo reuse)
+bool gemm_sk_eligible(const fs2_gemm& g, const GemmKP& kp);                // gemm_sk.cu (small K, resident weights,
+int gemm_sk_launch(const fs2_gemm& g, GemmKP& kp, cudaStream_t stream);    //  TMA-store epilogue)
 
 int gemm_tc_launch(const fs2_gemm& g, cudaStream_t stream) {
   GemmKP kp;
@@ -406,6 +408,7 @@ int gemm_tc_launch(const fs2_gemm& g, cudaStream_t stream) {
   const int pad256 = ((n + 255) / 256) * 256, pad128 = ((n + 127) / 128) * 128;
   const bool use128 = (n <= 128) || (pad128 * 100 < pad256 * 92);
   if (use128) return launch_tc<128, 6>(g, kp, stream);
+  if (gemm_sk_eligible(g, kp)) return gemm_sk_launch(g, kp, stream);
   // Conv1d (taps > 1, K-major activations): one activation tile with halo serves every tap, 2-CTA tiles
   static const bool no_halo = getenv("FS2_CONV_NO_HALO") != nullptr;
   // (with a ragged schedule and shared weights the pair kernels team up ANY two row tiles, so even

@@ -384,3 +384,34 @@ def test_relu_bitmask_forward_and_backward(impl, lens):
     assert torch.equal(outs[0][valid], outs[1][valid])
     ref = (dy.float() @ w2.float()) * (h > 0)
     assert rel_err(outs[0][valid], ref[valid]) < 1e-2
+
+
+# ---- gemm_sk.cu: B-stationary small-K kernel (resident weights, TMA-store epilogue) ----------------------------------
+@pytest.mark.parametrize("lens", [None, [300, 1, 129, 0, 128, 257], [128, 128, 128], [5], [0, 0, 300]])
+@pytest.mark.parametrize("N,K,b_mn", [(768, 256, False), (256, 256, False), (1024, 256, True), (256, 128, True),
+                                      (320, 192, False), (512, 80, False)])
+def test_small_k_resident_weight_kernel(lens, N, K, b_mn):
+    """Shapes the dispatcher sends to gemm_sk_kernel (NORMAL, K <= 256, N >= 256, bf16 output): K- and MN-major
+    weights, partial column blocks (N = 320), K that is not a multiple of 64, odd numbers of row tiles (filler
+    half of the last CTA pair), empty utterances; the output is a column slice of a wider buffer (ldd > N) whose
+    other columns and whose rows past each utterance's T must stay untouched (TMA store clipping)."""
+    torch.manual_seed(N + K + (0 if lens is None else len(lens)))
+    B, T = (3, 300) if lens is None else (len(lens), 300)
+    x = rnd(B, T, K)
+    w = rnd(K, N, scale=K ** -0.5) if b_mn else rnd(N, K, scale=K ** -0.5)
+    bias = torch.randn(N, device="cuda")
+    ldd = N + 64
+    buf = torch.full((B, T + 3, ldd), 7.0, device="cuda", dtype=torch.bfloat16)  # 3 guard rows per utterance
+    d = buf[:, :T, 32:32 + N]
+    rl = None if lens is None else _lens(lens)
+    bop = G.operand(w, N, K, mn_major=True) if b_mn else G.operand(w, K, N)
+    G.gemm(G.operand(x, K, T, B), bop, d, T, N, K, Z=B, ldd=ldd, bias=bias, d_zdiv=1, d_zdiv_stride=(T + 3) * ldd,
+           row_lens=rl)
+    ref = x.float() @ (w.float() if b_mn else w.float().t()) + bias
+    if lens is not None:
+        valid = torch.arange(T, device="cuda")[None, :] < rl[:, None]
+        ref = ref * valid[..., None]
+    assert rel_err(d, ref) < 1e-2 or float(ref.norm()) == 0.0
+    if lens is not None:
+        assert float(d.float()[~valid].abs().sum()) == 0.0  # padded frames are written as zeros (tail_rows = 0)
+    assert (buf[:, T:, :] == 7.0).all() and (buf[:, :, :32] == 7.0).all() and (buf[:, :, 32 + N:] == 7.0).all()

@@ -194,8 +194,13 @@ gemm_sk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int za = p.a_batched ? t.z : 0;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(empty_bar(s), ph ^ 1u);
-          if (leader) mbar_arrive_expect_tx(full_bar(s), 2 * A_BYTES);
-          tma_load_3d_2sm(sbase + A_OFF + s * A_BYTES, &tmA, leader_full0 + 8u * s, p.a_inner_base + kb * BK, m0, za);
+          if (p.dbg & 4) {  // ablation: no activation loads
+            if (leader) mbar_arrive(full_bar(s));
+          } else {
+            if (leader) mbar_arrive_expect_tx(full_bar(s), 2 * A_BYTES);
+            tma_load_3d_2sm(sbase + A_OFF + s * A_BYTES, &tmA, leader_full0 + 8u * s, p.a_inner_base + kb * BK, m0,
+                            za);
+          }
           if (++s == STAGES) {
             s = 0;
             ph ^= 1u;
@@ -226,11 +231,13 @@ gemm_sk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           tc_fence_after();
           const uint32_t sa = sbase + A_OFF + s * A_BYTES;
           const uint32_t sb = sbase + B_OFF + kb * BKB_BYTES;
+          if (!(p.dbg & 8)) {
 #pragma unroll
-          for (int j = 0; j < BK / 16; ++j) {
-            const uint64_t ad = make_smem_desc(sa + j * 32u, 16u, 1024u);
-            const uint64_t bd = make_smem_desc(sb + j * b_kstep, b_lbo, 1024u);
-            umma_f16_2sm(tacc, ad, bd, idesc, (kb > 0 || j > 0) ? 1u : 0u);
+            for (int j = 0; j < BK / 16; ++j) {
+              const uint64_t ad = make_smem_desc(sa + j * 32u, 16u, 1024u);
+              const uint64_t bd = make_smem_desc(sb + j * b_kstep, b_lbo, 1024u);
+              umma_f16_2sm(tacc, ad, bd, idesc, (kb > 0 || j > 0) ? 1u : 0u);
+            }
           }
           umma_commit_2sm(empty_bar(s));
           if (++s == STAGES) {
@@ -273,7 +280,7 @@ gemm_sk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll 1
       for (int c0 = chalf * (BN / 2); c0 < (chalf + 1) * (BN / 2); c0 += 64) {
         const int n0 = t.tn * BN + c0;
-        if (n0 >= p.N) break;  // warp-uniform
+        if (n0 >= p.N || (p.dbg & 2)) break;  // warp-uniform
         float f[64];
         {
           uint32_t v[32], v2[32];

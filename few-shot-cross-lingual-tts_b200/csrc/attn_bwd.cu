@@ -15,6 +15,8 @@
 #include <cuda.h>
 #include <cuda_bf16.h>
 
+#include <cstdlib>
+
 #include "common.h"
 #include "ptx.cuh"
 #include "tmap.h"
@@ -35,6 +37,7 @@ struct AttnBwdP {
   int B, T, H, n_outer, n_inner;
   float scale, scale_log2;
   __nv_bfloat16* dqkv;  // [B][T][3*H*dk]
+  int dbg;              // FS2_ATTN_DBG ablation bits (tools only)
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -526,6 +529,229 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ128,  // qkv, box 64 x
   }
 }
 
+
+// ================================================================================================
+// dQ kernel, second generation: dS never touches shared memory.  The softmax warps write dS (bf16) back into
+// the TMEM columns of the S accumulator they just read (tcgen05.st) and the dQ MMA takes its A operand from
+// tensor memory (tcgen05.mma with [tmem] A); that frees 32 KiB of shared memory and the st.shared / proxy-fence
+// / membar sequence per tile.  The freed memory deepens the K / V ring to 4 stages (the 2-stage ring put the
+// TMA round trip into the per-tile dependency cycle) and S / dP get 3 TMEM stages, so the S / dP MMAs run two
+// tiles ahead of the softmax warps.
+// ================================================================================================
+namespace dq2 {
+using namespace ab;
+constexpr int KVS = 4, SPS = 3;
+constexpr int OFF_Q = 0;                        // [128 q x 128 d] 32 KiB
+constexpr int OFF_DO = OFF_Q + 2 * BLK128;      // 32 KiB
+constexpr int OFF_K = OFF_DO + 2 * BLK128;      // KVS stages x [64 keys x 128 d] 16 KiB
+constexpr int OFF_V = OFF_K + KVS * 2 * BLK64;  // KVS stages x 16 KiB
+constexpr int OFF_STG = OFF_K;                  // epilogue staging (the ring is idle by then)
+constexpr int OFF_BAR = OFF_V + KVS * 2 * BLK64;
+enum { QDO_FULL = 0, KV_FULL = 1, KV_EMPTY = KV_FULL + KVS, SP_FULL = KV_EMPTY + KVS, SP_EMPTY = SP_FULL + SPS,
+       DS_FULL = SP_EMPTY + SPS, ACC_FULL = DS_FULL + SPS, NUM_BARS = ACC_FULL + 1 };
+constexpr int OFF_TMEM = OFF_BAR + NUM_BARS * 8;
+constexpr int SMEM_BYTES = OFF_TMEM + 16 + 1024;
+}  // namespace dq2
+
+__global__ void __launch_bounds__(320, 1)
+attn_bwd_dq2_kernel(const __grid_constant__ CUtensorMap tmQ128,  // qkv, box 64 x 128 rows
+                    const __grid_constant__ CUtensorMap tmKV64,  // qkv, box 64 x 64 rows
+                    const __grid_constant__ CUtensorMap tmDO128, // dO,  box 64 x 128 rows
+                    const __grid_constant__ AttnBwdP p) {
+  pdl_sync();
+  using namespace dq2;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* sgen = smem_raw + (sbase - smem_u32(smem_raw));
+  auto bar = [&](int i) { return sbase + OFF_BAR + 8u * i; };
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int it = blockIdx.x % p.n_outer, z = blockIdx.x / p.n_outer;
+  const int b = z / p.H, h = z % p.H;
+  const int q0 = it * 128;
+  const int HD = p.H * DK;
+  const int len = min((int)p.lens[b], p.T);
+  if (q0 >= len) {  // a query tile of padded frames only (CTA-uniform): dQ = 0, no MMAs
+    __nv_bfloat16* gb = p.dqkv + (long long)b * p.T * 3 * HD;
+    for (int i = threadIdx.x; i < 128 * 16; i += blockDim.x) {
+      const int r = i >> 4, c = i & 15;
+      if (q0 + r < p.T)
+        *reinterpret_cast<uint4*>(gb + (long long)(q0 + r) * 3 * HD + h * DK + c * 8) = make_uint4(0u, 0u, 0u, 0u);
+    }
+    return;
+  }
+  const int n = min(p.n_inner, (len + 63) / 64);  // 64-key tiles with at least one valid key
+
+  if (threadIdx.x == 0) {
+    mbar_init(bar(QDO_FULL), 1);
+    for (int s = 0; s < KVS; ++s) {
+      mbar_init(bar(KV_FULL + s), 1);
+      mbar_init(bar(KV_EMPTY + s), 1);
+    }
+    for (int s = 0; s < SPS; ++s) {
+      mbar_init(bar(SP_FULL + s), 1);
+      mbar_init(bar(SP_EMPTY + s), 1);
+      mbar_init(bar(DS_FULL + s), 8);
+    }
+    mbar_init(bar(ACC_FULL), 1);
+    fence_mbar_init();
+  }
+  if (warp == 9) {
+    tmem_alloc(sbase + OFF_TMEM, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(sgen + OFF_TMEM);
+  // columns: S stages [0,192), dP stages [192,384), dQ [384,512)
+  const uint32_t tS = tmem_base, tdP = tmem_base + SPS * 64, tdQ = tmem_base + 2 * SPS * 64;
+
+  if (warp == 8) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(bar(QDO_FULL), 4 * BLK128);
+      for (int kb = 0; kb < 2; ++kb) {
+        tma_load_3d(sbase + OFF_Q + kb * BLK128, &tmQ128, bar(QDO_FULL), h * DK + kb * 64, q0, b);
+        tma_load_3d(sbase + OFF_DO + kb * BLK128, &tmDO128, bar(QDO_FULL), h * DK + kb * 64, q0, b);
+      }
+      for (int j = 0; j < n; ++j) {
+        const int s = j % KVS;
+        mbar_wait(bar(KV_EMPTY + s), ((j / KVS) & 1) ^ 1u);
+        if (p.dbg & 32) {
+          mbar_arrive(bar(KV_FULL + s));
+          continue;
+        }
+        mbar_arrive_expect_tx(bar(KV_FULL + s), 4 * BLK64);
+        for (int kb = 0; kb < 2; ++kb) {
+          tma_load_3d(sbase + OFF_K + s * 2 * BLK64 + kb * BLK64, &tmKV64, bar(KV_FULL + s),
+                      HD + h * DK + kb * 64, j * 64, b);
+          tma_load_3d(sbase + OFF_V + s * 2 * BLK64 + kb * BLK64, &tmKV64, bar(KV_FULL + s),
+                      2 * HD + h * DK + kb * 64, j * 64, b);
+        }
+      }
+    }
+  } else if (warp == 9) {
+    // MMA issuer: the whole warp runs the loop (uniform control flow), one elected lane issues
+    const uint32_t idesc_s = make_idesc_bf16(128, 64, 0, 0);   // S / dP: [128 q x 64 keys]
+    const uint32_t idesc_q = make_idesc_bf16(128, 128, 0, 1);  // dQ += dS K (A from TMEM, K tile as MN-major B)
+    // descriptors: constant high word; the low word is (address >> 4) + (LBO >> 4 << 16) -> add offsets >> 4
+    const uint64_t dQ0 = make_smem_desc(sbase + OFF_Q, 16, 1024), dDO0 = make_smem_desc(sbase + OFF_DO, 16, 1024);
+    const uint64_t dK0 = make_smem_desc(sbase + OFF_K, 16, 1024), dV0 = make_smem_desc(sbase + OFF_V, 16, 1024);
+    const uint64_t dKm0 = make_smem_desc(sbase + OFF_K, BLK64, 1024);  // K tile as MN-major B of the dQ MMA
+    auto issue_sp = [&](int j) {
+      const int s = j % KVS, s3 = j % SPS;
+      mbar_wait(bar(KV_FULL + s), (j / KVS) & 1);
+      mbar_wait(bar(SP_EMPTY + s3), ((j / SPS) & 1) ^ 1u);  // the dQ MMA of tile j-3 has consumed dS in this stage
+      tc_fence_after();
+      if (elect_one()) {
+        const uint64_t so = (uint64_t)((s * 2 * BLK64) >> 4);
+        if (!(p.dbg & 8)) {
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+          const uint64_t offa = (uint64_t)(((t >> 2) * BLK128 + (t & 3) * 32) >> 4);
+          const uint64_t offb = (uint64_t)(((t >> 2) * BLK64 + (t & 3) * 32) >> 4);
+          umma_f16(tS + s3 * 64, dQ0 + offa, dK0 + so + offb, idesc_s, t > 0);
+        }
+        }
+        if (!(p.dbg & 16))
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+          const uint64_t offa = (uint64_t)(((t >> 2) * BLK128 + (t & 3) * 32) >> 4);
+          const uint64_t offb = (uint64_t)(((t >> 2) * BLK64 + (t & 3) * 32) >> 4);
+          umma_f16(tdP + s3 * 64, dDO0 + offa, dV0 + so + offb, idesc_s, t > 0);
+        }
+        umma_commit(bar(SP_FULL + s3));
+      }
+      __syncwarp();
+    };
+    mbar_wait(bar(QDO_FULL), 0);
+    issue_sp(0);
+    if (n > 1) issue_sp(1);
+    for (int j = 0; j < n; ++j) {
+      const int s = j % KVS, s3 = j % SPS;
+      if (j + 2 < n) issue_sp(j + 2);
+      mbar_wait(bar(DS_FULL + s3), (j / SPS) & 1);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint64_t so = (uint64_t)((s * 2 * BLK64) >> 4);
+        if (!(p.dbg & 4))
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {  // K = 64 keys, 16 per step; dS of keys [32h, 32h+32) sits in S columns [32h, 32h+16)
+          umma_f16_ts(tdQ, tS + s3 * 64 + (t >> 1) * 32 + (t & 1) * 8, dKm0 + so + (uint64_t)((t * 2048) >> 4),
+                      idesc_q, (j > 0 || t > 0) ? 1u : 0u);
+        }
+        umma_commit(bar(KV_EMPTY + s));
+        umma_commit(bar(SP_EMPTY + s3));
+        if (j == n - 1) umma_commit(bar(ACC_FULL));
+      }
+      __syncwarp();
+    }
+  } else {
+    // softmax warps: thread = query row; warps w / w+4 take the key columns [0,32) / [32,64) of the tile
+    const int q4 = warp & 3, half = warp >> 2;
+    const int row = q4 * 32 + lane;
+    const int q = q0 + row;
+    const uint32_t lane_base = static_cast<uint32_t>(q4 * 32) << 16;
+    const bool q_ok = q < len;
+    const float l2 = q_ok ? p.lse2[(long long)z * p.T + q] : INFINITY;  // +inf => P = 0
+    const float dq_sum = q_ok ? p.dsum[(long long)z * p.T + q] : 0.f;
+    for (int j = 0; j < n; ++j) {
+      const int s3 = j % SPS;
+      mbar_wait(bar(SP_FULL + s3), (j / SPS) & 1);
+      tc_fence_after();
+      uint32_t vs[32], vd[32];
+      if (!(p.dbg & 64)) {
+        tmem_ld32(tS + s3 * 64 + lane_base + half * 32, vs);
+        if (!(p.dbg & 2)) tmem_ld32(tdP + s3 * 64 + lane_base + half * 32, vd);
+        tmem_ld_wait();
+      }
+      uint32_t w[16];
+      const int kb = j * 64 + half * 32;
+      if (p.dbg & 1) {
+#pragma unroll
+        for (int t = 0; t < 16; ++t) w[t] = vs[t] ^ vd[t];
+      } else
+      if (kb + 32 <= len) {  // warp-uniform fast path: every key of this slice is valid
+#pragma unroll
+        for (int t = 0; t < 16; ++t) {
+          const float p0 = ex2_fast(fmaf(__uint_as_float(vs[2 * t]), p.scale_log2, -l2));
+          const float p1 = ex2_fast(fmaf(__uint_as_float(vs[2 * t + 1]), p.scale_log2, -l2));
+          __nv_bfloat162 b2 = __floats2bfloat162_rn(p0 * fmaf(__uint_as_float(vd[2 * t]), p.scale, -dq_sum),
+                                                    p1 * fmaf(__uint_as_float(vd[2 * t + 1]), p.scale, -dq_sum));
+          w[t] = *reinterpret_cast<uint32_t*>(&b2);
+        }
+      } else {
+#pragma unroll
+        for (int t = 0; t < 16; ++t) {
+          const float p0 = ex2_fast(fmaf(__uint_as_float(vs[2 * t]), p.scale_log2, -l2));
+          const float p1 = ex2_fast(fmaf(__uint_as_float(vs[2 * t + 1]), p.scale_log2, -l2));
+          const float d0 = p0 * fmaf(__uint_as_float(vd[2 * t]), p.scale, -dq_sum);
+          const float d1 = p1 * fmaf(__uint_as_float(vd[2 * t + 1]), p.scale, -dq_sum);
+          __nv_bfloat162 b2 = __floats2bfloat162_rn(kb + 2 * t < len ? d0 : 0.f, kb + 2 * t + 1 < len ? d1 : 0.f);
+          w[t] = *reinterpret_cast<uint32_t*>(&b2);
+        }
+      }
+      if (!(p.dbg & 64)) {
+        tmem_st16(tS + s3 * 64 + lane_base + half * 32, w);  // dS over the S columns this warp has just consumed
+        tmem_st_wait();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar(DS_FULL + s3));
+    }
+    mbar_wait(bar(ACC_FULL), 0);
+    tc_fence_after();
+    uint8_t* stg = sgen + OFF_STG + warp * 4096;
+    __nv_bfloat16* gb = p.dqkv + (long long)b * p.T * 3 * HD;
+    store_acc_half(tdQ, lane_base, stg, q4, lane, half, gb + h * DK, 3 * HD, q0, p.T);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 9) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
 }  // namespace fs2
 
 extern "C" {
@@ -543,6 +769,8 @@ int fs2_attn_bwd_bf16(const void* qkv, const void* o, const void* d_o, const flo
                                          dkv::SMEM_BYTES);
     if (e == cudaSuccess)
       e = cudaFuncSetAttribute(attn_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dq::SMEM_BYTES);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(attn_bwd_dq2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dq2::SMEM_BYTES);
     if (e != cudaSuccess) return set_cuda_error("cudaFuncSetAttribute(attn_bwd)", e);
     attr = true;
   }
@@ -565,13 +793,20 @@ int fs2_attn_bwd_bf16(const void* qkv, const void* o, const void* d_o, const flo
   p.scale = 1.f / sqrtf((float)dk);
   p.scale_log2 = 1.4426950408889634f * p.scale;
   p.dqkv = static_cast<__nv_bfloat16*>(dqkv);
+  static const int dbg = getenv("FS2_ATTN_DBG") ? atoi(getenv("FS2_ATTN_DBG")) : 0;
+  p.dbg = dbg;
   p.n_outer = (T + 127) / 128;
   p.n_inner = (T + 63) / 64;
   const unsigned grid = (unsigned)(p.n_outer * B * H);
   FS2_LAUNCH((attn_bwd_dkv_kernel), grid, 320, dkv::SMEM_BYTES, s, tm128, tm64, tmdo64, p);
   count_launch();
   if (int rc = check_launch("attn_bwd_dkv_kernel")) return rc;
-  FS2_LAUNCH((attn_bwd_dq_kernel), grid, 320, dq::SMEM_BYTES, s, tm128, tm64, tmdo128, p);
+  static const bool old_dq = getenv("FS2_ATTN_OLD") != nullptr;  // A/B switch: first-generation kernels
+  if (old_dq) {
+    FS2_LAUNCH((attn_bwd_dq_kernel), grid, 320, dq::SMEM_BYTES, s, tm128, tm64, tmdo128, p);
+  } else {
+    FS2_LAUNCH((attn_bwd_dq2_kernel), grid, 320, dq2::SMEM_BYTES, s, tm128, tm64, tmdo128, p);
+  }
   count_launch();
   return check_launch("attn_bwd_dq_kernel");
 }

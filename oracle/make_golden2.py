@@ -125,9 +125,49 @@ def run_ada_loss():
     print("ada losses", [c["losses"].tolist() for c in cases])
 
 
+def _exec_reference_function(path, name, ns):
+    """exec one top-level function of a reference source file (its imports are not executable here)"""
+    src = open(os.path.join(ref_loader.REF, path)).read().split("\n")
+    start = next(i for i, l in enumerate(src) if l.startswith("def %s(" % name))
+    end = next((i for i in range(start + 1, len(src)) if src[i].startswith("def ")), len(src))
+    exec("\n".join(src[start:end]), ns)
+    return ns[name]
+
+
+def run_collate():
+    """The reference's own `reprocess` (lightning/collates/utils.py:8-111) with its own pad_1D / pad_2D
+    (lightning/utils/tool.py:134-165), exec'd from source, on seeded ragged items, all three modes."""
+    import numpy as np
+
+    ns = {"np": np, "torch": torch}
+    _exec_reference_function("lightning/utils/tool.py", "pad_1D", ns)
+    _exec_reference_function("lightning/utils/tool.py", "pad_2D", ns)
+    reprocess = _exec_reference_function("lightning/collates/utils.py", "reprocess", ns)
+    cases = []
+    for seed in (0, 1):
+        rng = np.random.default_rng(seed)
+        items = []
+        for i in range(9):
+            L = int(rng.integers(3, 40))
+            dur = rng.integers(0, 9, L).astype(np.int64)
+            T = max(int(dur.sum()), 1)
+            items.append({"id": "utt%d" % i, "raw_text": "text %d" % i, "speaker": int(rng.integers(0, 7)),
+                          "lang_id": int(rng.integers(0, 3)), "text": rng.integers(1, 80, L).astype(np.int64),
+                          "mel": rng.standard_normal((T, 80)).astype(np.float32),
+                          "pitch": rng.standard_normal(L).astype(np.float32),
+                          "energy": rng.standard_normal(L).astype(np.float64 if seed % 2 else np.float32),
+                          "duration": dur})
+        idxs = [4, 0, 7, 2, 8]
+        cases.append({"items": items, "idxs": idxs,
+                      "out": {m: reprocess(items, idxs, mode=m) for m in ("sup", "unsup", "inference")}})
+    torch.save(cases, os.path.join(OUT, "collate.pt"))
+    print("collate fixture:", [len(c["out"]["sup"]) for c in cases], [len(c["out"]["inference"]) for c in cases])
+
+
 if __name__ == "__main__":
     assert ref_loader.available(), "needs /root/reference"
     torch.manual_seed(0)
     run_eval_cases()
     run_frame_level()
     run_ada_loss()
+    run_collate()

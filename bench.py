@@ -326,11 +326,12 @@ def kernel_rooflines(base, cfg, bf16_peak, hbm_peak, step_ms, traffic):
     fam("output projection weight-gradient", "gemm_tc2_kernel", 2.0 * V * D * D,
         lambda: ops.linear_wgrad(dy2, attn2, gwo, lens=lens, T=Tm))
     dk = D // H
-    o3, lse = ops.attn_fwd(qkv, lens, H, dk)
+    sched = ops.attn_schedule(lens, Tm, H)  # longest-first work order, as transformer/Models.py::_run_layers builds it
+    o3, lse = ops.attn_fwd(qkv, lens, H, dk, sched)
     fam("fused attention fwd (QK^T, softmax, PV)", "attn_fwd_kernel", 4.0 * sq * D,
-        lambda: ops.attn_fwd(qkv, lens, H, dk))
+        lambda: ops.attn_fwd(qkv, lens, H, dk, sched))
     fam("fused attention bwd (dK/dV + dQ kernels)", "attn_bwd_*_kernel", 8.0 * sq * D,
-        lambda: ops.attn_bwd(qkv, o3, dy, lse, lens, H, dk))
+        lambda: ops.attn_bwd(qkv, o3, dy, lse, lens, H, dk, sched))
     for f in fams:
         f["bound"], f["peak"], f["unit"] = "tensor", bf16_peak, "TFLOP/s"
         f["frac"] = f["achieved"] / bf16_peak

@@ -32,6 +32,7 @@ constexpr int BLK64 = 64 * 128;    // [ 64 rows x 64 cols] bf16 block =  8 KiB
 
 struct AttnBwdP {
   const int64_t* lens;
+  const int32_t* sched;  // optional work order (fs2_attn_schedule)
   const float* lse2;  // [Z][T]
   const float* dsum;  // [Z][T]  D_q
   int B, T, H, n_outer, n_inner;
@@ -160,7 +161,12 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmKV,   // qkv, box 64 x
   uint8_t* sgen = smem_raw + (sbase - smem_u32(smem_raw));
   auto bar = [&](int i) { return sbase + OFF_BAR + 8u * i; };
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int jt = blockIdx.x % p.n_outer, z = blockIdx.x / p.n_outer;
+  int jt = blockIdx.x % p.n_outer, z = blockIdx.x / p.n_outer;
+  if (p.sched) {
+    const int e = p.sched[blockIdx.x];
+    z = e >> 8;
+    jt = e & 255;
+  }
   const int b = z / p.H, h = z % p.H;
   const int k0 = jt * 128;
   const int HD = p.H * DK;
@@ -370,7 +376,12 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ128,  // qkv, box 64 x
   uint8_t* sgen = smem_raw + (sbase - smem_u32(smem_raw));
   auto bar = [&](int i) { return sbase + OFF_BAR + 8u * i; };
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int it = blockIdx.x % p.n_outer, z = blockIdx.x / p.n_outer;
+  int it = blockIdx.x % p.n_outer, z = blockIdx.x / p.n_outer;
+  if (p.sched) {
+    const int e = p.sched[blockIdx.x];
+    z = e >> 8;
+    it = e & 255;
+  }
   const int b = z / p.H, h = z % p.H;
   const int q0 = it * 128;
   const int HD = p.H * DK;
@@ -565,7 +576,12 @@ attn_bwd_dq2_kernel(const __grid_constant__ CUtensorMap tmQ128,  // qkv, box 64 
   uint8_t* sgen = smem_raw + (sbase - smem_u32(smem_raw));
   auto bar = [&](int i) { return sbase + OFF_BAR + 8u * i; };
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int it = blockIdx.x % p.n_outer, z = blockIdx.x / p.n_outer;
+  int it = blockIdx.x % p.n_outer, z = blockIdx.x / p.n_outer;
+  if (p.sched) {
+    const int e = p.sched[blockIdx.x];
+    z = e >> 8;
+    it = e & 255;
+  }
   const int b = z / p.H, h = z % p.H;
   const int q0 = it * 128;
   const int HD = p.H * DK;
@@ -759,7 +775,7 @@ extern "C" {
 // qkv: bf16 [B][T][3*H*128]; o, d_o: bf16 [B][T][H*128]; lse2: f32 [B*H][T] from the forward;
 // dsum: f32 [B*H][T] workspace; dqkv: bf16 [B][T][3*H*128] (every element is written).
 int fs2_attn_bwd_bf16(const void* qkv, const void* o, const void* d_o, const float* lse2, const int64_t* lens,
-                      int B, int T, int H, int dk, float* dsum, void* dqkv, void* stream) {
+                      const int32_t* sched, int B, int T, int H, int dk, float* dsum, void* dqkv, void* stream) {
   using namespace fs2;
   if (dk != ab::DK) return set_error("attn_bwd: d_k must be 128");
   if (B <= 0 || T <= 0) return 0;
@@ -788,7 +804,7 @@ int fs2_attn_bwd_bf16(const void* qkv, const void* o, const void* d_o, const flo
   if (int rc = make_tmap_bf16_3d(&tmdo128, d_o, HD, T, B, HD, (long long)T * HD, 64, 128)) return rc;
   if (int rc = make_tmap_bf16_3d(&tmdo64, d_o, HD, T, B, HD, (long long)T * HD, 64, 64)) return rc;
   AttnBwdP p{};
-  p.lens = lens; p.lse2 = lse2; p.dsum = dsum;
+  p.lens = lens; p.lse2 = lse2; p.dsum = dsum; p.sched = sched;
   p.B = B; p.T = T; p.H = H;
   p.scale = 1.f / sqrtf((float)dk);
   p.scale_log2 = 1.4426950408889634f * p.scale;

@@ -45,6 +45,7 @@ enum { Q_FULL = 0, K_FULL = 1, K_EMPTY = 3, V_FULL = 5, V_EMPTY = 7, S_FULL = 9,
 
 struct AttnFwdP {
   const int64_t* lens;
+  const int32_t* sched;  // optional work order (fs2_attn_schedule): entry = (z << 8) | tile
   int B, T, H, nq, nkv;
   float scale_log2;
   __nv_bfloat16* out;  // [B][T][H*dk]
@@ -68,7 +69,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constant_
   uint8_t* sgen = smem_raw + (sbase - smem_u32(smem_raw));
   auto bar = [&](int i) { return sbase + OFF_BAR + 8u * i; };
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int qt = blockIdx.x % p.nq, z = blockIdx.x / p.nq;
+  int qt = blockIdx.x % p.nq, z = blockIdx.x / p.nq;
+  if (p.sched) {  // longest utterances first (the CTAs of a ragged batch differ 8x in work)
+    const int e = p.sched[blockIdx.x];
+    z = e >> 8;
+    qt = e & 255;
+  }
   const int b = z / p.H, h = z % p.H;
   const int q0 = qt * BQ;
   const int HD = p.H * DK;
@@ -299,15 +305,72 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constant_
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Work order of the attention kernels for a ragged batch: one CTA = one (utterance*head z, 128-row tile); its work
+// is proportional to the utterance length, which varies 8x inside a LibriTTS-shaped batch while only ~4 working
+// CTAs land on each SM.  Longest-processing-time-first: tiles of the longest utterance first, tiles that hold only
+// padded frames (zero fill, no MMAs) last.  Built once per FFT stack call from the device-side lengths.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) attn_schedule_kernel(const int64_t* __restrict__ lens, int B, int T, int H,
+                                                             int nq, int32_t* __restrict__ sched) {
+  pdl_sync();
+  __shared__ int s_len[1024], s_rank[1024], s_basev[1024], s_basep[1024];
+  const int b = threadIdx.x;
+  if (b < B) {
+    long long l = lens[b];
+    s_len[b] = (int)(l < 0 ? 0 : (l > T ? T : l));
+  }
+  __syncthreads();
+  if (b < B) {
+    int r = 0;
+    for (int o = 0; o < B; ++o) r += (s_len[o] > s_len[b]) || (s_len[o] == s_len[b] && o < b);
+    s_rank[r] = b;  // utterance at sorted position r
+  }
+  __syncthreads();
+  if (b == 0) {
+    int accv = 0, accp = 0;
+    for (int r = 0; r < B; ++r) {
+      const int nv = (s_len[s_rank[r]] + 127) / 128;
+      s_basev[r] = accv;
+      s_basep[r] = accp;
+      accv += nv * H;
+      accp += (nq - nv) * H;
+    }
+    for (int r = 0; r < B; ++r) s_basep[r] += accv;  // padded tiles after all valid ones
+  }
+  __syncthreads();
+  if (b < B) {  // thread = sorted position
+    const int u = s_rank[b];
+    const int nv = (s_len[u] + 127) / 128;
+    for (int h = 0; h < H; ++h) {
+      const int z = u * H + h;
+      for (int t = 0; t < nv; ++t) sched[s_basev[b] + h * nv + t] = (z << 8) | t;
+      for (int t = nv; t < nq; ++t) sched[s_basep[b] + h * (nq - nv) + (t - nv)] = (z << 8) | t;
+    }
+  }
+}
+
 }  // namespace fs2
 
 extern "C" {
 
+// sched: int32 [B*H*ceil(T/128)] (written): work order for fs2_attn_fwd_bf16 / fs2_attn_bwd_bf16 on this batch.
+int fs2_attn_schedule(const int64_t* lens, int B, int T, int H, int32_t* sched, void* stream) {
+  using namespace fs2;
+  if (B <= 0 || T <= 0) return 0;
+  const int nq = (T + 127) / 128;
+  if (B > 1024 || nq > 255 || (long long)B * H >= (1 << 23)) return set_error("attn_schedule: B <= 1024, T <= 32640");
+  FS2_LAUNCH((attn_schedule_kernel), 1, 1024, 0, static_cast<cudaStream_t>(stream), lens, B, T, H, nq, sched);
+  count_launch();
+  return check_launch("attn_schedule_kernel");
+}
+
 // qkv: bf16 [B][T][3*H*128] (Q | K | V, head h = columns [h*128, (h+1)*128) of each third);
-// lens: int64 [B]; out: bf16 [B][T][H*128]; lse2: f32 [B*H][T] (log2-domain log-sum-exp of the scaled
+// lens: int64 [B]; sched: optional work order from fs2_attn_schedule (NULL = natural order);
+// out: bf16 [B][T][H*128]; lse2: f32 [B*H][T] (log2-domain log-sum-exp of the scaled
 // scores; +inf on padded rows).  scale = 1/sqrt(dk) is applied inside.
-int fs2_attn_fwd_bf16(const void* qkv, const int64_t* lens, int B, int T, int H, int dk, void* out,
-                      float* lse2, void* stream) {
+int fs2_attn_fwd_bf16(const void* qkv, const int64_t* lens, const int32_t* sched, int B, int T, int H, int dk,
+                      void* out, float* lse2, void* stream) {
   using namespace fs2;
   if (dk != af::DK) return set_error("attn_fwd: d_k must be 128");
   if (B <= 0 || T <= 0) return 0;
@@ -324,6 +387,7 @@ int fs2_attn_fwd_bf16(const void* qkv, const int64_t* lens, int B, int T, int H,
   if (int rc = make_tmap_bf16_3d(&tmV, qkv, C3, T, B, C3, (long long)T * C3, 64, 64)) return rc;
   AttnFwdP p{};
   p.lens = lens;
+  p.sched = sched;
   p.B = B; p.T = T; p.H = H;
   p.nq = (T + af::BQ - 1) / af::BQ;
   p.nkv = (T + af::BKV - 1) / af::BKV;

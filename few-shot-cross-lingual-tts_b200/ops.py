@@ -482,24 +482,59 @@ def ln_bwd(dy, x, res, gamma, mean, rstd, lens, p, mode, salt, dgamma, dbeta, wa
     return dx, dres
 
 
-def attn_fwd(qkv, lens, H, dk):
+# Work order of the attention kernels (csrc/attn_fwd.cu::attn_schedule_kernel): built once per FFT stack call by
+# `with attn_schedule_scope(lens, T, H)` (transformer/Models.py::_run_layers) and picked up by every attention launch
+# of that stack whose `lens` is the very same tensor object; no scope -> natural order.
+_sched_scope = []
+
+
+def attn_schedule(lens, T, H):
+    B = lens.shape[0]
+    if B > 1024 or (T + 127) // 128 > 255:
+        return None
+    sched = torch.empty(B * H * ((T + 127) // 128), dtype=torch.int32, device=lens.device)
+    _ck(_L().fs2_attn_schedule(_p(lens), B, T, H, _p(sched), _st()), "attn_schedule")
+    return sched
+
+
+class attn_schedule_scope:
+    def __init__(self, lens, T, H):
+        self.entry = (lens, T, H, attn_schedule(lens, T, H) if _os.environ.get("FS2_NO_ATTN_SCHED") is None else None)
+
+    def __enter__(self):
+        _sched_scope.append(self.entry)
+        return self
+
+    def __exit__(self, *exc):
+        _sched_scope.pop()
+        return False
+
+
+def current_sched(lens, T, H):
+    for l, t, h, sched in reversed(_sched_scope):
+        if l is lens and t == T and h == H:
+            return sched
+    return None
+
+
+def attn_fwd(qkv, lens, H, dk, sched=None):
     """Fused masked-softmax attention forward on the packed [B, T, 3*H*dk] projection.
     Returns (out bf16 [B, T, H*dk], lse2 f32 [B*H, T])."""
     B, T, C3 = qkv.shape
     assert C3 == 3 * H * dk and qkv.is_contiguous()
     out = torch.empty(B, T, H * dk, dtype=BF16, device=qkv.device)
     lse2 = torch.empty(B * H, T, dtype=F32, device=qkv.device)
-    _ck(_L().fs2_attn_fwd_bf16(_p(qkv), _p(lens), B, T, H, dk, _p(out), _p(lse2), _st()), "attn_fwd")
+    _ck(_L().fs2_attn_fwd_bf16(_p(qkv), _p(lens), _p(sched), B, T, H, dk, _p(out), _p(lse2), _st()), "attn_fwd")
     return out, lse2
 
 
-def attn_bwd(qkv, out, d_out, lse2, lens, H, dk):
+def attn_bwd(qkv, out, d_out, lse2, lens, H, dk, sched=None):
     """Fused attention backward: returns dqkv bf16 [B, T, 3*H*dk]."""
     B, T, C3 = qkv.shape
     dqkv = torch.empty_like(qkv)
     dsum = torch.empty(B * H, T, dtype=F32, device=qkv.device)
-    _ck(_L().fs2_attn_bwd_bf16(_p(qkv), _p(out), _p(d_out), _p(lse2), _p(lens), B, T, H, dk, _p(dsum), _p(dqkv),
-                               _st()), "attn_bwd")
+    _ck(_L().fs2_attn_bwd_bf16(_p(qkv), _p(out), _p(d_out), _p(lse2), _p(lens), _p(sched), B, T, H, dk, _p(dsum),
+                               _p(dqkv), _st()), "attn_bwd")
     return dqkv
 
 
@@ -578,7 +613,8 @@ class MHASublayer(torch.autograd.Function):
         Z = B * H
         C3 = 3 * HD
         if fused:
-            attn3, lse2 = attn_fwd(qkv.view(B, T, C3), lens, H, dk)
+            sched = current_sched(lens, T, H)
+            attn3, lse2 = attn_fwd(qkv.view(B, T, C3), lens, H, dk, sched)
             attn = attn3.view(B * T, HD)
             wo_bf = cast_bf16(wo)
             o = linear_fwd(attn, wo_bf, bo.detach(), lens=rl, T=T, tail=NO_TAIL)
@@ -586,6 +622,7 @@ class MHASublayer(torch.autograd.Function):
             y, mean, rstd = ln_fwd(o.view(B, T, D), x, gamma.detach(), beta.detach(),
                                    lens if zero_pad else None, p_drop, 1, salt)
             ctx.save_for_backward(x, lens, qkv, lse2, attn, o, mean, rstd, wqkv, wo_bf, gamma)
+            ctx.sched = sched
             ctx.params = (wq, bq, wk, bk, wv, bv, wo, bo, gamma, beta)
             ctx.cfg = (H, dk, p_drop, zero_pad, salt, Tp, True)
             return y
@@ -631,7 +668,7 @@ class MHASublayer(torch.autograd.Function):
         dattn = linear_dgrad(do2, wo_bf, lens=rl, T=T, tail=NO_TAIL)
         if fused:  # `P` slot of the saved tensors holds lse2; S / P / dS never touch HBM
             dqkv = attn_bwd(qkv.view(B, T, C3), attn.view(B, T, HD), dattn.view(B, T, HD), P, lens, H,
-                            dk).view(M, C3)
+                            dk, ctx.sched).view(M, C3)
             x2 = x.view(M, D)
             with fork_side():
                 qkv_param_grads(dqkv, x2, gbuf, HD, lens=rl, T=T)

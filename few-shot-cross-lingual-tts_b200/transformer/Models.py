@@ -44,8 +44,12 @@ class _FFTStack(nn.Module):
         return self.position_enc, T
 
     def _run_layers(self, x, lens):
-        for layer in self.layer_stack:
-            x, _ = layer(x, lens=lens)
+        if not self.layer_stack:
+            return x
+        # one longest-first work order for the attention kernels of all layers (same lengths in every layer)
+        with ops.attn_schedule_scope(lens, x.shape[1], self.layer_stack[0].slf_attn.n_head):
+            for layer in self.layer_stack:
+                x, _ = layer(x, lens=lens)
         return x
 
 

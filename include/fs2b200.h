@@ -155,11 +155,15 @@ int fs2_softmax_bwd(const void* P, const float* dP, const int64_t* lens, int Z, 
 /* merge of transformer/SubLayers.py:39-52).  qkv: bf16 [B][T][3*H*dk]; out: bf16 [B][T][H*dk]; */
 /* lse2: f32 [B*H][T] log2-domain log-sum-exp of the scaled scores (+inf on padded rows).       */
 /* ------------------------------------------------------------------------------------------ */
-int fs2_attn_fwd_bf16(const void* qkv, const int64_t* lens, int B, int T, int H, int dk, void* out,
-                      float* lse2, void* stream);
+/* sched (optional, NULL = natural order): int32 [B*H*ceil(T/128)] work order written by          */
+/* fs2_attn_schedule from the device-side lengths -- tiles of the longest utterances first,      */
+/* padded-only tiles last (the CTAs of a ragged batch differ 8x in work).                        */
+int fs2_attn_schedule(const int64_t* lens, int B, int T, int H, int32_t* sched, void* stream);
+int fs2_attn_fwd_bf16(const void* qkv, const int64_t* lens, const int32_t* sched, int B, int T, int H, int dk,
+                      void* out, float* lse2, void* stream);
 /* backward: o, d_o: bf16 [B][T][H*dk]; dsum: f32 [B*H][T] workspace; dqkv: bf16 [B][T][3*H*dk]   */
 int fs2_attn_bwd_bf16(const void* qkv, const void* o, const void* d_o, const float* lse2, const int64_t* lens,
-                      int B, int T, int H, int dk, float* dsum, void* dqkv, void* stream);
+                      const int32_t* sched, int B, int T, int H, int dk, float* dsum, void* dqkv, void* stream);
 
 /* ------------------------------------------------------------------------------------------ */
 /* LengthRegulator (lightning/model/modules.py:169-196, lightning/utils/tool.py:168-186)       */

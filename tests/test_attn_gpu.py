@@ -73,6 +73,30 @@ def test_attn_bwd(B, T, lens):
     assert dqkv[~qvalid].abs().sum() == 0
 
 
+@pytest.mark.parametrize("B,T,lens", [(5, 700, [700, 13, 400, 0, 129]), (3, 128, [128, 128, 1])])
+def test_attention_work_order_is_a_permutation_and_changes_no_bit(B, T, lens):
+    """fs2_attn_schedule: longest utterance first, padded-only tiles last, every (z, tile) exactly once; the kernels
+    produce bit-identical results in scheduled and natural order (same CTAs, different launch order)."""
+    torch.manual_seed(5)
+    H, dk = 2, 128
+    ops = sub("ops")
+    lens_t = torch.tensor(lens, device="cuda")
+    sched = ops.attn_schedule(lens_t, T, H)
+    nq = (T + 127) // 128
+    e = sched.cpu().tolist()
+    assert sorted(e) == sorted((z << 8) | t for z in range(B * H) for t in range(nq))
+    work = [lens[(x >> 8) // H] if (x & 255) * 128 < lens[(x >> 8) // H] else 0 for x in e]
+    assert work == sorted(work, reverse=True)
+    qkv = torch.randn(B, T, 3 * H * dk, device="cuda").to(BF16)
+    d_out = torch.randn(B, T, H * dk, device="cuda").to(BF16)
+    o1, l1 = ops.attn_fwd(qkv, lens_t, H, dk)
+    o2, l2 = ops.attn_fwd(qkv, lens_t, H, dk, sched)
+    assert torch.equal(o1, o2) and torch.equal(l1, l2)
+    g1 = ops.attn_bwd(qkv, o1, d_out, l1, lens_t, H, dk)
+    g2 = ops.attn_bwd(qkv, o1, d_out, l1, lens_t, H, dk, sched)
+    assert torch.equal(g1, g2)
+
+
 def test_fused_and_unfused_sublayer_agree(monkeypatch):
     """The fused attention path against the GEMM -> softmax -> GEMM composition, whole sub-layer fwd+bwd."""
     S = sub("transformer.SubLayers")

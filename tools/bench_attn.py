@@ -40,9 +40,10 @@ def main():
     d_o = torch.randn(B, T, H * dk, device="cuda").to(torch.bfloat16)
     for tag, lens in (("dense", dense), ("ragged C2", ragged)):
         fl = float((lens.double() ** 2).sum()) * 4 * dk * H  # QK^T + PV, algorithmic
-        out, lse2 = ops.attn_fwd(qkv, lens, H, dk)
-        us_f = timeit(lambda: ops.attn_fwd(qkv, lens, H, dk))
-        us_b = timeit(lambda: ops.attn_bwd(qkv, out, d_o, lse2, lens, H, dk))
+        sched = None if os.environ.get("FS2_NO_ATTN_SCHED") else ops.attn_schedule(lens, T, H)
+        out, lse2 = ops.attn_fwd(qkv, lens, H, dk, sched)
+        us_f = timeit(lambda: ops.attn_fwd(qkv, lens, H, dk, sched))
+        us_b = timeit(lambda: ops.attn_bwd(qkv, out, d_o, lse2, lens, H, dk, sched))
         print("%-10s fwd %7.1f us (%6.1f TFLOP/s algorithmic)   bwd %7.1f us (%6.1f TFLOP/s, 2.5x fwd flops)"
               % (tag, us_f, fl / us_f / 1e6, us_b, 2.5 * fl / us_b / 1e6))
 

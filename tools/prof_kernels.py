@@ -30,12 +30,13 @@ x2, dy2 = x.view(B * T, D), dy.view(B * T, D)
 NT = ops.NO_TAIL
 gamma, beta = torch.ones(D, device="cuda"), torch.zeros(D, device="cuda")
 dg, db, dbias = (torch.zeros(D, device="cuda") for _ in range(3))
-o3, lse = ops.attn_fwd(qkv, lens, H, D // H)
+sched = ops.attn_schedule(lens, T, H)
+o3, lse = ops.attn_fwd(qkv, lens, H, D // H, sched)
 y, mean, rstd = ops.ln_fwd(x, dy, gamma, beta, lens, 0.2, 1, 5)
 torch.cuda.synchronize()
 seq = [
-    lambda: ops.attn_fwd(qkv, lens, H, D // H),
-    lambda: ops.attn_bwd(qkv, o3, dy, lse, lens, H, D // H),
+    lambda: ops.attn_fwd(qkv, lens, H, D // H, sched),
+    lambda: ops.attn_bwd(qkv, o3, dy, lse, lens, H, D // H, sched),
     lambda: ops.linear_fwd(x2, wqkv, bq, lens=lens, T=T, tail=NT),
     lambda: ops.linear_fwd(x2, wo, bo, lens=lens, T=T, tail=NT),
     lambda: ops.conv_fwd(h, w2p, b2, lens=lens, tail=NT),

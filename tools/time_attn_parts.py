@@ -8,14 +8,15 @@ batch = synth.make_batch(**synth.CONFIGS["C2"])
 for tag, lens in (("dense", torch.full((B,), T, dtype=torch.int64, device="cuda")), ("ragged", batch[7].clamp(max=T).cuda())):
     qkv = torch.randn(B, T, 3 * H * dk, device="cuda").to(torch.bfloat16)
     d_o = torch.randn(B, T, H * dk, device="cuda").to(torch.bfloat16)
-    out, lse2 = ops.attn_fwd(qkv, lens, H, dk)
+    sched = None if os.environ.get("FS2_NO_ATTN_SCHED") else ops.attn_schedule(lens, T, H)
+    out, lse2 = ops.attn_fwd(qkv, lens, H, dk, sched)
     from torch.profiler import profile, ProfilerActivity
-    for _ in range(3): ops.attn_bwd(qkv, out, d_o, lse2, lens, H, dk)
+    for _ in range(3): ops.attn_bwd(qkv, out, d_o, lse2, lens, H, dk, sched)
     torch.cuda.synchronize()
     with profile(activities=[ProfilerActivity.CUDA]) as prof:
         for _ in range(5):
-            ops.attn_fwd(qkv, lens, H, dk)
-            ops.attn_bwd(qkv, out, d_o, lse2, lens, H, dk)
+            ops.attn_fwd(qkv, lens, H, dk, sched)
+            ops.attn_bwd(qkv, out, d_o, lse2, lens, H, dk, sched)
         torch.cuda.synchronize()
     print(tag, "FS2_ATTN_DBG=%s" % os.environ.get("FS2_ATTN_DBG", "0"))
     for e in prof.key_averages():

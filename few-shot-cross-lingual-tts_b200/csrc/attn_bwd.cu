@@ -542,6 +542,235 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ128,  // qkv, box 64 x
 
 
 // ================================================================================================
+// dK / dV kernel, second generation (same ideas as the dQ kernel below): P^T and dS^T never touch shared memory --
+// the softmax warps write them (bf16) over the S^T / dP^T accumulator columns they have just read and the dV / dK
+// MMAs take their A operand from tensor memory.  The 64 KiB of shared memory this frees deepen the Q / dO ring from
+// 2 to 4 stages (the TMA round trip leaves the per-tile dependency cycle); the S^T / dP^T MMAs and the dV / dK MMAs
+// are issued by two different warps so that neither waits behind the other's barriers; per-query statistics are
+// prefetched one tile ahead; MMA issue is warp-uniform (elect.sync).
+// ================================================================================================
+namespace dkv2 {
+using namespace ab;
+constexpr int QS = 4;
+constexpr int OFF_K = 0;                       // [128 keys x 128 d]  32 KiB
+constexpr int OFF_V = OFF_K + 2 * BLK128;      // 32 KiB
+constexpr int OFF_Q = OFF_V + 2 * BLK128;      // QS stages x [64 q x 128 d] 16 KiB
+constexpr int OFF_DO = OFF_Q + QS * 2 * BLK64; // QS stages x 16 KiB
+constexpr int OFF_STG = OFF_Q;                 // epilogue staging (the ring is idle by then)
+constexpr int OFF_STAT = OFF_DO + QS * 2 * BLK64;  // [2 parities][lse2 | dsum][64] f32
+constexpr int OFF_BAR = OFF_STAT + 2 * 2 * 64 * 4;
+enum { KV_FULL = 0, QDO_FULL = 1, QDO_EMPTY = QDO_FULL + QS, SP_FULL = QDO_EMPTY + QS, SP_EMPTY = SP_FULL + 2,
+       PDS_FULL = SP_EMPTY + 2, ACC_FULL = PDS_FULL + 2, NUM_BARS = ACC_FULL + 1 };
+constexpr int OFF_TMEM = OFF_BAR + NUM_BARS * 8;
+constexpr int SMEM_BYTES = OFF_TMEM + 16 + 1024;
+}  // namespace dkv2
+
+__global__ void __launch_bounds__(352, 1)
+attn_bwd_dkv2_kernel(const __grid_constant__ CUtensorMap tmKV,   // qkv, box 64 x 128 rows
+                     const __grid_constant__ CUtensorMap tmQ,    // qkv, box 64 x 64 rows
+                     const __grid_constant__ CUtensorMap tmDO,   // dO,  box 64 x 64 rows
+                     const __grid_constant__ AttnBwdP p) {
+  pdl_sync();
+  using namespace dkv2;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* sgen = smem_raw + (sbase - smem_u32(smem_raw));
+  auto bar = [&](int i) { return sbase + OFF_BAR + 8u * i; };
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int jt = blockIdx.x % p.n_outer, z = blockIdx.x / p.n_outer;
+  if (p.sched) {
+    const int e = p.sched[blockIdx.x];
+    z = e >> 8;
+    jt = e & 255;
+  }
+  const int b = z / p.H, h = z % p.H;
+  const int k0 = jt * 128;
+  const int HD = p.H * DK;
+  const int len = min((int)p.lens[b], p.T);
+  if (k0 >= len) {  // a key tile of padded frames only (CTA-uniform): dK = dV = 0, no MMAs
+    __nv_bfloat16* gb = p.dqkv + (long long)b * p.T * 3 * HD;
+    for (int i = threadIdx.x; i < 128 * 32; i += blockDim.x) {
+      const int r = i >> 5, c = i & 31;  // 32 x 16-byte vectors per row: 16 for dK, 16 for dV
+      if (k0 + r < p.T)
+        *reinterpret_cast<uint4*>(gb + (long long)(k0 + r) * 3 * HD + (1 + (c >> 4)) * HD + h * DK + (c & 15) * 8) =
+            make_uint4(0u, 0u, 0u, 0u);
+    }
+    return;
+  }
+  const int n = min(p.n_inner, (len + 63) / 64);  // 64-query tiles with at least one valid query
+
+  if (threadIdx.x == 0) {
+    mbar_init(bar(KV_FULL), 1);
+    for (int s = 0; s < QS; ++s) {
+      mbar_init(bar(QDO_FULL + s), 1);
+      mbar_init(bar(QDO_EMPTY + s), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(bar(SP_FULL + s), 1);
+      mbar_init(bar(SP_EMPTY + s), 1);   // committed after the dV / dK MMAs that read P^T / dS^T of this stage
+      mbar_init(bar(PDS_FULL + s), 8);
+    }
+    mbar_init(bar(ACC_FULL), 1);
+    fence_mbar_init();
+  }
+  if (warp == 9) {
+    tmem_alloc(sbase + OFF_TMEM, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(sgen + OFF_TMEM);
+  const uint32_t tSt = tmem_base, tdPt = tmem_base + 128, tdV = tmem_base + 256, tdK = tmem_base + 384;
+
+  if (warp == 8) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(bar(KV_FULL), 4 * BLK128);
+      for (int kb = 0; kb < 2; ++kb) {
+        tma_load_3d(sbase + OFF_K + kb * BLK128, &tmKV, bar(KV_FULL), HD + h * DK + kb * 64, k0, b);
+        tma_load_3d(sbase + OFF_V + kb * BLK128, &tmKV, bar(KV_FULL), 2 * HD + h * DK + kb * 64, k0, b);
+      }
+      for (int i = 0; i < n; ++i) {
+        const int s = i % QS;
+        mbar_wait(bar(QDO_EMPTY + s), ((i / QS) & 1) ^ 1u);
+        mbar_arrive_expect_tx(bar(QDO_FULL + s), 4 * BLK64);
+        for (int kb = 0; kb < 2; ++kb) {
+          tma_load_3d(sbase + OFF_Q + s * 2 * BLK64 + kb * BLK64, &tmQ, bar(QDO_FULL + s), h * DK + kb * 64,
+                      i * 64, b);
+          tma_load_3d(sbase + OFF_DO + s * 2 * BLK64 + kb * BLK64, &tmDO, bar(QDO_FULL + s), h * DK + kb * 64,
+                      i * 64, b);
+        }
+      }
+    }
+  } else if (warp == 9) {
+    // ---- issuer 1: S^T = K Q^T and dP^T = V dO^T for tile i into stage i & 1
+    const uint32_t idesc_s = make_idesc_bf16(128, 64, 0, 0);
+    const uint64_t dK0 = make_smem_desc(sbase + OFF_K, 16, 1024), dV0 = make_smem_desc(sbase + OFF_V, 16, 1024);
+    const uint64_t dQ0 = make_smem_desc(sbase + OFF_Q, 16, 1024), dDO0 = make_smem_desc(sbase + OFF_DO, 16, 1024);
+    mbar_wait(bar(KV_FULL), 0);
+    for (int i = 0; i < n; ++i) {
+      const int s = i & 1, qs = i % QS;
+      mbar_wait(bar(QDO_FULL + qs), (i / QS) & 1);
+      mbar_wait(bar(SP_EMPTY + s), ((i >> 1) & 1) ^ 1u);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint64_t so = (uint64_t)((qs * 2 * BLK64) >> 4);
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+          const uint64_t offa = (uint64_t)(((t >> 2) * BLK128 + (t & 3) * 32) >> 4);
+          const uint64_t offb = (uint64_t)(((t >> 2) * BLK64 + (t & 3) * 32) >> 4);
+          umma_f16(tSt + s * 64, dK0 + offa, dQ0 + so + offb, idesc_s, t > 0);
+        }
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+          const uint64_t offa = (uint64_t)(((t >> 2) * BLK128 + (t & 3) * 32) >> 4);
+          const uint64_t offb = (uint64_t)(((t >> 2) * BLK64 + (t & 3) * 32) >> 4);
+          umma_f16(tdPt + s * 64, dV0 + offa, dDO0 + so + offb, idesc_s, t > 0);
+        }
+        umma_commit(bar(SP_FULL + s));
+      }
+      __syncwarp();
+    }
+  } else if (warp == 10) {
+    // ---- issuer 2: dV += P^T dO, dK += dS^T Q with the A operands in tensor memory
+    const uint32_t idesc_a = make_idesc_bf16(128, 128, 0, 1);  // B operand (dO / Q tile) MN-major
+    const uint64_t dQm0 = make_smem_desc(sbase + OFF_Q, BLK64, 1024), dDOm0 = make_smem_desc(sbase + OFF_DO, BLK64, 1024);
+    for (int i = 0; i < n; ++i) {
+      const int s = i & 1, qs = i % QS;
+      mbar_wait(bar(PDS_FULL + s), (i >> 1) & 1);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint64_t so = (uint64_t)((qs * 2 * BLK64) >> 4);
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {  // K = 64 queries, 16 per step; queries [32h, 32h+32) sit in columns [32h, 32h+16)
+          const uint32_t acol = s * 64 + (t >> 1) * 32 + (t & 1) * 8;
+          umma_f16_ts(tdV, tSt + acol, dDOm0 + so + (uint64_t)((t * 2048) >> 4), idesc_a, (i > 0 || t > 0) ? 1u : 0u);
+        }
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const uint32_t acol = s * 64 + (t >> 1) * 32 + (t & 1) * 8;
+          umma_f16_ts(tdK, tdPt + acol, dQm0 + so + (uint64_t)((t * 2048) >> 4), idesc_a, (i > 0 || t > 0) ? 1u : 0u);
+        }
+        umma_commit(bar(QDO_EMPTY + qs));
+        umma_commit(bar(SP_EMPTY + s));
+        if (i == n - 1) umma_commit(bar(ACC_FULL));
+      }
+      __syncwarp();
+    }
+  } else {
+    // softmax warps: thread = key row; warps w / w+4 take the query columns [0,32) / [32,64) of the tile
+    const int q4 = warp & 3, half = warp >> 2;
+    const int row = q4 * 32 + lane;
+    const int key = k0 + row;
+    const bool key_valid = key < len;
+    const uint32_t lane_base = static_cast<uint32_t>(q4 * 32) << 16;
+    float* s_stat = reinterpret_cast<float*>(sgen + OFF_STAT);
+    const int tid = threadIdx.x;  // 0..255 here
+    const float* lse2 = p.lse2 + (long long)z * p.T;
+    const float* dsum = p.dsum + (long long)z * p.T;
+    auto load_stat = [&](int i) -> float {  // threads 0..63: lse2 of query i*64+tid, 64..127: dsum
+      const int qq = i * 64 + (tid & 63);
+      if (tid < 64) return qq < p.T ? __ldg(lse2 + qq) : INFINITY;  // +inf => P = 0 (padded queries too)
+      return qq < len ? __ldg(dsum + qq) : 0.f;                     // D of padded queries is not computed
+    };
+    float nxt = tid < 128 ? load_stat(0) : 0.f;
+    // invalid key rows (beyond the utterance) get P = dS = 0 through an infinite "lse" offset
+    const float kill = key_valid ? 0.f : INFINITY;
+    for (int i = 0; i < n; ++i) {
+      const int s = i & 1;
+      if (tid < 128) s_stat[s * 128 + tid] = nxt;  // (buffer s was last read in iteration i-2: a barrier lies between)
+      if (tid < 128 && i + 1 < n) nxt = load_stat(i + 1);  // in flight during this tile's math
+      softmax_bar_sync_bwd();
+      mbar_wait(bar(SP_FULL + s), (i >> 1) & 1);
+      tc_fence_after();
+      uint32_t vs[32], vd[32];
+      tmem_ld32(tSt + s * 64 + lane_base + half * 32, vs);
+      tmem_ld32(tdPt + s * 64 + lane_base + half * 32, vd);
+      tmem_ld_wait();
+      uint32_t wp[16], wd[16];
+      const float4* st_l = reinterpret_cast<const float4*>(s_stat + s * 128 + half * 32);
+      const float4* st_d = st_l + 16;
+#pragma unroll
+      for (int t4 = 0; t4 < 8; ++t4) {
+        const float4 l4 = st_l[t4], d4 = st_d[t4];
+        const float lv[4] = {l4.x, l4.y, l4.z, l4.w}, dv[4] = {d4.x, d4.y, d4.z, d4.w};
+        float pr[4], ds[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int t = t4 * 4 + e;
+          pr[e] = ex2_fast(fmaf(__uint_as_float(vs[t]), p.scale_log2, -(lv[e] + kill)));
+          ds[e] = pr[e] * fmaf(__uint_as_float(vd[t]), p.scale, -dv[e]);
+        }
+        __nv_bfloat162 a = __floats2bfloat162_rn(pr[0], pr[1]), c = __floats2bfloat162_rn(pr[2], pr[3]);
+        __nv_bfloat162 d0 = __floats2bfloat162_rn(ds[0], ds[1]), d1 = __floats2bfloat162_rn(ds[2], ds[3]);
+        wp[2 * t4] = *reinterpret_cast<uint32_t*>(&a);
+        wp[2 * t4 + 1] = *reinterpret_cast<uint32_t*>(&c);
+        wd[2 * t4] = *reinterpret_cast<uint32_t*>(&d0);
+        wd[2 * t4 + 1] = *reinterpret_cast<uint32_t*>(&d1);
+      }
+      tmem_st16(tSt + s * 64 + lane_base + half * 32, wp);   // P^T over the S^T columns this warp consumed
+      tmem_st16(tdPt + s * 64 + lane_base + half * 32, wd);  // dS^T over its dP^T columns
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar(PDS_FULL + s));
+    }
+    mbar_wait(bar(ACC_FULL), 0);
+    tc_fence_after();
+    uint8_t* stg = sgen + OFF_STG + warp * 4096;
+    __nv_bfloat16* gb = p.dqkv + (long long)b * p.T * 3 * HD;
+    store_acc_half(tdV, lane_base, stg, q4, lane, half, gb + 2 * HD + h * DK, 3 * HD, k0, p.T);
+    store_acc_half(tdK, lane_base, stg, q4, lane, half, gb + HD + h * DK, 3 * HD, k0, p.T);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 9) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ================================================================================================
 // dQ kernel, second generation: dS never touches shared memory.  The softmax warps write dS (bf16) back into
 // the TMEM columns of the S accumulator they just read (tcgen05.st) and the dQ MMA takes its A operand from
 // tensor memory (tcgen05.mma with [tmem] A); that frees 32 KiB of shared memory and the st.shared / proxy-fence
@@ -564,7 +793,7 @@ constexpr int OFF_TMEM = OFF_BAR + NUM_BARS * 8;
 constexpr int SMEM_BYTES = OFF_TMEM + 16 + 1024;
 }  // namespace dq2
 
-__global__ void __launch_bounds__(320, 1)
+__global__ void __launch_bounds__(352, 1)
 attn_bwd_dq2_kernel(const __grid_constant__ CUtensorMap tmQ128,  // qkv, box 64 x 128 rows
                     const __grid_constant__ CUtensorMap tmKV64,  // qkv, box 64 x 64 rows
                     const __grid_constant__ CUtensorMap tmDO128, // dO,  box 64 x 128 rows
@@ -646,14 +875,13 @@ attn_bwd_dq2_kernel(const __grid_constant__ CUtensorMap tmQ128,  // qkv, box 64 
       }
     }
   } else if (warp == 9) {
-    // MMA issuer: the whole warp runs the loop (uniform control flow), one elected lane issues
+    // ---- issuer 1: S = Q K^T and dP = dO V^T for tile j into stage j % SPS (warp-uniform loop, one elected lane)
     const uint32_t idesc_s = make_idesc_bf16(128, 64, 0, 0);   // S / dP: [128 q x 64 keys]
-    const uint32_t idesc_q = make_idesc_bf16(128, 128, 0, 1);  // dQ += dS K (A from TMEM, K tile as MN-major B)
     // descriptors: constant high word; the low word is (address >> 4) + (LBO >> 4 << 16) -> add offsets >> 4
     const uint64_t dQ0 = make_smem_desc(sbase + OFF_Q, 16, 1024), dDO0 = make_smem_desc(sbase + OFF_DO, 16, 1024);
     const uint64_t dK0 = make_smem_desc(sbase + OFF_K, 16, 1024), dV0 = make_smem_desc(sbase + OFF_V, 16, 1024);
-    const uint64_t dKm0 = make_smem_desc(sbase + OFF_K, BLK64, 1024);  // K tile as MN-major B of the dQ MMA
-    auto issue_sp = [&](int j) {
+    mbar_wait(bar(QDO_FULL), 0);
+    for (int j = 0; j < n; ++j) {
       const int s = j % KVS, s3 = j % SPS;
       mbar_wait(bar(KV_FULL + s), (j / KVS) & 1);
       mbar_wait(bar(SP_EMPTY + s3), ((j / SPS) & 1) ^ 1u);  // the dQ MMA of tile j-3 has consumed dS in this stage
@@ -662,38 +890,40 @@ attn_bwd_dq2_kernel(const __grid_constant__ CUtensorMap tmQ128,  // qkv, box 64 
         const uint64_t so = (uint64_t)((s * 2 * BLK64) >> 4);
         if (!(p.dbg & 8)) {
 #pragma unroll
-        for (int t = 0; t < 8; ++t) {
-          const uint64_t offa = (uint64_t)(((t >> 2) * BLK128 + (t & 3) * 32) >> 4);
-          const uint64_t offb = (uint64_t)(((t >> 2) * BLK64 + (t & 3) * 32) >> 4);
-          umma_f16(tS + s3 * 64, dQ0 + offa, dK0 + so + offb, idesc_s, t > 0);
+          for (int t = 0; t < 8; ++t) {
+            const uint64_t offa = (uint64_t)(((t >> 2) * BLK128 + (t & 3) * 32) >> 4);
+            const uint64_t offb = (uint64_t)(((t >> 2) * BLK64 + (t & 3) * 32) >> 4);
+            umma_f16(tS + s3 * 64, dQ0 + offa, dK0 + so + offb, idesc_s, t > 0);
+          }
         }
-        }
-        if (!(p.dbg & 16))
+        if (!(p.dbg & 16)) {
 #pragma unroll
-        for (int t = 0; t < 8; ++t) {
-          const uint64_t offa = (uint64_t)(((t >> 2) * BLK128 + (t & 3) * 32) >> 4);
-          const uint64_t offb = (uint64_t)(((t >> 2) * BLK64 + (t & 3) * 32) >> 4);
-          umma_f16(tdP + s3 * 64, dDO0 + offa, dV0 + so + offb, idesc_s, t > 0);
+          for (int t = 0; t < 8; ++t) {
+            const uint64_t offa = (uint64_t)(((t >> 2) * BLK128 + (t & 3) * 32) >> 4);
+            const uint64_t offb = (uint64_t)(((t >> 2) * BLK64 + (t & 3) * 32) >> 4);
+            umma_f16(tdP + s3 * 64, dDO0 + offa, dV0 + so + offb, idesc_s, t > 0);
+          }
         }
         umma_commit(bar(SP_FULL + s3));
       }
       __syncwarp();
-    };
-    mbar_wait(bar(QDO_FULL), 0);
-    issue_sp(0);
-    if (n > 1) issue_sp(1);
+    }
+  } else if (warp == 10) {
+    // ---- issuer 2: dQ += dS K with dS read from tensor memory
+    const uint32_t idesc_q = make_idesc_bf16(128, 128, 0, 1);  // K tile as MN-major B
+    const uint64_t dKm0 = make_smem_desc(sbase + OFF_K, BLK64, 1024);
     for (int j = 0; j < n; ++j) {
       const int s = j % KVS, s3 = j % SPS;
-      if (j + 2 < n) issue_sp(j + 2);
       mbar_wait(bar(DS_FULL + s3), (j / SPS) & 1);
       tc_fence_after();
       if (elect_one()) {
         const uint64_t so = (uint64_t)((s * 2 * BLK64) >> 4);
-        if (!(p.dbg & 4))
+        if (!(p.dbg & 4)) {
 #pragma unroll
-        for (int t = 0; t < 4; ++t) {  // K = 64 keys, 16 per step; dS of keys [32h, 32h+32) sits in S columns [32h, 32h+16)
-          umma_f16_ts(tdQ, tS + s3 * 64 + (t >> 1) * 32 + (t & 1) * 8, dKm0 + so + (uint64_t)((t * 2048) >> 4),
-                      idesc_q, (j > 0 || t > 0) ? 1u : 0u);
+          for (int t = 0; t < 4; ++t) {  // K = 64 keys, 16 per step; dS of keys [32h, 32h+32) sits in S columns [32h, 32h+16)
+            umma_f16_ts(tdQ, tS + s3 * 64 + (t >> 1) * 32 + (t & 1) * 8, dKm0 + so + (uint64_t)((t * 2048) >> 4),
+                        idesc_q, (j > 0 || t > 0) ? 1u : 0u);
+          }
         }
         umma_commit(bar(KV_EMPTY + s));
         umma_commit(bar(SP_EMPTY + s3));
@@ -787,6 +1017,8 @@ int fs2_attn_bwd_bf16(const void* qkv, const void* o, const void* d_o, const flo
       e = cudaFuncSetAttribute(attn_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dq::SMEM_BYTES);
     if (e == cudaSuccess)
       e = cudaFuncSetAttribute(attn_bwd_dq2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dq2::SMEM_BYTES);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(attn_bwd_dkv2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dkv2::SMEM_BYTES);
     if (e != cudaSuccess) return set_cuda_error("cudaFuncSetAttribute(attn_bwd)", e);
     attr = true;
   }
@@ -814,14 +1046,18 @@ int fs2_attn_bwd_bf16(const void* qkv, const void* o, const void* d_o, const flo
   p.n_outer = (T + 127) / 128;
   p.n_inner = (T + 63) / 64;
   const unsigned grid = (unsigned)(p.n_outer * B * H);
-  FS2_LAUNCH((attn_bwd_dkv_kernel), grid, 320, dkv::SMEM_BYTES, s, tm128, tm64, tmdo64, p);
+  static const bool old_dq = getenv("FS2_ATTN_OLD") != nullptr;  // A/B switch: first-generation kernels
+  if (old_dq) {
+    FS2_LAUNCH((attn_bwd_dkv_kernel), grid, 320, dkv::SMEM_BYTES, s, tm128, tm64, tmdo64, p);
+  } else {
+    FS2_LAUNCH((attn_bwd_dkv2_kernel), grid, 352, dkv2::SMEM_BYTES, s, tm128, tm64, tmdo64, p);
+  }
   count_launch();
   if (int rc = check_launch("attn_bwd_dkv_kernel")) return rc;
-  static const bool old_dq = getenv("FS2_ATTN_OLD") != nullptr;  // A/B switch: first-generation kernels
   if (old_dq) {
     FS2_LAUNCH((attn_bwd_dq_kernel), grid, 320, dq::SMEM_BYTES, s, tm128, tm64, tmdo128, p);
   } else {
-    FS2_LAUNCH((attn_bwd_dq2_kernel), grid, 320, dq2::SMEM_BYTES, s, tm128, tm64, tmdo128, p);
+    FS2_LAUNCH((attn_bwd_dq2_kernel), grid, 352, dq2::SMEM_BYTES, s, tm128, tm64, tmdo128, p);
   }
   count_launch();
   return check_launch("attn_bwd_dq_kernel");

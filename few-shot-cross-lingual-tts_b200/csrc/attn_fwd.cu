@@ -20,6 +20,8 @@
 #include <cuda.h>
 #include <cuda_bf16.h>
 
+#include <cstdlib>
+
 #include "common.h"
 #include "ptx.cuh"
 #include "tmap.h"
@@ -305,6 +307,290 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constant_
   }
 }
 
+// ================================================================================================
+// Forward, second generation.  Same exact two-pass softmax, restructured around what bounds these kernels on B200
+// (measured: barrier round trips and single-thread issue latency, not FLOPs -- profiles/README.md):
+//   * P never touches shared memory: the softmax warps write it (bf16) over the S accumulator columns they have
+//     just read (tcgen05.st) and the PV MMA takes its A operand from tensor memory;
+//   * two issuer warps (QK^T / PV) so that neither waits behind the other's barriers, warp-uniform issue loops
+//     with elect.sync and precomputed descriptors;
+//   * 3 S stages in TMEM and a 3-stage K ring (the 64 KiB that P occupied), so the QK^T MMAs run two tiles ahead.
+// ================================================================================================
+namespace af2 {
+constexpr int DK = 128, BQ = 128, BKV = 128;
+constexpr int TILE_BYTES = 128 * 128 * 2;  // 32 KiB: two [128 x 64] bf16 swizzle-128B blocks
+constexpr int BLK = 16384;                 // one [128 rows x 64 cols] block
+constexpr int KS = 3, VS = 2, SS = 3;
+constexpr int OFF_Q = 0;
+constexpr int OFF_K = OFF_Q + TILE_BYTES;
+constexpr int OFF_V = OFF_K + KS * TILE_BYTES;
+constexpr int OFF_STG = OFF_K;                    // epilogue staging: the K ring is idle by then
+constexpr int OFF_RED = OFF_V + VS * TILE_BYTES;  // [2 halves][128 rows] f32 exchange of max / sum
+constexpr int OFF_BAR = OFF_RED + 2 * 128 * 4;
+enum { Q_FULL = 0, K_FULL = 1, K_EMPTY = K_FULL + KS, V_FULL = K_EMPTY + KS, V_EMPTY = V_FULL + VS,
+       S_FULL = V_EMPTY + VS, S_EMPTY = S_FULL + SS, P_FULL = S_EMPTY + SS, O_FULL = P_FULL + SS, NUM_BARS = O_FULL + 1 };
+constexpr int OFF_TMEM = OFF_BAR + NUM_BARS * 8;
+constexpr int SMEM_BYTES = OFF_TMEM + 16 + 1024;
+}  // namespace af2
+
+__global__ void __launch_bounds__(352, 1)
+attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constant__ CUtensorMap tmV,
+                 const __grid_constant__ AttnFwdP p) {
+  pdl_sync();
+  using namespace af2;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* sgen = smem_raw + (sbase - smem_u32(smem_raw));
+  auto bar = [&](int i) { return sbase + OFF_BAR + 8u * i; };
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int qt = blockIdx.x % p.nq, z = blockIdx.x / p.nq;
+  if (p.sched) {  // longest utterances first (the CTAs of a ragged batch differ 8x in work)
+    const int e = p.sched[blockIdx.x];
+    z = e >> 8;
+    qt = e & 255;
+  }
+  const int b = z / p.H, h = z % p.H;
+  const int q0 = qt * BQ;
+  const int HD = p.H * DK;
+  const int len = min((int)p.lens[b], p.T);
+  if (q0 >= len) {  // a query tile of padded frames only (CTA-uniform): out = 0, lse2 = +inf, no MMAs
+    for (int i = threadIdx.x; i < BQ * 16; i += blockDim.x) {
+      const int r = i >> 4, c = i & 15;
+      if (q0 + r < p.T)
+        *reinterpret_cast<uint4*>(p.out + ((long long)b * p.T + q0 + r) * HD + h * DK + c * 8) =
+            make_uint4(0u, 0u, 0u, 0u);
+    }
+    for (int r = threadIdx.x; r < BQ; r += blockDim.x)
+      if (q0 + r < p.T) p.lse2[(long long)z * p.T + q0 + r] = INFINITY;
+    return;
+  }
+  const int n = min(p.nkv, (len + BKV - 1) / BKV);  // key tiles that hold at least one valid key
+
+  if (threadIdx.x == 0) {
+    mbar_init(bar(Q_FULL), 1);
+    for (int s = 0; s < KS; ++s) {
+      mbar_init(bar(K_FULL + s), 1);
+      mbar_init(bar(K_EMPTY + s), 1);
+    }
+    for (int s = 0; s < VS; ++s) {
+      mbar_init(bar(V_FULL + s), 1);
+      mbar_init(bar(V_EMPTY + s), 1);
+    }
+    for (int s = 0; s < SS; ++s) {
+      mbar_init(bar(S_FULL + s), 1);
+      mbar_init(bar(S_EMPTY + s), 1);  // pass A: plain arrive of the PV warp; pass B: commit after the PV MMAs
+      mbar_init(bar(P_FULL + s), 8);
+    }
+    mbar_init(bar(O_FULL), 1);
+    fence_mbar_init();
+  }
+  if (warp == 9) {
+    tmem_alloc(sbase + OFF_TMEM, 512);
+    tmem_relinquish();
+  }
+  if (warp == 8 && lane == 0) {
+    tma_prefetch_desc(&tmQK);
+    tma_prefetch_desc(&tmV);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(sgen + OFF_TMEM);
+  const uint32_t tS0 = tmem_base, tO = tmem_base + SS * 128;
+
+  if (warp == 8) {
+    // ============================== TMA producer ==============================
+    if (lane == 0) {
+      mbar_arrive_expect_tx(bar(Q_FULL), TILE_BYTES);
+      for (int kb = 0; kb < 2; ++kb)
+        tma_load_3d(sbase + OFF_Q + kb * BLK, &tmQK, bar(Q_FULL), h * DK + kb * 64, q0, b);
+      for (int u = 0; u < 2 * n; ++u) {
+        const int j = u % n, s = u % KS;
+        mbar_wait(bar(K_EMPTY + s), ((u / KS) & 1) ^ 1u);
+        mbar_arrive_expect_tx(bar(K_FULL + s), TILE_BYTES);
+        for (int kb = 0; kb < 2; ++kb)
+          tma_load_3d(sbase + OFF_K + s * TILE_BYTES + kb * BLK, &tmQK, bar(K_FULL + s),
+                      HD + h * DK + kb * 64, j * BKV, b);
+        if (u >= n) {
+          const int vs = j % VS;
+          mbar_wait(bar(V_EMPTY + vs), ((j / VS) & 1) ^ 1u);
+          mbar_arrive_expect_tx(bar(V_FULL + vs), TILE_BYTES);
+          for (int dh = 0; dh < 2; ++dh)
+            for (int kh = 0; kh < 2; ++kh)
+              tma_load_3d(sbase + OFF_V + vs * TILE_BYTES + dh * BLK + kh * 8192, &tmV, bar(V_FULL + vs),
+                          2 * HD + h * DK + dh * 64, j * BKV + kh * 64, b);
+        }
+      }
+    }
+  } else if (warp == 9) {
+    // ============================== issuer 1: S = Q K^T ==============================
+    const uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);  // both K-major
+    const uint64_t dQ0 = make_smem_desc(sbase + OFF_Q, 16, 1024), dK0 = make_smem_desc(sbase + OFF_K, 16, 1024);
+    mbar_wait(bar(Q_FULL), 0);
+    for (int u = 0; u < 2 * n; ++u) {
+      const int s = u % KS, s3 = u % SS;
+      mbar_wait(bar(K_FULL + s), (u / KS) & 1);
+      mbar_wait(bar(S_EMPTY + s3), ((u / SS) & 1) ^ 1u);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint64_t so = (uint64_t)((s * TILE_BYTES) >> 4);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const uint64_t off = (uint64_t)(((i >> 2) * BLK + (i & 3) * 32) >> 4);
+          umma_f16(tS0 + s3 * 128, dQ0 + off, dK0 + so + off, idesc_s, i > 0);
+        }
+        umma_commit(bar(K_EMPTY + s));
+        umma_commit(bar(S_FULL + s3));
+      }
+      __syncwarp();
+    }
+  } else if (warp == 10) {
+    // ============================== issuer 2: O += P V (P from tensor memory) ==============================
+    const uint32_t idesc_o = make_idesc_bf16(128, 128, 0, 1);  // V is MN-major
+    const uint64_t dV0 = make_smem_desc(sbase + OFF_V, BLK, 1024);
+    for (int u = 0; u < 2 * n; ++u) {
+      const int s3 = u % SS;
+      mbar_wait(bar(P_FULL + s3), (u / SS) & 1);
+      if (u < n) {  // pass A: the softmax warps only took the row maxima; hand the stage back
+        if (lane == 0) mbar_arrive(bar(S_EMPTY + s3));
+        __syncwarp();
+        continue;
+      }
+      const int j = u - n, vs = j % VS;
+      mbar_wait(bar(V_FULL + vs), (j / VS) & 1);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint64_t so = (uint64_t)((vs * TILE_BYTES) >> 4);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          // A = P: keys [16i, 16i+16) = 8 TMEM columns; keys of half hf = i >> 2 start at column 64 * hf
+          const uint32_t acol = s3 * 128 + (i >> 2) * 64 + (i & 3) * 8;
+          umma_f16_ts(tO, tS0 + acol, dV0 + so + (uint64_t)((i * 2048) >> 4), idesc_o, (j > 0 || i > 0) ? 1u : 0u);
+        }
+        umma_commit(bar(V_EMPTY + vs));
+        umma_commit(bar(S_EMPTY + s3));
+        if (j == n - 1) umma_commit(bar(O_FULL));
+      }
+      __syncwarp();
+    }
+  } else {
+    // ============================== softmax + epilogue warps ==============================
+    const int q4 = warp & 3, half = warp >> 2;  // TMEM lane quarter, column half
+    const int row = q4 * 32 + lane;
+    const int q = q0 + row;
+    const bool row_valid = q < len;
+    const uint32_t lane_base = static_cast<uint32_t>(q4 * 32) << 16;
+    float* s_red = reinterpret_cast<float*>(sgen + OFF_RED);
+    float mx = -INFINITY, m2 = 0.f, l = 0.f;
+    for (int u = 0; u < 2 * n; ++u) {
+      const int j = u % n, s3 = u % SS;
+      const bool pass_b = u >= n;
+      if (u == n) {  // combine the row maxima of the two column halves (once per CTA)
+        s_red[half * 128 + row] = mx;
+        softmax_bar_sync();
+        const float m = fmaxf(s_red[row], s_red[128 + row]);
+        m2 = (m == -INFINITY) ? 0.f : m * p.scale_log2;
+        softmax_bar_sync();
+      }
+      mbar_wait(bar(S_FULL + s3), (u / SS) & 1);
+      tc_fence_after();
+      const uint32_t tS = tS0 + s3 * 128 + lane_base + half * 64;
+      if (!pass_b) {
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          uint32_t v[32];
+          tmem_ld32(tS + c * 32, v);
+          tmem_ld_wait();
+          const int k0 = j * BKV + half * 64 + c * 32;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, (k0 + i < len) ? __uint_as_float(v[i]) : -INFINITY);
+        }
+      } else {
+        uint32_t w[32];
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          uint32_t v[32];
+          tmem_ld32(tS + c * 32, v);
+          tmem_ld_wait();
+          const int k0 = j * BKV + half * 64 + c * 32;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float e0 = ex2_approx(fmaf(__uint_as_float(v[2 * i]), p.scale_log2, -m2));
+            const float e1 = ex2_approx(fmaf(__uint_as_float(v[2 * i + 1]), p.scale_log2, -m2));
+            const float p0 = (row_valid && k0 + 2 * i < len) ? e0 : 0.f;
+            const float p1 = (row_valid && k0 + 2 * i + 1 < len) ? e1 : 0.f;
+            l += p0 + p1;
+            __nv_bfloat162 b2 = __floats2bfloat162_rn(p0, p1);
+            w[c * 16 + i] = *reinterpret_cast<uint32_t*>(&b2);
+          }
+        }
+        // P (64 keys of this half, bf16) over the first 32 of the 64 S columns this warp has just consumed
+        uint32_t w0[16], w1[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          w0[i] = w[i];
+          w1[i] = w[16 + i];
+        }
+        tmem_st16(tS, w0);
+        tmem_st16(tS + 16, w1);
+        tmem_st_wait();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar(P_FULL + s3));
+    }
+    // ---- combine the row sums, then epilogue: O / l -> bf16 -> staging (the K ring is idle once the last QK^T
+    //      has retired, which it has long before O_FULL) -> coalesced global store; each half stores 64 columns
+    s_red[half * 128 + row] = l;
+    softmax_bar_sync();
+    l = s_red[row] + s_red[128 + row];
+    mbar_wait(bar(O_FULL), 0);
+    tc_fence_after();
+    const float inv = l > 0.f ? 1.f / l : 0.f;
+    if (half == 0 && q < p.T) p.lse2[(long long)z * p.T + q] = l > 0.f ? m2 + log2f(l) : INFINITY;
+    uint8_t* stg = sgen + OFF_STG + warp * 4096;
+    uint8_t* my = stg + lane * 128;
+    const int lsw = lane & 7;
+    {
+      float f[64];
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t v[32];
+        tmem_ld32(tO + lane_base + half * 64 + c * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) f[c * 32 + i] = __uint_as_float(v[i]) * inv;
+      }
+#pragma unroll
+      for (int ch = 0; ch < 8; ++ch) {
+        uint32_t w[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          __nv_bfloat162 b2 = __floats2bfloat162_rn(f[ch * 8 + 2 * t], f[ch * 8 + 2 * t + 1]);
+          w[t] = *reinterpret_cast<uint32_t*>(&b2);
+        }
+        *reinterpret_cast<uint4*>(my + ((ch ^ lsw) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+      }
+      __syncwarp();
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const int r = it * 4 + (lane >> 3), ch = lane & 7;
+        const int gq = q0 + q4 * 32 + r;
+        if (gq < p.T) {
+          const uint4 val = *reinterpret_cast<const uint4*>(stg + r * 128 + ((ch ^ (r & 7)) << 4));
+          *reinterpret_cast<uint4*>(p.out + ((long long)b * p.T + gq) * HD + h * DK + half * 64 + ch * 8) = val;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 9) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Work order of the attention kernels for a ragged batch: one CTA = one (utterance*head z, 128-row tile); its work
 // is proportional to the utterance length, which varies 8x inside a LibriTTS-shaped batch while only ~4 working
@@ -378,6 +664,8 @@ int fs2_attn_fwd_bf16(const void* qkv, const int64_t* lens, const int32_t* sched
   if (!attr) {
     cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          af::SMEM_BYTES);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(attn_fwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, af2::SMEM_BYTES);
     if (e != cudaSuccess) return set_cuda_error("cudaFuncSetAttribute(attn_fwd)", e);
     attr = true;
   }
@@ -394,7 +682,13 @@ int fs2_attn_fwd_bf16(const void* qkv, const int64_t* lens, const int32_t* sched
   p.scale_log2 = 1.4426950408889634f / sqrtf((float)dk);
   p.out = static_cast<__nv_bfloat16*>(out);
   p.lse2 = lse2;
-  FS2_LAUNCH((attn_fwd_kernel), p.nq * B * H, 320, af::SMEM_BYTES, static_cast<cudaStream_t>(stream), tmQK, tmV, p);
+  static const bool old_fwd = getenv("FS2_ATTN_OLD") != nullptr;  // A/B switch: first-generation kernel
+  if (old_fwd) {
+    FS2_LAUNCH((attn_fwd_kernel), p.nq * B * H, 320, af::SMEM_BYTES, static_cast<cudaStream_t>(stream), tmQK, tmV, p);
+  } else {
+    FS2_LAUNCH((attn_fwd2_kernel), p.nq * B * H, 352, af2::SMEM_BYTES, static_cast<cudaStream_t>(stream), tmQK, tmV,
+               p);
+  }
   count_launch();
   return check_launch("attn_fwd_kernel");
 }

@@ -163,11 +163,14 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       }
     }
   } else if (warp == 1) {
-    // ======================= MMA issuer (leader CTA only, one thread) =======================
-    if (leader && lane == 0) {
+    // ======================= MMA issuer (leader CTA only; warp-uniform loop, one elected lane issues) ========
+    if (leader) {
       const uint32_t idesc = make_idesc_bf16(256, BN, 0, p.b_mn);
       const uint32_t b_lbo = p.b_mn ? kChunkBytes : 16u;
       const uint32_t b_kstep = p.b_mn ? 16u * 128u : 32u;
+      // descriptors: constant high word; low word = (address >> 4) | (LBO >> 4) << 16 -> offsets are added >> 4
+      const uint64_t ad0 = make_smem_desc(sbase, 16u, 1024u);
+      const uint64_t bd0 = make_smem_desc(sbase + B_OFF, b_lbo, 1024u);
       int sa_i = 0, sb_i = 0, as = 0;
       uint32_t pha = 0, phb = 0, aph = 0;
       for (int ptile = pair; ptile < total_pair_tiles; ptile += num_pairs) {
@@ -177,31 +180,35 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         for (int c = 0; c < p.kb_per_tap; ++c) {
           mbar_wait(afull_bar(sa_i), pha);
           tc_fence_after();
-          const uint32_t sa = sbase + sa_i * A_BUF_BYTES;
+          const uint64_t ad_c = ad0 + (uint64_t)((sa_i * A_BUF_BYTES) >> 4);
           for (int tap = 0; tap < taps; ++tap) {
             mbar_wait(bfull_bar(sb_i), phb);
             tc_fence_after();
-            const uint32_t sb = sbase + B_OFF + sb_i * B_BYTES;
+            if (elect_one()) {
+              const uint64_t bd_s = bd0 + (uint64_t)((sb_i * B_BYTES) >> 4);
 #pragma unroll
-            for (int j = 0; j < BK / 16; ++j) {
-              // A: rows [tap, tap + 128) of the halo tile = the same bytes, start shifted by tap * 128 B
-              const uint64_t ad = make_smem_desc(sa + tap * 128u + j * 32u, 16u, 1024u);
-              const uint64_t bd = make_smem_desc(sb + j * b_kstep, b_lbo, 1024u);
-              umma_f16_2sm(tacc, ad, bd, idesc, (c > 0 || tap > 0 || j > 0) ? 1u : 0u);
+              for (int j = 0; j < BK / 16; ++j) {
+                // A: rows [tap, tap + 128) of the halo tile = the same bytes, start shifted by tap * 128 B
+                umma_f16_2sm(tacc, ad_c + (uint64_t)((tap * 128 + j * 32) >> 4), bd_s + (uint64_t)((j * b_kstep) >> 4),
+                             idesc, (c > 0 || tap > 0 || j > 0) ? 1u : 0u);
+              }
+              umma_commit_2sm(bempty_bar(sb_i));
+              if (tap == taps - 1) {
+                umma_commit_2sm(aempty_bar(sa_i));  // every tap of this channel block has read the halo tile
+                if (c == p.kb_per_tap - 1) umma_commit_2sm(tfull_bar(as));
+              }
             }
-            umma_commit_2sm(bempty_bar(sb_i));
+            __syncwarp();
             if (++sb_i == B_STAGES) {
               sb_i = 0;
               phb ^= 1u;
             }
           }
-          umma_commit_2sm(aempty_bar(sa_i));  // every tap of this channel block has read the halo tile
           if (++sa_i == A_BUFS) {
             sa_i = 0;
             pha ^= 1u;
           }
         }
-        umma_commit_2sm(tfull_bar(as));
         if (++as == 2) {
           as = 0;
           aph ^= 1u;

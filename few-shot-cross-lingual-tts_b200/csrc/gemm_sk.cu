@@ -209,11 +209,13 @@ gemm_sk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   } else if (warp == 1) {
-    // ======================= MMA issuer (leader CTA only, one thread) =======================
-    if (leader && lane == 0 && item0 < item1) {
+    // ======================= MMA issuer (leader CTA only; warp-uniform loop, one elected lane issues) ========
+    if (leader && item0 < item1) {
       const uint32_t idesc = make_idesc_bf16(256, BN, 0, p.b_mn);
       const uint32_t b_lbo = p.b_mn ? kChunkBytes : 16u;
       const uint32_t b_kstep = p.b_mn ? 16u * 128u : 32u;
+      const uint64_t ad0 = make_smem_desc(sbase + A_OFF, 16u, 1024u);
+      const uint64_t bd0 = make_smem_desc(sbase + B_OFF, b_lbo, 1024u);
       int s = 0, as = 0, cur_tn = -1;
       uint32_t ph = 0, aph = 0, bph = 0;
       for (int item = item0; item < item1; ++item) {
@@ -226,32 +228,36 @@ gemm_sk_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         mbar_wait(tempty_bar(as), aph ^ 1u);
         tc_fence_after();
         const uint32_t tacc = tmem_base + as * BN;
+        const bool last_of_tn = (item + 1 == item1) || ((item + 1) / pair_rows != tn);
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(full_bar(s), ph);
           tc_fence_after();
-          const uint32_t sa = sbase + A_OFF + s * A_BYTES;
-          const uint32_t sb = sbase + B_OFF + kb * BKB_BYTES;
-          if (!(p.dbg & 8)) {
+          if (elect_one()) {
+            const uint64_t ad_s = ad0 + (uint64_t)((s * A_BYTES) >> 4);
+            const uint64_t bd_k = bd0 + (uint64_t)((kb * BKB_BYTES) >> 4);
+            if (!(p.dbg & 8)) {
 #pragma unroll
-            for (int j = 0; j < BK / 16; ++j) {
-              const uint64_t ad = make_smem_desc(sa + j * 32u, 16u, 1024u);
-              const uint64_t bd = make_smem_desc(sb + j * b_kstep, b_lbo, 1024u);
-              umma_f16_2sm(tacc, ad, bd, idesc, (kb > 0 || j > 0) ? 1u : 0u);
+              for (int j = 0; j < BK / 16; ++j) {
+                umma_f16_2sm(tacc, ad_s + (uint64_t)((j * 32) >> 4), bd_k + (uint64_t)((j * b_kstep) >> 4), idesc,
+                             (kb > 0 || j > 0) ? 1u : 0u);
+              }
+            }
+            umma_commit_2sm(empty_bar(s));
+            if (kb == num_kb - 1) {
+              umma_commit_2sm(tfull_bar(as));
+              if (last_of_tn && item + 1 < item1) umma_commit_2sm(bempty_bar);  // the weights may be replaced
             }
           }
-          umma_commit_2sm(empty_bar(s));
+          __syncwarp();
           if (++s == STAGES) {
             s = 0;
             ph ^= 1u;
           }
         }
-        umma_commit_2sm(tfull_bar(as));
         if (++as == 2) {
           as = 0;
           aph ^= 1u;
         }
-        const bool last_of_tn = (item + 1 == item1) || ((item + 1) / pair_rows != tn);
-        if (last_of_tn && item + 1 < item1) umma_commit_2sm(bempty_bar);  // the weights may be replaced
       }
     }
   } else if (warp >= 4) {

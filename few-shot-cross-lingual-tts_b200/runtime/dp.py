@@ -58,6 +58,7 @@ class GradBuckets:
         self._late = set()  # buckets that received a gradient announcement after they went on the wire
         self.comm_stream = torch.cuda.Stream(device) if device.type == "cuda" else None
         self.overlap = True
+        self.sync_enabled = True  # False: gradients stay local (inner-loop steps of the few-shot adaptation)
         # NCCL averages inside the collective (no separate divide pass over the 138 MB); gloo has no AVG
         self._avg = False
         if self.world > 1:
@@ -65,6 +66,30 @@ class GradBuckets:
                 self._avg = dist.get_backend(process_group) == "nccl"
             except Exception:
                 self._avg = False
+
+    def rehome_parameters(self):
+        """Move every parameter into ONE flat fp32 buffer with the same element offsets (and the same [Co][k][Ci]
+        order for Conv1d weights) as its gradient in `self.flat`, so that optimizers and the few-shot inner loop
+        update all of them with one launch.  Idempotent; returns the flat parameter buffer."""
+        fp = getattr(self, "flat_param", None)
+        if fp is not None:
+            return fp
+        g = self.flat
+        fp = torch.zeros_like(g)
+        for p in self.params:
+            off = p.main_grad.data_ptr() - g.data_ptr()
+            assert off % 4 == 0
+            flat = fp[off // 4: off // 4 + p.numel()]
+            if p.main_grad.is_contiguous():
+                view = flat.view(p.shape)
+            else:  # Conv1d weight whose gradient is kept in [Co][k][Ci] order: same element order for the value
+                Co, Ci, k = p.shape
+                assert p.main_grad.stride() == (k * Ci, 1, Ci)
+                view = flat.view(Co, k, Ci).permute(0, 2, 1)
+            view.copy_(p.data)
+            p.data = view
+        self.flat_param = fp
+        return fp
 
     # -- per-step protocol ---------------------------------------------------------------------------
     def zero(self):
@@ -99,7 +124,7 @@ class GradBuckets:
 
     def notify(self, params):
         """Called by the backward functions when the gradients of `params` are final."""
-        if self.world == 1 or not self.overlap:
+        if self.world == 1 or not self.overlap or not self.sync_enabled:
             return
         for p in params:
             b = self._bucket_of.get(id(p))
@@ -121,7 +146,7 @@ class GradBuckets:
             raise RuntimeError("GradBuckets: gradients of bucket(s) %s were announced again after the bucket had been "
                                "all-reduced (a module ran twice in one backward pass); set buckets.overlap = False "
                                "for such steps so that every bucket is reduced in finish()" % sorted(self._late))
-        if self.world > 1:
+        if self.world > 1 and self.sync_enabled:
             for b in range(len(self.buckets)):
                 if not self._launched[b]:
                     self._launch(b)

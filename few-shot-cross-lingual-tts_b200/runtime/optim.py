@@ -43,19 +43,7 @@ class FusedAdam:
         if not g.is_cuda:
             raise RuntimeError("FusedAdam runs on sm_100a CUDA kernels only (there is no CPU path)")
         # re-home the parameters: same offsets as their gradients in buckets.flat
-        self.flat_param = torch.zeros_like(g)
-        for p in buckets.params:
-            off = p.main_grad.data_ptr() - g.data_ptr()
-            assert off % 4 == 0
-            flat = self.flat_param[off // 4: off // 4 + p.numel()]
-            if p.main_grad.is_contiguous():
-                view = flat.view(p.shape)
-            else:  # Conv1d weight whose gradient is kept in [Co][k][Ci] order: same element order for the value
-                Co, Ci, k = p.shape
-                assert p.main_grad.stride() == (k * Ci, 1, Ci)
-                view = flat.view(Co, k, Ci).permute(0, 2, 1)
-            view.copy_(p.data)
-            p.data = view
+        self.flat_param = buckets.rehome_parameters()
         self.exp_avg = torch.zeros_like(g)
         self.exp_avg_sq = torch.zeros_like(g)
         self.step_dev = torch.zeros(1, dtype=torch.int64, device=g.device)

@@ -337,6 +337,9 @@ int fs2_adam_step_f32(float* p, const float* g, float* m, float* v, int64_t n, c
                       float max_norm, int sched_type, int warmup, const int32_t* anneal_steps, int n_anneal,
                       float anneal_rate, void* stream);
 int fs2_optim_advance(int64_t* step, float* gnorm_sq, float* gnorm_out, void* stream);
+/* y += alpha * x on flat f32 buffers (16-byte aligned): the inner-loop SGD step of the first-order few-shot      */
+/* adaptation, theta' = theta - lr * grad (config/algorithm/language/fscl-orig.yaml:38-43).      */
+int fs2_axpy_f32(float* y, const float* x, float alpha, int64_t n, void* stream);
 
 #ifdef __cplusplus
 }

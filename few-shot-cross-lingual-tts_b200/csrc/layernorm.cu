@@ -40,8 +40,9 @@ struct LnArgs {
 
 __device__ __forceinline__ bool ln_row_masked(const LnArgs& a, long long row) {
   if (!a.lens) return false;
-  const int b = row / a.T;
-  return row - (long long)b * a.T >= a.lens[b];
+  const int r = (int)row;  // rows = B * T < 2^31 (checked on the host): 32-bit division
+  const int b = r / a.T;
+  return r - b * a.T >= a.lens[b];
 }
 
 template <int NV>
@@ -55,6 +56,19 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const LnArgs a) {
   const uint64_t seed = mix_seed(a.seed_dev, a.seed);
   const long long stride = (long long)gridDim.x * warps_per_block;
   long long row = (long long)blockIdx.x * warps_per_block + (threadIdx.x >> 5);
+  float gam[NV][8], bet[NV][8];  // this lane's affine parameters: loop invariant
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int col = i * 256 + lane * 8;
+    const float4 g0 = *reinterpret_cast<const float4*>(a.gamma + col);
+    const float4 g1 = *reinterpret_cast<const float4*>(a.gamma + col + 4);
+    const float4 b0 = *reinterpret_cast<const float4*>(a.beta + col);
+    const float4 b1 = *reinterpret_cast<const float4*>(a.beta + col + 4);
+    gam[i][0] = g0.x; gam[i][1] = g0.y; gam[i][2] = g0.z; gam[i][3] = g0.w;
+    gam[i][4] = g1.x; gam[i][5] = g1.y; gam[i][6] = g1.z; gam[i][7] = g1.w;
+    bet[i][0] = b0.x; bet[i][1] = b0.y; bet[i][2] = b0.z; bet[i][3] = b0.w;
+    bet[i][4] = b1.x; bet[i][5] = b1.y; bet[i][6] = b1.z; bet[i][7] = b1.w;
+  }
   // software pipeline: the next row's 16-byte vectors are in flight while this row is reduced
   bf16x8 nx[NV], nr[NV];
   bool nmask = row < a.rows && ln_row_masked(a, row);  // padded rows are never read
@@ -130,14 +144,8 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const LnArgs a) {
       const int col = i * 256 + lane * 8;
       float o[8];
       {
-        const float4 g0 = *reinterpret_cast<const float4*>(a.gamma + col);
-        const float4 g1 = *reinterpret_cast<const float4*>(a.gamma + col + 4);
-        const float4 b0 = *reinterpret_cast<const float4*>(a.beta + col);
-        const float4 b1 = *reinterpret_cast<const float4*>(a.beta + col + 4);
-        const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-        const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = (v[i][j] - mean) * rstd * g[j] + bb[j];
+        for (int j = 0; j < 8; ++j) o[j] = (v[i][j] - mean) * rstd * gam[i][j] + bet[i][j];
         if (a.drop_mode == 2 && thresh) {
           const uint32_t keep = dropout_keep8(seed, (uint64_t)row * C + col, thresh);
 #pragma unroll
@@ -167,6 +175,15 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const LnArgs a) {
 
   const long long stride = (long long)gridDim.x * warps_per_block;
   long long row = (long long)blockIdx.x * warps_per_block + warp;
+  float gam[NV][8];  // loop invariant
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int col = i * 256 + lane * 8;
+    const float4 g0 = *reinterpret_cast<const float4*>(a.gamma + col);
+    const float4 g1 = *reinterpret_cast<const float4*>(a.gamma + col + 4);
+    gam[i][0] = g0.x; gam[i][1] = g0.y; gam[i][2] = g0.z; gam[i][3] = g0.w;
+    gam[i][4] = g1.x; gam[i][5] = g1.y; gam[i][6] = g1.z; gam[i][7] = g1.w;
+  }
   bf16x8 nx[NV], nd[NV], nr[NV];
   bool nmask = row < a.rows && ln_row_masked(a, row);  // padded rows are never read
   if (row < a.rows && !nmask) {
@@ -237,15 +254,12 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const LnArgs a) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) xv[j] += r[j];
       }
-      const float4 g0 = *reinterpret_cast<const float4*>(a.gamma + col);
-      const float4 g1 = *reinterpret_cast<const float4*>(a.gamma + col + 4);
-      const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         xh[i][j] = (xv[j] - mean) * rstd;
         acc_g[i][j] += dyv[j] * xh[i][j];
         acc_b[i][j] += dyv[j];
-        gy[i][j] = dyv[j] * g[j];
+        gy[i][j] = dyv[j] * gam[i][j];
         s1 += gy[i][j];
         s2 += gy[i][j] * xh[i][j];
       }
@@ -294,6 +308,7 @@ static int ln_grid(int rows, int cap) {
 template <bool BWD>
 static int ln_dispatch(const LnArgs& a, int C, cudaStream_t s) {
   if (a.rows <= 0) return 0;
+  if ((long long)a.rows >= (1ll << 31) - 1) return set_error("layernorm: B * T must be < 2^31");
   if (a.p_drop < 0.f || a.p_drop >= 1.f) return set_error("layernorm: dropout p must be in [0,1)");
   const int grid = BWD ? ln_grid(a.rows, 148 * 4) : ln_grid(a.rows, 148 * 8);
   switch (C) {

@@ -46,13 +46,17 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
-// ---- Philox4x32-10 (Salmon et al.), one call -> 4 x 32 random bits --------------------------------
+// ---- Philox4x32-7 (Salmon et al., "Parallel random numbers: as easy as 1, 2, 3": 7 rounds is the smallest
+// crush-resistant variant; the default 10 is a safety margin), one call -> 4 x 32 random bits.  The dropout masks
+// are regenerated (never stored) in the backward kernels, and these rounds are a visible share of the otherwise
+// HBM-bound LayerNorm / BatchNorm kernels' instruction stream.
+constexpr int kPhiloxRounds = 7;
 __device__ __forceinline__ uint4 philox4x32(uint64_t seed, uint64_t ctr) {
   uint32_t k0 = static_cast<uint32_t>(seed), k1 = static_cast<uint32_t>(seed >> 32);
   uint32_t c0 = static_cast<uint32_t>(ctr), c1 = static_cast<uint32_t>(ctr >> 32), c2 = 0x243F6A88u,
            c3 = 0x85A308D3u;
 #pragma unroll
-  for (int r = 0; r < 10; ++r) {
+  for (int r = 0; r < kPhiloxRounds; ++r) {
     const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
     const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
     const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;

@@ -21,10 +21,11 @@ def test_first_order_inner_loop_matches_torch_loop_on_the_oracle():
     model = disable_dropout(model.cuda().train())
     loss_fn = M.FastSpeech2Loss(cfg)
     kw = dict(average_spk_emb=True)
-    k, lr = 3, 0.02  # a learning rate large enough for the adaptation to matter in three steps
+    k, lr = 3, 0.002  # large enough for three plain-SGD steps to matter (8.50 -> 5.21 on the oracle), small enough to be stable
     support = [synth.make_batch(B=8, src_len=(20, 70), dur=synth.uniform_dur(2, 9), seed=300 + i, n_speaker=11,
                                 n_lang=8) for i in range(k)]
-    query = synth.make_batch(B=8, src_len=(20, 70), dur=synth.uniform_dur(2, 9), seed=399, n_speaker=11, n_lang=8)
+    # the query repeats the first support batch: three SGD steps at this rate must lower its loss visibly
+    query = synth.make_batch(B=8, src_len=(20, 70), dur=synth.uniform_dur(2, 9), seed=300, n_speaker=11, n_lang=8)
     sd0 = {n: v.detach().cpu().clone() for n, v in model.state_dict().items()}
 
     task = rt.FirstOrderTaskStep(model, loss_fn, inner_lr=lr, model_kwargs=kw)
@@ -56,7 +57,7 @@ def test_first_order_inner_loop_matches_torch_loop_on_the_oracle():
                 sd[n] = sd[n] - lr * gi
     o_losses, o_grads = grads_of(sd, query)
     adapted_loss = float(o_losses[0])
-    assert abs(adapted_loss - unadapted_loss) > 0.05 * abs(unadapted_loss)  # the inner loop changed the model
+    assert adapted_loss < unadapted_loss - 0.02 * abs(unadapted_loss), (adapted_loss, unadapted_loss)
     assert abs(float(losses[0]) - adapted_loss) <= 1e-2 * abs(adapted_loss), (float(losses[0]), adapted_loss)
     gmax = max(float(g.norm()) for g in o_grads.values() if g is not None)
     worst = (1.0, None)

@@ -19,7 +19,7 @@ _TENSOR_SLOTS = (2, 3, 4, 6, 7, 9, 10, 11, 12)
 
 class TrainStep:
     def __init__(self, model, loss_fn, example_batch, use_graph=True, buckets=None, device=None, optimizer=None,
-                 embedding_model=None, model_kwargs=None):
+                 embedding_model=None, model_kwargs=None, wcache=None):
         """optimizer: optional runtime.FusedAdam built on `buckets`; its clip + Adam + LR-schedule launches then
         become part of the captured step.
 
@@ -48,7 +48,8 @@ class TrainStep:
                 raise ValueError("TrainStep: `buckets` does not cover the embedding model's parameters")
         ops.set_grad_listener(self.buckets.notify)
         # all bf16 operand copies of the weights are refreshed by one launch at the start of every step
-        self.wcache = ops.WeightCache(model)
+        # (`wcache`: share one set of copies between several captured steps, runtime/cache.py)
+        self.wcache = wcache if wcache is not None else ops.WeightCache(model)
         self.static = list(example_batch)
         self.host = {}
         for i in _TENSOR_SLOTS:

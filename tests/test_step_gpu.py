@@ -128,3 +128,41 @@ def test_fused_adam_first_step_moves_every_weight_against_its_gradient():
         assert torch.allclose(delta.abs()[big], torch.full_like(delta[big], lr), rtol=2e-2), k
     # state_dict still has the reference's shapes, whatever the storage order
     assert model.state_dict()["decoder.layer_stack.0.pos_ffn.w_1.weight"].shape == (1024, 256, 9)
+
+
+def test_shape_bucketed_step_cache_reuses_graphs_and_matches_the_padded_batch():
+    """runtime.TrainStepCache: batches with different (max_src_len, max_mel_len) that fall into one bucket share ONE
+    captured graph; the result equals a fresh step on the bucket-padded batch (which is what the reference computes
+    for that padded batch), and a batch of another bucket triggers exactly one more capture."""
+    rt = sub("runtime")
+    model, loss_fn, _ = _build()
+    cache = rt.TrainStepCache(model, loss_fn, bucket=(32, 128), max_graphs=2)
+    b1 = synth.make_batch(B=4, src_len=(10, 28), dur=synth.uniform_dur(1, 4), seed=41)
+    b2 = synth.make_batch(B=4, src_len=(12, 30), dur=synth.uniform_dur(1, 4), seed=42)
+    assert (int(b1[5]), int(b1[8])) != (int(b2[5]), int(b2[8])) and cache.key_for(b1) == cache.key_for(b2)
+    l1 = cache.run(b1).clone()
+    g1 = cache.buckets.flat.clone()
+    l2 = cache.run(b2).clone()
+    assert cache.captures == 1 and len(cache.steps) == 1
+    assert not torch.allclose(l1, l2)
+    # the same batch again reproduces itself bit-exactly through the shared graph (activations deterministic;
+    # atomically accumulated weight gradients to fp32 round-off)
+    l1b = cache.run(b1).clone()
+    assert torch.equal(l1, l1b) and rel_err(cache.buckets.flat, g1) < 1e-5
+    # against an independent eager step on the explicitly padded batch
+    model_e, loss_fn_e, _ = _build()
+    key = cache.key_for(b1)
+    padded = rt.pad_batch(b1, key[1], key[2])
+    assert padded[3].shape[1] == key[1] and padded[6].shape[1] == key[2] and padded[8] == key[2]
+    pb = cuda_batch(padded)
+    out = model_e(pb[2], pb[3], *pb[4:12], lang_args=pb[12])
+    le = loss_fn_e(pb[:-1], out)
+    for a, r in zip(l1.tolist(), [float(x) for x in le]):
+        assert abs(a - r) <= 1e-4 * abs(r), (a, r)
+    # another bucket: one more capture; a third bucket evicts the least recently used graph (max_graphs = 2)
+    b3 = synth.make_batch(B=4, src_len=(40, 60), dur=synth.uniform_dur(2, 5), seed=43)
+    cache.run(b3)
+    assert cache.captures == 2 and len(cache.steps) == 2
+    b4 = synth.make_batch(B=4, src_len=(70, 90), dur=synth.uniform_dur(2, 5), seed=44)
+    cache.run(b4)
+    assert cache.captures == 3 and len(cache.steps) == 2 and cache.key_for(b1) not in cache.steps

@@ -397,16 +397,17 @@ def kernel_rooflines(base, cfg, bf16_peak, hbm_peak, step_ms, traffic):
     stats, dstats = torch.empty(2, C, device=dev), torch.empty(2, C, device=dev)
     gb, bb = torch.ones(C, device=dev), torch.zeros(C, device=dev)
     nxt, dyb = torch.empty_like(yb), torch.empty_like(yb)
+    keepb = torch.empty(M, C // 8, dtype=torch.uint8, device=dev)
     seed = ops._Rng.tensor(dev)
     rec("BatchNorm statistics (fixed-order, + finalize)", M * C * 2,
         lambda: L.fs2_bn_stats_bf16(yb.data_ptr(), M, C, ws.data_ptr(), stats.data_ptr(), 0.1, None, None, None,
                                     ops._st()), 3)
     rec("BatchNorm apply + tanh + dropout", 2 * M * C * 2,
         lambda: L.fs2_bn_apply_fwd(yb.data_ptr(), stats.data_ptr(), gb.data_ptr(), bb.data_ptr(), M, C, 1, 0.5, 7,
-                                   seed.data_ptr(), nxt.data_ptr(), None, None, ops._st()), 3)
+                                   seed.data_ptr(), nxt.data_ptr(), None, None, keepb.data_ptr(), ops._st()), 3)
     rec("BatchNorm bwd (reduce + finalize + apply)", 5 * M * C * 2,
         lambda: L.fs2_bn_bwd(dob.data_ptr(), 0, yb.data_ptr(), stats.data_ptr(), gb.data_ptr(), bb.data_ptr(), M, C,
-                             1, 0.5, 7, seed.data_ptr(), ws.data_ptr(), dstats.data_ptr(), None, None,
+                             1, 0.5, 7, seed.data_ptr(), keepb.data_ptr(), ws.data_ptr(), dstats.data_ptr(), None, None,
                              dyb.data_ptr(), ops._st()), 3)
     return roof, fams, hb
 

@@ -37,6 +37,8 @@ struct BnArgs {
   int dout_is_f32;
   __nv_bfloat16* dy;
   int rows_per_block;
+  uint8_t* keep_out;       // forward (optional): dropout keep bits, one byte per 8 channels [M][C/8]
+  const uint8_t* keep_in;  // backward (optional): the same bits instead of regenerating the Philox stream
 };
 
 __device__ __forceinline__ void load_vec8(const __nv_bfloat16* p, float (&f)[8]) { unpack8(ld8(p), f); }
@@ -195,6 +197,7 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const BnArgs a) {
       float (&f)[8] = u == 0 ? f0 : f1;
       const long long rr = r + u * rs;
       const uint32_t keep = thresh ? dropout_keep8(seed, (uint64_t)rr * a.C + c, thresh) : 0xFFu;
+      if (a.keep_out) a.keep_out[rr * vpr + v] = static_cast<uint8_t>(keep);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         float z = fmaf(f[j], A[j], Bc[j]);
@@ -238,9 +241,7 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const BnArgs a) {
     const uint64_t seed = mix_seed(a.seed_dev, a.seed);
     const long long r0 = (long long)blockIdx.x * a.rows_per_block;
     const long long r1 = min(r0 + a.rows_per_block, a.M);
-    for (long long r = r0 + ro; r < r1; r += rs) {
-      float f[8], g[8];
-      load_vec8(a.y + r * a.C + c, f);
+    auto load_g = [&](long long r, float (&g)[8]) {
       if (a.dout_is_f32) {
         const float4* d = reinterpret_cast<const float4*>(static_cast<const float*>(a.dout) + r * a.C + c);
         const float4 d0 = d[0], d1 = d[1];
@@ -249,7 +250,9 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const BnArgs a) {
       } else {
         load_vec8(static_cast<const __nv_bfloat16*>(a.dout) + r * a.C + c, g);
       }
-      const uint32_t keep = thresh ? dropout_keep8(seed, (uint64_t)r * a.C + c, thresh) : 0xFFu;
+    };
+    auto accum = [&](long long r, const float (&f)[8], const float (&g)[8], uint32_t kbits) {
+      const uint32_t keep = !thresh ? 0xFFu : (a.keep_in ? kbits : dropout_keep8(seed, (uint64_t)r * a.C + c, thresh));
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const float yh = fmaf(f[j], rsd[j], sh[j]);
@@ -261,6 +264,21 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const BnArgs a) {
         sb[j] += gg;
         sg[j] += gg * yh;
       }
+    };
+    for (long long r = r0 + ro; r < r1; r += 2 * rs) {  // two rows per iteration: four 16-byte loads in flight
+      const bool two = r + rs < r1;
+      float f0[8], g0[8], f1[8], g1[8];
+      uint32_t k0 = 0xFFu, k1 = 0xFFu;
+      load_vec8(a.y + r * a.C + c, f0);
+      load_g(r, g0);
+      if (a.keep_in) k0 = a.keep_in[r * vpr + v];
+      if (two) {
+        load_vec8(a.y + (r + rs) * a.C + c, f1);
+        load_g(r + rs, g1);
+        if (a.keep_in) k1 = a.keep_in[(r + rs) * vpr + v];
+      }
+      accum(r, f0, g0, k0);
+      if (two) accum(r + rs, f1, g1, k1);
     }
   }
   block_partial_store(s_acc, sb, sg, v, ro, rs, a.C, a.part + (size_t)blockIdx.x * 2 * a.C);
@@ -301,7 +319,8 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BnArgs a) {
     } else {
       load_vec8(static_cast<const __nv_bfloat16*>(a.dout) + r * a.C + c, g);
     }
-    const uint32_t keep = thresh ? dropout_keep8(seed, (uint64_t)r * a.C + c, thresh) : 0xFFu;
+    const uint32_t keep = !thresh ? 0xFFu : (a.keep_in ? a.keep_in[r * vpr + v]
+                                                       : dropout_keep8(seed, (uint64_t)r * a.C + c, thresh));
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const float yh = fmaf(f[j], rsd[j], sh[j]);
@@ -326,6 +345,12 @@ static int rows_per_block_for(long long M) {
   if (rpb < 32) rpb = 32;
   return (int)rpb;
 }
+// the two reduction kernels: fewer, longer blocks (4 per SM) -> 4x fewer partial vectors to write and re-read
+static int rows_per_block_reduce(long long M) {
+  long long rpb = (M + 148 * 4 - 1) / (148 * 4);
+  if (rpb < 32) rpb = 32;
+  return (int)rpb;
+}
 static unsigned ew_grid(long long n_vec) {
   long long g = (n_vec + 255) / 256;
   if (g > 148 * 8) g = 148 * 8;
@@ -339,7 +364,7 @@ extern "C" {
 // floats of workspace the statistics / backward reductions need for [M][C] (per-block partial sums)
 int64_t fs2_bn_workspace_floats(int64_t M, int C) {
   if (M <= 0 || C <= 0) return 0;
-  const int rpb = fs2::rows_per_block_for(M);
+  const int rpb = fs2::rows_per_block_reduce(M);
   return ((M + rpb - 1) / rpb) * 2 * C;
 }
 
@@ -362,7 +387,7 @@ int fs2_bn_stats_bf16(const void* y, int64_t M, int C, float* ws, float* stats, 
   fs2::BnArgs a{};
   a.y = static_cast<const __nv_bfloat16*>(y);
   a.M = M; a.C = C; a.part = ws;
-  a.rows_per_block = fs2::rows_per_block_for(M);
+  a.rows_per_block = fs2::rows_per_block_reduce(M);
   const unsigned grid = (unsigned)((M + a.rows_per_block - 1) / a.rows_per_block);
   const int rs = 256 / (C / 8);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -374,10 +399,11 @@ int fs2_bn_stats_bf16(const void* y, int64_t M, int C, float* ws, float* stats, 
 }
 
 // out = dropout(act(bn(y)));  exactly one of out_bf16 / out_f32 is non-NULL; res_f32 (optional) is
-// added to the f32 output (the postnet residual).
+// added to the f32 output (the postnet residual).  keep_out (optional, uint8 [M][C/8]): the dropout keep bits, so
+// that the backward reads 1 bit per element instead of regenerating the Philox stream in both of its passes.
 int fs2_bn_apply_fwd(const void* y, const float* stats, const float* gamma, const float* beta, int64_t M,
                      int C, int act_tanh, float p_drop, uint64_t seed, const uint64_t* seed_dev,
-                     void* out_bf16, float* out_f32, const float* res_f32, void* stream) {
+                     void* out_bf16, float* out_f32, const float* res_f32, uint8_t* keep_out, void* stream) {
   if (int rc = fs2::bn_check(M, C)) return rc;
   if ((out_bf16 == nullptr) == (out_f32 == nullptr)) return fs2::set_error("bn_apply: one output");
   fs2::BnArgs a{};
@@ -385,6 +411,7 @@ int fs2_bn_apply_fwd(const void* y, const float* stats, const float* gamma, cons
   a.M = M; a.C = C; a.fstats = stats; a.gamma = gamma; a.beta = beta;
   a.act_tanh = act_tanh; a.p_drop = p_drop; a.seed = seed; a.seed_dev = seed_dev;
   a.out_bf16 = static_cast<__nv_bfloat16*>(out_bf16); a.out_f32 = out_f32; a.res_f32 = res_f32;
+  a.keep_out = p_drop > 0.f ? keep_out : nullptr;
   a.rows_per_block = fs2::rows_per_block_for(M);
   FS2_LAUNCH((fs2::bn_apply_kernel), (unsigned)((M + a.rows_per_block - 1) / a.rows_per_block), 256, 0, static_cast<cudaStream_t>(stream), a);
   fs2::count_launch();
@@ -396,24 +423,27 @@ int fs2_bn_apply_fwd(const void* y, const float* stats, const float* gamma, cons
 // dout is bf16 [M][C] (dout_is_f32 = 0) or f32.
 int fs2_bn_bwd(const void* dout, int dout_is_f32, const void* y, const float* stats, const float* gamma,
                const float* beta, int64_t M, int C, int act_tanh, float p_drop, uint64_t seed,
-               const uint64_t* seed_dev, float* ws, float* dstats, float* dbeta_acc, float* dgamma_acc, void* dy,
-               void* stream) {
+               const uint64_t* seed_dev, const uint8_t* keep_in, float* ws, float* dstats, float* dbeta_acc,
+               float* dgamma_acc, void* dy, void* stream) {
   if (int rc = fs2::bn_check(M, C)) return rc;
   fs2::BnArgs a{};
   a.y = static_cast<const __nv_bfloat16*>(y);
   a.M = M; a.C = C; a.fstats = stats; a.gamma = gamma; a.beta = beta;
   a.act_tanh = act_tanh; a.p_drop = p_drop; a.seed = seed; a.seed_dev = seed_dev;
   a.dout = dout; a.dout_is_f32 = dout_is_f32; a.stats = dstats; a.part = ws;
+  a.keep_in = p_drop > 0.f ? keep_in : nullptr;
   a.dy = static_cast<__nv_bfloat16*>(dy);
-  a.rows_per_block = fs2::rows_per_block_for(M);
+  a.rows_per_block = fs2::rows_per_block_reduce(M);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  const unsigned grid = (unsigned)((M + a.rows_per_block - 1) / a.rows_per_block);
+  const unsigned grid_r = (unsigned)((M + a.rows_per_block - 1) / a.rows_per_block);
   const int rs = 256 / (C / 8);
-  FS2_LAUNCH((fs2::bn_bwd_reduce_kernel), grid, 256, (size_t)rs * 2 * C * sizeof(float), s, a);
+  FS2_LAUNCH((fs2::bn_bwd_reduce_kernel), grid_r, 256, (size_t)rs * 2 * C * sizeof(float), s, a);
   fs2::count_launch();
   if (int rc = fs2::check_launch("bn_bwd_reduce_kernel")) return rc;
-  if (int rc = bn_finalize(ws, (int)grid, C, dstats, M, 0.f, nullptr, nullptr, nullptr, dbeta_acc, dgamma_acc, s))
+  if (int rc = bn_finalize(ws, (int)grid_r, C, dstats, M, 0.f, nullptr, nullptr, nullptr, dbeta_acc, dgamma_acc, s))
     return rc;
+  a.rows_per_block = fs2::rows_per_block_for(M);
+  const unsigned grid = (unsigned)((M + a.rows_per_block - 1) / a.rows_per_block);
   FS2_LAUNCH((fs2::bn_bwd_apply_kernel), grid, 256, 0, s, a);
   fs2::count_launch();
   return fs2::check_launch("bn_bwd_apply_kernel");

@@ -1094,7 +1094,7 @@ class PostNetFn(torch.autograd.Function):
         M = B * T
         x = torch.empty(B, T, n_mel, dtype=BF16, device=dev)
         _ck(_L().fs2_cast_f32_bf16(_p(mel), mel.numel(), _p(x), _st()), "cast(mel)")
-        saved, salts, params = [], [], []
+        saved, salts, params, keeps = [], [], [], []
         out = None
         p = p_drop if training else 0.0
         for i in range(n_layers):
@@ -1112,20 +1112,25 @@ class PostNetFn(torch.autograd.Function):
                 stats = torch.stack([rm * M, (rv + rm * rm) * M]).to(F32).contiguous()
             salt = _Rng.next_salt()
             seed_dev = _Rng.tensor(dev) if p > 0 else None
+            # dropout keep bits (1 bit / element) for the backward, which would otherwise regenerate the Philox
+            # stream in both of its passes
+            keep = torch.empty(M, Co // 8, dtype=torch.uint8, device=dev) if (p > 0 and training) else None
             if last:
                 out = torch.empty(B, T, Co, dtype=F32, device=dev)
                 _ck(_L().fs2_bn_apply_fwd(_p(y), _p(stats), _p(bw.detach()), _p(bb.detach()), M, Co, 0, p, salt,
-                                          _p(seed_dev), None, _p(out), _p(mel), _st()), "bn_apply(last)")
+                                          _p(seed_dev), None, _p(out), _p(mel), _p(keep), _st()), "bn_apply(last)")
                 nx = None
             else:
                 nx = torch.empty(B, T, Co, dtype=BF16, device=dev)
                 _ck(_L().fs2_bn_apply_fwd(_p(y), _p(stats), _p(bw.detach()), _p(bb.detach()), M, Co, 1, p, salt,
-                                          _p(seed_dev), _p(nx), None, None, _st()), "bn_apply")
+                                          _p(seed_dev), _p(nx), None, None, _p(keep), _st()), "bn_apply")
             saved += [x, y, stats, wp]
+            keeps.append(keep)
             salts.append(salt)
             params.append((cw, cb, bw, bb))
             x = nx
         ctx.save_for_backward(*saved)
+        ctx.keeps = keeps
         ctx.params = params
         ctx.cfg = (p, n_layers, salts, training)
         return out
@@ -1152,8 +1157,8 @@ class PostNetFn(torch.autograd.Function):
             (gcw, rcw), (gcb, rcb), (gbw, rbw), (gbb, rbb) = (grad_target(t) for t in (cw, cb, bw, bb))
             # dbeta / dgamma are accumulated into the parameter gradients by the reduction's finalize kernel
             _ck(_L().fs2_bn_bwd(_p(d), d_is_f32, _p(y), _p(stats), _p(bw.detach()), _p(bb.detach()), M, Co,
-                                0 if i == n_layers - 1 else 1, p, salts[i], _p(seed_dev), _p(ws), _p(dstats),
-                                _p(gbb), _p(gbw), _p(dy), _st()), "bn_bwd")
+                                0 if i == n_layers - 1 else 1, p, salts[i], _p(seed_dev), _p(ctx.keeps[i]), _p(ws),
+                                _p(dstats), _p(gbb), _p(gbw), _p(dy), _st()), "bn_bwd")
             with fork_side():
                 conv_wgrad(dy, x, gcw)
             # conv.bias: its gradient is sum_rows(dy), and the backward of a train-mode BatchNorm removes the

@@ -263,18 +263,20 @@ int fs2_loss_bwd(const float* gout6, const float* out10, const float* mel_pred, 
 /* fs2_bn_stats_bf16 also performs nn.BatchNorm1d's running-statistics update (momentum,        */
 /* unbiased variance, num_batches_tracked += 1) when running_mean is non-NULL.                  */
 /* fs2_bn_bwd: dstats f32 [2][C] written (dbeta, dgamma); dbeta_acc / dgamma_acc (optional,     */
-/* f32 [C]) accumulate them into the parameter gradients.                                       */
+/* f32 [C]) accumulate them into the parameter gradients.  keep_out / keep_in (optional, uint8    */
+/* [M][C/8]): dropout keep bits written by the forward apply and read by the backward instead of */
+/* regenerating the Philox stream.                                                               */
 /* ------------------------------------------------------------------------------------------ */
 int64_t fs2_bn_workspace_floats(int64_t M, int C);
 int fs2_bn_stats_bf16(const void* y, int64_t M, int C, float* ws, float* stats, float momentum, float* running_mean,
                       float* running_var, int64_t* num_batches_tracked, void* stream);
 int fs2_bn_apply_fwd(const void* y, const float* stats, const float* gamma, const float* beta, int64_t M,
                      int C, int act_tanh, float p_drop, uint64_t seed, const uint64_t* seed_dev,
-                     void* out_bf16, float* out_f32, const float* res_f32, void* stream);
+                     void* out_bf16, float* out_f32, const float* res_f32, uint8_t* keep_out, void* stream);
 int fs2_bn_bwd(const void* dout, int dout_is_f32, const void* y, const float* stats, const float* gamma,
                const float* beta, int64_t M, int C, int act_tanh, float p_drop, uint64_t seed,
-               const uint64_t* seed_dev, float* ws, float* dstats, float* dbeta_acc, float* dgamma_acc, void* dy,
-               void* stream);
+               const uint64_t* seed_dev, const uint8_t* keep_in, float* ws, float* dstats, float* dbeta_acc,
+               float* dgamma_acc, void* dy, void* stream);
 
 /* ------------------------------------------------------------------------------------------ */
 /* Phoneme-embedding front-end of the few-shot systems                      */

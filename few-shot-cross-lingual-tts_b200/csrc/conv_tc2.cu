@@ -32,12 +32,12 @@
 namespace fs2 {
 
 namespace c2 {
-constexpr int BN = 256;
+constexpr int BN_MAX = 256;
 constexpr int MAX_TAPS = 16;
 constexpr int A_BUFS = 2;
 constexpr int A_BUF_BYTES = 18 * 1024;        // (128 + MAX_TAPS - 1) rows x 128 B = 18304 B, 1 KiB aligned
 constexpr int B_STAGES = 8;
-constexpr int B_BYTES = (BN / 2) * BK * 2;    // 16 KiB: this CTA's half of the 256 weight rows
+constexpr int B_BYTES = (BN_MAX / 2) * BK * 2; // 16 KiB stage: this CTA's half of the (up to) 256 weight rows
 constexpr int B_OFF = A_BUFS * A_BUF_BYTES;
 constexpr int STAGING_OFF = B_OFF + B_STAGES * B_BYTES;
 constexpr int STAGING_BYTES = 8 * 32 * 128;
@@ -55,6 +55,10 @@ constexpr int kThreadsC2 = 384;
 // absolute shared-memory address bits, exactly like TMA when it wrote the tile; filling in (start >> 7) & 7
 // produces wrong results.
 
+// BN = 256: the default pair tile (256 rows x 256 columns).  BN = 128: outputs that are only 256 columns wide (the
+// k = 9 input gradient) -- half-size tiles cut the loss of the last partial wave (157 pair tiles on 74 CTA pairs are
+// 2.12 waves = 3 rounds; 314 half tiles are 4.24 waves = 5 half rounds).
+template <int BN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(c2::kThreadsC2, 1)
 conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const __grid_constant__ GemmKP p, const int taps) {
@@ -77,7 +81,8 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;
   const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
-  constexpr uint32_t TMEM_COLS = 512;
+  constexpr uint32_t TMEM_COLS = 2 * BN;
+  constexpr int B_TILE_BYTES = (BN / 2) * BK * 2;  // bytes this CTA loads per (tap, 64-channel block)
   const uint32_t a_box_bytes = static_cast<uint32_t>(BM + taps - 1) * 128u;
 
   if (warp == 0 && lane == 0) {
@@ -143,14 +148,14 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           }
           for (int tap = 0; tap < taps; ++tap) {
             mbar_wait(bempty_bar(sb_i), phb ^ 1u);
-            if (leader) mbar_arrive_expect_tx(bfull_bar(sb_i), 2 * B_BYTES);
+            if (leader) mbar_arrive_expect_tx(bfull_bar(sb_i), 2 * B_TILE_BYTES);
             const uint32_t lfull = leader_bfull0 + 8u * sb_i;
             const uint32_t sb = sbase + B_OFF + sb_i * B_BYTES;
             if (!p.b_mn) {
               tma_load_3d_2sm(sb, &tmB, lfull, ib + tap * p.b_tap_kstride + k0, n0, zb);
             } else {
 #pragma unroll
-              for (int h = 0; h < 2; ++h)
+              for (int h = 0; h < BN / 128; ++h)
                 tma_load_3d_2sm(sb + h * kChunkBytes, &tmB, lfull, ib + tap * p.b_tap_kstride + n0 + h * 64, k0,
                                 zb);
             }
@@ -249,11 +254,12 @@ conv_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 static int c2_num_sms = 0;
 
 // NORMAL mode, K-major A, taps in [2, 16], M > 128.  kp: output of gemm_fill_params.
-int conv_tc2_launch(const fs2_gemm& g, GemmKP& kp, cudaStream_t stream) {
+template <int BN>
+static int conv_tc2_launch_t(const fs2_gemm& g, GemmKP& kp, cudaStream_t stream) {
   using namespace c2;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DYN_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(conv_tc2_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, DYN_BYTES);
     if (e != cudaSuccess) return set_cuda_error("cudaFuncSetAttribute(conv_tc2)", e);
     attr_set = true;
   }
@@ -283,9 +289,18 @@ int conv_tc2_launch(const fs2_gemm& g, GemmKP& kp, cudaStream_t stream) {
   }
   const int max_pairs = c2_num_sms / 2;
   const int pairs = pair_tiles < max_pairs ? pair_tiles : max_pairs;
-  FS2_LAUNCH((conv_tc2_kernel), 2 * pairs, kThreadsC2, DYN_BYTES, stream, tmA, tmB, kp, taps);
+  FS2_LAUNCH((conv_tc2_kernel<BN>), 2 * pairs, kThreadsC2, DYN_BYTES, stream, tmA, tmB, kp, taps);
   count_launch();
   return check_launch("conv_tc2_kernel");
+}
+
+int conv_tc2_launch(const fs2_gemm& g, GemmKP& kp, cudaStream_t stream) {
+  // 128-column tiles for outputs that are one 256-column tile wide: better wave quantisation on paper, but measured
+  // SLOWER on B200 (k = 9 input gradient, ragged C2: 152 -> 172 us; the activation halo tile is loaded once per
+  // column tile, which doubles the L2 -> SM traffic of an already fabric-bound kernel).  Opt-in: FS2_CONV_BN128=1.
+  static const bool bn128 = getenv("FS2_CONV_BN128") && atoi(getenv("FS2_CONV_BN128")) == 1;
+  if (bn128 && g.N > 128 && g.N <= 256 && (long long)kp.tiles_m * kp.Z >= 148) return conv_tc2_launch_t<128>(g, kp, stream);
+  return conv_tc2_launch_t<256>(g, kp, stream);
 }
 
 }  // namespace fs2

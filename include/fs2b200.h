@@ -263,9 +263,9 @@ int fs2_loss_bwd(const float* gout6, const float* out10, const float* mel_pred, 
 /* fs2_bn_stats_bf16 also performs nn.BatchNorm1d's running-statistics update (momentum,        */
 /* unbiased variance, num_batches_tracked += 1) when running_mean is non-NULL.                  */
 /* fs2_bn_bwd: dstats f32 [2][C] written (dbeta, dgamma); dbeta_acc / dgamma_acc (optional,     */
-/* f32 [C]) accumulate them into the parameter gradients.  keep_out / keep_in (optional, uint8    */
-/* [M][C/8]): dropout keep bits written by the forward apply and read by the backward instead of */
-/* regenerating the Philox stream.                                                               */
+/* f32 [C]) accumulate them into the parameter gradients.  keep_out / keep_in (uint8 [M][C/8]):   */
+/* dropout keep bits (bit j of byte [m][c/8] = channel 8*(c/8)+j kept) written by the forward    */
+/* apply and READ by the backward (required there when p_drop > 0: nothing is regenerated).      */
 /* ------------------------------------------------------------------------------------------ */
 int64_t fs2_bn_workspace_floats(int64_t M, int C);
 int fs2_bn_stats_bf16(const void* y, int64_t M, int C, float* ws, float* stats, float momentum, float* running_mean,

@@ -343,6 +343,24 @@ def test_postnet_dropout_keep_rate():
     assert abs(keep - 0.5) < 0.02
 
 
+def test_postnet_dropout_backward_reads_the_forward_mask():
+    """Last block: out - x = dropout_0.5(bn(conv(h))) -- d(sum(out * w)) / d(bn.bias[c]) is exactly
+    2 * sum over the KEPT positions of w[:, c], so the backward must see the bits the forward drew
+    (transformer/Layers.py:135 F.dropout(..., 0.5, training))."""
+    L = sub("transformer.Layers")
+    pn = L.PostNet().cuda().train()
+    ops.manual_seed(11)
+    x = torch.randn(3, 70, 80, device="cuda")
+    out = pn.forward_residual(x)
+    kept = ((out - x) != 0).float()
+    assert 0.4 < kept.mean().item() < 0.6
+    w = torch.randn_like(out)
+    (out * w).sum().backward()
+    expect = 2.0 * (w * kept).sum(dim=(0, 1))
+    got = pn.convolutions[-1][1].bias.grad
+    assert torch.allclose(got, expect, rtol=1e-4, atol=1e-3), (got - expect).abs().max()
+
+
 # ------------------------------------------------------------------------------------------------------
 # variance predictor and FFT block against the oracle functions
 # ------------------------------------------------------------------------------------------------------

@@ -96,13 +96,15 @@ def main():
     dob = torch.randn(M, Cb, device="cuda").to(BF16)
     dst = torch.zeros(2, Cb, device="cuda")
     dyb = torch.empty_like(yb)
+    keepb = torch.empty(M, Cb // 8, dtype=torch.uint8, device="cuda")
     us = timeit(bn_stats)
     rec("bn_stats [64000 x 512] (fixed-order partials + finalize)", us, M * Cb * 2)
     us = timeit(lambda: L.fs2_bn_apply_fwd(yb.data_ptr(), stats.data_ptr(), gb.data_ptr(), bb.data_ptr(), M, Cb, 1,
-                                           0.5, 7, seed.data_ptr(), ob.data_ptr(), None, None, None, ops._st()))
+                                           0.5, 7, seed.data_ptr(), ob.data_ptr(), None, None, keepb.data_ptr(),
+                                           ops._st()))
     rec("bn_apply + tanh + dropout 0.5", us, 2 * M * Cb * 2)
     us = timeit(lambda: L.fs2_bn_bwd(dob.data_ptr(), 0, yb.data_ptr(), stats.data_ptr(), gb.data_ptr(),
-                                     bb.data_ptr(), M, Cb, 1, 0.5, 7, seed.data_ptr(), None, ws.data_ptr(),
+                                     bb.data_ptr(), M, Cb, 1, 0.5, 7, seed.data_ptr(), keepb.data_ptr(), ws.data_ptr(),
                                      dst.data_ptr(), None, None, dyb.data_ptr(), ops._st()))
     rec("bn_bwd (reduce + finalize + apply, 3 kernels)", us, 5 * M * Cb * 2)
 

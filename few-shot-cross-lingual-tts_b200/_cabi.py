@@ -30,6 +30,7 @@ class Gemm(ctypes.Structure):
         ("bias", c_vp), ("aux", c_vp), ("ld_aux", c_i64), ("aux_batch_stride", c_i64),
         ("d_seg_rows", c_i32), ("d_seg_pad", c_i32), ("d_seg", c_vp * 4),
         ("row_lens", c_vp), ("lens_zdiv", c_i32), ("tail_zero_rows", c_i32), ("relu_mask", c_vp),
+        ("workspace", c_vp), ("workspace_bytes", c_i64),
     ]
 
 

@@ -37,6 +37,13 @@ int fs2_version(void) { return FS2_ABI_VERSION; }
 const char* fs2_last_error(void) { return fs2::g_err; }
 int64_t fs2_launch_count(void) { return fs2::g_launches.load(); }
 
+int64_t fs2_gemm_workspace_bytes(void) {
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  return fs2::conv_tc2_workspace_bytes(sms / 2);
+}
+
 int fs2_gemm_bf16(const fs2_gemm* g, int impl, void* stream) {
   if (!g) return fs2::set_error("fs2_gemm_bf16: null descriptor");
   cudaStream_t s = static_cast<cudaStream_t>(stream);

@@ -53,4 +53,5 @@ int check_launch(const char* kernel_name);
 void count_launch();
 int gemm_tc_launch(const fs2_gemm& g, cudaStream_t stream);
 int gemm_simt_launch(const fs2_gemm& g, cudaStream_t stream);
+long long conv_tc2_workspace_bytes(int pairs);  // conv_tc2.cu: fs2_gemm::workspace for `pairs` CTA pairs
 }  // namespace fs2

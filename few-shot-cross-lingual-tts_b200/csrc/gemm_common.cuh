@@ -51,6 +51,7 @@ struct GemmKP {
   int dbg;         // FS2_GEMM_DBG ablation bits (tools only): 1 no global stores, 2 no epilogue math, 4 no TMA, 8 no MMA
   int pair_any;    // 2-CTA kernels, ragged NORMAL, shared (un-batched) B: the two CTAs of a pair take ANY two
                    // consecutive 128-row tiles of the compact list, also from different utterances
+  float* ws;       // conv_tc2: split-K scratch for the last partial wave (fs2_gemm::workspace), NULL = off
 };
 
 constexpr int kMaxRaggedZ = 256;  // prefix table lives in the ~1.9 KiB of shared memory left by the smem ring

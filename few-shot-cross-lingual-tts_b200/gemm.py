@@ -22,6 +22,21 @@ def _stream():
     return torch.cuda.current_stream().cuda_stream
 
 
+_WS = {}
+
+
+def _workspace():
+    """Split-K scratch of the Conv1d kernel (fs2_gemm::workspace): one zero-initialised buffer per stream, because
+    launches that may run concurrently must not share it; the kernel leaves its counters zero again."""
+    st = torch.cuda.current_stream()
+    key = (st.device_index, st.cuda_stream)
+    ws = _WS.get(key)
+    if ws is None:
+        ws = torch.zeros(int(_cabi.lib().fs2_gemm_workspace_bytes()), dtype=torch.uint8, device=st.device)
+        _WS[key] = ws
+    return ws
+
+
 def operand(t, inner, rows, batches=1, ld=None, batch_stride=None, mn_major=False, inner_base=0,
             zdiv=1, zmod_stride=0):
     """Describe bf16 tensor `t` as [batches][rows][inner] with explicit element strides."""
@@ -75,6 +90,9 @@ def gemm(a, b, d, M, N, K, Z=1, taps=1, tap_shift0=0, b_tap_kstride=0, ldd=None,
     if relu_mask is not None:  # int64 [Z*M, N/64]: written by EPI_RELU, read by EPI_RELU_BWD instead of `aux`
         assert relu_mask.dtype == torch.int64 and relu_mask.is_contiguous() and relu_mask.numel() == Z * M * (N // 64)
         g.relu_mask = relu_mask.data_ptr()
+    if g.taps > 1 and not g.d_f32:  # last partial wave of the Conv1d schedule: split over the reduction
+        ws = _workspace()
+        g.workspace, g.workspace_bytes = ws.data_ptr(), ws.numel()
     run(g, impl)
 
 

@@ -114,10 +114,19 @@ typedef struct fs2_gemm {
      tensor -- the backward of Conv1d -> ReLU -> Conv1d (transformer/SubLayers.py:87-89) then re-reads 1/16 of the
      bytes of the hidden activation.  NULL = off. */
   void* relu_mask;
+  /* optional scratch of the Conv1d kernel (NORMAL mode, taps > 1, bf16 D): with it, the tiles of the LAST, partially
+     filled wave of the persistent schedule are split over the reduction (channel blocks) across the idle CTA pairs;
+     partial accumulators meet in this buffer and are added in a fixed order (bit-reproducible).  Must be ZERO on
+     first use (the kernel leaves its counters zero again), at least fs2_gemm_workspace_bytes() bytes, and must not
+     be shared by launches that can run concurrently (one buffer per stream).  NULL = no split. */
+  void* workspace;
+  int64_t workspace_bytes;
 } fs2_gemm;
 
 /* impl: 0 = tcgen05 (product path), 1 = plain CUDA-core kernel (debug cross-check only). */
 int fs2_gemm_bf16(const fs2_gemm* g, int impl, void* stream);
+/* bytes of fs2_gemm::workspace that serve every launch on this device */
+int64_t fs2_gemm_workspace_bytes(void);
 
 
 /* ------------------------------------------------------------------------------------------ */

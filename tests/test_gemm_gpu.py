@@ -258,6 +258,73 @@ def test_ragged_conv(impl, lens, Cin, Cout, k):
         assert rel_err(y, ref) < 1e-2, rel_err(y, ref)
 
 
+def _split_lens(n_pair_tiles, T, seed):
+    """Utterance lengths whose 128-row tiles add up to 2 * n_pair_tiles (- 1 when `seed` is odd: filler half)."""
+    g = torch.Generator().manual_seed(seed)
+    want = 2 * n_pair_tiles - (seed & 1)
+    lens, tiles = [], 0
+    while tiles < want:
+        t = min(int(torch.randint(1, T // 128 + 1, (1,), generator=g)), want - tiles)
+        lens.append(min(T, t * 128 - int(torch.randint(0, 100, (1,), generator=g))))
+        tiles += t
+    return lens
+
+
+@pytest.mark.parametrize("Cin,Cout,k,epi,n_pair_tiles", [
+    (1024, 256, 9, "aux", 157),      # FFN k=9 input gradient at C2: rounds of 74, 74, 9 -> 4 slices of 4 channel blocks
+    (1024, 256, 9, "aux", 104),      # remainder 30 -> 2 slices
+    (1024, 512, 5, "relu_mask", 80),  # two column tiles: 160 pair tiles, remainder 12 -> 4 slices; mask written
+    (1024, 256, 5, "relu_bwd_mask", 85),  # mask read, odd tile count (filler half of the last pair)
+    (1024, 512, 5, "bias", 41),      # 82 pair tiles, remainder 8
+    (256, 1024, 9, "relu_mask", 40),  # short reduction (36 k-blocks): scheduled without a split
+])
+def test_conv_split_tail(Cin, Cout, k, epi, n_pair_tiles):
+    """Last partial round of the persistent Conv1d schedule split over the channel blocks (fs2_gemm::workspace):
+    same values as the CUDA-core kernel, bit-identical from launch to launch (fixed-order reduction; the counters in
+    the workspace return to zero)."""
+    T = 1000
+    seed = n_pair_tiles + k
+    lens = _split_lens(n_pair_tiles, T, seed)
+    B = len(lens)
+    torch.manual_seed(seed)
+    ln = _lens(lens)
+    valid = torch.arange(T, device="cuda")[None, :] < ln[:, None]
+    x = rnd(B, T, Cin) * valid[..., None]
+    wp = (torch.randn(Cout, k, Cin, device="cuda") * (Cin * k) ** -0.5).to(torch.bfloat16)
+    bias = torch.randn(Cout, device="cuda") if epi in ("bias", "relu_mask") else None
+    aux = rnd(B, T, Cout) if epi == "aux" else None
+    mask = None
+    if epi in ("relu_mask", "relu_bwd_mask"):
+        mask = torch.randint(-2 ** 62, 2 ** 62, (B * T, Cout // 64), device="cuda", dtype=torch.int64)
+    epilogue = {"aux": G.EPI_ADD_AUX, "bias": G.EPI_NONE, "relu_mask": G.EPI_RELU, "relu_bwd_mask": G.EPI_RELU_BWD}[epi]
+
+    def run(impl, m):
+        y = torch.full((B, T, Cout), float("nan"), device="cuda", dtype=torch.bfloat16)
+        G.gemm(G.operand(x, Cin, T, B), G.operand(wp, k * Cin, Cout), y, T, Cout, Cin, Z=B, taps=k,
+               tap_shift0=-((k - 1) // 2), b_tap_kstride=Cin, bias=bias, epilogue=epilogue, aux=aux, ld_aux=Cout,
+               aux_batch_stride=T * Cout, d_zdiv=1, d_zdiv_stride=T * Cout, row_lens=ln, relu_mask=m, impl=impl)
+        return y
+
+    m0 = mask.clone() if mask is not None else None
+    m1 = mask.clone() if mask is not None else None
+    if epi == "relu_mask":
+        m1.zero_()  # the CUDA-core cross-check ORs its bits in
+    ref = run(1, m1)
+    y = run(0, m0)
+    assert torch.isfinite(y.float()).all() and (y[~valid] == 0).all()
+    assert rel_err(y, ref) < 4e-3, rel_err(y, ref)
+    if epi == "relu_mask":  # the mask words of valid rows agree except where the pre-activation rounds across zero
+        vm = valid.reshape(-1)
+        diff = (m0[vm] ^ m1[vm])
+        flipped = sum(bin(int(v) & (2 ** 64 - 1)).count("1") for v in diff[diff != 0].tolist())
+        assert flipped <= 1e-4 * vm.sum().item() * Cout
+    for _ in range(3):  # counters reset, fixed summation order
+        m2 = mask.clone() if mask is not None else None
+        assert torch.equal(run(0, m2), y)
+        if epi == "relu_mask":
+            assert torch.equal(m2[valid.reshape(-1)], m0[valid.reshape(-1)])
+
+
 @pytest.mark.parametrize("impl", IMPLS)
 @pytest.mark.parametrize("lens", [[200, 1, 129, 0, 128, 77], [0, 0], [300, 64, 65]])
 @pytest.mark.parametrize("N,K,k,splits", [(768, 256, 1, 1), (768, 256, 1, 4), (256, 1024, 9, 3), (80, 256, 1, 2)])

@@ -111,6 +111,43 @@ embedding_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const IdxT* __restric
   }
 }
 
+// Small tables (the 256-bin pitch / energy embeddings: 12800 rows hit 256 table rows, ~50 writers per address):
+// block (x, y) owns 64 channels and a contiguous range of input rows and accumulates into its own shared-memory copy
+// of that table slice; only the non-zero sums go to the gradient with global atomics (one per touched table element
+// and block instead of one per input element: 55-63 us -> a few us at C2).
+constexpr int kEmbSliceC = 64;
+template <typename IdxT>
+__global__ void __launch_bounds__(256)
+embedding_bwd_smem_kernel(const __nv_bfloat16* __restrict__ dy, const IdxT* __restrict__ ids, long long rows, int C,
+                          int n_rows_table, int pad_idx, int rows_per_block, float* __restrict__ dtable) {
+  pdl_sync();
+  extern __shared__ float acc[];  // [n_rows_table][64]
+  const int n = n_rows_table * kEmbSliceC;
+  for (int i = threadIdx.x; i < n; i += 256) acc[i] = 0.f;
+  __syncthreads();
+  const int c0 = blockIdx.x * kEmbSliceC;
+  const int sub = threadIdx.x & 7, rl = threadIdx.x >> 3;  // 8 threads x 8 channels per row, 32 rows per pass
+  const long long r0 = (long long)blockIdx.y * rows_per_block;
+  const long long r1 = min(r0 + rows_per_block, rows);
+  if (c0 + sub * 8 < C) {
+    for (long long r = r0 + rl; r < r1; r += 32) {
+      const long long id = static_cast<long long>(ids[r]);
+      if (id < 0 || id >= n_rows_table || id == pad_idx) continue;  // padding_idx rows get no gradient
+      float f[8];
+      unpack8(ld8(dy + r * C + c0 + sub * 8), f);
+      float* a = acc + id * kEmbSliceC + sub * 8;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) atomicAdd(a + j, f[j]);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += 256) {
+    const float v = acc[i];
+    const int row = i / kEmbSliceC, c = c0 + (i % kEmbSliceC);
+    if (v != 0.f && c < C) atomicAdd(dtable + (long long)row * C + c, v);
+  }
+}
+
 // ---- lookup in the CONCATENATION of several tables without materialising it -----------------------------------
 // MultilingualEmbedding.forward (lightning/systems/language/embeddings.py:25-31) does torch.cat(all tables) on every
 // call and F.embedding(padding_idx) on the result; here the per-language tables stay where they are and a row id is
@@ -272,6 +309,27 @@ int fs2_embedding_bwd_f32(const void* dy, const void* ids, int ids_is_i64, int64
   if (C % 8) return fs2::set_error("embedding_bwd: C must be a multiple of 8");
   if (rows <= 0) return 0;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const size_t smem = (size_t)n_rows_table * fs2::kEmbSliceC * sizeof(float);
+  if (smem <= 200 * 1024 && rows >= 8 * (int64_t)n_rows_table) {  // many writers per table row: shared-memory slices
+    static bool attr_set = false;
+    if (!attr_set) {
+      cudaFuncSetAttribute(fs2::embedding_bwd_smem_kernel<int64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      cudaFuncSetAttribute(fs2::embedding_bwd_smem_kernel<int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      attr_set = true;
+    }
+    int chunks = (int)(rows / 1024);
+    chunks = chunks < 1 ? 1 : (chunks > 16 ? 16 : chunks);
+    const int rpb = (int)((rows + chunks - 1) / chunks);
+    const dim3 grid((C + fs2::kEmbSliceC - 1) / fs2::kEmbSliceC, (unsigned)((rows + rpb - 1) / rpb));
+    if (ids_is_i64)
+      FS2_LAUNCH((fs2::embedding_bwd_smem_kernel<int64_t>), grid, 256, smem, s, static_cast<const __nv_bfloat16*>(dy),
+                 static_cast<const int64_t*>(ids), rows, C, n_rows_table, pad_idx, rpb, dtable);
+    else
+      FS2_LAUNCH((fs2::embedding_bwd_smem_kernel<int32_t>), grid, 256, smem, s, static_cast<const __nv_bfloat16*>(dy),
+                 static_cast<const int32_t*>(ids), rows, C, n_rows_table, pad_idx, rpb, dtable);
+    fs2::count_launch();
+    return fs2::check_launch("embedding_bwd_smem_kernel");
+  }
   const unsigned grid = (unsigned)((rows + 8 * fs2::kEmbRowsPerWarp - 1) / (8 * fs2::kEmbRowsPerWarp));
   if (ids_is_i64)
     FS2_LAUNCH((fs2::embedding_bwd_kernel<int64_t>), grid, 256, 0, s, static_cast<const __nv_bfloat16*>(dy),

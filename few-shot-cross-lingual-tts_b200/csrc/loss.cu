@@ -63,14 +63,16 @@ __device__ __forceinline__ float energy_target(const LossArgs& a, long long i) {
   return a.e_tgt_is_f64 ? static_cast<float>(static_cast<const double*>(a.e_tgt)[i])
                         : static_cast<const float*>(a.e_tgt)[i];
 }
-// number of valid positions of a [B][T] feature
-__device__ __forceinline__ double count_valid(const int64_t* lens, int B, int T) {
-  double n = 0;
-  for (int b = 0; b < B; ++b) {
+// number of valid positions of a [B][T] feature, counted by ONE WARP (exact integer sum; every lane returns it)
+__device__ __forceinline__ double count_valid_warp(const int64_t* lens, int B, int T) {
+  long long n = 0;
+  for (int b = threadIdx.x & 31; b < B; b += 32) {
     const long long l = min((long long)lens[b], (long long)T);
-    n += (double)(l > 0 ? l : 0);
+    n += l > 0 ? l : 0;
   }
-  return n;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o);
+  return (double)n;
 }
 
 __global__ void __launch_bounds__(kLossThreads) loss_partial_kernel(const LossArgs a) {
@@ -132,17 +134,25 @@ __global__ void __launch_bounds__(kLossThreads) loss_partial_kernel(const LossAr
 __global__ void __launch_bounds__(kLossThreads) loss_final_kernel(const LossArgs a) {
   pdl_sync();
   __shared__ float sh[8];
+  __shared__ double cnt[4];
+  // the four normalisers, one warp each (this used to be 4 * B dependent loads of thread 0: 15 us at B = 64)
+  const int warp = threadIdx.x >> 5;
+  if (warp < 4) {
+    const double c = warp == 0 ? count_valid_warp(a.mel_lens, a.B, a.Tm) * a.n_mel
+                   : warp == 1 ? count_valid_warp(a.p_lens, a.B, a.p_T)
+                   : warp == 2 ? count_valid_warp(a.e_lens, a.B, a.e_T)
+                               : count_valid_warp(a.src_lens, a.B, a.Ts);
+    if ((threadIdx.x & 31) == 0) cnt[warp] = c;
+  }
   float s[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
   for (int i = threadIdx.x; i < a.n_blocks; i += kLossThreads)
 #pragma unroll
     for (int k = 0; k < 5; ++k) s[k] += a.partials[(long long)i * 5 + k];
   float r[5];
 #pragma unroll
-  for (int k = 0; k < 5; ++k) r[k] = block_sum(s[k], sh);
+  for (int k = 0; k < 5; ++k) r[k] = block_sum(s[k], sh);  // (its barriers also publish cnt[])
   if (threadIdx.x == 0) {
-    const double n_mel = count_valid(a.mel_lens, a.B, a.Tm) * a.n_mel;
-    const double n_p = count_valid(a.p_lens, a.B, a.p_T), n_e = count_valid(a.e_lens, a.B, a.e_T);
-    const double n_d = count_valid(a.src_lens, a.B, a.Ts);
+    const double n_mel = cnt[0], n_p = cnt[1], n_e = cnt[2], n_d = cnt[3];
     const float mel = r[0] / (float)n_mel, post = r[1] / (float)n_mel;
     const float pitch = r[2] / (float)n_p, energy = r[3] / (float)n_e, dur = r[4] / (float)n_d;
     a.out[0] = mel + post + dur + pitch + energy;  // same association order as loss.py:77-79

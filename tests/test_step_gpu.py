@@ -166,3 +166,39 @@ def test_shape_bucketed_step_cache_reuses_graphs_and_matches_the_padded_batch():
     b4 = synth.make_batch(B=4, src_len=(70, 90), dur=synth.uniform_dur(2, 5), seed=44)
     cache.run(b4)
     assert cache.captures == 3 and len(cache.steps) == 2 and cache.key_for(b1) not in cache.steps
+
+
+def test_weight_cache_refresh_matches_per_tensor_cast_and_pack():
+    """csrc/weight_prep.cu (one launch for every bf16 operand copy) against torch: Linear weights are cast, Conv1d
+    weights [Co][Ci][k] become [Co][k][Cpad] with zero channel padding, Q|K|V weights / biases are gathered."""
+    ops = sub("ops")
+    MHA = sub("transformer.SubLayers").MultiHeadAttention
+    model, _, _ = _build(seed=3)
+    wc = ops.WeightCache(model)
+    for t in wc.map.values():
+        t.fill_(7.0)
+    wc.refresh()
+    torch.cuda.synchronize()
+    n = 0
+    for m in model.modules():
+        if isinstance(m, torch.nn.Conv1d):
+            d = wc.lookup("conv", m.weight)
+            if d is None:
+                continue
+            Co, Ci, k = m.weight.shape
+            ref = torch.zeros_like(d)
+            ref[:, :, :Ci] = m.weight.detach().permute(0, 2, 1).to(torch.bfloat16)
+            assert torch.equal(d, ref), (Co, Ci, k)
+            n += 1
+        elif isinstance(m, MHA):
+            w = wc.lookup("qkv", m.w_qs.weight)
+            b = wc.lookup("bqkv", m.w_qs.bias)
+            assert torch.equal(w, torch.cat([m.w_qs.weight, m.w_ks.weight, m.w_vs.weight]).detach().to(torch.bfloat16))
+            assert torch.equal(b, torch.cat([m.w_qs.bias, m.w_ks.bias, m.w_vs.bias]).detach())
+            n += 1
+        elif isinstance(m, torch.nn.Linear):
+            d = wc.lookup("lin", m.weight)
+            if d is not None:
+                assert torch.equal(d, m.weight.detach().to(torch.bfloat16))
+                n += 1
+    assert n > 20

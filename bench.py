@@ -355,11 +355,11 @@ def kernel_rooflines(base, cfg, bf16_peak, hbm_peak, step_ms, traffic):
     p = t["decoder_dropout"]
     gamma, beta = torch.ones(D, device=dev), torch.zeros(D, device=dev)
     dg, db, dbias = (torch.zeros(D, device=dev) for _ in range(3))
-    y, mean, rstd = ops.ln_fwd(x, dy, gamma, beta, lens, p, 1, 5)
+    y, mean, rstd, keep = ops.ln_fwd(x, dy, gamma, beta, lens, p, 1, 5)
     rec("LayerNorm fwd (dropout + residual + LN + pad-zero)", (2 * V + B * Tm) * D * 2,
         lambda: ops.ln_fwd(x, dy, gamma, beta, lens, p, 1, 5), 2 * n_dec)
     rec("LayerNorm bwd (+dgamma/dbeta/dbias, dropout regenerated)", (3 * V + 2 * B * Tm) * D * 2,
-        lambda: ops.ln_bwd(dy, x, dy, gamma, mean, rstd, lens, p, 1, 5, dg, db, True, dbias=dbias), 2 * n_dec)
+        lambda: ops.ln_bwd(dy, x, dy, gamma, mean, rstd, lens, p, 1, keep, dg, db, True, dbias=dbias), 2 * n_dec)
     Ts = int(base[5])
     dur = base[11].to(dev)
     Tm_full = int(base[8])

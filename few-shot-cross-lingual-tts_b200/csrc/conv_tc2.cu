@@ -524,6 +524,7 @@ int conv_tc2_launch(const fs2_gemm& g, GemmKP& kp, cudaStream_t stream) {
   // column tile, which doubles the L2 -> SM traffic of an already fabric-bound kernel).  Opt-in: FS2_CONV_BN128=1.
   static const bool bn128 = getenv("FS2_CONV_BN128") && atoi(getenv("FS2_CONV_BN128")) == 1;
   if (bn128 && g.N > 128 && g.N <= 256 && (long long)kp.tiles_m * kp.Z >= 148) return conv_tc2_launch_t<128>(g, kp, stream);
+  if (g.N <= 128) return conv_tc2_launch_t<128>(g, kp, stream);  // narrow outputs: one 128-column tile
   return conv_tc2_launch_t<256>(g, kp, stream);
 }
 

@@ -405,6 +405,8 @@ int gemm_tc2_launch(const fs2_gemm& g, GemmKP& kp, cudaStream_t stream);  // gem
 int conv_tc2_launch(const fs2_gemm& g, GemmKP& kp, cudaStream_t stream);  // conv_tc2.cu (2-CTA + halo reuse)
 bool gemm_sk_eligible(const fs2_gemm& g, const GemmKP& kp);                // gemm_sk.cu (small K, resident weights,
 int gemm_sk_launch(const fs2_gemm& g, GemmKP& kp, cudaStream_t stream);    //  TMA-store epilogue)
+bool wgrad_taps_eligible(const fs2_gemm& g, const GemmKP& kp);             // wgrad_taps.cu (Conv1d weight gradient,
+int wgrad_taps_launch(const fs2_gemm& g, GemmKP& kp, cudaStream_t stream); //  operand reuse across taps)
 
 int gemm_tc_launch(const fs2_gemm& g, cudaStream_t stream) {
   GemmKP kp;
@@ -414,16 +416,19 @@ int gemm_tc_launch(const fs2_gemm& g, cudaStream_t stream) {
   const int n = g.N;
   const int pad256 = ((n + 255) / 256) * 256, pad128 = ((n + 127) / 128) * 128;
   const bool use128 = (n <= 128) || (pad128 * 100 < pad256 * 92);
-  if (use128) return launch_tc<128, 6>(g, kp, stream);
-  if (gemm_sk_eligible(g, kp)) return gemm_sk_launch(g, kp, stream);
-  // Conv1d (taps > 1, K-major activations): one activation tile with halo serves every tap, 2-CTA tiles
+  // Conv1d (taps > 1, K-major activations): one activation tile with halo serves every tap, 2-CTA tiles -- also for
+  // narrow outputs (the 512 -> 80 PostNet convolution and the input gradient of the 80 -> 512 one: 128-column
+  // pair tiles; the 1-CTA kernel re-read the activation tile once per tap: 94 / 72 us for 26 GFLOP)
   static const bool no_halo = getenv("FS2_CONV_NO_HALO") != nullptr;
   // (with a ragged schedule and shared weights the pair kernels team up ANY two row tiles, so even
   //  utterances of a single 128-row tile fill both CTAs)
   const bool pair_any = kp.pair_any != 0;
   if (!no_halo && g.mode == FS2_GEMM_NORMAL && g.taps > 1 && g.taps <= 16 && !g.a.mn_major &&
-      (g.M > 128 || pair_any))
+      (g.M > 128 || pair_any) && (!use128 || n <= 128))
     return conv_tc2_launch(g, kp, stream);
+  if (use128) return launch_tc<128, 6>(g, kp, stream);
+  if (gemm_sk_eligible(g, kp)) return gemm_sk_launch(g, kp, stream);
+  if (wgrad_taps_eligible(g, kp)) return wgrad_taps_launch(g, kp, stream);
   // 256-row x 256-column tiles on CTA pairs (cta_group::2) when every pair has two real row tiles:
   // halves the shared-memory traffic per FLOP, which is what limits the 1-CTA 128x256 tile.
   static const bool no_2cta = getenv("FS2_GEMM_NO_2CTA") != nullptr;

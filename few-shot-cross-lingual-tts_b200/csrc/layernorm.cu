@@ -7,10 +7,18 @@
 //   lightning/model/modules.py:222-225,234-237  `dropout(layer_norm(relu(conv)))`     (drop_mode 2)
 // One warp owns one row (C = 256/512/1024 channels = 1/2/4 16-byte vectors per lane), so the
 // statistics never leave registers.  HBM-bound: algorithmic bytes fwd = (2 or 3) * rows * C * 2.
+#include <cuda_fp16.h>
+
+#include <cstdlib>
+
 #include "common.h"
 #include "util.cuh"
 
 namespace fs2 {
+
+__device__ __forceinline__ uint32_t smem_u32_ln(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
 
 constexpr float kLnEps = 1e-5f;  // nn.LayerNorm default (the reference never overrides it)
 
@@ -29,6 +37,8 @@ struct LnArgs {
   __nv_bfloat16* y;
   float* mean;
   float* rstd;
+  uint8_t* keep;  // dropout keep bits [rows][C/8] (bit j of byte v = channel 8v + j): written by the forward,
+                  // read by the backward -- the Philox stream is drawn once per step
   // backward only
   const __nv_bfloat16* dy;
   __nv_bfloat16* dx;
@@ -38,11 +48,88 @@ struct LnArgs {
   float* dbias;  // optional: column sums of dx (bias gradient of the GEMM that produced x)
 };
 
-__device__ __forceinline__ bool ln_row_masked(const LnArgs& a, long long row) {
-  if (!a.lens) return false;
-  const int r = (int)row;  // rows = B * T < 2^31 (checked on the host): 32-bit division
-  const int b = r / a.T;
-  return r - b * a.T >= a.lens[b];
+// (utterance, frame) of the rows a warp visits: row += stride without a division per row
+struct RowCursor {
+  int b, t, T, qb, qt;
+  __device__ __forceinline__ RowCursor(long long row, long long stride, int T_) : T(T_) {
+    b = (int)(row / T_);
+    t = (int)(row - (long long)b * T_);
+    qb = (int)(stride / T_);
+    qt = (int)(stride - (long long)qb * T_);
+  }
+  __device__ __forceinline__ void next() {
+    b += qb;
+    t += qt;
+    if (t >= T) {
+      t -= T;
+      ++b;
+    }
+  }
+  __device__ __forceinline__ bool masked(const int64_t* lens) const { return lens && t >= lens[b]; }
+};
+
+// ---- dropout masks in bf16x2 lane form ------------------------------------------------------------------------
+// One Philox call gives 8 x 16 random bits for the 8 channels of a lane.  A pair of channels is kept / dropped by
+// ONE half2 compare on 13 of its 16 bits (mapped into [2, 4): finite, normal fp16 numbers, ordered like the
+// integers) that yields 0xFFFF / 0x0000 per half -- the mask is ANDed onto the packed bf16 pair, and the 1/(1-p)
+// scale rides on the FMA that adds the residual.  (The per-element form -- extract, compare, select, multiply --
+// was ~6 instructions per element of an otherwise HBM-bound kernel.)  Resolution of p: 1/8192.
+struct KeepMask {
+  uint32_t m[4];  // channel pairs (0,1) (2,3) (4,5) (6,7): 0xFFFF per kept half
+  __device__ __forceinline__ void draw(uint64_t seed, uint64_t ctr, uint32_t thresh_h2) {
+    const uint4 r = philox4x32(seed, ctr);
+    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+    const __half2 th = *reinterpret_cast<const __half2*>(&thresh_h2);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const uint32_t a = (w[i] & 0x1FFF1FFFu) | 0x40004000u;
+      m[i] = __hge2_mask(*reinterpret_cast<const __half2*>(&a), th);
+    }
+  }
+  __device__ __forceinline__ void all() { m[0] = m[1] = m[2] = m[3] = 0xFFFFFFFFu; }
+  __device__ __forceinline__ uint32_t to_byte() const {
+    uint32_t b = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) b |= ((m[i] & 1u) | ((m[i] >> 15) & 2u)) << (2 * i);
+    return b;
+  }
+  __device__ __forceinline__ void from_byte(uint32_t b) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const uint32_t t = b >> (2 * i);
+      m[i] = ((t & 1u) | ((t & 2u) << 15)) * 0xFFFFu;
+    }
+  }
+  __device__ __forceinline__ void apply(bf16x8& v) const {
+    uint32_t* w = reinterpret_cast<uint32_t*>(&v);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) w[i] &= m[i];
+  }
+};
+// threshold pair for KeepMask::draw: keep <=> 13 random bits >= p * 8192
+__host__ __device__ __forceinline__ uint32_t keep_thresh_h2(float p) {
+  float t = p * 8192.f;
+  const uint32_t k = t <= 0.f ? 0u : (t >= 8191.f ? 8191u : static_cast<uint32_t>(t + 0.5f));
+  const uint32_t h = 0x4000u | k;
+  return h | (h << 16);
+}
+
+
+// ---- per-warp cp.async ring (C = 256: the FFT-block / predictor LayerNorms) ----------------------------------
+// One row per warp and iteration leaves 1 KiB per warp in flight (x + residual, register prefetch of one row):
+// 32 KiB per SM, i.e. ~3 TB/s at the loaded HBM latency -- the kernels were latency-, not instruction-bound.  Here
+// every lane copies ITS OWN 16-byte pieces of the next D rows global -> shared with cp.async (no registers, no
+// barriers: a lane only ever reads back what it copied itself), so a warp keeps D KiB in flight.
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32_ln(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32_ln(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
 template <int NV>
@@ -51,12 +138,14 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const LnArgs a) {
   constexpr int C = NV * 256;
   const int lane = threadIdx.x & 31;
   const int warps_per_block = blockDim.x >> 5;
-  const uint32_t thresh = dropout_thresh(a.p_drop);
-  const float keep_scale = a.p_drop > 0.f ? 1.f / (1.f - a.p_drop) : 1.f;
+  const bool drop = a.drop_mode != 0;
+  const uint32_t thresh = keep_thresh_h2(a.p_drop);
+  const float keep_scale = drop ? 1.f / (1.f - a.p_drop) : 1.f;
+  const float in_scale = a.drop_mode == 1 ? keep_scale : 1.f;
   const uint64_t seed = mix_seed(a.seed_dev, a.seed);
   const long long stride = (long long)gridDim.x * warps_per_block;
   long long row = (long long)blockIdx.x * warps_per_block + (threadIdx.x >> 5);
-  float gam[NV][8], bet[NV][8];  // this lane's affine parameters: loop invariant
+  float gam[NV][8], bet[NV][8];  // this lane's affine parameters: loop invariant (mode 2: keep scale folded in)
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     const int col = i * 256 + lane * 8;
@@ -68,11 +157,20 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const LnArgs a) {
     gam[i][4] = g1.x; gam[i][5] = g1.y; gam[i][6] = g1.z; gam[i][7] = g1.w;
     bet[i][0] = b0.x; bet[i][1] = b0.y; bet[i][2] = b0.z; bet[i][3] = b0.w;
     bet[i][4] = b1.x; bet[i][5] = b1.y; bet[i][6] = b1.z; bet[i][7] = b1.w;
+    if (a.drop_mode == 2) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        gam[i][j] *= keep_scale;
+        bet[i][j] *= keep_scale;
+      }
+    }
   }
+  if (row >= a.rows) return;
+  RowCursor cur(row, stride, a.T);
   // software pipeline: the next row's 16-byte vectors are in flight while this row is reduced
   bf16x8 nx[NV], nr[NV];
-  bool nmask = row < a.rows && ln_row_masked(a, row);  // padded rows are never read
-  if (row < a.rows && !nmask) {
+  bool nmask = cur.masked(a.lens);  // padded rows are never read
+  if (!nmask) {
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       nx[i] = ld8(a.x + row * C + i * 256 + lane * 8);
@@ -87,12 +185,14 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const LnArgs a) {
       cx[i] = nx[i];
       cr[i] = nr[i];
     }
-    nmask = row + stride < a.rows && ln_row_masked(a, row + stride);
-    if (row + stride < a.rows && !nmask) {
+    cur.next();
+    const long long nrow = row + stride;
+    nmask = nrow < a.rows && cur.masked(a.lens);
+    if (nrow < a.rows && !nmask) {
 #pragma unroll
       for (int i = 0; i < NV; ++i) {
-        nx[i] = ld8(a.x + (row + stride) * C + i * 256 + lane * 8);
-        if (a.res) nr[i] = ld8(a.res + (row + stride) * C + i * 256 + lane * 8);
+        nx[i] = ld8(a.x + nrow * C + i * 256 + lane * 8);
+        if (a.res) nr[i] = ld8(a.res + nrow * C + i * 256 + lane * 8);
       }
     }
     if (masked) {  // transformer/Layers.py:25,28: the row is zero whatever the sub-layer produced
@@ -105,22 +205,28 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const LnArgs a) {
       }
       continue;
     }
+    KeepMask km[NV];
+    if (drop) {
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        km[i].draw(seed, ((uint64_t)row * C + i * 256 + lane * 8) >> 3, thresh);
+        if (a.keep) a.keep[row * (C / 8) + i * 32 + lane] = static_cast<uint8_t>(km[i].to_byte());
+      }
+    }
     float v[NV][8];
     float s = 0.f;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
-      const int col = i * 256 + lane * 8;
+      if (a.drop_mode == 1) km[i].apply(cx[i]);
       unpack8(cx[i], v[i]);
-      if (a.drop_mode == 1 && thresh) {
-        const uint32_t keep = dropout_keep8(seed, (uint64_t)row * C + col, thresh);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) v[i][j] = (keep >> j) & 1u ? v[i][j] * keep_scale : 0.f;
-      }
       if (a.res) {
         float r[8];
         unpack8(cr[i], r);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) v[i][j] += r[j];
+        for (int j = 0; j < 8; ++j) v[i][j] = fmaf(v[i][j], in_scale, r[j]);
+      } else if (a.drop_mode == 1) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[i][j] *= in_scale;
       }
 #pragma unroll
       for (int j = 0; j < 8; ++j) s += v[i][j];
@@ -132,29 +238,135 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const LnArgs a) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const float d = v[i][j] - mean;
-        q += d * d;
+        q = fmaf(d, d, q);
       }
     const float rstd = rsqrtf(warp_sum(q) * (1.f / C) + kLnEps);
     if (lane == 0) {
       a.mean[row] = mean;
       a.rstd[row] = rstd;
     }
+    const float nmr = -mean * rstd;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
-      const int col = i * 256 + lane * 8;
       float o[8];
-      {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = (v[i][j] - mean) * rstd * gam[i][j] + bet[i][j];
-        if (a.drop_mode == 2 && thresh) {
-          const uint32_t keep = dropout_keep8(seed, (uint64_t)row * C + col, thresh);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) o[j] = (keep >> j) & 1u ? o[j] * keep_scale : 0.f;
-        }
-      }
-      st8(a.y + row * C + col, pack8(o));
+      for (int j = 0; j < 8; ++j) o[j] = fmaf(fmaf(v[i][j], rstd, nmr), gam[i][j], bet[i][j]);
+      bf16x8 ov = pack8(o);
+      if (a.drop_mode == 2) km[i].apply(ov);
+      st8(a.y + row * C + i * 256 + lane * 8, ov);
     }
   }
+}
+
+// C = 256 forward with the cp.async ring (D rows ahead per warp)
+constexpr int kLnFwdDepth = 4;
+__global__ void __launch_bounds__(256) ln_fwd256_kernel(const LnArgs a) {
+  pdl_sync();
+  constexpr int C = 256, D = kLnFwdDepth;
+  __shared__ uint4 ring[8][D][2][32];  // [warp][stage][x | res][lane]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const bool drop = a.drop_mode != 0;
+  const uint32_t thresh = keep_thresh_h2(a.p_drop);
+  const float keep_scale = drop ? 1.f / (1.f - a.p_drop) : 1.f;
+  const float in_scale = a.drop_mode == 1 ? keep_scale : 1.f;
+  const uint64_t seed = mix_seed(a.seed_dev, a.seed);
+  const long long stride = (long long)gridDim.x * 8;
+  long long row = (long long)blockIdx.x * 8 + warp;
+  float gam[8], bet[8];
+  {
+    const int col = lane * 8;
+    const float4 g0 = *reinterpret_cast<const float4*>(a.gamma + col);
+    const float4 g1 = *reinterpret_cast<const float4*>(a.gamma + col + 4);
+    const float4 b0 = *reinterpret_cast<const float4*>(a.beta + col);
+    const float4 b1 = *reinterpret_cast<const float4*>(a.beta + col + 4);
+    gam[0] = g0.x; gam[1] = g0.y; gam[2] = g0.z; gam[3] = g0.w;
+    gam[4] = g1.x; gam[5] = g1.y; gam[6] = g1.z; gam[7] = g1.w;
+    bet[0] = b0.x; bet[1] = b0.y; bet[2] = b0.z; bet[3] = b0.w;
+    bet[4] = b1.x; bet[5] = b1.y; bet[6] = b1.z; bet[7] = b1.w;
+    if (a.drop_mode == 2) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        gam[j] *= keep_scale;
+        bet[j] *= keep_scale;
+      }
+    }
+  }
+  if (row >= a.rows) return;
+  // issue cursor (D rows ahead of the compute cursor); every row, masked or not, is one commit group
+  RowCursor icur(row, stride, a.T);
+  long long irow = row;
+  auto issue = [&](int stage) {
+    if (irow < a.rows && !icur.masked(a.lens)) {
+      cp_async16(&ring[warp][stage][0][lane], a.x + irow * C + lane * 8);
+      if (a.res) cp_async16(&ring[warp][stage][1][lane], a.res + irow * C + lane * 8);
+    }
+    cp_async_commit();
+    irow += stride;
+    icur.next();
+  };
+#pragma unroll
+  for (int d = 0; d < D; ++d) issue(d);
+  RowCursor cur(row, stride, a.T);
+  int stage = 0;
+  for (; row < a.rows; row += stride, cur.next(), stage = stage + 1 == D ? 0 : stage + 1) {
+    const bool masked = cur.masked(a.lens);
+    cp_async_wait<D - 1>();
+    bf16x8 cx, cr;
+    if (!masked) {
+      *reinterpret_cast<uint4*>(&cx) = ring[warp][stage][0][lane];
+      if (a.res) *reinterpret_cast<uint4*>(&cr) = ring[warp][stage][1][lane];
+    }
+    issue(stage);  // refill the slot just read with the row D iterations ahead
+    if (masked) {  // transformer/Layers.py:25,28: the row is zero whatever the sub-layer produced
+      const bf16x8 z = {};
+      st8(a.y + row * C + lane * 8, z);
+      if (lane == 0) {
+        a.mean[row] = 0.f;
+        a.rstd[row] = 0.f;
+      }
+      continue;
+    }
+    KeepMask km;
+    if (drop) {
+      km.draw(seed, ((uint64_t)row * C + lane * 8) >> 3, thresh);
+      if (a.keep) a.keep[row * (C / 8) + lane] = static_cast<uint8_t>(km.to_byte());
+    }
+    float v[8];
+    if (a.drop_mode == 1) km.apply(cx);
+    unpack8(cx, v);
+    if (a.res) {
+      float r[8];
+      unpack8(cr, r);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = fmaf(v[j], in_scale, r[j]);
+    } else if (a.drop_mode == 1) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] *= in_scale;
+    }
+    float sm = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sm += v[j];
+    const float mean = warp_sum(sm) * (1.f / C);
+    float q = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float d = v[j] - mean;
+      q = fmaf(d, d, q);
+    }
+    const float rstd = rsqrtf(warp_sum(q) * (1.f / C) + kLnEps);
+    if (lane == 0) {
+      a.mean[row] = mean;
+      a.rstd[row] = rstd;
+    }
+    const float nmr = -mean * rstd;
+    float o[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) o[j] = fmaf(fmaf(v[j], rstd, nmr), gam[j], bet[j]);
+    bf16x8 ov = pack8(o);
+    if (a.drop_mode == 2) km.apply(ov);
+    st8(a.y + row * C + lane * 8, ov);
+  }
+  cp_async_wait<0>();
 }
 
 template <int NV>
@@ -164,9 +376,9 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const LnArgs a) {
   __shared__ float red[8][C];  // per-warp partials, reused for dgamma then dbeta
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int warps_per_block = blockDim.x >> 5;
-  const uint32_t thresh = dropout_thresh(a.p_drop);
-  const float keep_scale = a.p_drop > 0.f ? 1.f / (1.f - a.p_drop) : 1.f;
-  const uint64_t seed = mix_seed(a.seed_dev, a.seed);
+  const bool drop = a.drop_mode != 0;
+  const float keep_scale = drop ? 1.f / (1.f - a.p_drop) : 1.f;
+  const float in_scale = a.drop_mode == 1 ? keep_scale : 1.f;
   float acc_g[NV][8], acc_b[NV][8], acc_x[NV][8];
 #pragma unroll
   for (int i = 0; i < NV; ++i)
@@ -175,7 +387,7 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const LnArgs a) {
 
   const long long stride = (long long)gridDim.x * warps_per_block;
   long long row = (long long)blockIdx.x * warps_per_block + warp;
-  float gam[NV][8];  // loop invariant
+  float gam[NV][8];  // loop invariant (mode 2: the keep scale of dy is folded in -- see gy below)
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     const int col = i * 256 + lane * 8;
@@ -184,101 +396,120 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const LnArgs a) {
     gam[i][0] = g0.x; gam[i][1] = g0.y; gam[i][2] = g0.z; gam[i][3] = g0.w;
     gam[i][4] = g1.x; gam[i][5] = g1.y; gam[i][6] = g1.z; gam[i][7] = g1.w;
   }
-  bf16x8 nx[NV], nd[NV], nr[NV];
-  bool nmask = row < a.rows && ln_row_masked(a, row);  // padded rows are never read
-  if (row < a.rows && !nmask) {
-#pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      nx[i] = ld8(a.x + row * C + i * 256 + lane * 8);
-      nd[i] = ld8(a.dy + row * C + i * 256 + lane * 8);
-      if (a.res) nr[i] = ld8(a.res + row * C + i * 256 + lane * 8);
-    }
-  }
-  for (; row < a.rows; row += stride) {
-    const bool masked = nmask;
-    bf16x8 cx[NV], cd[NV], cr[NV];
-#pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      cx[i] = nx[i];
-      cd[i] = nd[i];
-      cr[i] = nr[i];
-    }
-    nmask = row + stride < a.rows && ln_row_masked(a, row + stride);
-    if (row + stride < a.rows && !nmask) {
+  if (row < a.rows) {
+    RowCursor cur(row, stride, a.T);
+    bf16x8 nx[NV], nd[NV], nr[NV];
+    uint32_t nk[NV];
+    bool nmask = cur.masked(a.lens);  // padded rows are never read
+    if (!nmask) {
 #pragma unroll
       for (int i = 0; i < NV; ++i) {
-        nx[i] = ld8(a.x + (row + stride) * C + i * 256 + lane * 8);
-        nd[i] = ld8(a.dy + (row + stride) * C + i * 256 + lane * 8);
-        if (a.res) nr[i] = ld8(a.res + (row + stride) * C + i * 256 + lane * 8);
+        nx[i] = ld8(a.x + row * C + i * 256 + lane * 8);
+        nd[i] = ld8(a.dy + row * C + i * 256 + lane * 8);
+        if (a.res) nr[i] = ld8(a.res + row * C + i * 256 + lane * 8);
+        if (drop) nk[i] = a.keep[row * (C / 8) + i * 32 + lane];
       }
     }
-    if (masked) {
-      const bf16x8 z = {};
+    for (; row < a.rows; row += stride) {
+      const bool masked = nmask;
+      bf16x8 cx[NV], cd[NV], cr[NV];
+      uint32_t ck[NV];
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        cx[i] = nx[i];
+        cd[i] = nd[i];
+        cr[i] = nr[i];
+        ck[i] = nk[i];
+      }
+      cur.next();
+      const long long nrow = row + stride;
+      nmask = nrow < a.rows && cur.masked(a.lens);
+      if (nrow < a.rows && !nmask) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+          nx[i] = ld8(a.x + nrow * C + i * 256 + lane * 8);
+          nd[i] = ld8(a.dy + nrow * C + i * 256 + lane * 8);
+          if (a.res) nr[i] = ld8(a.res + nrow * C + i * 256 + lane * 8);
+          if (drop) nk[i] = a.keep[nrow * (C / 8) + i * 32 + lane];
+        }
+      }
+      if (masked) {
+        const bf16x8 z = {};
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+          const int col = i * 256 + lane * 8;
+          st8(a.dx + row * C + col, z);
+          if (a.dres) st8(a.dres + row * C + col, z);
+        }
+        continue;
+      }
+      const float mean = a.mean[row], rstd = a.rstd[row];
+      const float nmr = -mean * rstd;
+      float xh[NV][8], gy[NV][8];
+      KeepMask km[NV];
+      uint32_t relu_pos[NV];
+      float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        if (drop) km[i].from_byte(ck[i]); else km[i].all();
+        if (a.relu_x) {  // sign bits of the packed bf16 pairs: x > 0 <=> not negative and not zero
+          float xv0[8];
+          unpack8(cx[i], xv0);
+          uint32_t pos = 0;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) pos |= (xv0[j] > 0.f ? 1u : 0u) << j;
+          relu_pos[i] = pos;
+        }
+        if (a.drop_mode == 1) km[i].apply(cx[i]);
+        if (a.drop_mode == 2) km[i].apply(cd[i]);
+        float xv[8], dyv[8];
+        unpack8(cx[i], xv);
+        unpack8(cd[i], dyv);
+        if (a.res) {
+          float r[8];
+          unpack8(cr[i], r);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) xv[j] = fmaf(xv[j], in_scale, r[j]);
+        } else if (a.drop_mode == 1) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) xv[j] *= in_scale;
+        }
+        if (a.drop_mode == 2) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) dyv[j] *= keep_scale;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          xh[i][j] = fmaf(xv[j], rstd, nmr);
+          acc_g[i][j] = fmaf(dyv[j], xh[i][j], acc_g[i][j]);
+          acc_b[i][j] += dyv[j];
+          gy[i][j] = dyv[j] * gam[i][j];
+          s1 += gy[i][j];
+          s2 = fmaf(gy[i][j], xh[i][j], s2);
+        }
+      }
+      const float m1 = warp_sum(s1) * (1.f / C), m2 = warp_sum(s2) * (1.f / C);
 #pragma unroll
       for (int i = 0; i < NV; ++i) {
         const int col = i * 256 + lane * 8;
-        st8(a.dx + row * C + col, z);
-        if (a.dres) st8(a.dres + row * C + col, z);
+        float dpre[8], dxo[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          dpre[j] = rstd * (gy[i][j] - m1 - xh[i][j] * m2);
+          dxo[j] = dpre[j] * in_scale;
+          if (a.relu_x && !((relu_pos[i] >> j) & 1u)) dxo[j] = 0.f;
+        }
+        bf16x8 dxv = pack8(dxo);
+        if (a.drop_mode == 1) km[i].apply(dxv);
+        if (a.dbias) {  // column sums of what is stored (dropped elements contribute zero)
+          float st[8];
+          unpack8(dxv, st);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc_x[i][j] += a.drop_mode == 1 ? st[j] : dxo[j];
+        }
+        st8(a.dx + row * C + col, dxv);
+        if (a.dres) st8(a.dres + row * C + col, pack8(dpre));
       }
-      continue;
-    }
-    const float mean = a.mean[row], rstd = a.rstd[row];
-    float xh[NV][8], gy[NV][8];
-    uint32_t keep[NV], relu_pos[NV];
-    float s1 = 0.f, s2 = 0.f;
-#pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      const int col = i * 256 + lane * 8;
-      float xv[8], dyv[8];
-      unpack8(cx[i], xv);
-      unpack8(cd[i], dyv);
-      uint32_t pos = 0xFFu;
-      if (a.relu_x) {
-        pos = 0;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) pos |= (xv[j] > 0.f ? 1u : 0u) << j;
-      }
-      relu_pos[i] = pos;
-      keep[i] = thresh ? dropout_keep8(seed, (uint64_t)row * C + col, thresh) : 0xFFu;
-      if (a.drop_mode == 1 && thresh) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) xv[j] = (keep[i] >> j) & 1u ? xv[j] * keep_scale : 0.f;
-      }
-      if (a.drop_mode == 2 && thresh) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) dyv[j] = (keep[i] >> j) & 1u ? dyv[j] * keep_scale : 0.f;
-      }
-      if (a.res) {
-        float r[8];
-        unpack8(cr[i], r);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) xv[j] += r[j];
-      }
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        xh[i][j] = (xv[j] - mean) * rstd;
-        acc_g[i][j] += dyv[j] * xh[i][j];
-        acc_b[i][j] += dyv[j];
-        gy[i][j] = dyv[j] * gam[i][j];
-        s1 += gy[i][j];
-        s2 += gy[i][j] * xh[i][j];
-      }
-    }
-    const float m1 = warp_sum(s1) * (1.f / C), m2 = warp_sum(s2) * (1.f / C);
-#pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      const int col = i * 256 + lane * 8;
-      float dpre[8], dxo[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        dpre[j] = rstd * (gy[i][j] - m1 - xh[i][j] * m2);
-        dxo[j] = (a.drop_mode == 1 && thresh) ? ((keep[i] >> j) & 1u ? dpre[j] * keep_scale : 0.f)
-                                              : dpre[j];
-        if (!((relu_pos[i] >> j) & 1u)) dxo[j] = 0.f;
-        acc_x[i][j] += dxo[j];
-      }
-      st8(a.dx + row * C + col, pack8(dxo));
-      if (a.dres) st8(a.dres + row * C + col, pack8(dpre));
     }
   }
   // block reduction of the affine-parameter gradients, then one atomic per column per block
@@ -299,6 +530,143 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const LnArgs a) {
   }
 }
 
+// C = 256 backward with the cp.async ring: x, dy, residual and the 32 keep bytes of a row
+constexpr int kLnBwdDepth = 3;
+__global__ void __launch_bounds__(256) ln_bwd256_kernel(const LnArgs a) {
+  pdl_sync();
+  constexpr int C = 256, D = kLnBwdDepth;
+  __shared__ uint4 ring[8][D][3][32];      // [warp][stage][x | dy | res][lane]
+  __shared__ uint32_t kring[8][D][8];      // keep bytes of the row: 32 bytes, copied by lanes 0..7
+  __shared__ float red[8][C];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const bool drop = a.drop_mode != 0;
+  const float keep_scale = drop ? 1.f / (1.f - a.p_drop) : 1.f;
+  const float in_scale = a.drop_mode == 1 ? keep_scale : 1.f;
+  float acc_g[8], acc_b[8], acc_x[8], gam[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc_g[j] = acc_b[j] = acc_x[j] = 0.f;
+  {
+    const float4 g0 = *reinterpret_cast<const float4*>(a.gamma + lane * 8);
+    const float4 g1 = *reinterpret_cast<const float4*>(a.gamma + lane * 8 + 4);
+    gam[0] = g0.x; gam[1] = g0.y; gam[2] = g0.z; gam[3] = g0.w;
+    gam[4] = g1.x; gam[5] = g1.y; gam[6] = g1.z; gam[7] = g1.w;
+  }
+  const long long stride = (long long)gridDim.x * 8;
+  long long row = (long long)blockIdx.x * 8 + warp;
+  if (row < a.rows) {
+    RowCursor icur(row, stride, a.T);
+    long long irow = row;
+    auto issue = [&](int stage) {
+      if (irow < a.rows && !icur.masked(a.lens)) {
+        cp_async16(&ring[warp][stage][0][lane], a.x + irow * C + lane * 8);
+        cp_async16(&ring[warp][stage][1][lane], a.dy + irow * C + lane * 8);
+        if (a.res) cp_async16(&ring[warp][stage][2][lane], a.res + irow * C + lane * 8);
+        if (drop && lane < 8) cp_async4(&kring[warp][stage][lane], a.keep + irow * (C / 8) + lane * 4);
+      }
+      cp_async_commit();
+      irow += stride;
+      icur.next();
+    };
+#pragma unroll
+    for (int d = 0; d < D; ++d) issue(d);
+    RowCursor cur(row, stride, a.T);
+    int stage = 0;
+    for (; row < a.rows; row += stride, cur.next(), stage = stage + 1 == D ? 0 : stage + 1) {
+      const bool masked = cur.masked(a.lens);
+      cp_async_wait<D - 1>();
+      __syncwarp();  // the keep bytes were copied by other lanes
+      bf16x8 cx, cd, cr;
+      uint32_t ck = 0xFFu;
+      if (!masked) {
+        *reinterpret_cast<uint4*>(&cx) = ring[warp][stage][0][lane];
+        *reinterpret_cast<uint4*>(&cd) = ring[warp][stage][1][lane];
+        if (a.res) *reinterpret_cast<uint4*>(&cr) = ring[warp][stage][2][lane];
+        if (drop) ck = (kring[warp][stage][lane >> 2] >> (8 * (lane & 3))) & 0xFFu;
+      }
+      __syncwarp();  // every lane has read the slot before it is refilled
+      issue(stage);
+      if (masked) {
+        const bf16x8 z = {};
+        st8(a.dx + row * C + lane * 8, z);
+        if (a.dres) st8(a.dres + row * C + lane * 8, z);
+        continue;
+      }
+      const float mean = a.mean[row], rstd = a.rstd[row];
+      const float nmr = -mean * rstd;
+      KeepMask km;
+      if (drop) km.from_byte(ck); else km.all();
+      uint32_t relu_pos = 0xFFu;
+      if (a.relu_x) {
+        float xv0[8];
+        unpack8(cx, xv0);
+        relu_pos = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) relu_pos |= (xv0[j] > 0.f ? 1u : 0u) << j;
+      }
+      if (a.drop_mode == 1) km.apply(cx);
+      if (a.drop_mode == 2) km.apply(cd);
+      float xv[8], dyv[8], xh[8], gy[8];
+      unpack8(cx, xv);
+      unpack8(cd, dyv);
+      if (a.res) {
+        float r[8];
+        unpack8(cr, r);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) xv[j] = fmaf(xv[j], in_scale, r[j]);
+      } else if (a.drop_mode == 1) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) xv[j] *= in_scale;
+      }
+      if (a.drop_mode == 2) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) dyv[j] *= keep_scale;
+      }
+      float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        xh[j] = fmaf(xv[j], rstd, nmr);
+        acc_g[j] = fmaf(dyv[j], xh[j], acc_g[j]);
+        acc_b[j] += dyv[j];
+        gy[j] = dyv[j] * gam[j];
+        s1 += gy[j];
+        s2 = fmaf(gy[j], xh[j], s2);
+      }
+      const float m1 = warp_sum(s1) * (1.f / C), m2 = warp_sum(s2) * (1.f / C);
+      float dpre[8], dxo[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        dpre[j] = rstd * (gy[j] - m1 - xh[j] * m2);
+        dxo[j] = dpre[j] * in_scale;
+        if (a.relu_x && !((relu_pos >> j) & 1u)) dxo[j] = 0.f;
+      }
+      bf16x8 dxv = pack8(dxo);
+      if (a.drop_mode == 1) km.apply(dxv);
+      if (a.dbias) {
+        float st[8];
+        unpack8(dxv, st);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc_x[j] += a.drop_mode == 1 ? st[j] : dxo[j];
+      }
+      st8(a.dx + row * C + lane * 8, dxv);
+      if (a.dres) st8(a.dres + row * C + lane * 8, pack8(dpre));
+    }
+    cp_async_wait<0>();
+  }
+  for (int pass = 0; pass < (a.dbias ? 3 : 2); ++pass) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) red[warp][lane * 8 + j] = pass == 0 ? acc_g[j] : (pass == 1 ? acc_b[j] : acc_x[j]);
+    __syncthreads();
+    float* dst = pass == 0 ? a.dgamma : (pass == 1 ? a.dbeta : a.dbias);
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      float sum = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) sum += red[w][c];
+      atomicAdd(dst + c, sum);
+    }
+    __syncthreads();
+  }
+}
+
 static int ln_grid(int rows, int cap) {
   int g = (rows + 7) / 8;
   if (g > cap) g = cap;
@@ -312,9 +680,16 @@ static int ln_dispatch(const LnArgs& a, int C, cudaStream_t s) {
   if (a.p_drop < 0.f || a.p_drop >= 1.f) return set_error("layernorm: dropout p must be in [0,1)");
   const int grid = BWD ? ln_grid(a.rows, 148 * 4) : ln_grid(a.rows, 148 * 8);
   switch (C) {
-    case 256:
-      if (BWD) FS2_LAUNCH((ln_bwd_kernel<1>), grid, 256, 0, s, a); else FS2_LAUNCH((ln_fwd_kernel<1>), grid, 256, 0, s, a);
+    case 256: {
+      static const bool no_ring = getenv("FS2_LN_NO_RING") != nullptr;  // A/B switch: register-prefetch kernels
+      if (no_ring) {
+        if (BWD) FS2_LAUNCH((ln_bwd_kernel<1>), grid, 256, 0, s, a); else FS2_LAUNCH((ln_fwd_kernel<1>), grid, 256, 0, s, a);
+      } else {  // one wave: 4 (forward, 64 registers) / 2 (backward) resident blocks per SM
+        const int g1 = BWD ? ln_grid(a.rows, 148 * 2) : ln_grid(a.rows, 148 * 4);
+        if (BWD) FS2_LAUNCH((ln_bwd256_kernel), g1, 256, 0, s, a); else FS2_LAUNCH((ln_fwd256_kernel), g1, 256, 0, s, a);
+      }
       break;
+    }
     case 512:
       if (BWD) FS2_LAUNCH((ln_bwd_kernel<2>), grid, 256, 0, s, a); else FS2_LAUNCH((ln_fwd_kernel<2>), grid, 256, 0, s, a);
       break;
@@ -335,7 +710,7 @@ extern "C" {
 int fs2_ln_fwd_bf16(const void* x, const void* res, const float* gamma, const float* beta,
                     const int64_t* lens, int B, int T, int C, float p_drop, int drop_mode,
                     uint64_t seed, const uint64_t* seed_dev, void* y, float* mean, float* rstd,
-                    void* stream) {
+                    uint8_t* keep_out, void* stream) {
   fs2::LnArgs a{};
   a.x = static_cast<const __nv_bfloat16*>(x);
   a.res = static_cast<const __nv_bfloat16*>(res);
@@ -351,13 +726,15 @@ int fs2_ln_fwd_bf16(const void* x, const void* res, const float* gamma, const fl
   a.y = static_cast<__nv_bfloat16*>(y);
   a.mean = mean;
   a.rstd = rstd;
+  a.keep = keep_out;
   return fs2::ln_dispatch<false>(a, C, static_cast<cudaStream_t>(stream));
 }
 
 int fs2_ln_bwd_bf16(const void* dy, const void* x, const void* res, const float* gamma,
                     const float* mean, const float* rstd, const int64_t* lens, int B, int T, int C,
-                    float p_drop, int drop_mode, int relu_x, uint64_t seed, const uint64_t* seed_dev,
+                    float p_drop, int drop_mode, int relu_x, const uint8_t* keep_in,
                     void* dx, void* dres, float* dgamma, float* dbeta, float* dbias, void* stream) {
+  if (p_drop > 0.f && !keep_in) return fs2::set_error("ln_bwd: p_drop > 0 needs the keep bits written by fs2_ln_fwd_bf16");
   fs2::LnArgs a{};
   a.dy = static_cast<const __nv_bfloat16*>(dy);
   a.x = static_cast<const __nv_bfloat16*>(x);
@@ -370,8 +747,7 @@ int fs2_ln_bwd_bf16(const void* dy, const void* x, const void* res, const float*
   a.T = T;
   a.p_drop = p_drop;
   a.drop_mode = p_drop > 0.f ? drop_mode : 0;
-  a.seed = seed;
-  a.seed_dev = seed_dev;
+  a.keep = const_cast<uint8_t*>(keep_in);
   a.relu_x = relu_x;
   a.dx = static_cast<__nv_bfloat16*>(dx);
   a.dres = static_cast<__nv_bfloat16*>(dres);

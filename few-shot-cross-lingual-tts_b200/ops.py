@@ -457,25 +457,28 @@ def conv_wgrad(dy, x, dw, lens=None):
 
 
 def ln_fwd(x, res, gamma, beta, lens, p, mode, salt):
+    """-> (y, mean, rstd, keep): keep = the dropout keep bits (uint8 [B*T, C/8], None without dropout) that
+    ln_bwd reads back -- the Philox stream is drawn once per step."""
     B, T, C = x.shape
     y = torch.empty_like(x)
     mean = torch.empty(B * T, dtype=F32, device=x.device)
     rstd = torch.empty(B * T, dtype=F32, device=x.device)
     seed_dev = _Rng.tensor(x.device) if p > 0 else None
+    keep = torch.empty(B * T, C // 8, dtype=torch.uint8, device=x.device) if p > 0 else None
     _ck(_L().fs2_ln_fwd_bf16(_p(x), _p(res), _p(gamma), _p(beta), _p(lens), B, T, C, p, mode, salt,
-                             _p(seed_dev), _p(y), _p(mean), _p(rstd), _st()), "ln_fwd")
-    return y, mean, rstd
+                             _p(seed_dev), _p(y), _p(mean), _p(rstd), _p(keep), _st()), "ln_fwd")
+    return y, mean, rstd, keep
 
 
-def ln_bwd(dy, x, res, gamma, mean, rstd, lens, p, mode, salt, dgamma, dbeta, want_dres, relu_x=False,
+def ln_bwd(dy, x, res, gamma, mean, rstd, lens, p, mode, keep, dgamma, dbeta, want_dres, relu_x=False,
            dbias=None):
-    """dbias (fp32 [C], accumulated): column sums of dx = bias gradient of the GEMM / conv that produced x."""
+    """keep: the bits ln_fwd returned.  dbias (fp32 [C], accumulated): column sums of dx = bias gradient of the
+    GEMM / conv that produced x."""
     B, T, C = x.shape
     dx = torch.empty_like(x)
     dres = torch.empty_like(x) if want_dres and p > 0 and mode == 1 else None
-    seed_dev = _Rng.tensor(x.device) if p > 0 else None
     _ck(_L().fs2_ln_bwd_bf16(_p(dy), _p(x), _p(res), _p(gamma), _p(mean), _p(rstd), _p(lens), B, T, C, p,
-                             mode, 1 if relu_x else 0, salt, _p(seed_dev), _p(dx), _p(dres), _p(dgamma),
+                             mode, 1 if relu_x else 0, _p(keep), _p(dx), _p(dres), _p(dgamma),
                              _p(dbeta), _p(dbias), _st()), "ln_bwd")
     if want_dres and dres is None:
         dres = dx  # without pre-LN dropout the two gradients are the same tensor
@@ -619,8 +622,8 @@ class MHASublayer(torch.autograd.Function):
             wo_bf = cast_bf16(wo)
             o = linear_fwd(attn, wo_bf, bo.detach(), lens=rl, T=T, tail=NO_TAIL)
             salt = _Rng.next_salt()
-            y, mean, rstd = ln_fwd(o.view(B, T, D), x, gamma.detach(), beta.detach(),
-                                   lens if zero_pad else None, p_drop, 1, salt)
+            y, mean, rstd, ctx.keep = ln_fwd(o.view(B, T, D), x, gamma.detach(), beta.detach(),
+                                             lens if zero_pad else None, p_drop, 1, salt)
             ctx.save_for_backward(x, lens, qkv, lse2, attn, o, mean, rstd, wqkv, wo_bf, gamma)
             ctx.sched = sched
             ctx.params = (wq, bq, wk, bk, wv, bv, wo, bo, gamma, beta)
@@ -640,8 +643,8 @@ class MHASublayer(torch.autograd.Function):
         wo_bf = cast_bf16(wo)
         o = linear_fwd(attn, wo_bf, bo.detach())
         salt = _Rng.next_salt()
-        y, mean, rstd = ln_fwd(o.view(B, T, D), x, gamma.detach(), beta.detach(), lens if zero_pad else None,
-                               p_drop, 1, salt)
+        y, mean, rstd, ctx.keep = ln_fwd(o.view(B, T, D), x, gamma.detach(), beta.detach(),
+                                         lens if zero_pad else None, p_drop, 1, salt)
         ctx.save_for_backward(x, lens, qkv, P, attn, o, mean, rstd, wqkv, wo_bf, gamma)
         ctx.params = (wq, bq, wk, bk, wv, bv, wo, bo, gamma, beta)
         ctx.cfg = (H, dk, p_drop, zero_pad, salt, Tp, False)
@@ -660,7 +663,7 @@ class MHASublayer(torch.autograd.Function):
         rl = lens if (zero_pad and fused) else None
         # the output-projection bias gradient (column sums of `do`) comes out of the LayerNorm backward
         do, dres = ln_bwd(dy, o.view(B, T, D), x, gamma_t, mean, rstd, lens if zero_pad else None, p_drop, 1,
-                          salt, gbuf[8][0], gbuf[9][0], want_dres=True, dbias=gbuf[7][0])
+                          ctx.keep, gbuf[8][0], gbuf[9][0], want_dres=True, dbias=gbuf[7][0])
         do2 = do.view(M, D)
         # output projection
         with fork_side():
@@ -727,8 +730,8 @@ class FFNSublayer(torch.autograd.Function):
                      relu_mask=hmask)
         f = conv_fwd(h, w2p, b2.detach(), lens=rl, tail=NO_TAIL)
         salt = _Rng.next_salt()
-        y, mean, rstd = ln_fwd(f, x, gamma.detach(), beta.detach(), lens if zero_pad else None, p_drop, 1,
-                               salt)
+        y, mean, rstd, ctx.keep = ln_fwd(f, x, gamma.detach(), beta.detach(), lens if zero_pad else None, p_drop,
+                                         1, salt)
         ctx.save_for_backward(x, lens, h, f, mean, rstd, w1p, w2p, gamma)
         ctx.hmask = hmask
         ctx.params = (w1, b1, w2, b2, gamma, beta)
@@ -745,7 +748,7 @@ class FFNSublayer(torch.autograd.Function):
         dy = _contig(dy)
         gbuf = [grad_target(p) for p in (w1, b1, w2, b2, gamma, beta)]
         rl = lens if zero_pad else None
-        df, dres = ln_bwd(dy, f, x, gamma_t, mean, rstd, rl, p_drop, 1, salt,
+        df, dres = ln_bwd(dy, f, x, gamma_t, mean, rstd, rl, p_drop, 1, ctx.keep,
                           gbuf[4][0], gbuf[5][0], want_dres=True, dbias=gbuf[3][0])  # dbias: w_2.bias gradient
         # dh feeds the input gradient of w_1, which reads a (k1-1)//2-row halo behind the last valid frame
         with fork_side():
@@ -777,9 +780,10 @@ class VariancePredictorFn(torch.autograd.Function):
         c1p, c2p = pack_conv(c1w), pack_conv(c2w)
         a1 = conv_fwd(x, c1p, c1b.detach(), relu=True)
         s1, s2 = _Rng.next_salt(), _Rng.next_salt()
-        n1, m1, r1 = ln_fwd(a1, None, g1.detach(), be1.detach(), None, p_drop, 2, s1)
+        n1, m1, r1, k1 = ln_fwd(a1, None, g1.detach(), be1.detach(), None, p_drop, 2, s1)
         a2 = conv_fwd(n1, c2p, c2b.detach(), relu=True)
-        n2, m2, r2 = ln_fwd(a2, None, g2.detach(), be2.detach(), None, p_drop, 2, s2)
+        n2, m2, r2, k2 = ln_fwd(a2, None, g2.detach(), be2.detach(), None, p_drop, 2, s2)
+        ctx.keeps = (k1, k2)
         F_ = n2.shape[2]
         out = torch.empty(B, T, dtype=F32, device=x.device)
         lw2 = lw.detach().reshape(-1).contiguous()
@@ -803,12 +807,12 @@ class VariancePredictorFn(torch.autograd.Function):
         _ck(_L().fs2_rowdot_bwd(_p(dout), _p(n2), _p(lw2), _p(lens if use_mask else None), B, T, F_, _p(dn2),
                                 _p(gbuf[8][0]), _p(gbuf[9][0]), _st()), "rowdot_bwd")
         # the conv bias gradients (column sums of da2 / da1) come out of the LayerNorm backward kernels
-        da2, _ = ln_bwd(dn2, a2, None, g2t, m2, r2, None, p_drop, 2, s2, gbuf[6][0], gbuf[7][0],
+        da2, _ = ln_bwd(dn2, a2, None, g2t, m2, r2, None, p_drop, 2, ctx.keeps[1], gbuf[6][0], gbuf[7][0],
                         want_dres=False, relu_x=True, dbias=gbuf[5][0])
         with fork_side():
             conv_wgrad(da2, n1, gbuf[4][0])
         dn1 = conv_dgrad(da2, c2p, n1.shape[2])
-        da1, _ = ln_bwd(dn1, a1, None, g1t, m1, r1, None, p_drop, 2, s1, gbuf[2][0], gbuf[3][0],
+        da1, _ = ln_bwd(dn1, a1, None, g1t, m1, r1, None, p_drop, 2, ctx.keeps[0], gbuf[2][0], gbuf[3][0],
                         want_dres=False, relu_x=True, dbias=gbuf[1][0])
         with fork_side():
             conv_wgrad(da1, x, gbuf[0][0])

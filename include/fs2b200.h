@@ -135,8 +135,10 @@ int64_t fs2_gemm_workspace_bytes(void);
 /*   lightning/model/modules.py:222-225,234-237                                                */
 /*   x,res,y,dy,dx,dres: bf16 [B][T][C], C in {256,512,1024}; mean,rstd: f32 [B*T];           */
 /*   lens: int64 [B] or NULL (rows t >= lens[b] are zeroed); drop_mode 1: LN(drop(x)+res),      */
-/*   2: drop(LN(x+res)); the mask is regenerated in the backward (Philox4x32-10) from         */
-/*   seed_dev[0] (device step counter, may be NULL) mixed with the call-site salt `seed`.      */
+/*   2: drop(LN(x+res)); the mask comes from a Philox4x32-7 stream keyed by seed_dev[0]        */
+/*   (device step counter, may be NULL) mixed with the call-site salt `seed`; p is resolved to */
+/*   1/8192.  keep_out / keep_in: uint8 [B*T][C/8] keep bits (bit j of byte v = channel 8v+j),  */
+/*   written by the forward (optional there) and READ by the backward (required when p > 0).   */
 /*   dgamma/dbeta: f32 [C], accumulated with atomics (zero them first); dbias (optional, f32    */
 /*   [C]): column sums of dx, i.e. the bias gradient of the GEMM / conv that produced x.        */
 /*   Rows t >= lens[b] are never read: y / dx / dres are zero there.                            */
@@ -144,10 +146,10 @@ int64_t fs2_gemm_workspace_bytes(void);
 int fs2_ln_fwd_bf16(const void* x, const void* res, const float* gamma, const float* beta,
                     const int64_t* lens, int B, int T, int C, float p_drop, int drop_mode,
                     uint64_t seed, const uint64_t* seed_dev, void* y, float* mean, float* rstd,
-                    void* stream);
+                    uint8_t* keep_out, void* stream);
 int fs2_ln_bwd_bf16(const void* dy, const void* x, const void* res, const float* gamma,
                     const float* mean, const float* rstd, const int64_t* lens, int B, int T, int C,
-                    float p_drop, int drop_mode, int relu_x, uint64_t seed, const uint64_t* seed_dev,
+                    float p_drop, int drop_mode, int relu_x, const uint8_t* keep_in,
                     void* dx, void* dres, float* dgamma, float* dbeta, float* dbias, void* stream);
 
 /* ------------------------------------------------------------------------------------------ */

@@ -350,6 +350,39 @@ def test_ragged_wgrad(impl, lens, N, K, k, splits):
     assert rel_err(dw, ref) < 2e-3, rel_err(dw, ref)
 
 
+@pytest.mark.parametrize("Co,Ci,k,lens,T", [
+    (1024, 256, 9, [300, 64, 65, 1, 0, 257], 300),    # FFN conv: tap groups 3 + 3 + 3
+    (512, 512, 5, [130] * 7, 130),                      # PostNet conv (dense): groups 3 + 2 with their own split counts
+    (256, 256, 3, [200, 17, 90], 200),                  # predictor conv: one group
+    (256, 384, 2, [100, 100], 100),                     # even kernel size
+    (768, 128, 7, [500, 333], 500),                     # 1.5 co pair tiles, one ci tile, groups 4 + 3
+])
+def test_conv_wgrad_tap_groups(Co, Ci, k, lens, T):
+    """csrc/wgrad_taps.cu: one X tile with halo serves all taps of a group (row-shifted MN-major descriptors)."""
+    B = len(lens)
+    torch.manual_seed(Co + Ci + k)
+    ln = _lens(lens).clamp(max=T)
+    valid = torch.arange(T, device="cuda")[None, :] < ln[:, None]
+    dy = rnd(B, T, Co) * valid[..., None]
+    x = rnd(B, T, Ci) * valid[..., None]
+    dw = torch.full((Co, k, Ci), 0.5, device="cuda")
+    shift = -((k - 1) // 2)
+    G.wgrad(G.operand(dy, Co, T, B, mn_major=True), G.operand(x, Ci, T, B, mn_major=True), dw, Co, Ci, taps=k,
+            tap_shift0=shift, ldd=Ci * k, d_col_stride=1, d_tap_stride=Ci, splits=4, row_lens=_lens(lens))
+    # reference: dw[co][tap][ci] = sum_t dy[t][co] * x[t + tap + shift][ci]
+    xf, dyf = x.float(), dy.float()
+    ref = torch.empty(Co, k, Ci, device="cuda")
+    for tap in range(k):
+        s_ = tap + shift
+        xs = torch.zeros_like(xf)
+        if s_ >= 0:
+            xs[:, :T - s_] = xf[:, s_:]
+        else:
+            xs[:, -s_:] = xf[:, :T + s_]
+        ref[:, tap] = torch.einsum("btc,bti->ci", dyf, xs)
+    assert rel_err(dw, ref + 0.5) < 2e-3, rel_err(dw, ref + 0.5)
+
+
 def test_ragged_many_batches_falls_back_to_dense_schedule():
     """More utterances than the on-chip schedule table holds: every tile is computed, rows still zeroed."""
     B, T, N, K = 300, 40, 256, 256

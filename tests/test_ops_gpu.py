@@ -193,7 +193,7 @@ def test_layernorm_fwd_bwd(with_res, with_lens):
         pad = torch.arange(T, device="cuda")[None, :] >= lens[:, None]
         x = x.masked_fill(pad[..., None], float("nan"))
         res = res.masked_fill(pad[..., None], float("nan"))
-    y, mean, rstd = ops.ln_fwd(x, res, g, b, lens, 0.0, 1, 0)
+    y, mean, rstd, keep = ops.ln_fwd(x, res, g, b, lens, 0.0, 1, 0)
     gr, br = g.clone().requires_grad_(), b.clone().requires_grad_()
     ref = F.layer_norm(pre, (C,), gr, br)
     if with_lens:
@@ -206,7 +206,7 @@ def test_layernorm_fwd_bwd(with_res, with_lens):
     dbias = torch.ones(C, device="cuda")
     if with_lens:
         dy = dy.masked_fill(pad[..., None], float("nan"))
-    dx, dres = ops.ln_bwd(dy, x, res, g, mean, rstd, lens, 0.0, 1, 0, dg, db, want_dres=True, dbias=dbias)
+    dx, dres = ops.ln_bwd(dy, x, res, g, mean, rstd, lens, 0.0, 1, keep, dg, db, want_dres=True, dbias=dbias)
     assert torch.isfinite(dx.float()).all() and torch.isfinite(y.float()).all()
     assert rel_err(dx, pre.grad) < 5e-3
     assert rel_err(dg, gr.grad) < 2e-3 and rel_err(db, br.grad) < 2e-3
@@ -224,25 +224,25 @@ def test_layernorm_dropout_statistics_and_backward_consistency(mode):
     g, b = torch.ones(C, device="cuda"), torch.zeros(C, device="cuda")
     if mode == 2:  # drop(LN(x)): use a non-constant input so that LN(x) != 0
         x = torch.randn(B, T, C, device="cuda").to(BF16)
-    y, mean, rstd = ops.ln_fwd(x, None, g, b, None, p, mode, 1234)
+    y, mean, rstd, keep = ops.ln_fwd(x, None, g, b, None, p, mode, 1234)
     if mode == 2:
-        keep = (y != 0).float().mean().item()
-        assert abs(keep - (1 - p)) < 0.01
+        keep_rate = (y != 0).float().mean().item()
+        assert abs(keep_rate - (1 - p)) < 0.01
         ln = F.layer_norm(x.float(), (C,))
         kept = y.float() != 0
         assert rel_err(y.float()[kept], (ln / (1 - p))[kept]) < 1e-2
     dy = (torch.ones(B, T, C, device="cuda") if mode == 2 else torch.randn(B, T, C, device="cuda")).to(BF16)
     dg, db = torch.zeros(C, device="cuda"), torch.zeros(C, device="cuda")
-    dx, _ = ops.ln_bwd(dy, x, None, g, mean, rstd, None, p, mode, 1234, dg, db, want_dres=False)
+    dx, _ = ops.ln_bwd(dy, x, None, g, mean, rstd, None, p, mode, keep, dg, db, want_dres=False)
     if mode == 2:
         # dbeta = sum over rows of the masked, rescaled dy: same mask as the forward
         assert torch.allclose(db, ((y != 0).float() / (1 - p)).sum((0, 1)), rtol=1e-3)
     else:
         # pre-LN dropout: dx is zero exactly where the input element was dropped
-        y2, _, _ = ops.ln_fwd(x, None, g, b, None, p, mode, 1234)
+        y2, _, _, _ = ops.ln_fwd(x, None, g, b, None, p, mode, 1234)
         assert torch.equal(y, y2)  # same seed, same mask
         assert abs((dx == 0).float().mean().item() - p) < 0.02
-        y3, _, _ = ops.ln_fwd(x, None, g, b, None, p, mode, 99)
+        y3, _, _, _ = ops.ln_fwd(x, None, g, b, None, p, mode, 99)
         assert not torch.equal(y, y3)  # another call-site salt, another mask
 
 

@@ -72,11 +72,11 @@ def main():
     dg, db, dbias = (torch.zeros(C, device="cuda") for _ in range(3))
     for tag, lens, nrows in (("dense", full, B * T), ("ragged C2 lens", mel_lens, valid)):
         for p in (0.0, 0.2):
-            y, mean, rstd = ops.ln_fwd(x, res, g, b, lens, p, 1, 5)
+            y, mean, rstd, keep = ops.ln_fwd(x, res, g, b, lens, p, 1, 5)
             us = timeit(lambda: ops.ln_fwd(x, res, g, b, lens, p, 1, 5))
             # reads x, res on valid rows; writes y on all rows
             rec("ln_fwd dropout+res+LN+padzero p=%.1f %s" % (p, tag), us, (2 * nrows + B * T) * C * 2)
-            us = timeit(lambda: ops.ln_bwd(dy, x, res, g, mean, rstd, lens, p, 1, 5, dg, db, True, dbias=dbias))
+            us = timeit(lambda: ops.ln_bwd(dy, x, res, g, mean, rstd, lens, p, 1, keep, dg, db, True, dbias=dbias))
             nout = 2 if p > 0 else 1
             rec("ln_bwd (+dgamma,dbeta,dbias) p=%.1f %s" % (p, tag), us, (3 * nrows + nout * B * T) * C * 2)
 

@@ -32,7 +32,7 @@ gamma, beta = torch.ones(D, device="cuda"), torch.zeros(D, device="cuda")
 dg, db, dbias = (torch.zeros(D, device="cuda") for _ in range(3))
 sched = ops.attn_schedule(lens, T, H)
 o3, lse = ops.attn_fwd(qkv, lens, H, D // H, sched)
-y, mean, rstd = ops.ln_fwd(x, dy, gamma, beta, lens, 0.2, 1, 5)
+y, mean, rstd, keep = ops.ln_fwd(x, dy, gamma, beta, lens, 0.2, 1, 5)
 torch.cuda.synchronize()
 seq = [
     lambda: ops.attn_fwd(qkv, lens, H, D // H, sched),
@@ -46,7 +46,7 @@ seq = [
     lambda: ops.conv_dgrad(dh, w1p, D, epilogue=G.EPI_ADD_AUX, aux=x, lens=lens),
     lambda: ops.conv_wgrad(dh, x, gw1, lens=lens),
     lambda: ops.ln_fwd(x, dy, gamma, beta, lens, 0.2, 1, 5),
-    lambda: ops.ln_bwd(dy, x, dy, gamma, mean, rstd, lens, 0.2, 1, 5, dg, db, True, dbias=dbias),
+    lambda: ops.ln_bwd(dy, x, dy, gamma, mean, rstd, lens, 0.2, 1, keep, dg, db, True, dbias=dbias),
 ]
 for fn in seq:
     for _ in range(reps):

@@ -495,6 +495,9 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constant
       mbar_wait(bar(S_FULL + s3), (u / SS) & 1);
       tc_fence_after();
       const uint32_t tS = tS0 + s3 * 128 + lane_base + half * 64;
+      // only the LAST key tile can hold padded keys (n = ceil(len / 128)); rows of padded queries in this tile are
+      // computed like any other (their Q rows are zero-filled by the projection) and dropped in the epilogue
+      const bool key_mask = (j + 1) * BKV > len;
       if (!pass_b) {
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
@@ -502,8 +505,13 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constant
           tmem_ld32(tS + c * 32, v);
           tmem_ld_wait();
           const int k0 = j * BKV + half * 64 + c * 32;
+          if (key_mask) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, (k0 + i < len) ? __uint_as_float(v[i]) : -INFINITY);
+            for (int i = 0; i < 32; ++i) mx = fmaxf(mx, (k0 + i < len) ? __uint_as_float(v[i]) : -INFINITY);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
+          }
         }
       } else {
         uint32_t w[32];
@@ -515,10 +523,12 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constant
           const int k0 = j * BKV + half * 64 + c * 32;
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
-            const float e0 = ex2_approx(fmaf(__uint_as_float(v[2 * i]), p.scale_log2, -m2));
-            const float e1 = ex2_approx(fmaf(__uint_as_float(v[2 * i + 1]), p.scale_log2, -m2));
-            const float p0 = (row_valid && k0 + 2 * i < len) ? e0 : 0.f;
-            const float p1 = (row_valid && k0 + 2 * i + 1 < len) ? e1 : 0.f;
+            float p0 = ex2_approx(fmaf(__uint_as_float(v[2 * i]), p.scale_log2, -m2));
+            float p1 = ex2_approx(fmaf(__uint_as_float(v[2 * i + 1]), p.scale_log2, -m2));
+            if (key_mask) {
+              p0 = (k0 + 2 * i < len) ? p0 : 0.f;
+              p1 = (k0 + 2 * i + 1 < len) ? p1 : 0.f;
+            }
             l += p0 + p1;
             __nv_bfloat162 b2 = __floats2bfloat162_rn(p0, p1);
             w[c * 16 + i] = *reinterpret_cast<uint32_t*>(&b2);
@@ -546,8 +556,8 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constant
     l = s_red[row] + s_red[128 + row];
     mbar_wait(bar(O_FULL), 0);
     tc_fence_after();
-    const float inv = l > 0.f ? 1.f / l : 0.f;
-    if (half == 0 && q < p.T) p.lse2[(long long)z * p.T + q] = l > 0.f ? m2 + log2f(l) : INFINITY;
+    const float inv = (row_valid && l > 0.f) ? 1.f / l : 0.f;  // padded query rows: out = 0, lse2 = +inf
+    if (half == 0 && q < p.T) p.lse2[(long long)z * p.T + q] = (row_valid && l > 0.f) ? m2 + log2f(l) : INFINITY;
     uint8_t* stg = sgen + OFF_STG + warp * 4096;
     uint8_t* my = stg + lane * 128;
     const int lsw = lane & 7;
@@ -559,7 +569,7 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constant
         tmem_ld32(tO + lane_base + half * 64 + c * 32, v);
         tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 32; ++i) f[c * 32 + i] = __uint_as_float(v[i]) * inv;
+        for (int i = 0; i < 32; ++i) f[c * 32 + i] = row_valid ? __uint_as_float(v[i]) * inv : 0.f;
       }
 #pragma unroll
       for (int ch = 0; ch < 8; ++ch) {

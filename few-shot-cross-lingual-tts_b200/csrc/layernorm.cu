@@ -9,16 +9,10 @@
 // statistics never leave registers.  HBM-bound: algorithmic bytes fwd = (2 or 3) * rows * C * 2.
 #include <cuda_fp16.h>
 
-#include <cstdlib>
-
 #include "common.h"
 #include "util.cuh"
 
 namespace fs2 {
-
-__device__ __forceinline__ uint32_t smem_u32_ln(const void* p) {
-  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
-}
 
 constexpr float kLnEps = 1e-5f;  // nn.LayerNorm default (the reference never overrides it)
 
@@ -114,23 +108,6 @@ __host__ __device__ __forceinline__ uint32_t keep_thresh_h2(float p) {
   return h | (h << 16);
 }
 
-
-// ---- per-warp cp.async ring (C = 256: the FFT-block / predictor LayerNorms) ----------------------------------
-// One row per warp and iteration leaves 1 KiB per warp in flight (x + residual, register prefetch of one row):
-// 32 KiB per SM, i.e. ~3 TB/s at the loaded HBM latency -- the kernels were latency-, not instruction-bound.  Here
-// every lane copies ITS OWN 16-byte pieces of the next D rows global -> shared with cp.async (no registers, no
-// barriers: a lane only ever reads back what it copied itself), so a warp keeps D KiB in flight.
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32_ln(smem_dst)), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32_ln(smem_dst)), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() {
-  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
-}
 
 template <int NV>
 __global__ void __launch_bounds__(256) ln_fwd_kernel(const LnArgs a) {
@@ -256,117 +233,6 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const LnArgs a) {
       st8(a.y + row * C + i * 256 + lane * 8, ov);
     }
   }
-}
-
-// C = 256 forward with the cp.async ring (D rows ahead per warp)
-constexpr int kLnFwdDepth = 4;
-__global__ void __launch_bounds__(256) ln_fwd256_kernel(const LnArgs a) {
-  pdl_sync();
-  constexpr int C = 256, D = kLnFwdDepth;
-  __shared__ uint4 ring[8][D][2][32];  // [warp][stage][x | res][lane]
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const bool drop = a.drop_mode != 0;
-  const uint32_t thresh = keep_thresh_h2(a.p_drop);
-  const float keep_scale = drop ? 1.f / (1.f - a.p_drop) : 1.f;
-  const float in_scale = a.drop_mode == 1 ? keep_scale : 1.f;
-  const uint64_t seed = mix_seed(a.seed_dev, a.seed);
-  const long long stride = (long long)gridDim.x * 8;
-  long long row = (long long)blockIdx.x * 8 + warp;
-  float gam[8], bet[8];
-  {
-    const int col = lane * 8;
-    const float4 g0 = *reinterpret_cast<const float4*>(a.gamma + col);
-    const float4 g1 = *reinterpret_cast<const float4*>(a.gamma + col + 4);
-    const float4 b0 = *reinterpret_cast<const float4*>(a.beta + col);
-    const float4 b1 = *reinterpret_cast<const float4*>(a.beta + col + 4);
-    gam[0] = g0.x; gam[1] = g0.y; gam[2] = g0.z; gam[3] = g0.w;
-    gam[4] = g1.x; gam[5] = g1.y; gam[6] = g1.z; gam[7] = g1.w;
-    bet[0] = b0.x; bet[1] = b0.y; bet[2] = b0.z; bet[3] = b0.w;
-    bet[4] = b1.x; bet[5] = b1.y; bet[6] = b1.z; bet[7] = b1.w;
-    if (a.drop_mode == 2) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        gam[j] *= keep_scale;
-        bet[j] *= keep_scale;
-      }
-    }
-  }
-  if (row >= a.rows) return;
-  // issue cursor (D rows ahead of the compute cursor); every row, masked or not, is one commit group
-  RowCursor icur(row, stride, a.T);
-  long long irow = row;
-  auto issue = [&](int stage) {
-    if (irow < a.rows && !icur.masked(a.lens)) {
-      cp_async16(&ring[warp][stage][0][lane], a.x + irow * C + lane * 8);
-      if (a.res) cp_async16(&ring[warp][stage][1][lane], a.res + irow * C + lane * 8);
-    }
-    cp_async_commit();
-    irow += stride;
-    icur.next();
-  };
-#pragma unroll
-  for (int d = 0; d < D; ++d) issue(d);
-  RowCursor cur(row, stride, a.T);
-  int stage = 0;
-  for (; row < a.rows; row += stride, cur.next(), stage = stage + 1 == D ? 0 : stage + 1) {
-    const bool masked = cur.masked(a.lens);
-    cp_async_wait<D - 1>();
-    bf16x8 cx, cr;
-    if (!masked) {
-      *reinterpret_cast<uint4*>(&cx) = ring[warp][stage][0][lane];
-      if (a.res) *reinterpret_cast<uint4*>(&cr) = ring[warp][stage][1][lane];
-    }
-    issue(stage);  // refill the slot just read with the row D iterations ahead
-    if (masked) {  // transformer/Layers.py:25,28: the row is zero whatever the sub-layer produced
-      const bf16x8 z = {};
-      st8(a.y + row * C + lane * 8, z);
-      if (lane == 0) {
-        a.mean[row] = 0.f;
-        a.rstd[row] = 0.f;
-      }
-      continue;
-    }
-    KeepMask km;
-    if (drop) {
-      km.draw(seed, ((uint64_t)row * C + lane * 8) >> 3, thresh);
-      if (a.keep) a.keep[row * (C / 8) + lane] = static_cast<uint8_t>(km.to_byte());
-    }
-    float v[8];
-    if (a.drop_mode == 1) km.apply(cx);
-    unpack8(cx, v);
-    if (a.res) {
-      float r[8];
-      unpack8(cr, r);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] = fmaf(v[j], in_scale, r[j]);
-    } else if (a.drop_mode == 1) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] *= in_scale;
-    }
-    float sm = 0.f;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) sm += v[j];
-    const float mean = warp_sum(sm) * (1.f / C);
-    float q = 0.f;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float d = v[j] - mean;
-      q = fmaf(d, d, q);
-    }
-    const float rstd = rsqrtf(warp_sum(q) * (1.f / C) + kLnEps);
-    if (lane == 0) {
-      a.mean[row] = mean;
-      a.rstd[row] = rstd;
-    }
-    const float nmr = -mean * rstd;
-    float o[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) o[j] = fmaf(fmaf(v[j], rstd, nmr), gam[j], bet[j]);
-    bf16x8 ov = pack8(o);
-    if (a.drop_mode == 2) km.apply(ov);
-    st8(a.y + row * C + lane * 8, ov);
-  }
-  cp_async_wait<0>();
 }
 
 template <int NV>
@@ -530,143 +396,6 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const LnArgs a) {
   }
 }
 
-// C = 256 backward with the cp.async ring: x, dy, residual and the 32 keep bytes of a row
-constexpr int kLnBwdDepth = 3;
-__global__ void __launch_bounds__(256) ln_bwd256_kernel(const LnArgs a) {
-  pdl_sync();
-  constexpr int C = 256, D = kLnBwdDepth;
-  __shared__ uint4 ring[8][D][3][32];      // [warp][stage][x | dy | res][lane]
-  __shared__ uint32_t kring[8][D][8];      // keep bytes of the row: 32 bytes, copied by lanes 0..7
-  __shared__ float red[8][C];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const bool drop = a.drop_mode != 0;
-  const float keep_scale = drop ? 1.f / (1.f - a.p_drop) : 1.f;
-  const float in_scale = a.drop_mode == 1 ? keep_scale : 1.f;
-  float acc_g[8], acc_b[8], acc_x[8], gam[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) acc_g[j] = acc_b[j] = acc_x[j] = 0.f;
-  {
-    const float4 g0 = *reinterpret_cast<const float4*>(a.gamma + lane * 8);
-    const float4 g1 = *reinterpret_cast<const float4*>(a.gamma + lane * 8 + 4);
-    gam[0] = g0.x; gam[1] = g0.y; gam[2] = g0.z; gam[3] = g0.w;
-    gam[4] = g1.x; gam[5] = g1.y; gam[6] = g1.z; gam[7] = g1.w;
-  }
-  const long long stride = (long long)gridDim.x * 8;
-  long long row = (long long)blockIdx.x * 8 + warp;
-  if (row < a.rows) {
-    RowCursor icur(row, stride, a.T);
-    long long irow = row;
-    auto issue = [&](int stage) {
-      if (irow < a.rows && !icur.masked(a.lens)) {
-        cp_async16(&ring[warp][stage][0][lane], a.x + irow * C + lane * 8);
-        cp_async16(&ring[warp][stage][1][lane], a.dy + irow * C + lane * 8);
-        if (a.res) cp_async16(&ring[warp][stage][2][lane], a.res + irow * C + lane * 8);
-        if (drop && lane < 8) cp_async4(&kring[warp][stage][lane], a.keep + irow * (C / 8) + lane * 4);
-      }
-      cp_async_commit();
-      irow += stride;
-      icur.next();
-    };
-#pragma unroll
-    for (int d = 0; d < D; ++d) issue(d);
-    RowCursor cur(row, stride, a.T);
-    int stage = 0;
-    for (; row < a.rows; row += stride, cur.next(), stage = stage + 1 == D ? 0 : stage + 1) {
-      const bool masked = cur.masked(a.lens);
-      cp_async_wait<D - 1>();
-      __syncwarp();  // the keep bytes were copied by other lanes
-      bf16x8 cx, cd, cr;
-      uint32_t ck = 0xFFu;
-      if (!masked) {
-        *reinterpret_cast<uint4*>(&cx) = ring[warp][stage][0][lane];
-        *reinterpret_cast<uint4*>(&cd) = ring[warp][stage][1][lane];
-        if (a.res) *reinterpret_cast<uint4*>(&cr) = ring[warp][stage][2][lane];
-        if (drop) ck = (kring[warp][stage][lane >> 2] >> (8 * (lane & 3))) & 0xFFu;
-      }
-      __syncwarp();  // every lane has read the slot before it is refilled
-      issue(stage);
-      if (masked) {
-        const bf16x8 z = {};
-        st8(a.dx + row * C + lane * 8, z);
-        if (a.dres) st8(a.dres + row * C + lane * 8, z);
-        continue;
-      }
-      const float mean = a.mean[row], rstd = a.rstd[row];
-      const float nmr = -mean * rstd;
-      KeepMask km;
-      if (drop) km.from_byte(ck); else km.all();
-      uint32_t relu_pos = 0xFFu;
-      if (a.relu_x) {
-        float xv0[8];
-        unpack8(cx, xv0);
-        relu_pos = 0;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) relu_pos |= (xv0[j] > 0.f ? 1u : 0u) << j;
-      }
-      if (a.drop_mode == 1) km.apply(cx);
-      if (a.drop_mode == 2) km.apply(cd);
-      float xv[8], dyv[8], xh[8], gy[8];
-      unpack8(cx, xv);
-      unpack8(cd, dyv);
-      if (a.res) {
-        float r[8];
-        unpack8(cr, r);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) xv[j] = fmaf(xv[j], in_scale, r[j]);
-      } else if (a.drop_mode == 1) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) xv[j] *= in_scale;
-      }
-      if (a.drop_mode == 2) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) dyv[j] *= keep_scale;
-      }
-      float s1 = 0.f, s2 = 0.f;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        xh[j] = fmaf(xv[j], rstd, nmr);
-        acc_g[j] = fmaf(dyv[j], xh[j], acc_g[j]);
-        acc_b[j] += dyv[j];
-        gy[j] = dyv[j] * gam[j];
-        s1 += gy[j];
-        s2 = fmaf(gy[j], xh[j], s2);
-      }
-      const float m1 = warp_sum(s1) * (1.f / C), m2 = warp_sum(s2) * (1.f / C);
-      float dpre[8], dxo[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        dpre[j] = rstd * (gy[j] - m1 - xh[j] * m2);
-        dxo[j] = dpre[j] * in_scale;
-        if (a.relu_x && !((relu_pos >> j) & 1u)) dxo[j] = 0.f;
-      }
-      bf16x8 dxv = pack8(dxo);
-      if (a.drop_mode == 1) km.apply(dxv);
-      if (a.dbias) {
-        float st[8];
-        unpack8(dxv, st);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) acc_x[j] += a.drop_mode == 1 ? st[j] : dxo[j];
-      }
-      st8(a.dx + row * C + lane * 8, dxv);
-      if (a.dres) st8(a.dres + row * C + lane * 8, pack8(dpre));
-    }
-    cp_async_wait<0>();
-  }
-  for (int pass = 0; pass < (a.dbias ? 3 : 2); ++pass) {
-#pragma unroll
-    for (int j = 0; j < 8; ++j) red[warp][lane * 8 + j] = pass == 0 ? acc_g[j] : (pass == 1 ? acc_b[j] : acc_x[j]);
-    __syncthreads();
-    float* dst = pass == 0 ? a.dgamma : (pass == 1 ? a.dbeta : a.dbias);
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
-      float sum = 0.f;
-#pragma unroll
-      for (int w = 0; w < 8; ++w) sum += red[w][c];
-      atomicAdd(dst + c, sum);
-    }
-    __syncthreads();
-  }
-}
-
 static int ln_grid(int rows, int cap) {
   int g = (rows + 7) / 8;
   if (g > cap) g = cap;
@@ -680,16 +409,9 @@ static int ln_dispatch(const LnArgs& a, int C, cudaStream_t s) {
   if (a.p_drop < 0.f || a.p_drop >= 1.f) return set_error("layernorm: dropout p must be in [0,1)");
   const int grid = BWD ? ln_grid(a.rows, 148 * 4) : ln_grid(a.rows, 148 * 8);
   switch (C) {
-    case 256: {
-      static const bool no_ring = getenv("FS2_LN_NO_RING") != nullptr;  // A/B switch: register-prefetch kernels
-      if (no_ring) {
-        if (BWD) FS2_LAUNCH((ln_bwd_kernel<1>), grid, 256, 0, s, a); else FS2_LAUNCH((ln_fwd_kernel<1>), grid, 256, 0, s, a);
-      } else {  // one wave: 4 (forward, 64 registers) / 2 (backward) resident blocks per SM
-        const int g1 = BWD ? ln_grid(a.rows, 148 * 2) : ln_grid(a.rows, 148 * 4);
-        if (BWD) FS2_LAUNCH((ln_bwd256_kernel), g1, 256, 0, s, a); else FS2_LAUNCH((ln_fwd256_kernel), g1, 256, 0, s, a);
-      }
+    case 256:
+      if (BWD) FS2_LAUNCH((ln_bwd_kernel<1>), grid, 256, 0, s, a); else FS2_LAUNCH((ln_fwd_kernel<1>), grid, 256, 0, s, a);
       break;
-    }
     case 512:
       if (BWD) FS2_LAUNCH((ln_bwd_kernel<2>), grid, 256, 0, s, a); else FS2_LAUNCH((ln_fwd_kernel<2>), grid, 256, 0, s, a);
       break;

@@ -56,7 +56,7 @@ class FastSpeech2(nn.Module):
             mel_lens = mel_lens.to(dev, torch.int64)
             mel_masks = get_mask_from_lengths(mel_lens, int(max_mel_len))
 
-        x = self.encoder(texts, src_masks, lens=src_lens)
+        x = self.encoder(texts, src_masks, lens=src_lens, out_dtype=torch.bfloat16)
         if x.dtype != torch.bfloat16:
             x = x.to(torch.bfloat16)
         spk = None
@@ -80,7 +80,7 @@ class FastSpeech2(nn.Module):
                 pos_table = self.decoder._table_for(T_lr, dev)[0]
             else:
                 pos_table = self.decoder.position_enc
-            spk2 = self._speaker_rows(speaker_args, B, average_spk_emb) if self.speaker_emb is not None else None
+            spk2 = spk  # the same rows as above (one gather, one backward)
             fused = (t_dec, spk2, pos_table)
         else:
             fused = None

@@ -60,9 +60,11 @@ class Encoder2(_FFTStack):
         super().__init__()
         self._build(config, "encoder")
 
-    def forward(self, emb_src_seq, mask, return_attns=False, *, lens=None):
+    def forward(self, emb_src_seq, mask, return_attns=False, *, lens=None, out_dtype=None):
+        """out_dtype (keyword, not in the reference signature): FastSpeech2.forward asks for the bf16 activations
+        directly instead of a caller-dtype (fp32) copy that it would cast back."""
         B, T = emb_src_seq.shape[0], emb_src_seq.shape[1]
-        dt = emb_src_seq.dtype
+        dt = out_dtype if out_dtype is not None else emb_src_seq.dtype
         if not emb_src_seq.is_cuda:
             to_act(emb_src_seq)  # raises: no CPU path
         if lens is None:
@@ -87,14 +89,14 @@ class Encoder(_FFTStack):
                                          padding_idx=Constants.PAD)
         self._build(config, "encoder")
 
-    def forward(self, src_seq, mask, return_attns=False, *, lens=None):
+    def forward(self, src_seq, mask, return_attns=False, *, lens=None, out_dtype=None):
         B, T = src_seq.shape
         if lens is None:
             lens = lens_from_mask(mask, T, B, src_seq.device)
         emb = ops.EmbeddingFn.apply(src_seq, self.src_word_emb.weight, Constants.PAD)
         table, _ = self._table_for(T, src_seq.device)
         x = ops.PosEncAdd.apply(emb, table, T)
-        return from_act(self._run_layers(x, lens), torch.float32)
+        return from_act(self._run_layers(x, lens), out_dtype if out_dtype is not None else torch.float32)
 
 
 class Decoder(_FFTStack):

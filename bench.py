@@ -297,6 +297,8 @@ def kernel_rooflines(base, cfg, bf16_peak, hbm_peak, step_ms, traffic):
 
     def fam(label, kernel, flops, fn, per_layer=1):
         ms = timer(fn)
+        if "+" not in kernel and not kernel.startswith("attn"):  # the engine the descriptor was routed to
+            kernel = ops._L().fs2_last_kernel().decode() or kernel
         fams.append({"label": label, "kernel": kernel, "avg_launch_ms": ms, "flops_per_launch": flops,
                      "achieved": flops / ms / 1e9, "launches_per_step": per_layer * n_dec,
                      "share_of_step": per_layer * n_dec * ms / step_ms})
@@ -317,7 +319,7 @@ def kernel_rooflines(base, cfg, bf16_peak, hbm_peak, step_ms, traffic):
         lambda: ops.linear_fwd(x2, wqkv, bq, lens=lens, T=Tm, tail=NT))
     fam("QKV projection input-gradient (+residual)", "gemm_tc2_kernel", 2.0 * V * 3 * D * D,
         lambda: ops.linear_dgrad(dqkv.view(B * Tm, 3 * D), wqkv, epilogue=G.EPI_ADD_AUX, aux=x2, lens=lens, T=Tm))
-    fam("QKV projection weight-gradient", "gemm_tc2_kernel", 2.0 * V * 3 * D * D,
+    fam("QKV projection weight-gradient (+ Q / V bias column sums)", "gemm_tc2_kernel + colsum_kernel", 2.0 * V * 3 * D * D,
         lambda: ops.qkv_param_grads(dqkv.view(B * Tm, 3 * D), x2, gqkv, D, lens=lens, T=Tm))
     fam("output projection fwd", "gemm_tc2_kernel", 2.0 * V * D * D,
         lambda: ops.linear_fwd(attn2, wo, bo, lens=lens, T=Tm, tail=NT))
@@ -328,9 +330,9 @@ def kernel_rooflines(base, cfg, bf16_peak, hbm_peak, step_ms, traffic):
     dk = D // H
     sched = ops.attn_schedule(lens, Tm, H)  # longest-first work order, as transformer/Models.py::_run_layers builds it
     o3, lse = ops.attn_fwd(qkv, lens, H, dk, sched)
-    fam("fused attention fwd (QK^T, softmax, PV)", "attn_fwd_kernel", 4.0 * sq * D,
+    fam("fused attention fwd (QK^T, softmax, PV)", "attn_fwd2_kernel", 4.0 * sq * D,
         lambda: ops.attn_fwd(qkv, lens, H, dk, sched))
-    fam("fused attention bwd (dK/dV + dQ kernels)", "attn_bwd_*_kernel", 8.0 * sq * D,
+    fam("fused attention bwd (dK/dV + dQ kernels)", "attn_bwd_prep + attn_bwd_dkv2 + attn_bwd_dq2", 8.0 * sq * D,
         lambda: ops.attn_bwd(qkv, o3, dy, lse, lens, H, dk, sched))
     for f in fams:
         f["bound"], f["peak"], f["unit"] = "tensor", bf16_peak, "TFLOP/s"
@@ -659,17 +661,28 @@ def run_ours(args):
     eager_launches = cabi.launch_count() - n_before
     dbg("timed loop done %.2f ms" % dev_ms)
 
-    def e2e_iter(i):
+    def e2e_iter_sync(i):
         # public API, one training step: run on the batch prefetched during the previous step, start the
         # pinned-host -> device copy of the next batch (overlaps this step), read this step's six losses back
+        # and WAIT for them (the host enqueues the next step only after this one has finished)
         step.run()
         step.prefetch_batch(pinned=variants[(i + 1) % 3])
         step.read_losses()
 
+    def e2e_iter(i):
+        # the same three calls with asynchronous logging: the 24-byte read of this step's losses is enqueued and
+        # the host picks up the PREVIOUS step's values, so step i+1 is enqueued while step i runs
+        step.run()
+        step.prefetch_batch(pinned=variants[(i + 1) % 3])
+        step.read_losses_lagged()
+
     step.prefetch_batch(pinned=variants[0])
     for i in range(2):
+        e2e_iter_sync(i)
+    e2e_ms, e2e_wall = timed(e2e_iter_sync, args.steps)
+    for i in range(2):
         e2e_iter(i)
-    e2e_ms, e2e_wall = timed(e2e_iter, args.steps)
+    e2e_lag_ms, e2e_lag_wall = timed(e2e_iter, args.steps)
     clk = clocks.stop() if clocks else None
     losses = step.read_losses().tolist()
 
@@ -722,7 +735,13 @@ def run_ours(args):
                        else "independent draw per rank",
                        "l2": "step working set (~GBs of activations) exceeds the 126 MB L2; no explicit flush"},
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": step.h2d_bytes,
-                    "d2h_bytes_per_step": step.d2h_bytes, "ms_per_step": max(e2e_ms, e2e_wall) / args.steps},
+                    "d2h_bytes_per_step": step.d2h_bytes, "ms_per_step": max(e2e_ms, e2e_wall) / args.steps,
+                    "loss_readback": "blocking: the host waits for the six losses of every step before it enqueues "
+                                     "the next one",
+                    # the same loop with TrainStep.read_losses_lagged (losses picked up one step late, the host
+                    # never waits for the step it has just launched): no idle gaps between steps -- and therefore
+                    # the clocks of a sustained run rather than of a burst
+                    "ms_per_step_lagged_readback": max(e2e_lag_ms, e2e_lag_wall) / args.steps},
             "gpu_launches": launches, "launches_per_step": launches_per_step,
             "step_tensor": {"algorithmic_tflop_per_step": fl / 1e12, "padded_shape_tflop_per_step": fl_padded / 1e12,
                             "achieved_tflops": step_tf, "frac_of_sustained_peak": step_tf / bf16_sus,

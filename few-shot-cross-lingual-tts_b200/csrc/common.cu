@@ -8,6 +8,7 @@
 namespace fs2 {
 static thread_local char g_err[512] = "";
 static std::atomic<int64_t> g_launches{0};
+static thread_local const char* g_last_kernel = "";
 
 int set_error(const char* msg) {
   std::snprintf(g_err, sizeof g_err, "%s", msg);
@@ -18,6 +19,7 @@ int set_cuda_error(const char* what, cudaError_t e) {
   return 2;
 }
 int check_launch(const char* kernel_name) {
+  g_last_kernel = kernel_name;  // string literal of the call site
   cudaError_t e = cudaPeekAtLastError();
   if (e != cudaSuccess) {
     cudaGetLastError();
@@ -36,6 +38,7 @@ extern "C" {
 int fs2_version(void) { return FS2_ABI_VERSION; }
 const char* fs2_last_error(void) { return fs2::g_err; }
 int64_t fs2_launch_count(void) { return fs2::g_launches.load(); }
+const char* fs2_last_kernel(void) { return fs2::g_last_kernel; }
 
 int64_t fs2_gemm_workspace_bytes(void) {
   int dev = 0, sms = 148;

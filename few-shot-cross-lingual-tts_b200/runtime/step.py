@@ -50,21 +50,42 @@ class TrainStep:
         # all bf16 operand copies of the weights are refreshed by one launch at the start of every step
         # (`wcache`: share one set of copies between several captured steps, runtime/cache.py)
         self.wcache = wcache if wcache is not None else ops.WeightCache(model)
+        # The tensors of a batch live in ONE flat buffer per role (256-byte aligned slots; `static[i]` / `stage[i]` /
+        # `host[i]` are views): the graph's static inputs, the device staging copy of the next batch, the pinned host
+        # copy -- so a batch moves with one copy per hop instead of one per tensor.
         self.static = list(example_batch)
-        self.host = {}
+        offs, total = {}, 0
         for i in _TENSOR_SLOTS:
             t = example_batch[i]
-            self.static[i] = t.to(self.device).clone()
-            self.host[i] = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
-            self.host[i].copy_(t)
+            offs[i] = total
+            total += (t.numel() * t.element_size() + 255) // 256 * 256
+
+        def views(flat):
+            out = {}
+            for i in _TENSOR_SLOTS:
+                t = example_batch[i]
+                n = t.numel() * t.element_size()
+                out[i] = flat[offs[i]:offs[i] + n].view(t.dtype).view(t.shape)
+            return out
+
+        self._static_flat = torch.zeros(total, dtype=torch.uint8, device=self.device)
+        self._stage_flat = torch.zeros(total, dtype=torch.uint8, device=self.device)
+        self._host_flat = torch.zeros(total, dtype=torch.uint8).pin_memory()
+        sv, self.stage, self.host = views(self._static_flat), views(self._stage_flat), views(self._host_flat)
+        for i in _TENSOR_SLOTS:
+            self.host[i].copy_(example_batch[i])
+            sv[i].copy_(example_batch[i])
+            self.static[i] = sv[i]
         self.losses = torch.zeros(6, dtype=torch.float32, device=self.device)
         self.losses_host = torch.empty(6, dtype=torch.float32, pin_memory=True)
+        self._lag_host = [torch.zeros(6, dtype=torch.float32).pin_memory() for _ in range(2)]
+        self._lag_event = [None, None]
+        self._lag_n = 0
         self.h2d_bytes = sum(t.numel() * t.element_size() for t in self.host.values())
         self.d2h_bytes = self.losses_host.numel() * 4
-        # double-buffered input path: the next batch is copied host -> device on a copy stream into staging
-        # buffers while the current step runs; run() then moves it into the graph's static buffers (device to
-        # device, ~10 us for 34 MB)
-        self.stage = {i: torch.empty_like(self.static[i]) for i in _TENSOR_SLOTS}
+        # double-buffered input path: the next batch is copied host -> device on a copy stream into the staging
+        # buffer while the current step runs; run() then moves it into the graph's static buffer (one device to
+        # device copy, ~10 us for 34 MB)
         self.copy_stream = torch.cuda.Stream(self.device)
         self._staged = False
         self._stage_free = None
@@ -157,8 +178,7 @@ class TrainStep:
         if batch is not None:
             for i in _TENSOR_SLOTS:
                 self.host[i].copy_(batch[i])
-        for i in _TENSOR_SLOTS:
-            self.static[i].copy_(self.host[i], non_blocking=True)
+        self._static_flat.copy_(self._host_flat, non_blocking=True)
 
     def prefetch_batch(self, batch=None, pinned=None):
         """Asynchronous host -> device copy of the NEXT batch on a copy stream into device staging buffers: it
@@ -177,8 +197,11 @@ class TrainStep:
         if self._stage_free is not None:
             self.copy_stream.wait_event(self._stage_free)
         with torch.cuda.stream(self.copy_stream):
-            for i in _TENSOR_SLOTS:
-                self.stage[i].copy_(src[i], non_blocking=True)
+            if src is self.host:
+                self._stage_flat.copy_(self._host_flat, non_blocking=True)
+            else:
+                for i in _TENSOR_SLOTS:
+                    self.stage[i].copy_(src[i], non_blocking=True)
         self._staged = True
 
     def run(self):
@@ -186,8 +209,7 @@ class TrainStep:
         if self._staged:
             cur = torch.cuda.current_stream()
             cur.wait_stream(self.copy_stream)
-            for i in _TENSOR_SLOTS:
-                self.static[i].copy_(self.stage[i], non_blocking=True)
+            self._static_flat.copy_(self._stage_flat, non_blocking=True)
             self._stage_free = torch.cuda.Event()
             self._stage_free.record(cur)
             self._staged = False
@@ -200,6 +222,23 @@ class TrainStep:
         self.losses_host.copy_(self.losses, non_blocking=True)
         torch.cuda.current_stream().synchronize()
         return self.losses_host
+
+    def read_losses_lagged(self):
+        """Asynchronous logging: enqueue the 24-byte device -> host read of THIS step's losses and return the host
+        copy of the PREVIOUS step's (None after the first call).  The host never waits for the step it has just
+        launched, so the next step is enqueued while this one runs and the GPU does not idle between steps
+        (pytorch_lightning logs the same way: `self.log` keeps the tensor and syncs at the logging interval)."""
+        k = self._lag_n & 1
+        self._lag_host[k].copy_(self.losses, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream())
+        self._lag_event[k] = ev
+        self._lag_n += 1
+        prev = self._lag_event[k ^ 1]
+        if prev is None:
+            return None
+        prev.synchronize()
+        return self._lag_host[k ^ 1]
 
     def step_e2e(self, batch=None):
         """What a user calls: H2D of the batch, the step, D2H of the six losses."""

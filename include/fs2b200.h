@@ -31,6 +31,8 @@ int fs2_version(void);
 const char* fs2_last_error(void);
 /* number of kernels this library has launched in this process (bench.py's gpu_launches). */
 int64_t fs2_launch_count(void);
+/* name of the kernel this thread launched last (which engine a GEMM descriptor was routed to: tools / bench) */
+const char* fs2_last_kernel(void);
 
 /* ------------------------------------------------------------------------------------------ */
 /* tcgen05 / TMEM / TMA GEMM family                                                            */

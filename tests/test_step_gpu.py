@@ -202,3 +202,29 @@ def test_weight_cache_refresh_matches_per_tensor_cast_and_pack():
                 assert torch.equal(d, m.weight.detach().to(torch.bfloat16))
                 n += 1
     assert n > 20
+
+
+def test_lagged_loss_readback_returns_the_previous_step():
+    """TrainStep.read_losses_lagged: the host picks the losses up one step late and never waits for the step it
+    has just launched; flat batch buffers: prefetch -> run moves a whole batch with one copy per hop."""
+    rt = sub("runtime")
+    batch = synth.make_batch(B=4, src_len=(10, 40), dur=synth.uniform_dur(1, 8), seed=23)
+    other = list(batch)  # same padded shape, other targets
+    other[9] = batch[9] * 0.5 + 0.25
+    other = tuple(other)
+    model, loss_fn, _ = _build(seed=2)
+    step = rt.TrainStep(model, loss_fn, batch, use_graph=True)
+    la = step.step_e2e(batch).clone()
+    lb = step.step_e2e(other).clone()
+    assert not torch.allclose(la, lb)
+    step.prefetch_batch(batch)
+    step.run()
+    assert step.read_losses_lagged() is None
+    step.prefetch_batch(other)
+    step.run()
+    r = step.read_losses_lagged()
+    assert torch.allclose(r, la, rtol=1e-5), (r, la)
+    step.prefetch_batch(batch)
+    step.run()
+    r = step.read_losses_lagged()
+    assert torch.allclose(r, lb, rtol=1e-5), (r, lb)

@@ -111,40 +111,109 @@ embedding_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const IdxT* __restric
   }
 }
 
-// Small tables (the 256-bin pitch / energy embeddings: 12800 rows hit 256 table rows, ~50 writers per address):
-// block (x, y) owns 64 channels and a contiguous range of input rows and accumulates into its own shared-memory copy
-// of that table slice; only the non-zero sums go to the gradient with global atomics (one per touched table element
-// and block instead of one per input element: 55-63 us -> a few us at C2).
-constexpr int kEmbSliceC = 64;
+// Small tables (the 256-bin pitch / energy embeddings: 12800 rows hit 256 table rows, and ALL padded phonemes hit the
+// bin of 0.0 -- the scatter-add above spends 55-63 us on 3.3 M atomics, thousands of them on the same addresses).
+// Counting sort instead: block (x, y, z) owns 64 channels, 32 table rows ("bins") and one slice of the input rows.
+// It histograms the ids of its row slice that fall into its bins, turns the counts into segment starts and scatters
+// (bin, row) pairs into a shared-memory list ordered by bin (integer shared-memory atomics only); the 32 warps then
+// take EQUAL shares of that list (a bin with thousands of rows is spread over many warps), add up 128-byte row slices
+// with eight loads in flight and flush a partial sum whenever the bin changes.  One global atomic per touched table
+// element and block at the end (instead of one per input element).
+constexpr int kEmbSliceC = 64, kEmbBinsPerBlock = 32;
 template <typename IdxT>
-__global__ void __launch_bounds__(256)
-embedding_bwd_smem_kernel(const __nv_bfloat16* __restrict__ dy, const IdxT* __restrict__ ids, long long rows, int C,
-                          int n_rows_table, int pad_idx, int rows_per_block, float* __restrict__ dtable) {
+__global__ void __launch_bounds__(1024)
+embedding_bwd_sorted_kernel(const __nv_bfloat16* __restrict__ dy, const IdxT* __restrict__ ids, int rows, int C,
+                            int n_rows_table, int pad_idx, int rows_per_z, float* __restrict__ dtable) {
   pdl_sync();
-  extern __shared__ float acc[];  // [n_rows_table][64]
-  const int n = n_rows_table * kEmbSliceC;
-  for (int i = threadIdx.x; i < n; i += 256) acc[i] = 0.f;
-  __syncthreads();
+  extern __shared__ int s_order[];  // [rows_per_z] (bin << 20 | row - r0), grouped by bin
+  __shared__ int s_cnt[kEmbBinsPerBlock], s_cur[kEmbBinsPerBlock], s_total;
+  __shared__ float s_acc[kEmbBinsPerBlock][kEmbSliceC];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int c0 = blockIdx.x * kEmbSliceC;
-  const int sub = threadIdx.x & 7, rl = threadIdx.x >> 3;  // 8 threads x 8 channels per row, 32 rows per pass
-  const long long r0 = (long long)blockIdx.y * rows_per_block;
-  const long long r1 = min(r0 + rows_per_block, rows);
-  if (c0 + sub * 8 < C) {
-    for (long long r = r0 + rl; r < r1; r += 32) {
-      const long long id = static_cast<long long>(ids[r]);
-      if (id < 0 || id >= n_rows_table || id == pad_idx) continue;  // padding_idx rows get no gradient
-      float f[8];
-      unpack8(ld8(dy + r * C + c0 + sub * 8), f);
-      float* a = acc + id * kEmbSliceC + sub * 8;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) atomicAdd(a + j, f[j]);
-    }
+  const int bin0 = blockIdx.y * kEmbBinsPerBlock;
+  const int r0 = blockIdx.z * rows_per_z, r1 = min(r0 + rows_per_z, rows);
+  if (threadIdx.x < kEmbBinsPerBlock) s_cnt[threadIdx.x] = 0;
+  for (int i = threadIdx.x; i < kEmbBinsPerBlock * kEmbSliceC; i += 1024) (&s_acc[0][0])[i] = 0.f;
+  __syncthreads();
+  auto local_bin = [&](int r) {
+    const long long id = static_cast<long long>(ids[r]);
+    if (id < 0 || id >= n_rows_table || id == pad_idx) return -1;  // padding_idx rows get no gradient
+    const long long lb = id - bin0;
+    return (lb >= 0 && lb < kEmbBinsPerBlock) ? (int)lb : -1;
+  };
+  for (int r = r0 + threadIdx.x; r < r1; r += 1024) {
+    const int lb = local_bin(r);
+    if (lb >= 0) atomicAdd(&s_cnt[lb], 1);
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < n; i += 256) {
-    const float v = acc[i];
-    const int row = i / kEmbSliceC, c = c0 + (i % kEmbSliceC);
-    if (v != 0.f && c < C) atomicAdd(dtable + (long long)row * C + c, v);
+  if (warp == 0) {  // exclusive scan of the 32 counts
+    const int v = s_cnt[lane];
+    int inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += t;
+    }
+    s_cur[lane] = inc - v;
+    if (lane == 31) s_total = inc;
+  }
+  __syncthreads();
+  for (int r = r0 + threadIdx.x; r < r1; r += 1024) {
+    const int lb = local_bin(r);
+    if (lb >= 0) s_order[atomicAdd(&s_cur[lb], 1)] = (lb << 20) | (r - r0);
+  }
+  __syncthreads();
+  const int n = s_total;
+  const int col = c0 + 2 * lane;
+  if (n > 0 && col < C) {
+    const int per = (n + 31) / 32;
+    int k = warp * per;
+    const int kend = min(k + per, n);
+    float ax = 0.f, ay = 0.f;
+    int cur = k < kend ? (s_order[k] >> 20) : 0;
+    auto flush = [&](int bin) {
+      atomicAdd(&s_acc[bin][2 * lane], ax);
+      atomicAdd(&s_acc[bin][2 * lane + 1], ay);
+      ax = ay = 0.f;
+    };
+    const __nv_bfloat16* base = dy + (long long)r0 * C + col;
+    for (; k + 8 <= kend; k += 8) {
+      int e[8];
+      __nv_bfloat162 v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        e[u] = s_order[k + u];
+        v[u] = *reinterpret_cast<const __nv_bfloat162*>(base + (long long)(e[u] & 0xFFFFF) * C);
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int bin = e[u] >> 20;
+        if (bin != cur) {
+          flush(cur);
+          cur = bin;
+        }
+        const float2 f = __bfloat1622float2(v[u]);
+        ax += f.x;
+        ay += f.y;
+      }
+    }
+    for (; k < kend; ++k) {
+      const int e = s_order[k], bin = e >> 20;
+      if (bin != cur) {
+        flush(cur);
+        cur = bin;
+      }
+      const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(base + (long long)(e & 0xFFFFF) * C));
+      ax += f.x;
+      ay += f.y;
+    }
+    if (warp * per < kend) flush(cur);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < kEmbBinsPerBlock * kEmbSliceC; i += 1024) {
+    const int bin = i / kEmbSliceC, c = c0 + (i % kEmbSliceC);
+    const float v = s_acc[bin][i % kEmbSliceC];
+    if (v != 0.f && c < C && bin0 + bin < n_rows_table) atomicAdd(dtable + (long long)(bin0 + bin) * C + c, v);
   }
 }
 
@@ -309,26 +378,28 @@ int fs2_embedding_bwd_f32(const void* dy, const void* ids, int ids_is_i64, int64
   if (C % 8) return fs2::set_error("embedding_bwd: C must be a multiple of 8");
   if (rows <= 0) return 0;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  const size_t smem = (size_t)n_rows_table * fs2::kEmbSliceC * sizeof(float);
-  if (smem <= 200 * 1024 && rows >= 8 * (int64_t)n_rows_table) {  // many writers per table row: shared-memory slices
+  int zs = (int)(rows / 2048);
+  zs = zs < 1 ? 1 : (zs > 8 ? 8 : zs);
+  const int rows_per_z = (int)((rows + zs - 1) / zs);
+  const size_t smem = (size_t)rows_per_z * sizeof(int);
+  if (smem <= 160 * 1024 && rows_per_z < (1 << 20) && rows >= 8 * (int64_t)n_rows_table && !(C & 1) && rows < (1ll << 31)) {
+    // many writers per table row: counting sort, see embedding_bwd_sorted_kernel
     static bool attr_set = false;
     if (!attr_set) {
-      cudaFuncSetAttribute(fs2::embedding_bwd_smem_kernel<int64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-      cudaFuncSetAttribute(fs2::embedding_bwd_smem_kernel<int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      cudaFuncSetAttribute(fs2::embedding_bwd_sorted_kernel<int64_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+      cudaFuncSetAttribute(fs2::embedding_bwd_sorted_kernel<int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
       attr_set = true;
     }
-    int chunks = (int)(rows / 1024);
-    chunks = chunks < 1 ? 1 : (chunks > 16 ? 16 : chunks);
-    const int rpb = (int)((rows + chunks - 1) / chunks);
-    const dim3 grid((C + fs2::kEmbSliceC - 1) / fs2::kEmbSliceC, (unsigned)((rows + rpb - 1) / rpb));
+    const dim3 grid((C + fs2::kEmbSliceC - 1) / fs2::kEmbSliceC,
+                    (n_rows_table + fs2::kEmbBinsPerBlock - 1) / fs2::kEmbBinsPerBlock, (unsigned)((rows + rows_per_z - 1) / rows_per_z));
     if (ids_is_i64)
-      FS2_LAUNCH((fs2::embedding_bwd_smem_kernel<int64_t>), grid, 256, smem, s, static_cast<const __nv_bfloat16*>(dy),
-                 static_cast<const int64_t*>(ids), rows, C, n_rows_table, pad_idx, rpb, dtable);
+      FS2_LAUNCH((fs2::embedding_bwd_sorted_kernel<int64_t>), grid, 1024, smem, s, static_cast<const __nv_bfloat16*>(dy),
+                 static_cast<const int64_t*>(ids), (int)rows, C, n_rows_table, pad_idx, rows_per_z, dtable);
     else
-      FS2_LAUNCH((fs2::embedding_bwd_smem_kernel<int32_t>), grid, 256, smem, s, static_cast<const __nv_bfloat16*>(dy),
-                 static_cast<const int32_t*>(ids), rows, C, n_rows_table, pad_idx, rpb, dtable);
+      FS2_LAUNCH((fs2::embedding_bwd_sorted_kernel<int32_t>), grid, 1024, smem, s, static_cast<const __nv_bfloat16*>(dy),
+                 static_cast<const int32_t*>(ids), (int)rows, C, n_rows_table, pad_idx, rows_per_z, dtable);
     fs2::count_launch();
-    return fs2::check_launch("embedding_bwd_smem_kernel");
+    return fs2::check_launch("embedding_bwd_sorted_kernel");
   }
   const unsigned grid = (unsigned)((rows + 8 * fs2::kEmbRowsPerWarp - 1) / (8 * fs2::kEmbRowsPerWarp));
   if (ids_is_i64)

@@ -104,5 +104,6 @@ class FastSpeech2(nn.Module):
                 x = x.to(torch.bfloat16)
         mel = ops.LinearF32Out.apply(x, self.mel_linear.weight, self.mel_linear.bias)
         postnet_mel = self.postnet.forward_residual(mel)
+        ops.join_branches()  # the variance predictors ran next to the decoder / PostNet (ops.branch)
         return (mel, postnet_mel, p_pred, e_pred, log_d_pred, d_rounded, src_masks, mel_masks, src_lens,
                 mel_lens_out)

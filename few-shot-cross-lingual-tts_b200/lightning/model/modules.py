@@ -126,7 +126,13 @@ class VarianceAdaptor(nn.Module):
         self.energy_embedding = nn.Embedding(n_bins, d)
 
     # -- (prediction, x + embedding): the reference returns the embedding; adding it is fused here --------
-    def _variance(self, predictor, table, bins, x, target, mask, lens, control):
+    def _variance(self, predictor, table, bins, x, target, mask, lens, control, branch=None):
+        if target is not None and branch is not None:
+            # teacher forcing: the prediction only feeds the loss -- its launches go on a branch stream, the
+            # embedding of the TARGET is added on the current one (ops.branch)
+            with ops.branch(branch):
+                prediction = predictor(x, mask, lens=lens)
+            return prediction, ops.BucketEmbedAdd.apply(x, target, bins, table.weight)
         prediction = predictor(x, mask, lens=lens)
         if target is None:
             prediction = prediction * control
@@ -154,14 +160,18 @@ class VarianceAdaptor(nn.Module):
         B, Ts, _ = xb.shape
         if src_lens is None:
             src_lens = lens_from_mask(src_mask, Ts, B, xb.device)
-        log_d = self.duration_predictor(xb, src_mask, lens=src_lens)
+        if duration_target is not None:  # the durations come from the batch: log_d only feeds the loss
+            with ops.branch(0):
+                log_d = self.duration_predictor(xb, src_mask, lens=src_lens)
+        else:
+            log_d = self.duration_predictor(xb, src_mask, lens=src_lens)
         pitch_pred = energy_pred = None
         if self.pitch_feature_level == "phoneme_level":
             pitch_pred, xb = self._variance(self.pitch_predictor, self.pitch_embedding, self.pitch_bins, xb,
-                                            pitch_target, src_mask, src_lens, p_control)
+                                            pitch_target, src_mask, src_lens, p_control, branch=1)
         if self.energy_feature_level == "phoneme_level":
             energy_pred, xb = self._variance(self.energy_predictor, self.energy_embedding, self.energy_bins,
-                                             xb, energy_target, src_mask, src_lens, e_control)
+                                             xb, energy_target, src_mask, src_lens, e_control, branch=2)
         if duration_target is not None:
             durations = duration_target
             duration_rounded = duration_target
@@ -192,4 +202,5 @@ class VarianceAdaptor(nn.Module):
                                                  e_control)
         if _fused is None:
             xo = from_act(xo, dt)
+            ops.join_branches()  # stand-alone use: every returned tensor is ready on the caller's stream
         return xo, pitch_pred, energy_pred, log_d, duration_rounded, mel_len, mel_mask

@@ -78,6 +78,61 @@ class fork_side:
         return False
 
 
+# --------------------------------------------------------------------------------------------------
+# branch streams: independent sub-graphs of the FORWARD pass (the three variance predictors under teacher forcing)
+# --------------------------------------------------------------------------------------------------
+# With ground-truth pitch / energy / duration (training) the predictors' outputs only feed the loss: the duration
+# predictor reads x, the pitch predictor reads x, the energy predictor reads x + pitch_embedding(target) -- none of
+# them is on the path to the decoder.  Their ~15 small launches each (12800-row convolutions, LayerNorms, a row dot)
+# are latency-bound, so `with branch(i):` issues them on their own streams next to the LengthRegulator / decoder /
+# PostNet kernels; autograd runs their backward on the same streams, next to the decoder backward.  The forks and
+# joins are captured as parallel branches of the step's CUDA graph.  FS2_NO_BRANCH=1 keeps everything on one stream.
+BRANCH = OVERLAP and _os.environ.get("FS2_NO_BRANCH") is None
+_branch_streams = {}
+_open_branches = []
+
+
+class branch:
+    """`with branch(i):` -- run the enclosed forward ops on branch stream i, after everything issued so far on the
+    current stream.  The current stream must `join_branches()` before it reads what they produced."""
+
+    def __init__(self, idx):
+        self.idx = idx
+
+    def __enter__(self):
+        if not BRANCH:
+            return self
+        cur = torch.cuda.current_stream()
+        key = (cur.device, self.idx)
+        s = _branch_streams.get(key)
+        if s is None:
+            s = _branch_streams[key] = torch.cuda.Stream(cur.device)
+        s.wait_stream(cur)
+        _open_branches.append(s)
+        self._ctx = torch.cuda.stream(s)
+        self._ctx.__enter__()
+        return self
+
+    def __exit__(self, *exc):
+        if BRANCH:
+            self._ctx.__exit__(*exc)
+        return False
+
+
+def join_branches():
+    """Order the current stream after every branch opened since the last join."""
+    if _open_branches:
+        cur = torch.cuda.current_stream()
+        for s in _open_branches:
+            cur.wait_stream(s)
+        _open_branches.clear()
+
+
+def branch_streams(device):
+    """Every branch stream of `device` (runtime/dp.py: a gradient bucket may hold gradients produced on them)."""
+    return [s for (d, _i), s in _branch_streams.items() if d == device]
+
+
 # Deferred joins (runtime.TrainStep sets DEFER_JOIN around its backward pass): a Function then does NOT wait for
 # its weight-gradient kernels before returning -- it only parks the tensors those kernels read in `_keepalive` (the
 # autograd engine would otherwise free them, and the allocator could hand their memory to the main stream while the
@@ -103,6 +158,8 @@ def join_side(*side_inputs):
 def final_join():
     if OVERLAP:
         cur = torch.cuda.current_stream()
+        for s in branch_streams(cur.device):  # backward of the branched forward ops (they may have forked the side stream)
+            cur.wait_stream(s)
         side = _side_streams.get(cur.device)
         if side is not None:
             cur.wait_stream(side)

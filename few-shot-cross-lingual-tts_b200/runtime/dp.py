@@ -93,6 +93,7 @@ class GradBuckets:
 
     # -- per-step protocol ---------------------------------------------------------------------------
     def zero(self):
+        self._main_stream = torch.cuda.current_stream() if self.flat.is_cuda else None
         self.flat.zero_()
         self._pending = [set(m) for m in self._members]
         self._launched = [False] * len(self.buckets)
@@ -113,7 +114,12 @@ class GradBuckets:
         if self.comm_stream is not None:
             cur = torch.cuda.current_stream()
             self.comm_stream.wait_stream(cur)
+            main = getattr(self, "_main_stream", None)
+            if main is not None and main != cur:  # announced from a branch stream: the bucket also holds gradients
+                self.comm_stream.wait_stream(main)  # produced on the stream that runs the step
             from .. import ops  # weight gradients are produced on the side stream (ops.fork_side)
+            for bs in ops.branch_streams(cur.device):  # backward of the variance predictors runs on branch streams
+                self.comm_stream.wait_stream(bs)
             side = ops.side_stream_of(cur.device)
             if side is not None:
                 self.comm_stream.wait_stream(side)

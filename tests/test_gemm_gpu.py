@@ -299,10 +299,15 @@ def test_conv_split_tail(Cin, Cout, k, epi, n_pair_tiles):
     epilogue = {"aux": G.EPI_ADD_AUX, "bias": G.EPI_NONE, "relu_mask": G.EPI_RELU, "relu_bwd_mask": G.EPI_RELU_BWD}[epi]
 
     def run(impl, m):
-        y = torch.full((B, T, Cout), float("nan"), device="cuda", dtype=torch.bfloat16)
+        guard = 8192  # the split-K epilogue computes its own addresses: nothing may land outside D
+        buf = torch.full((guard + B * T * Cout + guard,), float("nan"), device="cuda", dtype=torch.bfloat16)
+        buf[:guard] = 7.0
+        buf[-guard:] = 7.0
+        y = buf[guard:guard + B * T * Cout].view(B, T, Cout)
         G.gemm(G.operand(x, Cin, T, B), G.operand(wp, k * Cin, Cout), y, T, Cout, Cin, Z=B, taps=k,
                tap_shift0=-((k - 1) // 2), b_tap_kstride=Cin, bias=bias, epilogue=epilogue, aux=aux, ld_aux=Cout,
                aux_batch_stride=T * Cout, d_zdiv=1, d_zdiv_stride=T * Cout, row_lens=ln, relu_mask=m, impl=impl)
+        assert (buf[:guard] == 7.0).all() and (buf[-guard:] == 7.0).all()
         return y
 
     m0 = mask.clone() if mask is not None else None

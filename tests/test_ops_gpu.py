@@ -103,6 +103,13 @@ def test_embedding_backward_scatter_add(B, T):
                                                         w.float().view(-1, C))
     assert rel_err(table.grad, ref) < 1e-5
     assert torch.equal(x.grad, w)
+    # the C entry point writes nothing outside the table gradient (guard rows on both sides)
+    ids = torch.bucketize(target, bins).flatten().to(torch.int32)
+    buf = torch.full((8 + 256 + 8, C), 7.0, device="cuda")
+    buf[8:264].zero_()
+    ops._ck(ops._L().fs2_embedding_bwd_f32(w.view(-1, C).data_ptr(), ids.data_ptr(), 0, B * T, C, 256, -1,
+                                           buf[8:264].data_ptr(), ops._st()), "embedding_bwd")
+    assert (buf[:8] == 7.0).all() and (buf[264:] == 7.0).all() and rel_err(buf[8:264], ref) < 1e-5
 
 
 def test_embedding_fn_and_multilingual_embedding_match_f_embedding():

@@ -360,7 +360,7 @@ def kernel_rooflines(base, cfg, bf16_peak, hbm_peak, step_ms, traffic):
     y, mean, rstd, keep = ops.ln_fwd(x, dy, gamma, beta, lens, p, 1, 5)
     rec("LayerNorm fwd (dropout + residual + LN + pad-zero)", (2 * V + B * Tm) * D * 2,
         lambda: ops.ln_fwd(x, dy, gamma, beta, lens, p, 1, 5), 2 * n_dec)
-    rec("LayerNorm bwd (+dgamma/dbeta/dbias, dropout regenerated)", (3 * V + 2 * B * Tm) * D * 2,
+    rec("LayerNorm bwd (+dgamma/dbeta/dbias, stored keep bits)", (3 * V + 2 * B * Tm) * D * 2,
         lambda: ops.ln_bwd(dy, x, dy, gamma, mean, rstd, lens, p, 1, keep, dg, db, True, dbias=dbias), 2 * n_dec)
     Ts = int(base[5])
     dur = base[11].to(dev)

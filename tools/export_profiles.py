@@ -26,7 +26,7 @@ ORDER = [
     ("FFN Conv1d k=9 input-gradient (+residual)", 1),
     ("FFN Conv1d k=9 weight-gradient", 1),
     ("LayerNorm fwd (dropout + residual + LN + pad-zero)", 1),
-    ("LayerNorm bwd (+dgamma/dbeta/dbias, dropout regenerated)", 1),
+    ("LayerNorm bwd (+dgamma/dbeta/dbias, stored keep bits)", 1),
 ]
 COLS = [("gpu__time_duration.sum", "us"), ("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed", "tensor%"),
         ("dram__bytes_read.sum", "rdMB"), ("dram__bytes_write.sum", "wrMB"),

@@ -498,12 +498,15 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constant
       // only the LAST key tile can hold padded keys (n = ceil(len / 128)); rows of padded queries in this tile are
       // computed like any other (their Q rows are zero-filled by the projection) and dropped in the epilogue
       const bool key_mask = (j + 1) * BKV > len;
+      // both 32-column loads of this warp's slice are issued before the single wait (one TMEM round trip per tile)
+      uint32_t vv[2][32];
+      tmem_ld32(tS, vv[0]);
+      tmem_ld32(tS + 32, vv[1]);
+      tmem_ld_wait();
       if (!pass_b) {
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
-          uint32_t v[32];
-          tmem_ld32(tS + c * 32, v);
-          tmem_ld_wait();
+          const uint32_t (&v)[32] = vv[c];
           const int k0 = j * BKV + half * 64 + c * 32;
           if (key_mask) {
 #pragma unroll
@@ -517,9 +520,7 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQK, const __grid_constant
         uint32_t w[32];
 #pragma unroll
         for (int c = 0; c < 2; ++c) {
-          uint32_t v[32];
-          tmem_ld32(tS + c * 32, v);
-          tmem_ld_wait();
+          const uint32_t (&v)[32] = vv[c];
           const int k0 = j * BKV + half * 64 + c * 32;
 #pragma unroll
           for (int i = 0; i < 16; ++i) {

@@ -31,6 +31,9 @@ class Gemm(ctypes.Structure):
         ("d_seg_rows", c_i32), ("d_seg_pad", c_i32), ("d_seg", c_vp * 4),
         ("row_lens", c_vp), ("lens_zdiv", c_i32), ("tail_zero_rows", c_i32), ("relu_mask", c_vp),
         ("workspace", c_vp), ("workspace_bytes", c_i64),
+        ("ln_gamma", c_vp), ("ln_beta", c_vp), ("ln_res", c_vp), ("ld_res", c_i64), ("res_batch_stride", c_i64),
+        ("ln_p_drop", c_f32), ("ln_pad0", c_i32), ("ln_seed", ctypes.c_uint64), ("ln_seed_dev", c_vp),
+        ("ln_v", c_vp), ("ln_mean", c_vp), ("ln_rstd", c_vp), ("ln_keep", c_vp),
     ]
 
 

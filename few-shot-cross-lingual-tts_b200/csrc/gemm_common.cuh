@@ -52,6 +52,18 @@ struct GemmKP {
   int pair_any;    // 2-CTA kernels, ragged NORMAL, shared (un-batched) B: the two CTAs of a pair take ANY two
                    // consecutive 128-row tiles of the compact list, also from different utterances
   float* ws;       // conv_tc2: split-K scratch for the last partial wave (fs2_gemm::workspace), NULL = off
+  // gemm_tc2<LN>: fused dropout + residual + LayerNorm + pad-zero epilogue (fs2_gemm::ln_*), ln_gamma != NULL
+  const float* ln_gamma;
+  const float* ln_beta;
+  const __nv_bfloat16* ln_res;
+  long long ld_res, res_batch_stride;
+  float ln_p_drop;
+  unsigned long long ln_seed;
+  const unsigned long long* ln_seed_dev;
+  __nv_bfloat16* ln_v;
+  float* ln_mean;
+  float* ln_rstd;
+  unsigned char* ln_keep;
 };
 
 constexpr int kMaxRaggedZ = 256;  // prefix table lives in the ~1.9 KiB of shared memory left by the smem ring

@@ -426,6 +426,7 @@ int gemm_tc_launch(const fs2_gemm& g, cudaStream_t stream) {
   if (!no_halo && g.mode == FS2_GEMM_NORMAL && g.taps > 1 && g.taps <= 16 && !g.a.mn_major &&
       (g.M > 128 || pair_any) && (!use128 || n <= 128))
     return conv_tc2_launch(g, kp, stream);
+  if (g.ln_gamma) return gemm_tc2_launch(g, kp, stream);  // fused LayerNorm epilogue: validated there
   if (use128) return launch_tc<128, 6>(g, kp, stream);
   if (gemm_sk_eligible(g, kp)) return gemm_sk_launch(g, kp, stream);
   if (wgrad_taps_eligible(g, kp)) return wgrad_taps_launch(g, kp, stream);

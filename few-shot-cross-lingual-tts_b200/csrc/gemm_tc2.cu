@@ -26,6 +26,7 @@
 #include "ptx.cuh"
 #include "ptx2sm.cuh"
 #include "tmap.h"
+#include "util.cuh"
 
 namespace fs2 {
 
@@ -45,6 +46,183 @@ constexpr int DYN_BYTES = CUM_OFF + kMaxRaggedZ * 4 + 1024;
 constexpr int kThreads2 = 384;
 }  // namespace g2
 
+
+// ------------------------------------------------------------------------------------------------------------
+// Fused LayerNorm epilogue (fs2_gemm::ln_*): transformer/SubLayers.py:88-91 `layer_norm(dropout(w_2(h)) + residual)`
+// and the padding-row zeroing of transformer/Layers.py:28 inside the GEMM that computes w_2 (N = 256: a CTA's 128
+// accumulator rows are complete LayerNorm rows).  The K = 1024 main loop of that GEMM is bound by operand ingest
+// (~1100 clk per k-block), so the 8 epilogue warps have ~18k cycles per tile: enough for the dropout mask (the same
+// Philox stream, counters and 13-bit compare as layernorm.cu, so both paths draw identical masks), the residual add,
+// the row statistics and the normalisation.  The fp32 pre-norm sum v goes back into the accumulator columns
+// (tcgen05.st) between the passes instead of living in registers.  Thread = one row x 128 columns (warps w / w + 4
+// split the columns); the two halves exchange their partial sums through shared memory (parity double-buffered).
+// Outputs: D = y (bf16), ln_v (bf16 v for the backward), ln_mean / ln_rstd, ln_keep (1 bit per element).
+// ------------------------------------------------------------------------------------------------------------
+namespace g2 {
+constexpr int LN_STAGES = 5;                       // the sixth stage's shared memory holds gamma / beta / exchange
+constexpr int LN_GB_OFF = LN_STAGES * STAGE_BYTES;  // gamma[256], beta[256] f32
+constexpr int LN_RED_OFF = LN_GB_OFF + 2 * 256 * 4;  // [parity 2][sum | sum of squares][half 2][128] f32
+}  // namespace g2
+
+__device__ __forceinline__ void bar_sync_epi2() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32]) {
+  uint32_t a[16], b[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    a[i] = v[i];
+    b[i] = v[16 + i];
+  }
+  tmem_st16(taddr, a);
+  tmem_st16(taddr + 16, b);
+}
+// 64 bf16 columns (32 packed words) of this thread's row -> the warp's staging tile -> global rows (coalesced)
+__device__ __forceinline__ void ln_flush64(uint8_t* stg, int lane, const uint32_t (&w)[32], __nv_bfloat16* base,
+                                           long long ld, int m_w0, int M) {
+  const int sw = lane & 7;
+  uint8_t* my_row = stg + lane * 128;
+#pragma unroll
+  for (int ch = 0; ch < 8; ++ch)
+    *reinterpret_cast<uint4*>(my_row + ((ch ^ sw) << 4)) = make_uint4(w[4 * ch], w[4 * ch + 1], w[4 * ch + 2], w[4 * ch + 3]);
+  __syncwarp();
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const int r = it * 4 + (lane >> 3), ch = lane & 7;
+    if (m_w0 + r < M)
+      *reinterpret_cast<uint4*>(base + (long long)r * ld + ch * 8) =
+          *reinterpret_cast<const uint4*>(stg + r * 128 + ((ch ^ (r & 7)) << 4));
+  }
+  __syncwarp();
+}
+
+__device__ __forceinline__ void epilogue_ln_tile(const GemmKP& p, const TileCoord& t, uint32_t tmem_acc, uint8_t* stg,
+                                                 int q, int chalf, int lane, const float* s_gb, float* s_red,
+                                                 int parity) {
+  constexpr int C = 256;
+  if (!t.valid) return;  // filler half of an odd pair (uniform over the CTA): nothing to store, no barriers
+  const int row = q * 32 + lane;
+  const int m_w0 = t.tm * BM + q * 32;
+  const int gm = m_w0 + lane;
+  const bool in_rows = gm < p.M;
+  bool row_ok = in_rows;
+  if (p.row_lens) row_ok = in_rows && gm < p.row_lens[t.z / p.lens_zdiv];
+  const long long R = (long long)t.z * p.M + (in_rows ? gm : 0);  // dense row index
+  const uint32_t taddr = tmem_acc + (static_cast<uint32_t>(q * 32) << 16) + chalf * 128;
+  const int colb = chalf * 128;
+  const bool drop = p.ln_p_drop > 0.f;
+  const float scale = drop ? 1.f / (1.f - p.ln_p_drop) : 1.f;
+  const uint32_t thresh = keep_thresh_h2(p.ln_p_drop);
+  const uint64_t seed = mix_seed(reinterpret_cast<const uint64_t*>(p.ln_seed_dev), p.ln_seed);
+  const __nv_bfloat16* res_row = p.ln_res + (long long)t.z * p.res_batch_stride + (long long)(in_rows ? gm : 0) * p.ld_res + colb;
+  float* red0 = s_red + (parity * 2 + 0) * 256;  // [half][128]
+  float* red1 = s_red + (parity * 2 + 1) * 256;
+  // ---- pass 1: v = dropout(bf16(acc + bias)) / (1 - p) + residual; v -> TMEM (fp32) and -> ln_v (bf16)
+  float sum = 0.f, sumsq = 0.f;
+  uint32_t kbytes[4] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};
+  uint32_t wv[32];
+  // the residual row pieces (64 B per 32 columns, one row per thread) are requested one chunk ahead: their global
+  // latency hides behind the tensor-memory load and the Philox rounds of the current chunk
+  uint4 rnext[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) rnext[j] = row_ok ? __ldg(reinterpret_cast<const uint4*>(res_row) + j) : make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll 1
+  for (int c = 0; c < 4; ++c) {
+    const int col0 = colb + c * 32;
+    uint32_t v[32];
+    tmem_ld32(taddr + c * 32, v);
+    uint4 rr[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) rr[j] = rnext[j];
+    if (c < 3) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        rnext[j] = row_ok ? __ldg(reinterpret_cast<const uint4*>(res_row + (c + 1) * 32) + j) : make_uint4(0u, 0u, 0u, 0u);
+    }
+    tmem_ld_wait();
+    uint32_t w[16];
+    {
+      const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.bias) bv = __ldg(b4 + j);
+        const __nv_bfloat162 lo = __floats2bfloat162_rn(__uint_as_float(v[4 * j]) + bv.x, __uint_as_float(v[4 * j + 1]) + bv.y);
+        const __nv_bfloat162 hi = __floats2bfloat162_rn(__uint_as_float(v[4 * j + 2]) + bv.z, __uint_as_float(v[4 * j + 3]) + bv.w);
+        w[2 * j] = *reinterpret_cast<const uint32_t*>(&lo);
+        w[2 * j + 1] = *reinterpret_cast<const uint32_t*>(&hi);
+      }
+    }
+    if (drop) {
+      uint32_t kb = 0;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        KeepMask km;
+        km.draw(seed, (uint64_t)R * (C / 8) + ((col0 >> 3) + g), thresh);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) w[4 * g + i] &= km.m[i];
+        kb |= km.to_byte() << (8 * g);
+      }
+      kbytes[c] = kb;
+    }
+    const uint32_t* rw = reinterpret_cast<const uint32_t*>(rr);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const float f0 = __uint_as_float(w[j] << 16), f1 = __uint_as_float(w[j] & 0xFFFF0000u);
+      const float r0 = __uint_as_float(rw[j] << 16), r1 = __uint_as_float(rw[j] & 0xFFFF0000u);
+      const float v0 = row_ok ? fmaf(f0, scale, r0) : 0.f, v1 = row_ok ? fmaf(f1, scale, r1) : 0.f;
+      sum += v0 + v1;
+      sumsq = fmaf(v0, v0, fmaf(v1, v1, sumsq));
+      v[2 * j] = __float_as_uint(v0);
+      v[2 * j + 1] = __float_as_uint(v1);
+      const __nv_bfloat162 b2 = __floats2bfloat162_rn(v0, v1);
+      wv[(c & 1) * 16 + j] = *reinterpret_cast<const uint32_t*>(&b2);
+    }
+    tmem_st32(taddr + c * 32, v);
+    if (c & 1)
+      ln_flush64(stg, lane, wv, p.ln_v + ((long long)t.z * p.M + m_w0) * C + colb + (c - 1) * 32, C, m_w0, p.M);
+  }
+  tmem_st_wait();
+  if (in_rows && p.ln_keep && drop)
+    *reinterpret_cast<uint4*>(p.ln_keep + R * (C / 8) + chalf * 16) = make_uint4(kbytes[0], kbytes[1], kbytes[2], kbytes[3]);
+  // ---- row statistics from the two column halves: one exchange.  var = E[v^2] - mean^2 in fp32: the rows are
+  //      residual-stream activations (|mean| is a fraction of the standard deviation), so the cancellation costs
+  //      ~1e-6 of the variance -- and it saves a whole pass over tensor memory and a second barrier per tile
+  red0[chalf * 128 + row] = sum;
+  red1[chalf * 128 + row] = sumsq;
+  bar_sync_epi2();
+  const float mean = (red0[row] + red0[128 + row]) * (1.f / C);
+  const float var = fmaxf((red1[row] + red1[128 + row]) * (1.f / C) - mean * mean, 0.f);
+  const float rstd = rsqrtf(var + 1e-5f);
+  if (chalf == 0 && in_rows) {
+    p.ln_mean[R] = row_ok ? mean : 0.f;
+    p.ln_rstd[R] = row_ok ? rstd : 0.f;
+  }
+  // ---- pass 2: normalise, affine, zero the padded rows, store
+  const float nmr = -mean * rstd;
+  const long long base_off = (long long)(t.z / p.d_zdiv) * p.d_zdiv_stride + (long long)(t.z % p.d_zdiv) * p.d_zmod_stride;
+  __nv_bfloat16* dbase = static_cast<__nv_bfloat16*>(p.d) + base_off + (long long)m_w0 * p.ldd + colb;
+#pragma unroll 1
+  for (int c = 0; c < 4; c += 2) {  // 64 columns per tensor-memory round trip
+    uint32_t va[32], vb[32];
+    tmem_ld32(taddr + c * 32, va);
+    tmem_ld32(taddr + c * 32 + 32, vb);
+    tmem_ld_wait();
+    const float* gam = s_gb + colb + c * 32;
+    const float* bet = s_gb + 256 + colb + c * 32;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const float o0 = row_ok ? fmaf(fmaf(__uint_as_float(va[2 * j]), rstd, nmr), gam[2 * j], bet[2 * j]) : 0.f;
+      const float o1 = row_ok ? fmaf(fmaf(__uint_as_float(va[2 * j + 1]), rstd, nmr), gam[2 * j + 1], bet[2 * j + 1]) : 0.f;
+      const float o2 = row_ok ? fmaf(fmaf(__uint_as_float(vb[2 * j]), rstd, nmr), gam[32 + 2 * j], bet[32 + 2 * j]) : 0.f;
+      const float o3 = row_ok ? fmaf(fmaf(__uint_as_float(vb[2 * j + 1]), rstd, nmr), gam[32 + 2 * j + 1], bet[32 + 2 * j + 1]) : 0.f;
+      const __nv_bfloat162 b2 = __floats2bfloat162_rn(o0, o1), b3 = __floats2bfloat162_rn(o2, o3);
+      wv[j] = *reinterpret_cast<const uint32_t*>(&b2);
+      wv[16 + j] = *reinterpret_cast<const uint32_t*>(&b3);
+    }
+    ln_flush64(stg, lane, wv, dbase + c * 32, p.ldd, m_w0, p.M);
+  }
+}
+
+template <bool LN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(g2::kThreads2, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const __grid_constant__ GemmKP p) {
@@ -66,6 +244,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const bool leader = rank == 0;
   const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
   constexpr uint32_t TMEM_COLS = 512;
+  constexpr int NST = LN ? LN_STAGES : STAGES;  // operand ring depth
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -89,6 +268,13 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   }
   pdl_wait();  // everything above is independent of the previous kernel's output
   if (warp == 3 && p.ragged) build_ragged_table(p, reinterpret_cast<int*>(sgen + CUM_OFF), lane);
+  if (LN && warp == 2) {  // LayerNorm affine parameters -> shared memory (broadcast reads in the epilogue)
+    float* gb = reinterpret_cast<float*>(sgen + LN_GB_OFF);
+    for (int i = lane; i < 256; i += 32) {
+      gb[i] = p.ln_gamma[i];
+      gb[256 + i] = p.ln_beta[i];
+    }
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -123,7 +309,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           mbar_wait(empty_bar(s), ph ^ 1u);
           if (p.dbg & 4) {  // ablation: no operand loads
             if (leader) mbar_arrive(full_bar(s));
-            if (++s == STAGES) {
+            if (++s == NST) {
               s = 0;
               ph ^= 1u;
             }
@@ -170,7 +356,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
               tma_load_3d_2sm(sb + h * kChunkBytes, &tmB, lfull, p.b_inner_base + c0 + h * 64,
                               r0 + p.tap_shift0 + tap, zb);
           }
-          if (++s == STAGES) {
+          if (++s == NST) {
             s = 0;
             ph ^= 1u;
           }
@@ -208,7 +394,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             if (kb == t.nkb - 1) umma_commit_2sm(tfull_bar(as));
           }
           __syncwarp();
-          if (++s == STAGES) {
+          if (++s == NST) {
             s = 0;
             ph ^= 1u;
           }
@@ -226,7 +412,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   } else if (warp >= 4) {
     // ======================= epilogue (both CTAs drain their own 128 rows) =======================
     const int q = warp & 3, chalf = (warp - 4) >> 2;
-    int as = 0;
+    int as = 0, ln_parity = 0;
     uint32_t aph = 0;
     uint8_t* stg = sgen + STAGING_OFF + (warp - 4) * 4096;
     const uint32_t leader_tempty0 = mapa_rank(tempty_bar(0), 0);
@@ -236,7 +422,13 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const TileCoord t = decode_pair(ptile);
       mbar_wait(tfull_bar(as), aph);
       tc_fence_after();
-      if (!(p.dbg & 2)) epilogue_tile<BN>(p, t, tmem_base + as * BN, stg, q, chalf, lane);
+      if (LN) {
+        epilogue_ln_tile(p, t, tmem_base + as * BN, stg, q, chalf, lane, reinterpret_cast<const float*>(sgen + LN_GB_OFF),
+                         reinterpret_cast<float*>(sgen + LN_RED_OFF), ln_parity);
+        ln_parity ^= 1;
+      } else if (!(p.dbg & 2)) {
+        epilogue_tile<BN>(p, t, tmem_base + as * BN, stg, q, chalf, lane);
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_remote(leader_tempty0 + 8u * as);
@@ -261,7 +453,7 @@ int gemm_tc2_launch(const fs2_gemm& g, GemmKP& kp, cudaStream_t stream) {
   using namespace g2;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DYN_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, DYN_BYTES);
     if (e != cudaSuccess) return set_cuda_error("cudaFuncSetAttribute(gemm_tc2)", e);
     attr_set = true;
   }
@@ -292,7 +484,31 @@ int gemm_tc2_launch(const fs2_gemm& g, GemmKP& kp, cudaStream_t stream) {
   }
   const int max_pairs = g2_num_sms / 2;
   const int pairs = pair_tiles < max_pairs ? pair_tiles : max_pairs;
-  FS2_LAUNCH((gemm_tc2_kernel), 2 * pairs, kThreads2, DYN_BYTES, stream, tmA, tmB, kp);
+  if (g.ln_gamma) {
+    if (g.mode != FS2_GEMM_NORMAL || g.N != 256 || g.d_f32 || taps != 1 || g.epilogue != FS2_EPI_NONE || g.alpha != 1.f ||
+        !g.ln_beta || !g.ln_res || !g.ln_v || !g.ln_mean || !g.ln_rstd || (g.ld_res & 7) || (g.res_batch_stride & 7) ||
+        (reinterpret_cast<uintptr_t>(g.ln_res) & 15) || (reinterpret_cast<uintptr_t>(g.ln_v) & 15) ||
+        (g.ln_p_drop > 0.f && (!g.ln_keep || (reinterpret_cast<uintptr_t>(g.ln_keep) & 15))) || g.ln_p_drop >= 1.f)
+      return set_error("gemm: the fused LayerNorm epilogue needs NORMAL mode, taps = 1, N = 256, a bf16 output, no other "
+                       "epilogue and all ln_* buffers (16-byte aligned)");
+    static bool ln_attr = false;
+    if (!ln_attr) {
+      cudaError_t e = cudaFuncSetAttribute(gemm_tc2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, DYN_BYTES);
+      if (e != cudaSuccess) return set_cuda_error("cudaFuncSetAttribute(gemm_tc2<LN>)", e);
+      ln_attr = true;
+    }
+    kp.ln_gamma = g.ln_gamma; kp.ln_beta = g.ln_beta;
+    kp.ln_res = static_cast<const __nv_bfloat16*>(g.ln_res);
+    kp.ld_res = g.ld_res; kp.res_batch_stride = g.res_batch_stride;
+    kp.ln_p_drop = g.ln_p_drop; kp.ln_seed = g.ln_seed;
+    kp.ln_seed_dev = reinterpret_cast<const unsigned long long*>(g.ln_seed_dev);
+    kp.ln_v = static_cast<__nv_bfloat16*>(g.ln_v);
+    kp.ln_mean = g.ln_mean; kp.ln_rstd = g.ln_rstd; kp.ln_keep = g.ln_keep;
+    FS2_LAUNCH((gemm_tc2_kernel<true>), 2 * pairs, kThreads2, DYN_BYTES, stream, tmA, tmB, kp);
+    count_launch();
+    return check_launch("gemm_tc2_kernel<LN>");
+  }
+  FS2_LAUNCH((gemm_tc2_kernel<false>), 2 * pairs, kThreads2, DYN_BYTES, stream, tmA, tmB, kp);
   count_launch();
   return check_launch("gemm_tc2_kernel");
 }

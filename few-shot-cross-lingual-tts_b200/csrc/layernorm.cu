@@ -7,7 +7,6 @@
 //   lightning/model/modules.py:222-225,234-237  `dropout(layer_norm(relu(conv)))`     (drop_mode 2)
 // One warp owns one row (C = 256/512/1024 channels = 1/2/4 16-byte vectors per lane), so the
 // statistics never leave registers.  HBM-bound: algorithmic bytes fwd = (2 or 3) * rows * C * 2.
-#include <cuda_fp16.h>
 
 #include "common.h"
 #include "util.cuh"
@@ -61,53 +60,6 @@ struct RowCursor {
   }
   __device__ __forceinline__ bool masked(const int64_t* lens) const { return lens && t >= lens[b]; }
 };
-
-// ---- dropout masks in bf16x2 lane form ------------------------------------------------------------------------
-// One Philox call gives 8 x 16 random bits for the 8 channels of a lane.  A pair of channels is kept / dropped by
-// ONE half2 compare on 13 of its 16 bits (mapped into [2, 4): finite, normal fp16 numbers, ordered like the
-// integers) that yields 0xFFFF / 0x0000 per half -- the mask is ANDed onto the packed bf16 pair, and the 1/(1-p)
-// scale rides on the FMA that adds the residual.  (The per-element form -- extract, compare, select, multiply --
-// was ~6 instructions per element of an otherwise HBM-bound kernel.)  Resolution of p: 1/8192.
-struct KeepMask {
-  uint32_t m[4];  // channel pairs (0,1) (2,3) (4,5) (6,7): 0xFFFF per kept half
-  __device__ __forceinline__ void draw(uint64_t seed, uint64_t ctr, uint32_t thresh_h2) {
-    const uint4 r = philox4x32(seed, ctr);
-    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
-    const __half2 th = *reinterpret_cast<const __half2*>(&thresh_h2);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const uint32_t a = (w[i] & 0x1FFF1FFFu) | 0x40004000u;
-      m[i] = __hge2_mask(*reinterpret_cast<const __half2*>(&a), th);
-    }
-  }
-  __device__ __forceinline__ void all() { m[0] = m[1] = m[2] = m[3] = 0xFFFFFFFFu; }
-  __device__ __forceinline__ uint32_t to_byte() const {
-    uint32_t b = 0;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) b |= ((m[i] & 1u) | ((m[i] >> 15) & 2u)) << (2 * i);
-    return b;
-  }
-  __device__ __forceinline__ void from_byte(uint32_t b) {
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const uint32_t t = b >> (2 * i);
-      m[i] = ((t & 1u) | ((t & 2u) << 15)) * 0xFFFFu;
-    }
-  }
-  __device__ __forceinline__ void apply(bf16x8& v) const {
-    uint32_t* w = reinterpret_cast<uint32_t*>(&v);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) w[i] &= m[i];
-  }
-};
-// threshold pair for KeepMask::draw: keep <=> 13 random bits >= p * 8192
-__host__ __device__ __forceinline__ uint32_t keep_thresh_h2(float p) {
-  float t = p * 8192.f;
-  const uint32_t k = t <= 0.f ? 0u : (t >= 8191.f ? 8191u : static_cast<uint32_t>(t + 0.5f));
-  const uint32_t h = 0x4000u | k;
-  return h | (h << 16);
-}
-
 
 template <int NV>
 __global__ void __launch_bounds__(256) ln_fwd_kernel(const LnArgs a) {
@@ -245,6 +197,10 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const LnArgs a) {
   const bool drop = a.drop_mode != 0;
   const float keep_scale = drop ? 1.f / (1.f - a.p_drop) : 1.f;
   const float in_scale = a.drop_mode == 1 ? keep_scale : 1.f;
+  // mode 3: x is already the pre-norm sum v = dropout(f) / (1 - p) + res (written by the fused GEMM epilogue,
+  // fs2_gemm::ln_v): nothing to rebuild on the input side, the mask / scale only apply to dx
+  const bool out_mask = a.drop_mode == 1 || a.drop_mode == 3;
+  const float out_scale = out_mask ? keep_scale : 1.f;
   float acc_g[NV][8], acc_b[NV][8], acc_x[NV][8];
 #pragma unroll
   for (int i = 0; i < NV; ++i)
@@ -362,16 +318,16 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const LnArgs a) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           dpre[j] = rstd * (gy[i][j] - m1 - xh[i][j] * m2);
-          dxo[j] = dpre[j] * in_scale;
+          dxo[j] = dpre[j] * out_scale;
           if (a.relu_x && !((relu_pos[i] >> j) & 1u)) dxo[j] = 0.f;
         }
         bf16x8 dxv = pack8(dxo);
-        if (a.drop_mode == 1) km[i].apply(dxv);
+        if (out_mask) km[i].apply(dxv);
         if (a.dbias) {  // column sums of what is stored (dropped elements contribute zero)
           float st[8];
           unpack8(dxv, st);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) acc_x[i][j] += a.drop_mode == 1 ? st[j] : dxo[j];
+          for (int j = 0; j < 8; ++j) acc_x[i][j] += out_mask ? st[j] : dxo[j];
         }
         st8(a.dx + row * C + col, dxv);
         if (a.dres) st8(a.dres + row * C + col, pack8(dpre));

@@ -2,6 +2,7 @@
 // Philox4x32-10 counter RNG for dropout (regenerated, never stored, in the backward kernels).
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
 #include <cstdint>
@@ -83,6 +84,53 @@ __device__ __forceinline__ uint32_t dropout_keep8(uint64_t seed, uint64_t elem0,
   }
   return m;
 }
+// ---- dropout masks in bf16x2 lane form ------------------------------------------------------------------------
+// One Philox call gives 8 x 16 random bits for the 8 channels of a lane.  A pair of channels is kept / dropped by
+// ONE half2 compare on 13 of its 16 bits (mapped into [2, 4): finite, normal fp16 numbers, ordered like the
+// integers) that yields 0xFFFF / 0x0000 per half -- the mask is ANDed onto the packed bf16 pair, and the 1/(1-p)
+// scale rides on the FMA that adds the residual.  (The per-element form -- extract, compare, select, multiply --
+// was ~6 instructions per element of an otherwise HBM-bound kernel.)  Resolution of p: 1/8192.
+struct KeepMask {
+  uint32_t m[4];  // channel pairs (0,1) (2,3) (4,5) (6,7): 0xFFFF per kept half
+  __device__ __forceinline__ void draw(uint64_t seed, uint64_t ctr, uint32_t thresh_h2) {
+    const uint4 r = philox4x32(seed, ctr);
+    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+    const __half2 th = *reinterpret_cast<const __half2*>(&thresh_h2);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const uint32_t a = (w[i] & 0x1FFF1FFFu) | 0x40004000u;
+      m[i] = __hge2_mask(*reinterpret_cast<const __half2*>(&a), th);
+    }
+  }
+  __device__ __forceinline__ void all() { m[0] = m[1] = m[2] = m[3] = 0xFFFFFFFFu; }
+  __device__ __forceinline__ uint32_t to_byte() const {
+    uint32_t b = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) b |= ((m[i] & 1u) | ((m[i] >> 15) & 2u)) << (2 * i);
+    return b;
+  }
+  __device__ __forceinline__ void from_byte(uint32_t b) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const uint32_t t = b >> (2 * i);
+      m[i] = ((t & 1u) | ((t & 2u) << 15)) * 0xFFFFu;
+    }
+  }
+  __device__ __forceinline__ void apply(bf16x8& v) const {
+    uint32_t* w = reinterpret_cast<uint32_t*>(&v);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) w[i] &= m[i];
+  }
+};
+// threshold pair for KeepMask::draw: keep <=> 13 random bits >= p * 8192
+__host__ __device__ __forceinline__ uint32_t keep_thresh_h2(float p) {
+  float t = p * 8192.f;
+  const uint32_t k = t <= 0.f ? 0u : (t >= 8191.f ? 8191u : static_cast<uint32_t>(t + 0.5f));
+  const uint32_t h = 0x4000u | k;
+  return h | (h << 16);
+}
+
+
 // Per-step seed: a device-resident counter (so that a replayed CUDA graph draws fresh masks every
 // step) mixed with a per-call-site salt.
 __device__ __forceinline__ uint64_t mix_seed(const uint64_t* seed_dev, uint64_t salt) {

@@ -59,7 +59,8 @@ def run(g, impl=None):
 
 def gemm(a, b, d, M, N, K, Z=1, taps=1, tap_shift0=0, b_tap_kstride=0, ldd=None, bias=None,
          epilogue=EPI_NONE, aux=None, ld_aux=0, aux_batch_stride=0, alpha=1.0, d_zdiv=1,
-         d_zdiv_stride=0, d_zmod_stride=0, impl=None, row_lens=None, lens_zdiv=1, tail_rows=0, relu_mask=None):
+         d_zdiv_stride=0, d_zmod_stride=0, impl=None, row_lens=None, lens_zdiv=1, tail_rows=0, relu_mask=None,
+         ln=None):
     """D[z] = epi(alpha * sum_tap A[z][m+shift+tap] . B[z][n][tap*kstride+k] + bias).
 
     row_lens (int64 [Z / lens_zdiv]): rows m >= row_lens of D[z] are written as zero and row tiles that
@@ -90,6 +91,15 @@ def gemm(a, b, d, M, N, K, Z=1, taps=1, tap_shift0=0, b_tap_kstride=0, ldd=None,
     if relu_mask is not None:  # int64 [Z*M, N/64]: written by EPI_RELU, read by EPI_RELU_BWD instead of `aux`
         assert relu_mask.dtype == torch.int64 and relu_mask.is_contiguous() and relu_mask.numel() == Z * M * (N // 64)
         g.relu_mask = relu_mask.data_ptr()
+    if ln is not None:  # fused dropout + residual + LayerNorm + pad-zero epilogue (fs2_gemm::ln_*)
+        g.ln_gamma, g.ln_beta = ln["gamma"].data_ptr(), ln["beta"].data_ptr()
+        res = ln["res"]
+        assert res.dtype == torch.bfloat16 and res.is_contiguous()
+        g.ln_res, g.ld_res, g.res_batch_stride = res.data_ptr(), int(N), int(M * N)
+        g.ln_p_drop, g.ln_seed = float(ln["p"]), int(ln["salt"])
+        g.ln_seed_dev = ln["seed_dev"].data_ptr() if ln.get("seed_dev") is not None else None
+        g.ln_v, g.ln_mean, g.ln_rstd = ln["v"].data_ptr(), ln["mean"].data_ptr(), ln["rstd"].data_ptr()
+        g.ln_keep = ln["keep"].data_ptr() if ln.get("keep") is not None else None
     if g.taps > 1 and not g.d_f32:  # last partial wave of the Conv1d schedule: split over the reduction
         ws = _workspace()
         g.workspace, g.workspace_bytes = ws.data_ptr(), ws.numel()

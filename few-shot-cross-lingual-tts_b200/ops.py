@@ -88,6 +88,8 @@ class fork_side:
 # PostNet kernels; autograd runs their backward on the same streams, next to the decoder backward.  The forks and
 # joins are captured as parallel branches of the step's CUDA graph.  FS2_NO_BRANCH=1 keeps everything on one stream.
 BRANCH = OVERLAP and _os.environ.get("FS2_NO_BRANCH") is None
+LN_FUSE = _os.environ.get("FS2_NO_LN_FUSE") is None  # LayerNorm in the epilogue of the k = 1 FFN convolution
+LN_FUSE_MIN_ROWS = 32768  # ... when every CTA pair gets at least ~2 row tiles (B * T rows)
 _branch_streams = {}
 _open_branches = []
 
@@ -533,7 +535,7 @@ def ln_bwd(dy, x, res, gamma, mean, rstd, lens, p, mode, keep, dgamma, dbeta, wa
     GEMM / conv that produced x."""
     B, T, C = x.shape
     dx = torch.empty_like(x)
-    dres = torch.empty_like(x) if want_dres and p > 0 and mode == 1 else None
+    dres = torch.empty_like(x) if want_dres and p > 0 and mode in (1, 3) else None
     _ck(_L().fs2_ln_bwd_bf16(_p(dy), _p(x), _p(res), _p(gamma), _p(mean), _p(rstd), _p(lens), B, T, C, p,
                              mode, 1 if relu_x else 0, _p(keep), _p(dx), _p(dres), _p(dgamma),
                              _p(dbeta), _p(dbias), _st()), "ln_bwd")
@@ -785,10 +787,31 @@ class FFNSublayer(torch.autograd.Function):
         hmask = torch.empty(B * T, Dh_ // 64, dtype=torch.int64, device=x.device) if use_mask else None
         h = conv_fwd(x, w1p, b1.detach(), relu=True, lens=rl, tail=(w2p.shape[1] - 1) // 2 or NO_TAIL,
                      relu_mask=hmask)
-        f = conv_fwd(h, w2p, b2.detach(), lens=rl, tail=NO_TAIL)
         salt = _Rng.next_salt()
-        y, mean, rstd, ctx.keep = ln_fwd(f, x, gamma.detach(), beta.detach(), lens if zero_pad else None, p_drop,
-                                         1, salt)
+        # w_2 with k = 1 and 256 output channels: dropout + residual + LayerNorm + pad-zero run in the epilogue of the
+        # GEMM (fs2_gemm::ln_*, csrc/gemm_tc2.cu) -- no LayerNorm launch, `f` never reaches HBM; the backward gets the
+        # pre-norm sum v instead of (f, x).  FS2_NO_LN_FUSE=1: separate kernels.
+        # Measured (B200): C2 (64000 rows) fused 63.5-67.6 us vs 66.6-69.6 us for the two kernels -- the epilogue takes
+        # ~15 us per tile and the last tile's is exposed; with one tile per CTA (C1 / C3 / C5) it is slower than the
+        # separate LayerNorm launch, so small batches keep the two kernels.
+        ctx.fused = (LN_FUSE and w2p.shape[1] == 1 and D == 256 and h.shape[2] == w2p.shape[2] and
+                     0.0 <= p_drop < 1.0 and x.dtype == BF16 and B * T >= LN_FUSE_MIN_ROWS)
+        if ctx.fused:
+            y = torch.empty(B, T, D, dtype=BF16, device=x.device)
+            f = torch.empty(B, T, D, dtype=BF16, device=x.device)  # holds v = dropout(f) / (1 - p) + x
+            mean = torch.empty(B * T, dtype=F32, device=x.device)
+            rstd = torch.empty(B * T, dtype=F32, device=x.device)
+            ctx.keep = torch.empty(B * T, D // 8, dtype=torch.uint8, device=x.device) if p_drop > 0 else None
+            Kp = w2p.shape[2]
+            G.gemm(G.operand(h, Kp, T, B), G.operand(w2p, Kp, D), y, T, D, Kp, Z=B, bias=b2.detach(), d_zdiv=1,
+                   d_zdiv_stride=T * D, row_lens=rl, tail_rows=0,
+                   ln=dict(gamma=gamma.detach(), beta=beta.detach(), res=x, p=p_drop, salt=salt,
+                           seed_dev=_Rng.tensor(x.device) if p_drop > 0 else None, v=f, mean=mean, rstd=rstd,
+                           keep=ctx.keep))
+        else:
+            f = conv_fwd(h, w2p, b2.detach(), lens=rl, tail=NO_TAIL)
+            y, mean, rstd, ctx.keep = ln_fwd(f, x, gamma.detach(), beta.detach(), lens if zero_pad else None,
+                                             p_drop, 1, salt)
         ctx.save_for_backward(x, lens, h, f, mean, rstd, w1p, w2p, gamma)
         ctx.hmask = hmask
         ctx.params = (w1, b1, w2, b2, gamma, beta)
@@ -805,8 +828,12 @@ class FFNSublayer(torch.autograd.Function):
         dy = _contig(dy)
         gbuf = [grad_target(p) for p in (w1, b1, w2, b2, gamma, beta)]
         rl = lens if zero_pad else None
-        df, dres = ln_bwd(dy, f, x, gamma_t, mean, rstd, rl, p_drop, 1, ctx.keep,
-                          gbuf[4][0], gbuf[5][0], want_dres=True, dbias=gbuf[3][0])  # dbias: w_2.bias gradient
+        if ctx.fused:  # f holds the pre-norm sum: nothing to rebuild, the mask / scale only apply to df
+            df, dres = ln_bwd(dy, f, None, gamma_t, mean, rstd, rl, p_drop, 3, ctx.keep,
+                              gbuf[4][0], gbuf[5][0], want_dres=True, dbias=gbuf[3][0])
+        else:
+            df, dres = ln_bwd(dy, f, x, gamma_t, mean, rstd, rl, p_drop, 1, ctx.keep,
+                              gbuf[4][0], gbuf[5][0], want_dres=True, dbias=gbuf[3][0])  # dbias: w_2.bias gradient
         # dh feeds the input gradient of w_1, which reads a (k1-1)//2-row halo behind the last valid frame
         with fork_side():
             conv_wgrad(df, h, gbuf[2][0], lens=rl)

@@ -123,6 +123,25 @@ typedef struct fs2_gemm {
      be shared by launches that can run concurrently (one buffer per stream).  NULL = no split. */
   void* workspace;
   int64_t workspace_bytes;
+  /* optional fused LayerNorm epilogue (NORMAL mode, taps = 1, N == 256, bf16 D; transformer/SubLayers.py:88-91
+     `layer_norm(dropout(w_2(h)) + residual)` + transformer/Layers.py:28 masked_fill in the GEMM that computes w_2):
+       f = bf16(acc + bias); v = dropout(f) / (1 - p) + ln_res; D = (v - mean) * rstd * ln_gamma + ln_beta,
+     rows m >= row_lens[z] of D are zero.  ln_gamma != NULL enables it.  Also written, all indexed by the dense row
+     z * M + m: ln_v (bf16 [Z*M][256], the pre-norm sum the backward needs), ln_mean / ln_rstd (f32 [Z*M]) and
+     ln_keep (uint8 [Z*M][32] dropout keep bits, same stream and layout as fs2_ln_fwd_bf16 with the same seed). */
+  const float* ln_gamma;
+  const float* ln_beta;
+  const void* ln_res;          /* bf16 [Z][M][ld_res] */
+  int64_t ld_res;
+  int64_t res_batch_stride;
+  float ln_p_drop;
+  int32_t ln_pad0;
+  uint64_t ln_seed;
+  const uint64_t* ln_seed_dev;
+  void* ln_v;
+  float* ln_mean;
+  float* ln_rstd;
+  uint8_t* ln_keep;
 } fs2_gemm;
 
 /* impl: 0 = tcgen05 (product path), 1 = plain CUDA-core kernel (debug cross-check only). */
@@ -141,6 +160,8 @@ int64_t fs2_gemm_workspace_bytes(void);
 /*   (device step counter, may be NULL) mixed with the call-site salt `seed`; p is resolved to */
 /*   1/8192.  keep_out / keep_in: uint8 [B*T][C/8] keep bits (bit j of byte v = channel 8v+j),  */
 /*   written by the forward (optional there) and READ by the backward (required when p > 0).   */
+/*   Backward only, drop_mode 3: x is the pre-norm sum written by the fused GEMM epilogue        */
+/*   (fs2_gemm::ln_v), res must be NULL; dx = mask / (1 - p) * dpre, dres = dpre.               */
 /*   dgamma/dbeta: f32 [C], accumulated with atomics (zero them first); dbias (optional, f32    */
 /*   [C]): column sums of dx, i.e. the bias gradient of the GEMM / conv that produced x.        */
 /*   Rows t >= lens[b] are never read: y / dx / dres are zero there.                            */

@@ -458,3 +458,50 @@ def test_colsum_ragged_skips_padded_rows():
     out3 = torch.ones(256, device="cuda")
     ops.colsum(x.view(B * T, C), out3, col0=512, cols=256, lens=lens, T=T)
     assert rel_err(out3, ref[512:768]) < 1e-5
+
+
+@pytest.mark.parametrize("p_drop", [0.0, 0.2])
+@pytest.mark.parametrize("lens", [None, [300, 5, 140, 129, 0, 257]])
+def test_ffn_sublayer_layernorm_fused_into_the_k1_conv_epilogue(p_drop, lens):
+    """fs2_gemm::ln_* (csrc/gemm_tc2.cu): dropout + residual + LayerNorm + pad-zero in the epilogue of the k = 1
+    convolution against the separate GEMM + LayerNorm kernels -- same Philox stream, so also with dropout the two
+    paths agree up to the summation order of the row statistics; gradients through the mode-3 LayerNorm backward."""
+    torch.manual_seed(13)
+    B, T, D, Dh = (6 if lens is not None else 3), 300, 256, 1024
+    rl = None if lens is None else torch.tensor(lens, device="cuda")
+    valid = torch.ones(B, T, dtype=torch.bool, device="cuda") if rl is None else \
+        torch.arange(T, device="cuda")[None, :] < rl[:, None]
+    x0 = (torch.randn(B, T, D, device="cuda") * valid[..., None]).to(BF16)
+    w1 = (torch.randn(Dh, D, 9, device="cuda") * (D * 9) ** -0.5).requires_grad_()
+    b1 = (torch.randn(Dh, device="cuda") * 0.1).requires_grad_()
+    w2 = (torch.randn(D, Dh, 1, device="cuda") * Dh ** -0.5).requires_grad_()
+    b2 = (torch.randn(D, device="cuda") * 0.1).requires_grad_()
+    gamma = (1 + 0.1 * torch.randn(D, device="cuda")).requires_grad_()
+    beta = (0.1 * torch.randn(D, device="cuda")).requires_grad_()
+    wgt = torch.randn(B, T, D, device="cuda")
+    outs = []
+    min_rows = ops.LN_FUSE_MIN_ROWS
+    for fuse in (True, False):
+        ops.LN_FUSE = fuse
+        ops.LN_FUSE_MIN_ROWS = 0  # small test batch: force the fused path
+        try:
+            ops.manual_seed(99)
+            ops._Rng.salt = 4242  # both runs draw the same call-site salt
+            for t in (w1, b1, w2, b2, gamma, beta):
+                t.grad = None
+            x = x0.clone().requires_grad_()
+            y = ops.FFNSublayer.apply(x, rl if rl is not None else torch.full((B,), T, device="cuda"), w1, b1, w2, b2,
+                                      gamma, beta, p_drop, rl is not None)
+            (y.float() * wgt).sum().backward()
+            outs.append((y.detach().clone(), x.grad.clone(), [t.grad.clone() for t in (w1, b1, w2, b2, gamma, beta)]))
+        finally:
+            ops.LN_FUSE = True
+            ops.LN_FUSE_MIN_ROWS = min_rows
+    (yf, dxf, gf), (yu, dxu, gu) = outs
+    assert torch.isfinite(yf.float()).all() and (yf[~valid] == 0).all()
+    assert rel_err(yf, yu) < 2e-3, rel_err(yf, yu)  # bf16 outputs: a different last bit here and there
+    if p_drop > 0:  # identical masks: the outputs differ nowhere by more than bf16 rounding
+        assert (yf.float() - yu.float()).abs().max() < 0.1
+    assert rel_err(dxf, dxu) < 1e-2, rel_err(dxf, dxu)
+    for a, b, n in zip(gf, gu, ("w1", "b1", "w2", "b2", "gamma", "beta")):
+        assert rel_err(a, b) < 1e-2, (n, rel_err(a, b))

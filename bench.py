@@ -338,9 +338,11 @@ def kernel_rooflines(base, cfg, bf16_peak, hbm_peak, step_ms, traffic):
         f["bound"], f["peak"], f["unit"] = "tensor", bf16_peak, "TFLOP/s"
         f["frac"] = f["achieved"] / bf16_peak
         f["traffic"] = traffic.get(f["label"])
-    top = max(fams, key=lambda f: f["share_of_step"])
+    # the dominant KERNEL: entries that time several kernels in one call (attention backward = row-dot prologue + dK/dV
+    # + dQ; QKV weight gradient + column sums) explain the step below but are not one kernel's roofline
+    top = max((f for f in fams if "+" not in f["kernel"]), key=lambda f: f["share_of_step"])
     roof = dict(top)
-    roof["note"] = ("largest share of the step among the kernel launches of a decoder layer (share = launches per step "
+    roof["note"] = ("largest share of the step among the single-kernel launches of a decoder layer (share = launches per step "
                     "x this time / step time); timed ALONE on the ragged call the step makes (valid rows %d of %d "
                     "padded), L2 flushed, CUDA events on the launching stream; flops = valid rows only" % (V, B * Tm))
 

@@ -1339,6 +1339,17 @@ def phoneme_class_mean(representations, avg_frames, n_symbols, phonemes, two_sta
 # --------------------------------------------------------------------------------------------------
 # loss
 # --------------------------------------------------------------------------------------------------
+_UNIT0 = {}
+
+
+def _unit0(dev):
+    """[1, 0, 0, 0, 0, 0] on `dev` (cached constant)."""
+    t = _UNIT0.get(dev)
+    if t is None:
+        t = _UNIT0[dev] = torch.tensor([1.0, 0.0, 0.0, 0.0, 0.0, 0.0], dtype=F32, device=dev)
+    return t
+
+
 class FastSpeech2LossFn(torch.autograd.Function):
     """lightning/model/loss.py:15-89 in two kernels forward, one backward.  `p_frame` / `e_frame`: the pitch /
     energy feature is frame-level ([B, Tm] rows masked by the mel lengths, loss.py:50-52,57-59) instead of
@@ -1347,6 +1358,7 @@ class FastSpeech2LossFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, mel, post, p_pred, e_pred, d_pred, mel_tgt, p_tgt, e_tgt, d_tgt, src_lens, mel_lens,
                 p_frame=False, e_frame=False):
+        ctx.set_materialize_grads(False)  # unused loss terms reach backward() as None, not as zero tensors
         B, Tm, n_mel = mel.shape
         Ts = d_pred.shape[1]
         dev = mel.device
@@ -1386,8 +1398,9 @@ class FastSpeech2LossFn(torch.autograd.Function):
         B, Ts, Tm, Tm_t, n_mel, e64, p_frame, e_frame = ctx.meta
         dev = mel.device
         if gouts[0] is not None and all(g is None for g in gouts[1:]):
-            # the usual case (`losses[0].backward()`): one launch instead of five zero fills + a cat
-            g6 = torch.nn.functional.pad(gouts[0].reshape(1).to(F32), (0, 5))
+            # the usual case (`losses[0].backward()`; forward() turned grad materialisation off, so the five
+            # unused outputs arrive as None): one broadcast multiply instead of five zero fills + a cat
+            g6 = gouts[0].reshape(1).to(F32) * _unit0(dev)
         else:
             g6 = torch.stack([torch.zeros((), dtype=F32, device=dev) if g is None else g.to(F32).reshape(())
                               for g in gouts])

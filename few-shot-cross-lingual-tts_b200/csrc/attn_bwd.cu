@@ -39,6 +39,8 @@ struct AttnBwdP {
   float scale, scale_log2;
   __nv_bfloat16* dqkv;  // [B][T][3*H*dk]
   int dbg;              // FS2_ATTN_DBG ablation bits (tools only)
+  float* dbq;           // optional [H*dk] f32, accumulated: column sums of dQ / dV = gradients of the w_qs / w_vs
+  float* dbv;           // biases (the key bias has none: softmax is invariant to it)
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -93,9 +95,11 @@ __device__ __forceinline__ void store_row_chunks(uint8_t* row_ptr, int sw, int c
 
 // 64 columns [half*64, half*64+64) of a TMEM accumulator [128 lanes x 128 cols] -> bf16 -> this warp's
 // staging tile -> coalesced global rows (warp = lane quarter q4, rows row0 + q4*32 ...)
+// colsum (optional, f32 [128], accumulated): column sums of the stored bf16 tile over its rows < row_limit -- the
+// projection's bias gradient, taken from the staging tile on its way out (rows of padded queries / keys are zero)
 __device__ __forceinline__ void store_acc_half(uint32_t tacc, uint32_t lane_base, uint8_t* stg, int q4, int lane,
                                                int half, __nv_bfloat16* gbase, long long g_ld, int row0,
-                                               int row_limit) {
+                                               int row_limit, float* colsum = nullptr) {
   uint8_t* my = stg + lane * 128;
   const int lsw = lane & 7;
   float f[64];
@@ -118,6 +122,7 @@ __device__ __forceinline__ void store_acc_half(uint32_t tacc, uint32_t lane_base
     *reinterpret_cast<uint4*>(my + ((ch ^ lsw) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
   }
   __syncwarp();
+  float cs[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
   for (int it = 0; it < 8; ++it) {
     const int r = it * 4 + (lane >> 3), ch = lane & 7;
@@ -125,6 +130,25 @@ __device__ __forceinline__ void store_acc_half(uint32_t tacc, uint32_t lane_base
     if (grow < row_limit) {
       const uint4 val = *reinterpret_cast<const uint4*>(stg + r * 128 + ((ch ^ (r & 7)) << 4));
       *reinterpret_cast<uint4*>(gbase + (long long)grow * g_ld + half * 64 + ch * 8) = val;
+      if (colsum) {
+        const uint32_t w[4] = {val.x, val.y, val.z, val.w};
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          cs[2 * t] += __uint_as_float(w[t] << 16);
+          cs[2 * t + 1] += __uint_as_float(w[t] & 0xFFFF0000u);
+        }
+      }
+    }
+  }
+  if (colsum) {  // lanes with the same 8-column group (lane & 7) hold four row groups: fold them, 8 atomics per group
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      cs[j] += __shfl_xor_sync(0xffffffffu, cs[j], 8);
+      cs[j] += __shfl_xor_sync(0xffffffffu, cs[j], 16);
+    }
+    if (lane < 8) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) atomicAdd(colsum + half * 64 + lane * 8 + j, cs[j]);
     }
   }
   __syncwarp();
@@ -335,7 +359,8 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmKV,   // qkv, box 64 x
     tc_fence_after();
     uint8_t* stg = sgen + OFF_PT + warp * 4096;  // P^T / dS^T tiles (32 KiB) are free now
     __nv_bfloat16* gb = p.dqkv + (long long)b * p.T * 3 * HD;
-    store_acc_half(tdV, lane_base, stg, q4, lane, half, gb + 2 * HD + h * DK, 3 * HD, k0, p.T);
+    store_acc_half(tdV, lane_base, stg, q4, lane, half, gb + 2 * HD + h * DK, 3 * HD, k0, p.T,
+                   p.dbv ? p.dbv + h * DK : nullptr);
     store_acc_half(tdK, lane_base, stg, q4, lane, half, gb + HD + h * DK, 3 * HD, k0, p.T);
   }
   tc_fence_before();
@@ -530,7 +555,8 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ128,  // qkv, box 64 x
     tc_fence_after();
     uint8_t* stg = sgen + OFF_STG + warp * 4096;
     __nv_bfloat16* gb = p.dqkv + (long long)b * p.T * 3 * HD;
-    store_acc_half(tdQ, lane_base, stg, q4, lane, half, gb + h * DK, 3 * HD, q0, p.T);
+    store_acc_half(tdQ, lane_base, stg, q4, lane, half, gb + h * DK, 3 * HD, q0, p.T,
+                   p.dbq ? p.dbq + h * DK : nullptr);
   }
   tc_fence_before();
   __syncthreads();
@@ -759,7 +785,8 @@ attn_bwd_dkv2_kernel(const __grid_constant__ CUtensorMap tmKV,   // qkv, box 64 
     tc_fence_after();
     uint8_t* stg = sgen + OFF_STG + warp * 4096;
     __nv_bfloat16* gb = p.dqkv + (long long)b * p.T * 3 * HD;
-    store_acc_half(tdV, lane_base, stg, q4, lane, half, gb + 2 * HD + h * DK, 3 * HD, k0, p.T);
+    store_acc_half(tdV, lane_base, stg, q4, lane, half, gb + 2 * HD + h * DK, 3 * HD, k0, p.T,
+                   p.dbv ? p.dbv + h * DK : nullptr);
     store_acc_half(tdK, lane_base, stg, q4, lane, half, gb + HD + h * DK, 3 * HD, k0, p.T);
   }
   tc_fence_before();
@@ -988,7 +1015,8 @@ attn_bwd_dq2_kernel(const __grid_constant__ CUtensorMap tmQ128,  // qkv, box 64 
     tc_fence_after();
     uint8_t* stg = sgen + OFF_STG + warp * 4096;
     __nv_bfloat16* gb = p.dqkv + (long long)b * p.T * 3 * HD;
-    store_acc_half(tdQ, lane_base, stg, q4, lane, half, gb + h * DK, 3 * HD, q0, p.T);
+    store_acc_half(tdQ, lane_base, stg, q4, lane, half, gb + h * DK, 3 * HD, q0, p.T,
+                   p.dbq ? p.dbq + h * DK : nullptr);
   }
   tc_fence_before();
   __syncthreads();
@@ -1005,7 +1033,8 @@ extern "C" {
 // qkv: bf16 [B][T][3*H*128]; o, d_o: bf16 [B][T][H*128]; lse2: f32 [B*H][T] from the forward;
 // dsum: f32 [B*H][T] workspace; dqkv: bf16 [B][T][3*H*128] (every element is written).
 int fs2_attn_bwd_bf16(const void* qkv, const void* o, const void* d_o, const float* lse2, const int64_t* lens,
-                      const int32_t* sched, int B, int T, int H, int dk, float* dsum, void* dqkv, void* stream) {
+                      const int32_t* sched, int B, int T, int H, int dk, float* dsum, void* dqkv, float* dbias_q,
+                      float* dbias_v, void* stream) {
   using namespace fs2;
   if (dk != ab::DK) return set_error("attn_bwd: d_k must be 128");
   if (B <= 0 || T <= 0) return 0;
@@ -1041,6 +1070,8 @@ int fs2_attn_bwd_bf16(const void* qkv, const void* o, const void* d_o, const flo
   p.scale = 1.f / sqrtf((float)dk);
   p.scale_log2 = 1.4426950408889634f * p.scale;
   p.dqkv = static_cast<__nv_bfloat16*>(dqkv);
+  p.dbq = dbias_q;
+  p.dbv = dbias_v;
   static const int dbg = getenv("FS2_ATTN_DBG") ? atoi(getenv("FS2_ATTN_DBG")) : 0;
   p.dbg = dbg;
   p.n_outer = (T + 127) / 128;

@@ -89,6 +89,9 @@ class fork_side:
 # joins are captured as parallel branches of the step's CUDA graph.  FS2_NO_BRANCH=1 keeps everything on one stream.
 BRANCH = OVERLAP and _os.environ.get("FS2_NO_BRANCH") is None
 LN_FUSE = _os.environ.get("FS2_NO_LN_FUSE") is None  # LayerNorm in the epilogue of the k = 1 FFN convolution
+# Q / V bias gradients out of the attention-backward epilogues instead of a column-sum pass over dqkv: measured
+# SLOWER (step 9.3 -> 10.0 ms at C2: ~5000 warps per launch add into the same 256 addresses), so opt-in only.
+ATTN_DBIAS = _os.environ.get("FS2_ATTN_DBIAS") == "1"
 LN_FUSE_MIN_ROWS = 32768  # ... when every CTA pair gets at least ~2 row tiles (B * T rows)
 _branch_streams = {}
 _open_branches = []
@@ -430,14 +433,17 @@ def linear_wgrad(dy2d, x2d, dw, row0=0, rows=None, lens=None, T=None):
     G.wgrad(a, b, dw, rows, K, splits=_splits(rows, K, 1, (M + 63) // 64), row_lens=lens)
 
 
-def qkv_param_grads(dqkv, x2d, gbuf, HD, lens=None, T=None):
+def qkv_param_grads(dqkv, x2d, gbuf, HD, lens=None, T=None, bias_done=False):
     """Weight / bias gradients of the fused Q|K|V projection in ONE weight-gradient GEMM and one column
-    sum pass; row block i of the [3*HD, D] result lands directly in the i-th parameter's gradient."""
+    sum pass; row block i of the [3*HD, D] result lands directly in the i-th parameter's gradient.
+    bias_done: the fused attention backward has already accumulated the Q / V bias gradients (attn_bwd)."""
     M, C3 = dqkv.shape
     D = x2d.shape[1]
     a, b = _wgrad_operands(dqkv, x2d, lens, T)
     G.wgrad(a, b, None, C3, D, splits=_splits(C3, D, 1, (M + 63) // 64),
             segments=(HD, [gbuf[0][0], gbuf[2][0], gbuf[4][0]]), row_lens=lens)
+    if bias_done:
+        return
     # bias gradients = column sums of dQ and dV.  The K bias gets none: adding a constant to every key shifts all
     # scores of a query row by the same amount, which softmax ignores -- its gradient is identically zero (the
     # reference's autograd produces rounding noise of ~1e-8 there), so the dK column sum is not computed.
@@ -590,13 +596,14 @@ def attn_fwd(qkv, lens, H, dk, sched=None):
     return out, lse2
 
 
-def attn_bwd(qkv, out, d_out, lse2, lens, H, dk, sched=None):
-    """Fused attention backward: returns dqkv bf16 [B, T, 3*H*dk]."""
+def attn_bwd(qkv, out, d_out, lse2, lens, H, dk, sched=None, dbias_q=None, dbias_v=None):
+    """Fused attention backward: returns dqkv bf16 [B, T, 3*H*dk].  dbias_q / dbias_v (fp32 [H*dk], accumulated):
+    the Q / V projection bias gradients = column sums of dQ / dV, produced by the kernels' epilogues."""
     B, T, C3 = qkv.shape
     dqkv = torch.empty_like(qkv)
     dsum = torch.empty(B * H, T, dtype=F32, device=qkv.device)
     _ck(_L().fs2_attn_bwd_bf16(_p(qkv), _p(out), _p(d_out), _p(lse2), _p(lens), _p(sched), B, T, H, dk, _p(dsum),
-                               _p(dqkv), _st()), "attn_bwd")
+                               _p(dqkv), _p(dbias_q), _p(dbias_v), _st()), "attn_bwd")
     return dqkv
 
 
@@ -729,11 +736,13 @@ class MHASublayer(torch.autograd.Function):
             linear_wgrad(do2, attn, gbuf[6][0], lens=rl, T=T)
         dattn = linear_dgrad(do2, wo_bf, lens=rl, T=T, tail=NO_TAIL)
         if fused:  # `P` slot of the saved tensors holds lse2; S / P / dS never touch HBM
+            fb = ATTN_DBIAS  # (opt-in) Q / V bias gradients out of the attention backward epilogues
             dqkv = attn_bwd(qkv.view(B, T, C3), attn.view(B, T, HD), dattn.view(B, T, HD), P, lens, H,
-                            dk, ctx.sched).view(M, C3)
+                            dk, ctx.sched, dbias_q=gbuf[1][0] if fb else None,
+                            dbias_v=gbuf[5][0] if fb else None).view(M, C3)
             x2 = x.view(M, D)
             with fork_side():
-                qkv_param_grads(dqkv, x2, gbuf, HD, lens=rl, T=T)
+                qkv_param_grads(dqkv, x2, gbuf, HD, lens=rl, T=T, bias_done=fb)
             dx = linear_dgrad(dqkv, wqkv, epilogue=G.EPI_ADD_AUX, aux=dres.view(M, D), lens=rl, T=T)
             join_side(do, attn, dqkv, x, lens)
             grads_done((wq, bq, wk, bk, wv, bv, wo, bo, gamma, beta))

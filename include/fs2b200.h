@@ -195,9 +195,13 @@ int fs2_softmax_bwd(const void* P, const float* dP, const int64_t* lens, int Z, 
 int fs2_attn_schedule(const int64_t* lens, int B, int T, int H, int32_t* sched, void* stream);
 int fs2_attn_fwd_bf16(const void* qkv, const int64_t* lens, const int32_t* sched, int B, int T, int H, int dk,
                       void* out, float* lse2, void* stream);
-/* backward: o, d_o: bf16 [B][T][H*dk]; dsum: f32 [B*H][T] workspace; dqkv: bf16 [B][T][3*H*dk]   */
+/* backward: o, d_o: bf16 [B][T][H*dk]; dsum: f32 [B*H][T] workspace; dqkv: bf16 [B][T][3*H*dk];  */
+/* dbias_q / dbias_v (optional, f32 [H*dk], ACCUMULATED): column sums of dQ / dV over all frames = */
+/* the gradients of the w_qs / w_vs biases (transformer/SubLayers.py:18-20), taken from the tiles   */
+/* on their way out instead of re-reading dqkv (the key bias has no gradient: softmax ignores it). */
 int fs2_attn_bwd_bf16(const void* qkv, const void* o, const void* d_o, const float* lse2, const int64_t* lens,
-                      const int32_t* sched, int B, int T, int H, int dk, float* dsum, void* dqkv, void* stream);
+                      const int32_t* sched, int B, int T, int H, int dk, float* dsum, void* dqkv, float* dbias_q,
+                      float* dbias_v, void* stream);
 
 /* ------------------------------------------------------------------------------------------ */
 /* LengthRegulator (lightning/model/modules.py:169-196, lightning/utils/tool.py:168-186)       */

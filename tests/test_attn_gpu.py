@@ -58,7 +58,11 @@ def test_attn_bwd(B, T, lens):
     qvalid = torch.arange(T, device="cuda")[None, :] < lens_t[:, None]
     d_out = torch.randn(B, T, HD, device="cuda").to(BF16) * qvalid[..., None]  # padded rows carry no gradient
     out, lse2 = ops.attn_fwd(qkv, lens_t, H, dk)
-    dqkv = ops.attn_bwd(qkv, out, d_out, lse2, lens_t, H, dk)
+    dbq, dbv = torch.full((HD,), 0.5, device="cuda"), torch.full((HD,), -0.25, device="cuda")
+    dqkv = ops.attn_bwd(qkv, out, d_out, lse2, lens_t, H, dk, dbias_q=dbq, dbias_v=dbv)
+    # Q / V bias gradients: column sums of the stored (bf16) dQ / dV, accumulated on top of the buffers' contents
+    assert torch.allclose(dbq, dqkv[..., :HD].float().sum((0, 1)) + 0.5, rtol=2e-3, atol=2e-3)
+    assert torch.allclose(dbv, dqkv[..., 2 * HD:].float().sum((0, 1)) - 0.25, rtol=2e-3, atol=2e-3)
     qr = qkv.float().requires_grad_()
     ref, _, _ = reference(qr, lens_t, H, dk)
     (ref * qvalid[..., None]).backward(d_out.float())

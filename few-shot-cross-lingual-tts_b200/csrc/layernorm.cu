@@ -343,7 +343,7 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const LnArgs a) {
         red[warp][i * 256 + lane * 8 + j] = pass == 0 ? acc_g[i][j] : (pass == 1 ? acc_b[i][j] : acc_x[i][j]);
     __syncthreads();
     float* dst = pass == 0 ? a.dgamma : (pass == 1 ? a.dbeta : a.dbias);
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    for (int c = threadIdx.x; c < C && dst; c += blockDim.x) {
       float s = 0.f;
       for (int w = 0; w < warps_per_block; ++w) s += red[w][c];
       atomicAdd(dst + c, s);

@@ -388,7 +388,7 @@ def kernel_rooflines(base, cfg, bf16_peak, hbm_peak, step_ms, traffic):
     src_lens = base[4].to(dev)
     pt, et = base[9].to(dev), base[10].to(dev)
     lf = lambda: ops.FastSpeech2LossFn.apply(mel, post, pp, ep, dp, mel_t, pt, et, dur, src_lens, lens)
-    rec("masked loss fwd (5 terms, 2 kernels)", 3 * V * n_mel * 4 + 5 * B * Ts * 4, lf, 1)
+    rec("masked loss fwd (5 terms, one kernel)", 3 * V * n_mel * 4 + 5 * B * Ts * 4, lf, 1)
     melg, postg = mel.clone().requires_grad_(), post.clone().requires_grad_()
     out = ops.FastSpeech2LossFn.apply(melg, postg, pp, ep, dp, mel_t, pt, et, dur, src_lens, lens)
     rec("masked loss bwd", 3 * V * n_mel * 4 + 2 * B * Tm * n_mel * 4 + 5 * B * Ts * 4,

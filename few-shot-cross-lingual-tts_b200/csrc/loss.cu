@@ -1,5 +1,6 @@
 // FastSpeech2Loss: masked L1 on mel / postnet mel, masked MSE on pitch / energy / log-duration,
-// forward (deterministic two-stage reduction) and backward.
+// forward (deterministic two-stage reduction in ONE kernel: the last block to arrive sums the per-block partials in
+// block order) and backward.
 //
 // Replaces lightning/model/loss.py:15-89: the nine `masked_select` compactions, two nn.L1Loss and
 // three nn.MSELoss (each a mean over its OWN number of valid elements), the `log(d + 1)` target
@@ -34,7 +35,7 @@ struct LossArgs {
   const int64_t* p_lens;      // src_lens (phoneme level) or mel_lens (frame level)
   const int64_t* e_lens;
   int mel_blocks_per_b, n_blocks;
-  float* partials;  // [n_blocks][5]
+  float* partials;  // [5][n_blocks] + arrival counter (zero between calls)
   float* out;       // [10] total, mel, post, pitch, energy, duration, N_mel, N_pitch, N_energy, N_duration
   // backward
   const float* gout;  // [6] d(loss)/d(out[0..5])
@@ -73,6 +74,51 @@ __device__ __forceinline__ double count_valid_warp(const int64_t* lens, int B, i
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o);
   return (double)n;
+}
+
+__device__ __forceinline__ void loss_final(const LossArgs& a, float* sh) {
+  __shared__ double cnt[4];
+  // the four normalisers, one warp each (this used to be 4 * B dependent loads of thread 0: 15 us at B = 64)
+  const int warp = threadIdx.x >> 5;
+  if (warp < 4) {
+    const double c = warp == 0 ? count_valid_warp(a.mel_lens, a.B, a.Tm) * a.n_mel
+                   : warp == 1 ? count_valid_warp(a.p_lens, a.B, a.p_T)
+                   : warp == 2 ? count_valid_warp(a.e_lens, a.B, a.e_T)
+                               : count_valid_warp(a.src_lens, a.B, a.Ts);
+    if ((threadIdx.x & 31) == 0) cnt[warp] = c;
+  }
+  float s[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int i0 = threadIdx.x; i0 < a.n_blocks; i0 += 4 * kLossThreads) {  // 20 loads in flight per thread
+    float v[4][5];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = i0 + u * kLossThreads;
+#pragma unroll
+      for (int k = 0; k < 5; ++k) v[u][k] = i < a.n_blocks ? __ldcg(a.partials + (long long)k * a.n_blocks + i) : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int k = 0; k < 5; ++k) s[k] += v[u][k];
+  }
+  float r[5];
+#pragma unroll
+  for (int k = 0; k < 5; ++k) r[k] = block_sum(s[k], sh);  // (its barriers also publish cnt[])
+  if (threadIdx.x == 0) {
+    const double n_mel = cnt[0], n_p = cnt[1], n_e = cnt[2], n_d = cnt[3];
+    const float mel = r[0] / (float)n_mel, post = r[1] / (float)n_mel;
+    const float pitch = r[2] / (float)n_p, energy = r[3] / (float)n_e, dur = r[4] / (float)n_d;
+    a.out[0] = mel + post + dur + pitch + energy;  // same association order as loss.py:77-79
+    a.out[1] = mel;
+    a.out[2] = post;
+    a.out[3] = pitch;
+    a.out[4] = energy;
+    a.out[5] = dur;
+    a.out[6] = (float)n_mel;
+    a.out[7] = (float)n_p;
+    a.out[8] = (float)n_e;
+    a.out[9] = (float)n_d;
+  }
 }
 
 __global__ void __launch_bounds__(kLossThreads) loss_partial_kernel(const LossArgs a) {
@@ -124,48 +170,37 @@ __global__ void __launch_bounds__(kLossThreads) loss_partial_kernel(const LossAr
       }
     }
   }
+  // block sums of the five terms with one barrier pair, then the fixed-order final reduction by whichever block
+  // arrives last (partials are [5][n_blocks]; the arrival counter behind them is left at zero for the next call)
+  __shared__ float sh5[5][kLossThreads / 32];
+  __shared__ bool s_last;
+  {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
-  for (int k = 0; k < 5; ++k) {
-    const float r = block_sum(s[k], sh);
-    if (threadIdx.x == 0) a.partials[(long long)blockIdx.x * 5 + k] = r;
-  }
-}
-
-__global__ void __launch_bounds__(kLossThreads) loss_final_kernel(const LossArgs a) {
-  pdl_sync();
-  __shared__ float sh[8];
-  __shared__ double cnt[4];
-  // the four normalisers, one warp each (this used to be 4 * B dependent loads of thread 0: 15 us at B = 64)
-  const int warp = threadIdx.x >> 5;
-  if (warp < 4) {
-    const double c = warp == 0 ? count_valid_warp(a.mel_lens, a.B, a.Tm) * a.n_mel
-                   : warp == 1 ? count_valid_warp(a.p_lens, a.B, a.p_T)
-                   : warp == 2 ? count_valid_warp(a.e_lens, a.B, a.e_T)
-                               : count_valid_warp(a.src_lens, a.B, a.Ts);
-    if ((threadIdx.x & 31) == 0) cnt[warp] = c;
-  }
-  float s[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
-  for (int i = threadIdx.x; i < a.n_blocks; i += kLossThreads)
+    for (int k = 0; k < 5; ++k) {
+      const float r = warp_sum(s[k]);
+      if (lane == 0) sh5[k][warp] = r;
+    }
+    __syncthreads();
+    if (threadIdx.x < 5) {
+      float r = 0.f;
 #pragma unroll
-    for (int k = 0; k < 5; ++k) s[k] += a.partials[(long long)i * 5 + k];
-  float r[5];
-#pragma unroll
-  for (int k = 0; k < 5; ++k) r[k] = block_sum(s[k], sh);  // (its barriers also publish cnt[])
-  if (threadIdx.x == 0) {
-    const double n_mel = cnt[0], n_p = cnt[1], n_e = cnt[2], n_d = cnt[3];
-    const float mel = r[0] / (float)n_mel, post = r[1] / (float)n_mel;
-    const float pitch = r[2] / (float)n_p, energy = r[3] / (float)n_e, dur = r[4] / (float)n_d;
-    a.out[0] = mel + post + dur + pitch + energy;  // same association order as loss.py:77-79
-    a.out[1] = mel;
-    a.out[2] = post;
-    a.out[3] = pitch;
-    a.out[4] = energy;
-    a.out[5] = dur;
-    a.out[6] = (float)n_mel;
-    a.out[7] = (float)n_p;
-    a.out[8] = (float)n_e;
-    a.out[9] = (float)n_d;
+      for (int w = 0; w < kLossThreads / 32; ++w) r += sh5[threadIdx.x][w];
+      a.partials[(long long)threadIdx.x * a.n_blocks + blockIdx.x] = r;
+      __threadfence();
+    }
+    __syncwarp();
+    if (threadIdx.x == 0) {
+      __threadfence();
+      unsigned* counter = reinterpret_cast<unsigned*>(a.partials + 5ll * a.n_blocks);
+      s_last = atomicAdd(counter, 1u) == (unsigned)a.n_blocks - 1u;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
   }
+  loss_final(a, sh);
+  if (threadIdx.x == 0) *reinterpret_cast<unsigned*>(a.partials + 5ll * a.n_blocks) = 0u;
 }
 
 __device__ __forceinline__ float sgn(float v) { return v > 0.f ? 1.f : (v < 0.f ? -1.f : 0.f); }
@@ -246,7 +281,7 @@ int64_t fs2_loss_workspace_floats(int B, int T_feat, int Tm, int n_mel) {
   fs2::LossArgs a{};
   a.B = B; a.Ts = T_feat; a.Tm = Tm; a.Tm_tgt = Tm; a.n_mel = n_mel;
   if (fs2::fill_grid(a)) return -1;
-  return (int64_t)a.n_blocks * 5;
+  return (int64_t)a.n_blocks * 5 + 4;  // + the arrival counter (and padding)
 }
 
 static void loss_common(fs2::LossArgs& a, const float* mel_pred, const float* post_pred, const float* mel_tgt,
@@ -275,10 +310,7 @@ int fs2_loss_fwd(const float* mel_pred, const float* post_pred, const float* mel
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   FS2_LAUNCH((fs2::loss_partial_kernel), a.n_blocks, fs2::kLossThreads, 0, s, a);
   fs2::count_launch();
-  if (int rc = fs2::check_launch("loss_partial_kernel")) return rc;
-  FS2_LAUNCH((fs2::loss_final_kernel), 1, fs2::kLossThreads, 0, s, a);
-  fs2::count_launch();
-  return fs2::check_launch("loss_final_kernel");
+  return fs2::check_launch("loss_partial_kernel");
 }
 
 int fs2_loss_bwd(const float* gout6, const float* out10, const float* mel_pred, const float* post_pred,

@@ -1,5 +1,5 @@
 // Device helpers shared by the memory-bound kernels: 16-byte bf16 vectors, warp/block reductions,
-// Philox4x32-10 counter RNG for dropout (regenerated, never stored, in the backward kernels).
+// Philox4x32-7 counter RNG for dropout and the bf16x2 keep-mask form the LayerNorm kernels use.
 #pragma once
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
@@ -29,11 +29,16 @@ __device__ __forceinline__ bf16x8 pack8(const float (&f)[8]) {
   for (int i = 0; i < 4; ++i) p.v[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
   return p;
 }
+// Always ONE 16-byte access: copying the struct member-wise (__nv_bfloat162 has user-provided copy operations, so
+// bf16x8 is not trivially copyable) let the compiler emit four 32-bit LDG / STG at a 16-byte lane stride -- four
+// times the LSU requests and partially written sectors -- in most of the memory-bound kernels.
 __device__ __forceinline__ bf16x8 ld8(const __nv_bfloat16* p) {
-  return *reinterpret_cast<const bf16x8*>(p);
+  bf16x8 r;
+  *reinterpret_cast<uint4*>(&r) = *reinterpret_cast<const uint4*>(p);
+  return r;
 }
 __device__ __forceinline__ void st8(__nv_bfloat16* p, const bf16x8& v) {
-  *reinterpret_cast<bf16x8*>(p) = v;
+  *reinterpret_cast<uint4*>(p) = *reinterpret_cast<const uint4*>(&v);
 }
 
 __device__ __forceinline__ float warp_sum(float v) {

@@ -1359,8 +1359,22 @@ def _unit0(dev):
     return t
 
 
+_LOSS_WS = {}
+
+
+def _loss_workspace(n, dev):
+    """fs2_loss_fwd's partial sums + arrival counter: zero-initialised once per (stream, size) -- the kernel leaves
+    the counter at zero -- and never shared between streams that may run concurrently."""
+    st = torch.cuda.current_stream(dev)
+    key = (st.device_index, st.cuda_stream, int(n))
+    ws = _LOSS_WS.get(key)
+    if ws is None:
+        ws = _LOSS_WS[key] = torch.zeros(int(n), dtype=F32, device=dev)
+    return ws
+
+
 class FastSpeech2LossFn(torch.autograd.Function):
-    """lightning/model/loss.py:15-89 in two kernels forward, one backward.  `p_frame` / `e_frame`: the pitch /
+    """lightning/model/loss.py:15-89 in one kernel forward, one backward.  `p_frame` / `e_frame`: the pitch /
     energy feature is frame-level ([B, Tm] rows masked by the mel lengths, loss.py:50-52,57-59) instead of
     phoneme-level ([B, Ts], source lengths)."""
 
@@ -1388,7 +1402,7 @@ class FastSpeech2LossFn(torch.autograd.Function):
         nws = _L().fs2_loss_workspace_floats(B, max(Ts, p_T, e_T), Tm, n_mel)
         if nws < 0:
             _ck(1, "loss_workspace")
-        ws = torch.empty(nws, dtype=F32, device=dev)
+        ws = _loss_workspace(nws, dev)
         out10 = torch.empty(10, dtype=F32, device=dev)
         e64 = 1 if e_tgt.dtype == torch.float64 else 0
         _ck(_L().fs2_loss_fwd(_p(mel), _p(post), _p(mel_tgt), _p(p_pred), _p(p_tgt), feat[0], feat[1], _p(feat[2]),

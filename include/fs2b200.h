@@ -276,7 +276,9 @@ int fs2_rowdot_bwd(const float* dout, const void* x, const float* w, const int64
 /* ------------------------------------------------------------------------------------------ */
 /* FastSpeech2Loss (lightning/model/loss.py:15-89): out10 = total, mel, postnet, pitch, energy, */
 /* duration, N_mel, N_pitch, N_energy, N_duration.  partials: f32 workspace of                  */
-/* fs2_loss_workspace_floats(B, max(Ts, p_T, e_T), Tm, n_mel) elements.  Pitch / energy are     */
+/* fs2_loss_workspace_floats(B, max(Ts, p_T, e_T), Tm, n_mel) elements that the caller ZEROES    */
+/* ONCE (it ends with the block arrival counter of the one-kernel reduction, which every call   */
+/* leaves at zero) and does not share between concurrently running calls.  Pitch / energy are   */
 /* phoneme-level (p_T = Ts, p_lens = src_lens) or frame-level (p_T = Tm, p_lens = mel_lens),    */
 /* loss.py:47-60; p_ld / e_ld = row stride of the target (>= p_T / e_T).                        */
 /* ------------------------------------------------------------------------------------------ */

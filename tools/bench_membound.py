@@ -147,7 +147,7 @@ def main():
         return ops.FastSpeech2LossFn.apply(mel, post, pp, ep, dp, mel_t, pt, et, dur, src_lens, mel_lens)
 
     us = timeit(loss_fwd2)
-    rec("loss fwd (2 kernels + torch glue)", us, 3 * B * T * n_mel * 4 + 5 * B * Ts * 4)
+    rec("loss fwd (1 kernel + torch glue)", us, 3 * B * T * n_mel * 4 + 5 * B * Ts * 4)
     out6 = loss_fwd2()
 
     def loss_bwd():

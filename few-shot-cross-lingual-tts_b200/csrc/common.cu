@@ -51,7 +51,10 @@ int fs2_gemm_bf16(const fs2_gemm* g, int impl, void* stream) {
   if (!g) return fs2::set_error("fs2_gemm_bf16: null descriptor");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (impl == 0) return fs2::gemm_tc_launch(*g, s);
-  if (impl == 1) return fs2::gemm_simt_launch(*g, s);
+  if (impl == 1) {
+    if (g->a_colsum) return fs2::set_error("fs2_gemm_bf16: a_colsum is not implemented by the debug kernel (impl 1)");
+    return fs2::gemm_simt_launch(*g, s);
+  }
   return fs2::set_error("fs2_gemm_bf16: unknown impl");
 }
 }

@@ -408,14 +408,32 @@ int gemm_sk_launch(const fs2_gemm& g, GemmKP& kp, cudaStream_t stream);    //  T
 bool wgrad_taps_eligible(const fs2_gemm& g, const GemmKP& kp);             // wgrad_taps.cu (Conv1d weight gradient,
 int wgrad_taps_launch(const fs2_gemm& g, GemmKP& kp, cudaStream_t stream); //  operand reuse across taps)
 
+// fs2_gemm::a_colsum without the fused kernel: one column-sum launch over the (valid rows of the) A operand
+static int a_colsum_fallback(const fs2_gemm& g, cudaStream_t stream) {
+  if (!g.a.mn_major || g.a.batch_stride != g.a.rows * g.a.ld || (g.row_lens && g.lens_zdiv != 1) || (g.M % 8))
+    return set_error("gemm: a_colsum needs a densely batched MN-major A (batch_stride == rows * ld), M % 8 == 0");
+  const __nv_bfloat16* x = static_cast<const __nv_bfloat16*>(g.a.ptr) + g.a.inner_base;
+  if (g.row_lens)
+    return fs2_colsum_ragged_bf16(x, g.a.ld, (int)g.a.batches, (int)g.a.rows, g.M, g.row_lens, g.a_colsum, stream);
+  return fs2_colsum_bf16(x, g.a.ld, 1, (int)(g.a.batches * g.a.rows), g.M, g.a_colsum, stream);
+}
+
 int gemm_tc_launch(const fs2_gemm& g, cudaStream_t stream) {
   GemmKP kp;
   if (int rc = gemm_fill_params(g, kp)) return rc;
+  kp.a_colsum = nullptr;
   // Tile-N choice: 256 columns (128x256 is the shape that can reach the tensor-pipe peak from one
   // CTA) unless the 128-wide tiling wastes clearly less of a ragged N.
   const int n = g.N;
   const int pad256 = ((n + 255) / 256) * 256, pad128 = ((n + 127) / 128) * 128;
   const bool use128 = (n <= 128) || (pad128 * 100 < pad256 * 92);
+  if (g.a_colsum) {  // fused only where the tap-group weight-gradient kernel is the one that runs (order below)
+    if (g.mode != FS2_GEMM_WGRAD) return set_error("gemm: a_colsum is a weight-gradient (WGRAD) option");
+    static const bool no_fuse = getenv("FS2_NO_FUSED_COLSUM") != nullptr;  // A/B switch
+    const bool fused = !no_fuse && !g.ln_gamma && !use128 && !gemm_sk_eligible(g, kp) && wgrad_taps_eligible(g, kp);
+    if (!fused)
+      if (int rc = a_colsum_fallback(g, stream)) return rc;
+  }
   // Conv1d (taps > 1, K-major activations): one activation tile with halo serves every tap, 2-CTA tiles -- also for
   // narrow outputs (the 512 -> 80 PostNet convolution and the input gradient of the 80 -> 512 one: 128-column
   // pair tiles; the 1-CTA kernel re-read the activation tile once per tap: 94 / 72 us for 26 GFLOP)

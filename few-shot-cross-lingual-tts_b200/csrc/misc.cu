@@ -1,5 +1,6 @@
 // Small memory-bound kernels around the GEMM engine: sinusoid add, casts / weight packing,
 // broadcast row-vector add, column sums (bias gradients), the 256->1 predictor head.
+#include <cstdlib>
 #include "common.h"
 #include "util.cuh"
 
@@ -341,6 +342,7 @@ static int colsum_launch(const void* x, int64_t ld, int groups, int rows_per_gro
                          const int64_t* lens, int out_group_stride, void* stream, int seg_stride = 0,
                          float* out_b = nullptr) {
   if (groups <= 0 || rows_per_group <= 0) return 0;
+  if (getenv("FS2_DBG_SKIP_COLSUM")) return 0;
   if ((ld % 8) || (C % 8) || C / 8 > 256 || (reinterpret_cast<uintptr_t>(x) & 15))
     return fs2::set_error("colsum: ld and C must be multiples of 8 (16-byte aligned rows), C <= 2048");
   int rpb = (rows_per_group * groups + 148 * 8 - 1) / (148 * 8);

@@ -2,6 +2,7 @@
 // implicit-GEMM Conv1d with operand-halo reuse (conv_tc2.cu).
 #pragma once
 #include <cstdint>
+#include <cstdio>
 
 namespace fs2 {
 
@@ -21,6 +22,30 @@ __device__ __forceinline__ uint32_t mapa_rank(uint32_t smem_addr, uint32_t rank)
 }
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// generic-proxy reads of a peer CTA's shared memory whose TMA fill was signalled on OUR mbarrier: wait with
+// cluster-scope acquire, then ld.shared::cluster through a mapa address (wgrad_taps.cu: fused column sums)
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+  uint32_t spins = 0, ok = 0;
+  for (;;) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (ok) break;
+    if (++spins > (1u << 26)) {
+      printf("fs2: cluster mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ uint32_t ld_shared_cluster_u32(uint32_t cluster_addr) {
+  uint32_t v;
+  asm volatile("ld.shared::cluster.u32 %0, [%1];" : "=r"(v) : "r"(cluster_addr) : "memory");
+  return v;
 }
 __device__ __forceinline__ void tma_load_3d_2sm(uint32_t smem_dst, const void* tmap, uint32_t leader_bar, int c0,
                                                 int c1, int c2) {

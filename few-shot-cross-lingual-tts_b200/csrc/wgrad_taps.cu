@@ -18,6 +18,11 @@
 // Work units = (co pair tile, ci tile, tap group, split of the frame-block list); groups of different size get
 // split counts in proportion to their taps (host), one unit per CTA pair in the common case.  Partial sums meet in
 // the fp32 gradient with 16-byte vector reductions (the shared epilogue of gemm_common.cuh).
+// Optional fused bias gradient (fs2_gemm::a_colsum): db[co] += sum_{z,t} dY[z][t][co].  The dY tiles are in shared
+// memory anyway and the epilogue warps idle during the main loop, so the leader CTA's eight epilogue warps read
+// both CTAs' tiles (the peer's through ld.shared::cluster) between the tile's full barrier and an extra arrival on
+// its empty barrier; units of tap group 0 share the frame blocks of a (co tile, split) among the ci tiles.  This
+// replaces a separate 73 MB column-sum launch per FFN layer (27 us alone, ~1.7 % of the C2 step).
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
@@ -117,7 +122,7 @@ wgrad_taps_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), 1);
+      mbar_init(empty_bar(s), p.a_colsum ? 5 : 1);  // MMA commit (+ four reader warps of the leader CTA)
     }
     mbar_init(tfull_bar, 1);
     mbar_init(tempty_bar, 16);  // 8 epilogue warps x 2 CTAs (only the leader's copy is used)
@@ -217,8 +222,42 @@ wgrad_taps_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     uint32_t aph = 0;
     uint8_t* stg = sgen + STAGING_OFF + (warp - 4) * 4096;
     const uint32_t leader_tempty = mapa_rank(tempty_bar, 0);
+    // fused column sums of A: warps 4-7 read the leader's tile, 8-11 the peer's; within four warps: (64-co half,
+    // 32-frame half); a lane owns two adjacent co
+    const bool reader = p.a_colsum != nullptr && leader;
+    const int rtile = (warp - 4) >> 2, rh = (warp - 4) & 1, rf = ((warp - 4) >> 1) & 1;
+    const uint32_t rbase = mapa_rank(sbase, (uint32_t)rtile) + rh * kChunkBytes + rf * 32 * 128 + (lane & 3) * 4;
+    const uint32_t rempty0 = mapa_rank(empty_bar(0), (uint32_t)rtile);
+    int rs = 0;
+    uint32_t rph = 0;
     for (int unit = pair; unit < total_units; unit += num_pairs) {
       const WtUnit u = wt_decode(p, sc, cum, unit);
+      if (reader) {
+        float c0 = 0.f, c1 = 0.f;
+        for (int kb = 0; kb < u.nkb; ++kb) {
+          mbar_wait_cluster(full_bar(rs), rph);
+          if (u.g == 0 && (u.kb0 + kb) % sc.tiles_ci == u.tci) {
+            const uint32_t a = rbase + rs * STAGE_BYTES;
+#pragma unroll 8
+            for (int f = 0; f < 32; ++f) {  // frame rf*32 + f: 16-byte chunk index ^ (frame & 7) (SWIZZLE_128B)
+              const uint32_t v = ld_shared_cluster_u32(a + f * 128 + ((((uint32_t)lane >> 2) ^ (f & 7)) << 4));
+              c0 += __uint_as_float(v << 16);
+              c1 += __uint_as_float(v & 0xFFFF0000u);
+            }
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive_remote(rempty0 + 8u * rs);
+          if (++rs == STAGES) {
+            rs = 0;
+            rph ^= 1u;
+          }
+        }
+        if (u.g == 0 && u.nkb > 0) {
+          const int co = (2 * u.tm_pair + rtile) * BM + rh * 64 + lane * 2;
+          if (co < p.M) atomicAdd(p.a_colsum + co, c0);
+          if (co + 1 < p.M) atomicAdd(p.a_colsum + co + 1, c1);
+        }
+      }
       mbar_wait(tfull_bar, aph);
       tc_fence_after();
       TileCoord t;
@@ -310,6 +349,7 @@ int wgrad_taps_launch(const fs2_gemm& g, GemmKP& kp, cudaStream_t stream) {
     return rc;
   kp.n_tiles_per_tap = g.N / BNT;
   kp.n_per_tap = g.N;
+  kp.a_colsum = g.a_colsum;
   const int pairs = total_units < max_pairs ? total_units : max_pairs;
   FS2_LAUNCH((wgrad_taps_kernel), 2 * pairs, kThreadsW, DYN_BYTES, stream, tmA, tmB, kp, sc);
   count_launch();

@@ -492,8 +492,9 @@ def conv_dgrad(dy, wp, Ci, epilogue=G.EPI_NONE, aux=None, lens=None, tail=0, rel
     return dx
 
 
-def conv_wgrad(dy, x, dw, lens=None):
-    """dw[Co, Ci, k] (reference Conv1d.weight layout, fp32) += correlation of dy with x.
+def conv_wgrad(dy, x, dw, lens=None, dbias=None):
+    """dw[Co, Ci, k] (reference Conv1d.weight layout, fp32) += correlation of dy with x; dbias[Co] (fp32) += the
+    column sums of dy when given (fused into the tap-group kernel where it runs, fs2_gemm::a_colsum).
 
     k == 1 is a plain unit-stride weight gradient.  For k > 1 the split-K partial sums are reduced with
     coalesced 16-byte vector atomics in the GEMM's natural [Co][k][Ci] order: directly into the gradient
@@ -506,18 +507,18 @@ def conv_wgrad(dy, x, dw, lens=None):
     b = G.operand(x, Ci, T, B, mn_major=True)
     splits = _splits(Co, Ci, k, B * ((T + 63) // 64))
     if k == 1:
-        G.wgrad(a, b, dw, Co, Ci, splits=splits, row_lens=lens)
+        G.wgrad(a, b, dw, Co, Ci, splits=splits, row_lens=lens, a_colsum=dbias)
         return
     if dw.stride() == (k * Ci, 1, Ci):
         # the flat gradient bucket keeps Conv1d weight gradients in [Co][k][Ci] order (runtime/dp.py): `dw` is the
         # permuted view of it -> accumulate straight into the underlying buffer, no scratch, no re-layout kernel
         G.wgrad(a, b, dw.permute(0, 2, 1), Co, Ci, taps=k, tap_shift0=-((k - 1) // 2), ldd=Ci * k, d_col_stride=1,
-                d_tap_stride=Ci, splits=splits, row_lens=lens)
+                d_tap_stride=Ci, splits=splits, row_lens=lens, a_colsum=dbias)
         return
     assert dw.is_contiguous() and Ci % 4 == 0
     scratch = torch.zeros(Co, k, Ci, dtype=F32, device=dy.device)
     G.wgrad(a, b, scratch, Co, Ci, taps=k, tap_shift0=-((k - 1) // 2), ldd=Ci * k, d_col_stride=1,
-            d_tap_stride=Ci, splits=splits, row_lens=lens)
+            d_tap_stride=Ci, splits=splits, row_lens=lens, a_colsum=dbias)
     _ck(_L().fs2_unpack_add_conv_grad(_p(scratch), Co, Ci, k, _p(dw), _st()), "unpack_add_conv_grad")
 
 
@@ -850,8 +851,7 @@ class FFNSublayer(torch.autograd.Function):
         dh = conv_dgrad(df, w2p, Dh, epilogue=G.EPI_RELU_BWD, aux=None if hmask is not None else h, lens=rl,
                         tail=(w1p.shape[1] - 1) // 2 or NO_TAIL, relu_mask=hmask)
         with fork_side():
-            conv_wgrad(dh, x, gbuf[0][0], lens=rl)
-            colsum(dh.view(B * T, Dh), gbuf[1][0], lens=rl, T=T)
+            conv_wgrad(dh, x, gbuf[0][0], lens=rl, dbias=gbuf[1][0])  # + w_1.bias gradient (column sums of dh)
         dx = conv_dgrad(dh, w1p, D, epilogue=G.EPI_ADD_AUX, aux=dres, lens=rl)
         join_side(df, h, dh, x, lens)
         grads_done((w1, b1, w2, b2, gamma, beta))

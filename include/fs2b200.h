@@ -142,6 +142,12 @@ typedef struct fs2_gemm {
   float* ln_mean;
   float* ln_rstd;
   uint8_t* ln_keep;
+  /* optional, WGRAD mode: a_colsum[m] += sum over z and over the reduction rows r of A[z][r][m] (f32 [M]) -- the
+     bias gradient of the Conv1d / Linear whose weight gradient this call computes (autograd of `nn.Conv1d.bias`).
+     The tap-group weight-gradient kernel (taps >= 2, N % 128 == 0, M >= 256) sums the dY tiles it has in shared
+     memory anyway; any other kernel choice runs a separate column-sum launch on the same stream first (A must then
+     be densely batched: batch_stride == rows * ld, lens_zdiv == 1, M % 8 == 0).  NULL = off. */
+  float* a_colsum;
 } fs2_gemm;
 
 /* impl: 0 = tcgen05 (product path), 1 = plain CUDA-core kernel (debug cross-check only). */

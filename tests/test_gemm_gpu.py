@@ -388,6 +388,39 @@ def test_conv_wgrad_tap_groups(Co, Ci, k, lens, T):
     assert rel_err(dw, ref + 0.5) < 2e-3, rel_err(dw, ref + 0.5)
 
 
+@pytest.mark.parametrize("Co,Ci,k,lens,T,ragged", [
+    (1024, 256, 9, [300, 64, 65, 1, 0, 257], 300, True),   # FFN conv: fused into the tap-group kernel, 2 ci tiles
+    (1024, 256, 9, [1000, 613, 127, 899] * 4, 1000, True), # many frame blocks per split, both CTAs of every pair
+    (512, 512, 5, [130] * 7, 130, False),                  # dense, 4 ci tiles, groups of different size
+    (768, 128, 7, [500, 333], 500, True),                  # 1.5 co pair tiles (rows >= M of the last tile are skipped)
+    (256, 256, 1, [200, 17, 90], 200, True),               # k = 1: not the tap-group kernel -> separate column-sum launch
+    (256, 80, 5, [64, 200], 200, False),                   # Ci % 128 != 0: fallback, dense
+])
+def test_conv_wgrad_bias_gradient(Co, Ci, k, lens, T, ragged):
+    """fs2_gemm::a_colsum: db[co] += sum_{z,t} dY[z][t][co] next to the weight gradient -- read from the dY tiles of
+    csrc/wgrad_taps.cu (the peer CTA's through distributed shared memory), else one column-sum launch."""
+    B = len(lens)
+    torch.manual_seed(Co + Ci + k + B)
+    ln = _lens(lens).clamp(max=T)
+    valid = torch.arange(T, device="cuda")[None, :] < ln[:, None]
+    dy = rnd(B, T, Co) * valid[..., None]
+    x = rnd(B, T, Ci) * valid[..., None]
+    shift = -((k - 1) // 2)
+    out = []
+    for with_db in (False, True):
+        dw = torch.full((Co, k, Ci), 0.5, device="cuda")
+        db = torch.full((Co + 8,), 0.25, device="cuda")  # 8 guard elements behind the bias gradient
+        G.wgrad(G.operand(dy, Co, T, B, mn_major=True), G.operand(x, Ci, T, B, mn_major=True), dw, Co, Ci, taps=k,
+                tap_shift0=shift, ldd=Ci * k, d_col_stride=1, d_tap_stride=Ci, splits=4,
+                row_lens=_lens(lens) if ragged else None, a_colsum=db[:Co] if with_db else None)
+        out.append((dw, db))
+    (dw0, db0), (dw1, db1) = out
+    assert (db0 == 0.25).all() and (db1[Co:] == 0.25).all()
+    ref = dy.float().sum(dim=(0, 1)) + 0.25
+    assert rel_err(db1[:Co], ref) < 1e-5, rel_err(db1[:Co], ref)
+    assert rel_err(dw1, dw0) < 1e-5  # the weight gradient itself is unchanged (fp32 atomics: order only)
+
+
 def test_ragged_many_batches_falls_back_to_dense_schedule():
     """More utterances than the on-chip schedule table holds: every tile is computed, rows still zeroed."""
     B, T, N, K = 300, 40, 256, 256

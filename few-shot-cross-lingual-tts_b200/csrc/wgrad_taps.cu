@@ -62,6 +62,7 @@ struct Sched {
   int unit0[MAX_GROUPS + 1];  // first unit of group g; unit0[n_groups] = total units
   int tiles_co, tiles_ci;     // pair tiles over co (256 rows), tiles over ci (128 columns)
   int box_rows;               // frames of the X box: 64 + (largest group) - 1
+  int cs_all;                 // fused column sums: every tap group has the same split count (same frame-block ranges)
 };
 }  // namespace wt
 
@@ -234,15 +235,23 @@ wgrad_taps_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       const WtUnit u = wt_decode(p, sc, cum, unit);
       if (reader) {
         float c0 = 0.f, c1 = 0.f;
+        // who sums which frame block of a (co tile, split): the units of ALL tap groups and ci tiles take turns when
+        // every group has the same split ranges (sc.cs_all), else the ci tiles of group 0
+        const bool cs_mine = sc.cs_all || u.g == 0;
+        const int cs_mod = sc.cs_all ? sc.n_groups * sc.tiles_ci : sc.tiles_ci;
+        const int cs_idx = sc.cs_all ? u.g * sc.tiles_ci + u.tci : u.tci;
         for (int kb = 0; kb < u.nkb; ++kb) {
           mbar_wait_cluster(full_bar(rs), rph);
-          if (u.g == 0 && (u.kb0 + kb) % sc.tiles_ci == u.tci) {
+          if (cs_mine && (u.kb0 + kb) % cs_mod == cs_idx) {
             const uint32_t a = rbase + rs * STAGE_BYTES;
-#pragma unroll 8
-            for (int f = 0; f < 32; ++f) {  // frame rf*32 + f: 16-byte chunk index ^ (frame & 7) (SWIZZLE_128B)
-              const uint32_t v = ld_shared_cluster_u32(a + f * 128 + ((((uint32_t)lane >> 2) ^ (f & 7)) << 4));
-              c0 += __uint_as_float(v << 16);
-              c1 += __uint_as_float(v & 0xFFFF0000u);
+            uint32_t v[32];  // all 32 loads in flight: one (distributed) shared-memory latency per frame block
+#pragma unroll
+            for (int f = 0; f < 32; ++f)  // frame rf*32 + f: 16-byte chunk index ^ (frame & 7) (SWIZZLE_128B)
+              v[f] = ld_shared_cluster_u32(a + f * 128 + ((((uint32_t)lane >> 2) ^ (f & 7)) << 4));
+#pragma unroll
+            for (int f = 0; f < 32; ++f) {
+              c0 += __uint_as_float(v[f] << 16);
+              c1 += __uint_as_float(v[f] & 0xFFFF0000u);
             }
           }
           __syncwarp();
@@ -252,7 +261,7 @@ wgrad_taps_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             rph ^= 1u;
           }
         }
-        if (u.g == 0 && u.nkb > 0) {
+        if (cs_mine && u.nkb > 0) {
           const int co = (2 * u.tm_pair + rtile) * BM + rh * 64 + lane * 2;
           if (co < p.M) atomicAdd(p.a_colsum + co, c0);
           if (co + 1 < p.M) atomicAdd(p.a_colsum + co + 1, c1);
@@ -337,6 +346,9 @@ int wgrad_taps_launch(const fs2_gemm& g, GemmKP& kp, cudaStream_t stream) {
       units += tiles;
     }
   }
+  sc.cs_all = 1;
+  for (int i = 1; i < sc.n_groups; ++i)
+    if (sc.splits[i] != sc.splits[0]) sc.cs_all = 0;
   sc.unit0[0] = 0;
   for (int i = 0; i < sc.n_groups; ++i) sc.unit0[i + 1] = sc.unit0[i] + tiles * sc.splits[i];
   const int total_units = sc.unit0[sc.n_groups];

@@ -393,6 +393,7 @@ def test_conv_wgrad_tap_groups(Co, Ci, k, lens, T):
     (1024, 256, 9, [1000, 613, 127, 899] * 4, 1000, True), # many frame blocks per split, both CTAs of every pair
     (512, 512, 5, [130] * 7, 130, False),                  # dense, 4 ci tiles, groups of different size
     (768, 128, 7, [500, 333], 500, True),                  # 1.5 co pair tiles (rows >= M of the last tile are skipped)
+    (384, 256, 3, [200, 17, 90], 200, True),               # 1.5 co pair tiles in the fused kernel: the peer CTA of the last pair has no rows
     (256, 256, 1, [200, 17, 90], 200, True),               # k = 1: not the tap-group kernel -> separate column-sum launch
     (256, 80, 5, [64, 200], 200, False),                   # Ci % 128 != 0: fallback, dense
 ])

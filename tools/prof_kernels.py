@@ -25,6 +25,7 @@ qkv, dqkv = rnd(B, T, 3 * D), rnd(B, T, 3 * D)
 w1p, w2p, wqkv, wo = rnd(Dh, 9, D), rnd(D, 1, Dh), rnd(3 * D, D), rnd(D, D)
 b1, b2, bq, bo = (torch.zeros(n, device="cuda") for n in (Dh, D, 3 * D, D))
 gw1 = torch.zeros(Dh, 9, D, device="cuda").permute(0, 2, 1)
+gb1 = torch.zeros(Dh, device="cuda")
 hmask = torch.empty(B * T, Dh // 64, dtype=torch.int64, device="cuda")
 x2, dy2 = x.view(B * T, D), dy.view(B * T, D)
 NT = ops.NO_TAIL
@@ -44,7 +45,7 @@ seq = [
     lambda: ops.conv_dgrad(dy, w2p, Dh, epilogue=G.EPI_RELU_BWD, lens=lens, tail=4, relu_mask=hmask),
     lambda: ops.linear_dgrad(dqkv.view(B * T, 3 * D), wqkv, epilogue=G.EPI_ADD_AUX, aux=x2, lens=lens, T=T),
     lambda: ops.conv_dgrad(dh, w1p, D, epilogue=G.EPI_ADD_AUX, aux=x, lens=lens),
-    lambda: ops.conv_wgrad(dh, x, gw1, lens=lens),
+    lambda: ops.conv_wgrad(dh, x, gw1, lens=lens, dbias=gb1),  # + the fused bias gradient, as in the step
     lambda: ops.ln_fwd(x, dy, gamma, beta, lens, 0.2, 1, 5),
     lambda: ops.ln_bwd(dy, x, dy, gamma, mean, rstd, lens, 0.2, 1, keep, dg, db, True, dbias=dbias),
 ]

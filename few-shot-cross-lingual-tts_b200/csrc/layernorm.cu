@@ -8,6 +8,7 @@
 // One warp owns one row (C = 256/512/1024 channels = 1/2/4 16-byte vectors per lane), so the
 // statistics never leave registers.  HBM-bound: algorithmic bytes fwd = (2 or 3) * rows * C * 2.
 
+#include <cstdlib>
 #include "common.h"
 #include "util.cuh"
 
@@ -363,7 +364,23 @@ static int ln_dispatch(const LnArgs& a, int C, cudaStream_t s) {
   if (a.rows <= 0) return 0;
   if ((long long)a.rows >= (1ll << 31) - 1) return set_error("layernorm: B * T must be < 2^31");
   if (a.p_drop < 0.f || a.p_drop >= 1.f) return set_error("layernorm: dropout p must be in [0,1)");
-  const int grid = BWD ? ln_grid(a.rows, 148 * 4) : ln_grid(a.rows, 148 * 8);
+  // one wave of row-strided blocks: as many as are RESIDENT (the backward holds 116 registers -> 2 blocks of 256
+  // per SM; a grid of 4 per SM ran as two waves with twice the block reductions / atomics: 36.9 -> 34.8 us at C2)
+  static int slots[2][3] = {{0, 0, 0}, {0, 0, 0}};
+  const int vi = C == 256 ? 0 : (C == 512 ? 1 : 2);
+  if ((C == 256 || C == 512 || C == 1024) && !slots[BWD][vi]) {
+    int dev = 0, sms = 148, occ = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (BWD)
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+          &occ, C == 256 ? ln_bwd_kernel<1> : (C == 512 ? ln_bwd_kernel<2> : ln_bwd_kernel<4>), 256, 0);
+    else
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+          &occ, C == 256 ? ln_fwd_kernel<1> : (C == 512 ? ln_fwd_kernel<2> : ln_fwd_kernel<4>), 256, 0);
+    slots[BWD][vi] = sms * (occ > 0 ? occ : 1);
+  }
+  const int grid = ln_grid(a.rows, slots[BWD][vi] > 0 ? slots[BWD][vi] : 148);
   switch (C) {
     case 256:
       if (BWD) FS2_LAUNCH((ln_bwd_kernel<1>), grid, 256, 0, s, a); else FS2_LAUNCH((ln_fwd_kernel<1>), grid, 256, 0, s, a);

@@ -39,6 +39,15 @@ int fs2_version(void) { return FS2_ABI_VERSION; }
 const char* fs2_last_error(void) { return fs2::g_err; }
 int64_t fs2_launch_count(void) { return fs2::g_launches.load(); }
 const char* fs2_last_kernel(void) { return fs2::g_last_kernel; }
+int64_t fs2_stream_capture_id(void* stream) {
+  cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+  unsigned long long id = 0;
+  if (cudaStreamGetCaptureInfo(static_cast<cudaStream_t>(stream), &st, &id) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return st == cudaStreamCaptureStatusActive ? static_cast<int64_t>(id) : 0;
+}
 
 int64_t fs2_gemm_workspace_bytes(void) {
   int dev = 0, sms = 148;

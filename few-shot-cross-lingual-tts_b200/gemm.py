@@ -26,15 +26,30 @@ _WS = {}
 
 
 def _workspace():
-    """Split-K scratch of the Conv1d kernel (fs2_gemm::workspace): one zero-initialised buffer per stream, because
-    launches that may run concurrently must not share it; the kernel leaves its counters zero again."""
+    """Split-K scratch of the Conv1d kernel (fs2_gemm::workspace): one buffer per stream (launches that may run
+    concurrently must not share it) and per graph capture; the kernel leaves its counters zero again."""
     st = torch.cuda.current_stream()
-    key = (st.device_index, st.cuda_stream)
-    ws = _WS.get(key)
-    if ws is None:
-        ws = torch.zeros(int(_cabi.lib().fs2_gemm_workspace_bytes()), dtype=torch.uint8, device=st.device)
-        _WS[key] = ws
+    ws, fresh = scratch(_WS, st, (), int(_cabi.lib().fs2_gemm_workspace_bytes()), torch.uint8)
+    if fresh:
+        ws[:4096].zero_()  # the arrival counters; the partial-sum slabs are written before they are read
     return ws
+
+
+def scratch(cache, st, extra_key, numel, dtype):
+    """Self-resetting kernel scratch: one buffer per (device, stream, CUDA-graph capture).  Inside a capture the
+    buffer is new and the caller's zeroing becomes a node of THAT graph (it runs on every replay), so no graph relies
+    on another one -- or on a kernel that was aborted -- having left the counters at zero; buffers of finished
+    captures are dropped here (their memory stays with the graph that uses it).  -> (buffer, needs_zeroing)"""
+    cap = int(_cabi.lib().fs2_stream_capture_id(st.cuda_stream))
+    key = (st.device_index, st.cuda_stream, cap) + tuple(extra_key)
+    ws = cache.get(key)
+    if ws is not None:
+        return ws, False
+    if cap:
+        for k in [k for k in cache if k[:2] == key[:2] and k[2] not in (0, cap)]:
+            del cache[k]
+    ws = cache[key] = torch.empty(int(numel), dtype=dtype, device=st.device)
+    return ws, True
 
 
 def operand(t, inner, rows, batches=1, ld=None, batch_stride=None, mn_major=False, inner_base=0,

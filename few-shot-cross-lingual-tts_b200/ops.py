@@ -1363,13 +1363,11 @@ _LOSS_WS = {}
 
 
 def _loss_workspace(n, dev):
-    """fs2_loss_fwd's partial sums + arrival counter: zero-initialised once per (stream, size) -- the kernel leaves
-    the counter at zero -- and never shared between streams that may run concurrently."""
-    st = torch.cuda.current_stream(dev)
-    key = (st.device_index, st.cuda_stream, int(n))
-    ws = _LOSS_WS.get(key)
-    if ws is None:
-        ws = _LOSS_WS[key] = torch.zeros(int(n), dtype=F32, device=dev)
+    """fs2_loss_fwd's partial sums + arrival counter (the kernel leaves it at zero): one buffer per (stream, graph
+    capture, size) -- see gemm.scratch -- never shared between streams that may run concurrently."""
+    ws, fresh = G.scratch(_LOSS_WS, torch.cuda.current_stream(dev), (int(n),), int(n), F32)
+    if fresh:
+        ws[-4:].zero_()  # the arrival counter behind the [5][n_blocks] partial sums
     return ws
 
 

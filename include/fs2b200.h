@@ -33,6 +33,10 @@ const char* fs2_last_error(void);
 int64_t fs2_launch_count(void);
 /* name of the kernel this thread launched last (which engine a GEMM descriptor was routed to: tools / bench) */
 const char* fs2_last_kernel(void);
+/* id of the CUDA-graph capture `stream` is in (cudaStreamGetCaptureInfo), 0 when it is not capturing.  Callers that
+   hand out self-resetting scratch (fs2_gemm::workspace, the fs2_loss_fwd workspace) use one buffer per capture and
+   zero its counters INSIDE the captured graph, so that no graph depends on another one having run first. */
+int64_t fs2_stream_capture_id(void* stream);
 
 /* ------------------------------------------------------------------------------------------ */
 /* tcgen05 / TMEM / TMA GEMM family                                                            */
@@ -118,9 +122,10 @@ typedef struct fs2_gemm {
   void* relu_mask;
   /* optional scratch of the Conv1d kernel (NORMAL mode, taps > 1, bf16 D): with it, the tiles of the LAST, partially
      filled wave of the persistent schedule are split over the reduction (channel blocks) across the idle CTA pairs;
-     partial accumulators meet in this buffer and are added in a fixed order (bit-reproducible).  Must be ZERO on
-     first use (the kernel leaves its counters zero again), at least fs2_gemm_workspace_bytes() bytes, and must not
-     be shared by launches that can run concurrently (one buffer per stream).  NULL = no split. */
+     partial accumulators meet in this buffer and are added in a fixed order (bit-reproducible).  Its first 4096
+     bytes (arrival counters) must be ZERO on first use (the kernel leaves them zero again); at least
+     fs2_gemm_workspace_bytes() bytes; not shared by launches that can run concurrently (one buffer per stream).
+     NULL = no split. */
   void* workspace;
   int64_t workspace_bytes;
   /* optional fused LayerNorm epilogue (NORMAL mode, taps = 1, N == 256, bf16 D; transformer/SubLayers.py:88-91

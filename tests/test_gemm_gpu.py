@@ -388,6 +388,45 @@ def test_conv_wgrad_tap_groups(Co, Ci, k, lens, T):
     assert rel_err(dw, ref + 0.5) < 2e-3, rel_err(dw, ref + 0.5)
 
 
+def test_split_tail_scratch_is_per_graph_capture():
+    """fs2_gemm::workspace handed out by gemm.py: every CUDA-graph capture gets its own buffer whose counters are
+    zeroed by a node of THAT graph -- a graph that is replayed before any other graph (or eager call) has run on its
+    stream, and after the scratch of an earlier capture was dirtied, still reduces its split-K tail correctly."""
+    Cin, Cout, k, T = 1024, 256, 9, 1000
+    lens = _split_lens(157, T, 3)
+    B = len(lens)
+    torch.manual_seed(11)
+    ln = _lens(lens)
+    valid = torch.arange(T, device="cuda")[None, :] < ln[:, None]
+    x = rnd(B, T, Cin) * valid[..., None]
+    wp = (torch.randn(Cout, k, Cin, device="cuda") * (Cin * k) ** -0.5).to(torch.bfloat16)
+
+    def conv(y):
+        G.gemm(G.operand(x, Cin, T, B), G.operand(wp, k * Cin, Cout), y, T, Cout, Cin, Z=B, taps=k,
+               tap_shift0=-((k - 1) // 2), b_tap_kstride=Cin, d_zdiv=1, d_zdiv_stride=T * Cout, row_lens=ln)
+
+    ref = torch.empty(B, T, Cout, device="cuda", dtype=torch.bfloat16)
+    conv(ref)
+    torch.cuda.synchronize()
+    outs, graphs = [], []
+    for _ in range(2):
+        y = torch.full((B, T, Cout), float("nan"), device="cuda", dtype=torch.bfloat16)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            conv(y)
+        outs.append(y)
+        graphs.append(g)
+    # dirty every cached scratch buffer (as a kernel aborted half-way would), then replay the SECOND graph first
+    for ws in list(G._WS.values()):
+        ws.fill_(0x5A)
+    graphs[1].replay()
+    graphs[0].replay()
+    torch.cuda.synchronize()
+    for ws in list(G._WS.values()):
+        ws[:4096].zero_()  # leave the eager buffers usable for the tests that follow
+    assert torch.equal(outs[1], ref) and torch.equal(outs[0], ref)
+
+
 @pytest.mark.parametrize("Co,Ci,k,lens,T,ragged", [
     (1024, 256, 9, [300, 64, 65, 1, 0, 257], 300, True),   # FFN conv: fused into the tap-group kernel, 2 ci tiles
     (1024, 256, 9, [1000, 613, 127, 899] * 4, 1000, True), # many frame blocks per split, both CTAs of every pair

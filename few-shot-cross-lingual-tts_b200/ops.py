@@ -369,9 +369,11 @@ def grads_done(params):
 
 def _splits(m_out, n_out, taps, red_blocks):
     tiles = ((m_out + 127) // 128) * taps * ((n_out + 255) // 256 if n_out > 128 else 1)
-    # enough CTAs to fill the 148 SMs, but never less than ~32 reduction blocks (2048 rows) per CTA:
-    # short split-K slices are all prologue + fp32 atomics
-    return max(1, min(148 // max(tiles, 1), red_blocks // 32))
+    # enough CTAs to fill the 148 SMs, but never less than ~14 reduction blocks (of the padded row count; ~8 real
+    # ones on a LibriTTS-shaped batch) per CTA: shorter split-K slices are all prologue + fp32 atomics
+    # (tools/time_wgrad_small.py: the 256 x 256 output-projection gradient at C2 takes 25.6 us with 31 slices, 21.5 us
+    # with 74; the gradients with more output tiles are already capped by the SM count)
+    return max(1, min(148 // max(tiles, 1), red_blocks // 14))
 
 
 # --------------------------------------------------------------------------------------------------

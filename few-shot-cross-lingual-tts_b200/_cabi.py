@@ -34,7 +34,7 @@ class Gemm(ctypes.Structure):
         ("ln_gamma", c_vp), ("ln_beta", c_vp), ("ln_res", c_vp), ("ld_res", c_i64), ("res_batch_stride", c_i64),
         ("ln_p_drop", c_f32), ("ln_pad0", c_i32), ("ln_seed", ctypes.c_uint64), ("ln_seed_dev", c_vp),
         ("ln_v", c_vp), ("ln_mean", c_vp), ("ln_rstd", c_vp), ("ln_keep", c_vp),
-        ("a_colsum", c_vp),
+        ("a_colsum", c_vp), ("a_colsum_seg", c_vp * 4),
     ]
 
 

@@ -61,7 +61,7 @@ int fs2_gemm_bf16(const fs2_gemm* g, int impl, void* stream) {
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (impl == 0) return fs2::gemm_tc_launch(*g, s);
   if (impl == 1) {
-    if (g->a_colsum) return fs2::set_error("fs2_gemm_bf16: a_colsum is not implemented by the debug kernel (impl 1)");
+    if (g->a_colsum || g->a_colsum_seg[0] || g->a_colsum_seg[1] || g->a_colsum_seg[2] || g->a_colsum_seg[3]) return fs2::set_error("fs2_gemm_bf16: a_colsum is not implemented by the debug kernel (impl 1)");
     return fs2::gemm_simt_launch(*g, s);
   }
   return fs2::set_error("fs2_gemm_bf16: unknown impl");

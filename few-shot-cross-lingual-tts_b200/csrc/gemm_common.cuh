@@ -52,7 +52,9 @@ struct GemmKP {
   int pair_any;    // 2-CTA kernels, ragged NORMAL, shared (un-batched) B: the two CTAs of a pair take ANY two
                    // consecutive 128-row tiles of the compact list, also from different utterances
   float* ws;       // conv_tc2: split-K scratch for the last partial wave (fs2_gemm::workspace), NULL = off
-  float* a_colsum; // wgrad_taps: += column sums of A over the reduction (fs2_gemm::a_colsum), NULL = off
+  float* a_colsum; // wgrad_taps / gemm_tc2 WGRAD: += column sums of A over the reduction (fs2_gemm::a_colsum)
+  float* a_colsum_seg[4];  // ... per output segment (seg_rows > 0), NULL entries skipped
+  int a_colsum_on;         // any of the above set: the leader CTA's epilogue warps read the A tiles (empty count 5)
   // gemm_tc2<LN>: fused dropout + residual + LayerNorm + pad-zero epilogue (fs2_gemm::ln_*), ln_gamma != NULL
   const float* ln_gamma;
   const float* ln_beta;

@@ -413,26 +413,48 @@ static int a_colsum_fallback(const fs2_gemm& g, cudaStream_t stream) {
   if (!g.a.mn_major || g.a.batch_stride != g.a.rows * g.a.ld || (g.row_lens && g.lens_zdiv != 1) || (g.M % 8))
     return set_error("gemm: a_colsum needs a densely batched MN-major A (batch_stride == rows * ld), M % 8 == 0");
   const __nv_bfloat16* x = static_cast<const __nv_bfloat16*>(g.a.ptr) + g.a.inner_base;
-  if (g.row_lens)
-    return fs2_colsum_ragged_bf16(x, g.a.ld, (int)g.a.batches, (int)g.a.rows, g.M, g.row_lens, g.a_colsum, stream);
-  return fs2_colsum_bf16(x, g.a.ld, 1, (int)(g.a.batches * g.a.rows), g.M, g.a_colsum, stream);
+  const int nseg = g.d_seg_rows > 0 ? (g.M + g.d_seg_rows - 1) / g.d_seg_rows : 1;
+  for (int i = 0; i < nseg; ++i) {
+    float* out = g.d_seg_rows > 0 ? g.a_colsum_seg[i] : g.a_colsum;
+    if (!out) continue;
+    const int c0 = i * g.d_seg_rows, cols = g.d_seg_rows > 0 ? (g.M - c0 < g.d_seg_rows ? g.M - c0 : g.d_seg_rows) : g.M;
+    if ((c0 % 8) || (cols % 8)) return set_error("gemm: a_colsum segments must be multiples of 8 columns");
+    const int rc = g.row_lens ? fs2_colsum_ragged_bf16(x + c0, g.a.ld, (int)g.a.batches, (int)g.a.rows, cols, g.row_lens,
+                                                       out, stream)
+                              : fs2_colsum_bf16(x + c0, g.a.ld, 1, (int)(g.a.batches * g.a.rows), cols, out, stream);
+    if (rc) return rc;
+  }
+  return 0;
 }
 
 int gemm_tc_launch(const fs2_gemm& g, cudaStream_t stream) {
   GemmKP kp;
   if (int rc = gemm_fill_params(g, kp)) return rc;
   kp.a_colsum = nullptr;
+  kp.a_colsum_on = 0;
+  for (int i = 0; i < 4; ++i) kp.a_colsum_seg[i] = nullptr;
   // Tile-N choice: 256 columns (128x256 is the shape that can reach the tensor-pipe peak from one
   // CTA) unless the 128-wide tiling wastes clearly less of a ragged N.
   const int n = g.N;
   const int pad256 = ((n + 255) / 256) * 256, pad128 = ((n + 127) / 128) * 128;
   const bool use128 = (n <= 128) || (pad128 * 100 < pad256 * 92);
-  if (g.a_colsum) {  // fused only where the tap-group weight-gradient kernel is the one that runs (order below)
+  const bool want_seg = g.a_colsum_seg[0] || g.a_colsum_seg[1] || g.a_colsum_seg[2] || g.a_colsum_seg[3];
+  if (g.a_colsum || want_seg) {  // fused where one of the two kernels that read their dY tiles runs (order below)
     if (g.mode != FS2_GEMM_WGRAD) return set_error("gemm: a_colsum is a weight-gradient (WGRAD) option");
+    if ((g.d_seg_rows > 0) != want_seg || (want_seg && g.a_colsum))
+      return set_error("gemm: a_colsum_seg goes with a segmented output (d_seg_rows > 0), a_colsum with a plain one");
     static const bool no_fuse = getenv("FS2_NO_FUSED_COLSUM") != nullptr;  // A/B switch
-    const bool fused = !no_fuse && !g.ln_gamma && !use128 && !gemm_sk_eligible(g, kp) && wgrad_taps_eligible(g, kp);
-    if (!fused)
-      if (int rc = a_colsum_fallback(g, stream)) return rc;
+    static const bool no_2cta_ = getenv("FS2_GEMM_NO_2CTA") != nullptr;
+    const bool routed = !no_fuse && !g.ln_gamma && !use128 && !gemm_sk_eligible(g, kp);
+    const bool fused_taps = routed && wgrad_taps_eligible(g, kp);
+    const bool fused_tc2 = routed && !fused_taps && !no_2cta_ && (g.M >= 256 || kp.pair_any != 0);
+    if (fused_taps || fused_tc2) {
+      kp.a_colsum = g.a_colsum;
+      for (int i = 0; i < 4; ++i) kp.a_colsum_seg[i] = g.a_colsum_seg[i];
+      kp.a_colsum_on = 1;
+    } else if (int rc = a_colsum_fallback(g, stream)) {
+      return rc;
+    }
   }
   // Conv1d (taps > 1, K-major activations): one activation tile with halo serves every tap, 2-CTA tiles -- also for
   // narrow outputs (the 512 -> 80 PostNet convolution and the input gradient of the 80 -> 512 one: 128-column

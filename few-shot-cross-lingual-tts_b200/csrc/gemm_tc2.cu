@@ -253,7 +253,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), 1);
+      mbar_init(empty_bar(s), p.a_colsum_on ? 5 : 1);  // MMA commit (+ four reader warps of the leader CTA)
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), 1);
@@ -418,8 +418,53 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const uint32_t leader_tempty0 = mapa_rank(tempty_bar(0), 0);
     if (p.ragged && p.mode == FS2_GEMM_NORMAL)
       zero_fill_padded<BN>(p, cum, threadIdx.x - 128, blockIdx.x, gridDim.x);
+    // fused column sums of A (WGRAD, fs2_gemm::a_colsum): the scheme of wgrad_taps.cu -- the leader CTA's warps 4-7
+    // read its dY tile, 8-11 the peer's (ld.shared::cluster), one extra arrival per warp on the tile's empty barrier;
+    // the column tiles of a (row pair tile, split) take turns over its frame blocks
+    const bool reader = !LN && p.a_colsum_on && leader;
+    const int rtile = (warp - 4) >> 2, rh = (warp - 4) & 1, rf = ((warp - 4) >> 1) & 1;
+    const uint32_t rbase = mapa_rank(sbase, (uint32_t)rtile) + rh * kChunkBytes + rf * 32 * 128 + (lane & 3) * 4;
+    const uint32_t rempty0 = mapa_rank(empty_bar(0), (uint32_t)rtile);
+    int rs = 0;
+    uint32_t rph = 0;
     for (int ptile = pair; ptile < total_pair_tiles; ptile += num_pairs) {
       const TileCoord t = decode_pair(ptile);
+      if (reader) {
+        float c0 = 0.f, c1 = 0.f;
+        for (int kb = 0; kb < t.nkb; ++kb) {
+          mbar_wait_cluster(full_bar(rs), rph);
+          if ((t.kb0 + kb) % p.tiles_n == t.tn) {
+            const uint32_t a = rbase + rs * STAGE_BYTES;
+            uint32_t v[32];
+#pragma unroll
+            for (int f = 0; f < 32; ++f)  // frame rf*32 + f: 16-byte chunk index ^ (frame & 7) (SWIZZLE_128B)
+              v[f] = ld_shared_cluster_u32(a + f * 128 + ((((uint32_t)lane >> 2) ^ (f & 7)) << 4));
+#pragma unroll
+            for (int f = 0; f < 32; ++f) {
+              c0 += __uint_as_float(v[f] << 16);
+              c1 += __uint_as_float(v[f] & 0xFFFF0000u);
+            }
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive_remote(rempty0 + 8u * rs);
+          if (++rs == STAGES) {
+            rs = 0;
+            rph ^= 1u;
+          }
+        }
+        if (t.nkb > 0) {
+          const int co = (t.tm - (int)rank + rtile) * BM + rh * 64 + lane * 2;  // leader: t.tm = 2 * pair tile
+          float* dst = p.a_colsum;
+          int c = co;
+          if (p.seg_rows > 0 && co < p.M) {
+            const int sg = co / p.seg_rows;
+            dst = p.a_colsum_seg[sg];
+            c = co - sg * p.seg_rows;
+          }
+          if (dst && co < p.M) atomicAdd(dst + c, c0);
+          if (dst && co + 1 < p.M) atomicAdd(dst + c + 1, c1);
+        }
+      }
       mbar_wait(tfull_bar(as), aph);
       tc_fence_after();
       if (LN) {

@@ -360,8 +360,7 @@ int wgrad_taps_launch(const fs2_gemm& g, GemmKP& kp, cudaStream_t stream) {
                                  BK + tg - 1))
     return rc;
   kp.n_tiles_per_tap = g.N / BNT;
-  kp.n_per_tap = g.N;
-  kp.a_colsum = g.a_colsum;
+  kp.n_per_tap = g.N;  // (kp.a_colsum: set by the dispatcher when this kernel sums the dY tiles)
   const int pairs = total_units < max_pairs ? total_units : max_pairs;
   FS2_LAUNCH((wgrad_taps_kernel), 2 * pairs, kThreadsW, DYN_BYTES, stream, tmA, tmB, kp, sc);
   count_launch();

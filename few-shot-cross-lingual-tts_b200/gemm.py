@@ -129,11 +129,12 @@ def _set_lens(g, row_lens, lens_zdiv):
 
 
 def wgrad(a, b, d, M, N, taps=1, tap_shift0=0, ldd=None, d_col_stride=1, d_tap_stride=0, splits=1,
-          accumulate=True, impl=None, segments=None, row_lens=None, lens_zdiv=1, a_colsum=None):
+          accumulate=True, impl=None, segments=None, row_lens=None, lens_zdiv=1, a_colsum=None, a_colsum_seg=None):
     """D[m][tap][n] (+)= sum_{z,r} A[z][r][m] * B[z][r+shift+tap][n]; D is fp32.
 
     row_lens: promise that rows r >= row_lens[z] of A[z] are zero -> their 64-row blocks are skipped.
-    a_colsum: f32 [M] that receives += sum_{z,r} A[z][r][m] (the bias gradient; fs2_gemm::a_colsum)."""
+    a_colsum: f32 [M] that receives += sum_{z,r} A[z][r][m] (the bias gradient; fs2_gemm::a_colsum);
+    a_colsum_seg: with `segments`, one f32 [rows_per_segment] tensor (or None) per segment instead."""
     if segments is not None:  # (rows_per_segment, [tensor, ...]): row block i of D lives in tensors[i]
         d = segments[1][0]
     assert d.dtype == torch.float32
@@ -163,4 +164,10 @@ def wgrad(a, b, d, M, N, taps=1, tap_shift0=0, ldd=None, d_col_stride=1, d_tap_s
     if a_colsum is not None:
         assert a_colsum.dtype == torch.float32 and a_colsum.is_contiguous() and a_colsum.numel() == M
         g.a_colsum = a_colsum.data_ptr()
+    if a_colsum_seg is not None:
+        assert segments is not None and len(a_colsum_seg) == len(segments[1])
+        for i, t in enumerate(a_colsum_seg):
+            if t is not None:
+                assert t.dtype == torch.float32 and t.is_contiguous() and t.numel() == segments[0]
+                g.a_colsum_seg[i] = t.data_ptr()
     run(g, impl)

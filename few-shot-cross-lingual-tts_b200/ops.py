@@ -442,13 +442,17 @@ def qkv_param_grads(dqkv, x2d, gbuf, HD, lens=None, T=None, bias_done=False):
     M, C3 = dqkv.shape
     D = x2d.shape[1]
     a, b = _wgrad_operands(dqkv, x2d, lens, T)
-    G.wgrad(a, b, None, C3, D, splits=_splits(C3, D, 1, (M + 63) // 64),
-            segments=(HD, [gbuf[0][0], gbuf[2][0], gbuf[4][0]]), row_lens=lens)
-    if bias_done:
-        return
     # bias gradients = column sums of dQ and dV.  The K bias gets none: adding a constant to every key shifts all
     # scores of a query row by the same amount, which softmax ignores -- its gradient is identically zero (the
     # reference's autograd produces rounding noise of ~1e-8 there), so the dK column sum is not computed.
+    # They ride on the weight-gradient GEMM, whose idle epilogue warps sum the dQKV tiles it holds in shared memory
+    # (fs2_gemm::a_colsum_seg; a column-sum launch inside fs2_gemm where another kernel is chosen).
+    fuse = not bias_done and HD % 8 == 0 and (lens is None or T is not None)
+    G.wgrad(a, b, None, C3, D, splits=_splits(C3, D, 1, (M + 63) // 64),
+            segments=(HD, [gbuf[0][0], gbuf[2][0], gbuf[4][0]]), row_lens=lens,
+            a_colsum_seg=[gbuf[1][0], None, gbuf[5][0]] if fuse else None)
+    if bias_done or fuse:
+        return
     if lens is not None and HD % 8 == 0:  # Q and V column blocks of the same rows: one launch
         _ck(_L().fs2_colsum_ragged2_bf16(_p(dqkv), C3, M // T, T, HD, _p(lens), 2 * HD, _p(gbuf[1][0]),
                                          _p(gbuf[5][0]), _st()), "colsum_ragged2")

@@ -151,8 +151,12 @@ typedef struct fs2_gemm {
      bias gradient of the Conv1d / Linear whose weight gradient this call computes (autograd of `nn.Conv1d.bias`).
      The tap-group weight-gradient kernel (taps >= 2, N % 128 == 0, M >= 256) sums the dY tiles it has in shared
      memory anyway; any other kernel choice runs a separate column-sum launch on the same stream first (A must then
-     be densely batched: batch_stride == rows * ld, lens_zdiv == 1, M % 8 == 0).  NULL = off. */
+     be densely batched: batch_stride == rows * ld, lens_zdiv == 1, M % 8 == 0).  NULL = off.
+     With a segmented output (d_seg_rows > 0) the sums of row block i go to a_colsum_seg[i] instead (NULL entries
+     are skipped; a_colsum must then be NULL): the Q / K / V bias gradients next to the fused QKV weight gradient.
+     The 2-CTA weight-gradient kernel reads its dY tiles the same way as the tap-group kernel. */
   float* a_colsum;
+  float* a_colsum_seg[4];
 } fs2_gemm;
 
 /* impl: 0 = tcgen05 (product path), 1 = plain CUDA-core kernel (debug cross-check only). */

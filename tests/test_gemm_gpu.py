@@ -461,6 +461,39 @@ def test_conv_wgrad_bias_gradient(Co, Ci, k, lens, T, ragged):
     assert rel_err(dw1, dw0) < 1e-5  # the weight gradient itself is unchanged (fp32 atomics: order only)
 
 
+@pytest.mark.parametrize("HD,D,lens,T", [
+    (256, 256, [1000, 613, 127, 899, 64, 1] * 3, 1000),   # the QKV projection at C2 scale: 2-CTA kernel, readers on
+    (256, 256, None, 700),                                # dense single batch
+    (128, 512, [300, 17], 300),                           # 384 rows = 1.5 pair tiles, two column tiles share the duty
+    (64, 256, [200, 90], 200),                            # M = 192 < 256: 1-CTA kernel -> column-sum launches
+])
+def test_wgrad_segmented_bias_gradients(HD, D, lens, T):
+    """fs2_gemm::a_colsum_seg: the Q / V bias gradients (column sums of row blocks 0 and 2 of dQKV) next to the fused
+    QKV weight gradient; the K block is skipped (NULL)."""
+    torch.manual_seed(HD + D + T)
+    if lens is None:
+        B, ln = 1, None
+        valid = torch.ones(1, T, 1, device="cuda", dtype=torch.bool)
+    else:
+        B, ln = len(lens), _lens(lens)
+        valid = (torch.arange(T, device="cuda")[None, :] < ln[:, None])[..., None]
+    dqkv = rnd(B, T, 3 * HD) * valid
+    x = rnd(B, T, D) * valid
+    ws = [torch.full((HD, D), 0.5, device="cuda") for _ in range(3)]
+    bs = [torch.full((HD + 8,), 0.25, device="cuda") for _ in range(3)]
+    a = G.operand(dqkv, 3 * HD, T, B, mn_major=True)
+    b = G.operand(x, D, T, B, mn_major=True)
+    G.wgrad(a, b, None, 3 * HD, D, splits=5, segments=(HD, ws), row_lens=ln,
+            a_colsum_seg=[bs[0][:HD], None, bs[2][:HD]])
+    ref_w = torch.einsum("btc,btd->cd", dqkv.float(), x.float()) + 0.5
+    ref_b = dqkv.float().sum((0, 1)) + 0.25
+    for i in range(3):
+        assert rel_err(ws[i], ref_w[i * HD:(i + 1) * HD]) < 2e-3
+        assert (bs[i][HD:] == 0.25).all()
+    assert rel_err(bs[0][:HD], ref_b[:HD]) < 1e-5 and rel_err(bs[2][:HD], ref_b[2 * HD:]) < 1e-5
+    assert (bs[1] == 0.25).all()
+
+
 def test_ragged_many_batches_falls_back_to_dense_schedule():
     """More utterances than the on-chip schedule table holds: every tile is computed, rows still zeroed."""
     B, T, N, K = 300, 40, 256, 256

@@ -189,6 +189,46 @@ colsum_f32_kernel(const float* __restrict__ x, long long ld, int rows, int C, in
   }
 }
 
+// C % 4 == 0, C <= 1024, 16-byte aligned rows: a thread owns four adjacent columns (one 16-byte load per row), the
+// block's 256 / (C / 4) row lanes run side by side with four rows in flight each (the scalar kernel above read one
+// float per thread and row: 30 us for the 20 MB of the mel-projection gradient).
+__global__ void __launch_bounds__(256)
+colsum_f32v4_kernel(const float* __restrict__ x, long long ld, int rows, int C, int rows_per_block,
+                    float* __restrict__ out) {
+  pdl_sync();
+  __shared__ float s_acc[1024];
+  const int c4 = C >> 2, rpp = 256 / c4;  // column groups, row lanes per pass
+  for (int i = threadIdx.x; i < C; i += 256) s_acc[i] = 0.f;
+  __syncthreads();
+  const int cg = threadIdx.x % c4, rl = threadIdx.x / c4;
+  if (rl < rpp) {
+    const int r0 = blockIdx.x * rows_per_block;
+    const int r1 = min(r0 + rows_per_block, rows);
+    const float* base = x + cg * 4;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    int r = r0 + rl;
+    for (; r + 3 * rpp < r1; r += 4 * rpp) {
+      float4 t[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) t[u] = *reinterpret_cast<const float4*>(base + (long long)(r + u * rpp) * ld);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        acc.x += t[u].x; acc.y += t[u].y; acc.z += t[u].z; acc.w += t[u].w;
+      }
+    }
+    for (; r < r1; r += rpp) {
+      const float4 t = *reinterpret_cast<const float4*>(base + (long long)r * ld);
+      acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+    }
+    atomicAdd(&s_acc[cg * 4], acc.x);
+    atomicAdd(&s_acc[cg * 4 + 1], acc.y);
+    atomicAdd(&s_acc[cg * 4 + 2], acc.z);
+    atomicAdd(&s_acc[cg * 4 + 3], acc.w);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C; i += 256) atomicAdd(out + i, s_acc[i]);
+}
+
 // Predictor head: out[row] = mask(dot(x[row,:], w) + b)      (modules.py:242,246-252)
 __global__ void __launch_bounds__(256)
 rowdot_fwd_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w,
@@ -392,6 +432,14 @@ int fs2_unpack_add_conv_grad(const float* packed, int Co, int Ci, int k, float* 
 
 int fs2_colsum_f32(const float* x, int64_t ld, int rows, int C, float* out, void* stream) {
   if (rows <= 0) return 0;
+  if (C % 4 == 0 && C >= 4 && C <= 1024 && ld % 4 == 0 && !(reinterpret_cast<uintptr_t>(x) & 15)) {
+    int rpb = (rows + 148 * 4 - 1) / (148 * 4);
+    if (rpb < 32) rpb = 32;
+    FS2_LAUNCH((fs2::colsum_f32v4_kernel), (rows + rpb - 1) / rpb, 256, 0, static_cast<cudaStream_t>(stream),
+        x, ld, rows, C, rpb, out);
+    fs2::count_launch();
+    return fs2::check_launch("colsum_f32v4_kernel");
+  }
   const int rpb = 64;
   FS2_LAUNCH((fs2::colsum_f32_kernel), (rows + rpb - 1) / rpb, 128, 0, static_cast<cudaStream_t>(stream), 
       x, ld, rows, C, rpb, out);

@@ -1142,9 +1142,11 @@ class LinearF32Out(torch.autograd.Function):
         dy_bf = torch.empty(B * T, N, dtype=BF16, device=dy.device)
         _ck(_L().fs2_cast_f32_bf16(_p(dy), dy.numel(), _p(dy_bf), _st()), "cast(dmel)")
         (gw, rw), (gb, rb) = grad_target(w), grad_target(b)
+        with fork_side():  # the first weight gradients of the backward pass: the side stream is idle here
+            linear_wgrad(dy_bf, x.view(B * T, D), gw)
+            _ck(_L().fs2_colsum_f32(_p(dy), N, B * T, N, _p(gb), _st()), "colsum_f32")
         dx = linear_dgrad(dy_bf, w_bf)
-        linear_wgrad(dy_bf, x.view(B * T, D), gw)
-        _ck(_L().fs2_colsum_f32(_p(dy), N, B * T, N, _p(gb), _st()), "colsum_f32")
+        join_side(dy_bf, x, dy)
         grads_done((w, b))
         return dx.view(B, T, D), rw, rb
 

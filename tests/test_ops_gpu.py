@@ -460,6 +460,19 @@ def test_colsum_ragged_skips_padded_rows():
     assert rel_err(out3, ref[512:768]) < 1e-5
 
 
+@pytest.mark.parametrize("rows,C", [(64000, 80), (1234, 80), (777, 256), (300, 1024), (500, 82), (40, 4)])
+def test_colsum_f32(rows, C):
+    """fs2_colsum_f32 (bias gradient of mel_linear, fastspeech2m.py:143): 16-byte vector kernel for C % 4 == 0, scalar
+    kernel otherwise; accumulates on top of the existing contents, nothing lands behind the C outputs."""
+    torch.manual_seed(rows + C)
+    x = torch.randn(rows, C, device="cuda")
+    out = torch.full((C + 16,), 0.5, device="cuda")
+    ops._ck(ops._L().fs2_colsum_f32(x.data_ptr(), C, rows, C, out.data_ptr(), ops._st()), "colsum_f32")
+    ref = x.double().sum(0).float() + 0.5
+    assert (out[C:] == 0.5).all()
+    assert (out[:C] - ref).abs().max().item() < 1e-3 * max(1.0, rows ** 0.5)
+
+
 @pytest.mark.parametrize("p_drop", [0.0, 0.2])
 @pytest.mark.parametrize("lens", [None, [300, 5, 140, 129, 0, 257]])
 def test_ffn_sublayer_layernorm_fused_into_the_k1_conv_epilogue(p_drop, lens):

@@ -434,16 +434,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         for (int kb = 0; kb < t.nkb; ++kb) {
           mbar_wait_cluster(full_bar(rs), rph);
           if ((t.kb0 + kb) % p.tiles_n == t.tn) {
-            const uint32_t a = rbase + rs * STAGE_BYTES;
-            uint32_t v[32];
-#pragma unroll
-            for (int f = 0; f < 32; ++f)  // frame rf*32 + f: 16-byte chunk index ^ (frame & 7) (SWIZZLE_128B)
-              v[f] = ld_shared_cluster_u32(a + f * 128 + ((((uint32_t)lane >> 2) ^ (f & 7)) << 4));
-#pragma unroll
-            for (int f = 0; f < 32; ++f) {
-              c0 += __uint_as_float(v[f] << 16);
-              c1 += __uint_as_float(v[f] & 0xFFFF0000u);
-            }
+            colsum_tile_rows32(rbase + rs * STAGE_BYTES, lane, c0, c1);  // frames rf * 32 .. + 31 of this tile
           }
           __syncwarp();
           if (lane == 0) mbar_arrive_remote(rempty0 + 8u * rs);

@@ -47,6 +47,21 @@ __device__ __forceinline__ uint32_t ld_shared_cluster_u32(uint32_t cluster_addr)
   asm volatile("ld.shared::cluster.u32 %0, [%1];" : "=r"(v) : "r"(cluster_addr) : "memory");
   return v;
 }
+// Column sums of one MN-major operand tile (two 64 x 64 SWIZZLE_128B boxes, a row = 64 bf16 of one reduction row): this
+// lane adds the bf16 pair at column pair `lane` of 32 consecutive rows starting at `a` (the cluster address of the
+// lane's pair in the first of those rows).  All 32 loads are in flight at once: one (distributed) shared-memory
+// latency per tile.  Used by the fused bias gradients of wgrad_taps.cu and gemm_tc2.cu.
+__device__ __forceinline__ void colsum_tile_rows32(uint32_t a, int lane, float& c0, float& c1) {
+  uint32_t v[32];
+#pragma unroll
+  for (int f = 0; f < 32; ++f)  // 16-byte chunk index ^ (row & 7): the rows start at a multiple of 8
+    v[f] = ld_shared_cluster_u32(a + f * 128 + ((((uint32_t)lane >> 2) ^ (f & 7)) << 4));
+#pragma unroll
+  for (int f = 0; f < 32; ++f) {
+    c0 += __uint_as_float(v[f] << 16);
+    c1 += __uint_as_float(v[f] & 0xFFFF0000u);
+  }
+}
 __device__ __forceinline__ void tma_load_3d_2sm(uint32_t smem_dst, const void* tmap, uint32_t leader_bar, int c0,
                                                 int c1, int c2) {
   asm volatile(
